@@ -1,0 +1,1068 @@
+/*
+ * zanzibar_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+ * See zanzibar_oracle.h for scope, parity status and the reference call sites.
+ *
+ * Algorithm restated (SpiceDB v1.47.1 documented semantics):
+ *   Check(R#P@S) evaluates P's userset-rewrite expression at object R by plain
+ *   recursion (no result cache: pkg/spicedb/spicedb.go:44-46 disables them):
+ *     relation leaf : exact live tuple R#rel@S, or wildcard R#rel@type(S):* when S
+ *                     has no relation, or recurse through every userset subject
+ *                     R#rel@U:u#m -> Check(U:u#m @ S)
+ *     arrow rel->p  : for every tuple R#rel@X:x -> Check(X:x#p @ S); types that
+ *                     lack p contribute nothing
+ *     + & - nil     : OR / AND / AND-NOT / false
+ *     R#P == S      : a userset subject is trivially a member of itself
+ *     depth         : every userset / arrow hop is one dispatch; a path needing a
+ *                     51st hop is an error (pkg/spicedb/spicedb.go:33)
+ *   Results are three-valued {NO, HAS, ERROR} combined Kleene-style, which is the
+ *   order-independent reading of SpiceDB's short-circuiting union/intersection:
+ *   an error only surfaces when it could change the answer.
+ *   Expired relationships are invisible (spicedb.go:47 enables expiration).
+ */
+#define _GNU_SOURCE
+#include "zanzibar_oracle.h"
+
+#include <ctype.h>
+#include <pthread.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+/* ------------------------------------------------------------------ types */
+
+enum { E_NIL, E_REF, E_ARROW, E_UNION, E_INTER, E_EXCL };
+enum { V_F = 0, V_T = 1, V_E = 2 };
+
+typedef struct Expr {
+  int op;
+  int slot;    /* E_REF: slot; E_ARROW: tupleset relation slot */
+  int name_id; /* E_ARROW: name of the computed permission */
+  struct Expr *l, *r;
+} Expr;
+
+typedef struct {
+  int stype;
+  int srel; /* slot id, ZO_SREL_NONE or ZO_SREL_WILDCARD */
+  int expiry;
+  char *pending_rel; /* resolved after all definitions are parsed */
+} Allowed;
+
+typedef struct {
+  uint32_t res, subj, exp; /* exp: unix seconds, 0 = never */
+  uint16_t rel, stype, srel, pad;
+} Tuple;
+
+typedef struct {
+  char *name;
+  int name_id;
+  int type;
+  int is_perm;
+  Expr *expr;
+  Allowed *allowed;
+  int n_allowed;
+  uint64_t *row; /* row[res] .. row[res+1] : range in zo->sorted */
+  uint32_t nrow; /* number of resources covered (max res + 1)   */
+} Slot;
+
+typedef struct {
+  char **keys;
+  uint32_t *vals;
+  uint32_t cap, n;
+} StrMap;
+
+typedef struct {
+  char *name;
+  int *slots;
+  int n_slots;
+  StrMap objs;
+  char **obj_names;
+  uint32_t n_objs, cap_objs;
+  /* is-a-resource bitmap source for LookupResources: rebuilt by freeze() */
+  uint32_t *res_ids;
+  uint64_t n_res_ids;
+} Type;
+
+struct zo_oracle {
+  Type *types;
+  int n_types;
+  Slot *slots;
+  int n_slots;
+  char **names;
+  int n_names;
+  int use_expiration;
+
+  Tuple *log; /* live relationships, unordered */
+  uint64_t n_log, cap_log;
+  Tuple *sorted;
+  uint64_t n_sorted;
+  int dirty;
+  char err[512];
+};
+
+static void set_err(zo_oracle *z, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(z->err, sizeof z->err, fmt, ap);
+  va_end(ap);
+}
+const char *zo_last_error(const zo_oracle *z) { return z->err; }
+
+/* --------------------------------------------------------------- str map */
+
+static uint64_t fnv1a(const char *s) {
+  uint64_t h = 1469598103934665603ull;
+  for (; *s; ++s) {
+    h ^= (unsigned char)*s;
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+static void sm_grow(StrMap *m) {
+  uint32_t ncap = m->cap ? m->cap * 2 : 64;
+  char **nk = calloc(ncap, sizeof *nk);
+  uint32_t *nv = calloc(ncap, sizeof *nv);
+  for (uint32_t i = 0; i < m->cap; i++)
+    if (m->keys[i]) {
+      uint32_t j = (uint32_t)(fnv1a(m->keys[i]) & (ncap - 1));
+      while (nk[j]) j = (j + 1) & (ncap - 1);
+      nk[j] = m->keys[i];
+      nv[j] = m->vals[i];
+    }
+  free(m->keys);
+  free(m->vals);
+  m->keys = nk;
+  m->vals = nv;
+  m->cap = ncap;
+}
+static int64_t sm_find(const StrMap *m, const char *k) {
+  if (!m->cap) return -1;
+  uint32_t j = (uint32_t)(fnv1a(k) & (m->cap - 1));
+  while (m->keys[j]) {
+    if (strcmp(m->keys[j], k) == 0) return m->vals[j];
+    j = (j + 1) & (m->cap - 1);
+  }
+  return -1;
+}
+static void sm_put(StrMap *m, char *k, uint32_t v) {
+  if ((m->n + 1) * 2 > m->cap) sm_grow(m);
+  uint32_t j = (uint32_t)(fnv1a(k) & (m->cap - 1));
+  while (m->keys[j]) j = (j + 1) & (m->cap - 1);
+  m->keys[j] = k;
+  m->vals[j] = v;
+  m->n++;
+}
+
+/* ----------------------------------------------------------------- lexer */
+
+enum {
+  T_EOF, T_IDENT, T_LBRACE, T_RBRACE, T_COLON, T_PIPE, T_HASH, T_EQ, T_PLUS, T_AMP,
+  T_MINUS, T_ARROW, T_LPAREN, T_RPAREN, T_STAR, T_DOT, T_BAD
+};
+typedef struct {
+  const char *s;
+  size_t pos;
+  int tok;
+  char text[256];
+  zo_oracle *z;
+  int failed;
+} Lex;
+
+static int is_ident_ch(int c) { return isalnum(c) || c == '_' || c == '/'; }
+
+static void lex_next(Lex *L) {
+  const char *s = L->s;
+  for (;;) {
+    while (s[L->pos] && isspace((unsigned char)s[L->pos])) L->pos++;
+    if (s[L->pos] == '/' && s[L->pos + 1] == '/') {
+      while (s[L->pos] && s[L->pos] != '\n') L->pos++;
+      continue;
+    }
+    if (s[L->pos] == '/' && s[L->pos + 1] == '*') {
+      L->pos += 2;
+      while (s[L->pos] && !(s[L->pos] == '*' && s[L->pos + 1] == '/')) L->pos++;
+      if (s[L->pos]) L->pos += 2;
+      continue;
+    }
+    break;
+  }
+  int c = (unsigned char)s[L->pos];
+  L->text[0] = 0;
+  if (!c) { L->tok = T_EOF; return; }
+  if (isalpha(c) || c == '_') {
+    size_t n = 0;
+    while (is_ident_ch((unsigned char)s[L->pos]) && n < sizeof L->text - 1)
+      L->text[n++] = s[L->pos++];
+    L->text[n] = 0;
+    L->tok = T_IDENT;
+    return;
+  }
+  L->pos++;
+  switch (c) {
+    case '{': L->tok = T_LBRACE; return;
+    case '}': L->tok = T_RBRACE; return;
+    case ':': L->tok = T_COLON; return;
+    case '|': L->tok = T_PIPE; return;
+    case '#': L->tok = T_HASH; return;
+    case '=': L->tok = T_EQ; return;
+    case '+': L->tok = T_PLUS; return;
+    case '&': L->tok = T_AMP; return;
+    case '(': L->tok = T_LPAREN; return;
+    case ')': L->tok = T_RPAREN; return;
+    case '*': L->tok = T_STAR; return;
+    case '.': L->tok = T_DOT; return;
+    case '-':
+      if (s[L->pos] == '>') { L->pos++; L->tok = T_ARROW; } else L->tok = T_MINUS;
+      return;
+    default: L->tok = T_BAD; L->text[0] = (char)c; L->text[1] = 0; return;
+  }
+}
+static void lex_fail(Lex *L, const char *msg) {
+  if (!L->failed) {
+    int line = 1;
+    for (size_t i = 0; i < L->pos && L->s[i]; i++) line += L->s[i] == '\n';
+    set_err(L->z, "schema line %d: %s (near '%s')", line, msg, L->text);
+  }
+  L->failed = 1;
+}
+static int lex_expect(Lex *L, int tok, const char *what) {
+  if (L->tok != tok) { lex_fail(L, what); return 0; }
+  lex_next(L);
+  return 1;
+}
+
+/* ---------------------------------------------------------------- schema */
+
+static int name_id(zo_oracle *z, const char *n) {
+  for (int i = 0; i < z->n_names; i++)
+    if (strcmp(z->names[i], n) == 0) return i;
+  z->names = realloc(z->names, sizeof(char *) * (z->n_names + 1));
+  z->names[z->n_names] = strdup(n);
+  return z->n_names++;
+}
+int zo_type_id(const zo_oracle *z, const char *n) {
+  for (int i = 0; i < z->n_types; i++)
+    if (strcmp(z->types[i].name, n) == 0) return i;
+  return -1;
+}
+int zo_slot_id(const zo_oracle *z, int t, const char *n) {
+  if (t < 0 || t >= z->n_types) return -1;
+  for (int i = 0; i < z->types[t].n_slots; i++) {
+    int s = z->types[t].slots[i];
+    if (strcmp(z->slots[s].name, n) == 0) return s;
+  }
+  return -1;
+}
+static int slot_by_name_id(const zo_oracle *z, int t, int nid) {
+  for (int i = 0; i < z->types[t].n_slots; i++) {
+    int s = z->types[t].slots[i];
+    if (z->slots[s].name_id == nid) return s;
+  }
+  return -1;
+}
+int zo_num_types(const zo_oracle *z) { return z->n_types; }
+int zo_num_slots(const zo_oracle *z) { return z->n_slots; }
+int zo_slot_type(const zo_oracle *z, int s) { return z->slots[s].type; }
+int zo_slot_is_permission(const zo_oracle *z, int s) { return z->slots[s].is_perm; }
+const char *zo_slot_name(const zo_oracle *z, int s) { return z->slots[s].name; }
+const char *zo_type_name(const zo_oracle *z, int t) { return z->types[t].name; }
+
+typedef struct PExpr { /* parse-time expression with unresolved names */
+  int op;
+  char *a, *b;
+  struct PExpr *l, *r;
+} PExpr;
+
+static PExpr *pe_new(int op) {
+  PExpr *e = calloc(1, sizeof *e);
+  e->op = op;
+  return e;
+}
+static PExpr *parse_expr(Lex *L);
+
+static PExpr *parse_primary(Lex *L) {
+  if (L->tok == T_LPAREN) {
+    lex_next(L);
+    PExpr *e = parse_expr(L);
+    lex_expect(L, T_RPAREN, "expected ')'");
+    return e;
+  }
+  if (L->tok != T_IDENT) { lex_fail(L, "expected relation, permission, nil or '('"); return pe_new(E_NIL); }
+  if (strcmp(L->text, "nil") == 0) { lex_next(L); return pe_new(E_NIL); }
+  char *a = strdup(L->text);
+  lex_next(L);
+  if (L->tok == T_ARROW) {
+    lex_next(L);
+    if (L->tok != T_IDENT) { lex_fail(L, "expected permission after '->'"); free(a); return pe_new(E_NIL); }
+    PExpr *e = pe_new(E_ARROW);
+    e->a = a;
+    e->b = strdup(L->text);
+    lex_next(L);
+    return e;
+  }
+  if (L->tok == T_DOT) { /* rel.any(perm) == rel->perm ; rel.all(perm) unsupported */
+    lex_next(L);
+    if (L->tok != T_IDENT || strcmp(L->text, "any") != 0) {
+      lex_fail(L, "only .any(...) arrows are supported");
+      free(a);
+      return pe_new(E_NIL);
+    }
+    lex_next(L);
+    lex_expect(L, T_LPAREN, "expected '('");
+    PExpr *e = pe_new(E_ARROW);
+    e->a = a;
+    e->b = strdup(L->text);
+    lex_expect(L, T_IDENT, "expected permission name");
+    lex_expect(L, T_RPAREN, "expected ')'");
+    return e;
+  }
+  PExpr *e = pe_new(E_REF);
+  e->a = a;
+  return e;
+}
+/* Precedence (SpiceDB schema DSL): '+' binds tightest, then '&', then '-';
+ * each is left associative. */
+static PExpr *parse_level(Lex *L, int level) {
+  static const int tok[3] = {T_MINUS, T_AMP, T_PLUS};
+  static const int op[3] = {E_EXCL, E_INTER, E_UNION};
+  if (level == 3) return parse_primary(L);
+  PExpr *l = parse_level(L, level + 1);
+  while (L->tok == tok[level] && !L->failed) {
+    lex_next(L);
+    PExpr *r = parse_level(L, level + 1);
+    PExpr *e = pe_new(op[level]);
+    e->l = l;
+    e->r = r;
+    l = e;
+  }
+  return l;
+}
+static PExpr *parse_expr(Lex *L) { return parse_level(L, 0); }
+
+typedef struct { int slot; PExpr *pe; } PendingPerm;
+
+static Expr *resolve_expr(zo_oracle *z, int type, PExpr *pe, int *ok) {
+  Expr *e = calloc(1, sizeof *e);
+  e->op = pe->op;
+  switch (pe->op) {
+    case E_NIL: break;
+    case E_REF:
+      e->slot = zo_slot_id(z, type, pe->a);
+      if (e->slot < 0) {
+        set_err(z, "definition %s: unknown relation or permission '%s'", z->types[type].name, pe->a);
+        *ok = 0;
+      }
+      break;
+    case E_ARROW:
+      e->slot = zo_slot_id(z, type, pe->a);
+      if (e->slot < 0 || z->slots[e->slot].is_perm) {
+        set_err(z, "definition %s: arrow '%s->%s' needs a relation on the left", z->types[type].name, pe->a, pe->b);
+        *ok = 0;
+      }
+      e->name_id = name_id(z, pe->b);
+      break;
+    default:
+      e->l = resolve_expr(z, type, pe->l, ok);
+      e->r = resolve_expr(z, type, pe->r, ok);
+  }
+  return e;
+}
+static void pe_free(PExpr *e) {
+  if (!e) return;
+  pe_free(e->l);
+  pe_free(e->r);
+  free(e->a);
+  free(e->b);
+  free(e);
+}
+static void expr_free(Expr *e) {
+  if (!e) return;
+  expr_free(e->l);
+  expr_free(e->r);
+  free(e);
+}
+
+static int add_slot(zo_oracle *z, int type, const char *name, int is_perm) {
+  if (zo_slot_id(z, type, name) >= 0) {
+    set_err(z, "definition %s: duplicate name '%s'", z->types[type].name, name);
+    return -1;
+  }
+  z->slots = realloc(z->slots, sizeof(Slot) * (z->n_slots + 1));
+  Slot *s = &z->slots[z->n_slots];
+  memset(s, 0, sizeof *s);
+  s->name = strdup(name);
+  s->name_id = name_id(z, name);
+  s->type = type;
+  s->is_perm = is_perm;
+  Type *t = &z->types[type];
+  t->slots = realloc(t->slots, sizeof(int) * (t->n_slots + 1));
+  t->slots[t->n_slots++] = z->n_slots;
+  return z->n_slots++;
+}
+
+static int parse_schema(zo_oracle *z, const char *text) {
+  Lex L = {.s = text, .z = z};
+  PendingPerm *pp = NULL;
+  int npp = 0;
+  /* pass 1: collect type names so forward references resolve */
+  {
+    Lex P = {.s = text, .z = z};
+    lex_next(&P);
+    while (P.tok != T_EOF) {
+      if (P.tok == T_IDENT && strcmp(P.text, "definition") == 0) {
+        lex_next(&P);
+        if (P.tok == T_IDENT) {
+          if (zo_type_id(z, P.text) >= 0) { set_err(z, "duplicate definition '%s'", P.text); return -1; }
+          z->types = realloc(z->types, sizeof(Type) * (z->n_types + 1));
+          memset(&z->types[z->n_types], 0, sizeof(Type));
+          z->types[z->n_types++].name = strdup(P.text);
+        }
+      } else
+        lex_next(&P);
+    }
+  }
+  lex_next(&L);
+  while (L.tok != T_EOF && !L.failed) {
+    if (L.tok != T_IDENT) { lex_fail(&L, "expected 'definition'"); break; }
+    if (strcmp(L.text, "use") == 0) {
+      lex_next(&L);
+      if (L.tok == T_IDENT && strcmp(L.text, "expiration") == 0) z->use_expiration = 1;
+      lex_expect(&L, T_IDENT, "expected feature name after 'use'");
+      continue;
+    }
+    if (strcmp(L.text, "caveat") == 0) { lex_fail(&L, "caveats are not supported"); break; }
+    if (strcmp(L.text, "definition") != 0) { lex_fail(&L, "expected 'definition'"); break; }
+    lex_next(&L);
+    int type = zo_type_id(z, L.text);
+    if (!lex_expect(&L, T_IDENT, "expected definition name")) break;
+    if (!lex_expect(&L, T_LBRACE, "expected '{'")) break;
+    while (L.tok == T_IDENT && !L.failed) {
+      if (strcmp(L.text, "relation") == 0) {
+        lex_next(&L);
+        if (L.tok != T_IDENT) { lex_fail(&L, "expected relation name"); break; }
+        int s = add_slot(z, type, L.text, 0);
+        if (s < 0) { L.failed = 1; break; }
+        lex_next(&L);
+        if (!lex_expect(&L, T_COLON, "expected ':'")) break;
+        for (;;) {
+          if (L.tok != T_IDENT) { lex_fail(&L, "expected subject type"); break; }
+          Allowed a = {.stype = zo_type_id(z, L.text), .srel = ZO_SREL_NONE};
+          if (a.stype < 0) { lex_fail(&L, "unknown subject type"); break; }
+          lex_next(&L);
+          if (L.tok == T_COLON) {
+            lex_next(&L);
+            if (!lex_expect(&L, T_STAR, "expected '*'")) break;
+            a.srel = ZO_SREL_WILDCARD;
+          } else if (L.tok == T_HASH) {
+            lex_next(&L);
+            if (L.tok != T_IDENT) { lex_fail(&L, "expected subject relation"); break; }
+            if (strcmp(L.text, "...") != 0) a.pending_rel = strdup(L.text);
+            lex_next(&L);
+          }
+          if (L.tok == T_IDENT && strcmp(L.text, "with") == 0) {
+            lex_next(&L);
+            if (L.tok != T_IDENT || strcmp(L.text, "expiration") != 0) {
+              lex_fail(&L, "caveats are not supported (only 'with expiration')");
+              break;
+            }
+            a.expiry = 1;
+            lex_next(&L);
+          }
+          Slot *sl = &z->slots[s];
+          sl->allowed = realloc(sl->allowed, sizeof(Allowed) * (sl->n_allowed + 1));
+          sl->allowed[sl->n_allowed++] = a;
+          if (L.tok != T_PIPE) break;
+          lex_next(&L);
+        }
+      } else if (strcmp(L.text, "permission") == 0) {
+        lex_next(&L);
+        if (L.tok != T_IDENT) { lex_fail(&L, "expected permission name"); break; }
+        int s = add_slot(z, type, L.text, 1);
+        if (s < 0) { L.failed = 1; break; }
+        lex_next(&L);
+        if (!lex_expect(&L, T_EQ, "expected '='")) break;
+        PExpr *pe = parse_expr(&L);
+        pp = realloc(pp, sizeof *pp * (npp + 1));
+        pp[npp].slot = s;
+        pp[npp++].pe = pe;
+      } else {
+        lex_fail(&L, "expected 'relation' or 'permission'");
+      }
+    }
+    if (L.failed) break;
+    if (!lex_expect(&L, T_RBRACE, "expected '}'")) break;
+  }
+  int ok = !L.failed;
+  for (int s = 0; ok && s < z->n_slots; s++)
+    for (int i = 0; i < z->slots[s].n_allowed; i++) {
+      Allowed *a = &z->slots[s].allowed[i];
+      if (a->pending_rel) {
+        a->srel = zo_slot_id(z, a->stype, a->pending_rel);
+        if (a->srel < 0) {
+          set_err(z, "relation %s#%s: subject relation %s#%s does not exist",
+                  z->types[z->slots[s].type].name, z->slots[s].name, z->types[a->stype].name, a->pending_rel);
+          ok = 0;
+        }
+        free(a->pending_rel);
+        a->pending_rel = NULL;
+      }
+    }
+  for (int i = 0; i < npp; i++) {
+    if (ok) z->slots[pp[i].slot].expr = resolve_expr(z, z->slots[pp[i].slot].type, pp[i].pe, &ok);
+    pe_free(pp[i].pe);
+  }
+  free(pp);
+  return ok ? 0 : -1;
+}
+
+zo_oracle *zo_create(const char *schema, char *err, size_t errlen) {
+  zo_oracle *z = calloc(1, sizeof *z);
+  if (parse_schema(z, schema) != 0) {
+    if (err && errlen) snprintf(err, errlen, "%s", z->err);
+    zo_destroy(z);
+    return NULL;
+  }
+  z->dirty = 1;
+  return z;
+}
+
+void zo_destroy(zo_oracle *z) {
+  if (!z) return;
+  for (int t = 0; t < z->n_types; t++) {
+    Type *ty = &z->types[t];
+    free(ty->name);
+    free(ty->slots);
+    for (uint32_t i = 0; i < ty->n_objs; i++) free(ty->obj_names[i]);
+    free(ty->obj_names);
+    free(ty->objs.keys);
+    free(ty->objs.vals);
+    free(ty->res_ids);
+  }
+  for (int s = 0; s < z->n_slots; s++) {
+    free(z->slots[s].name);
+    free(z->slots[s].allowed);
+    expr_free(z->slots[s].expr);
+    free(z->slots[s].row);
+  }
+  for (int i = 0; i < z->n_names; i++) free(z->names[i]);
+  free(z->names);
+  free(z->types);
+  free(z->slots);
+  free(z->log);
+  free(z->sorted);
+  free(z);
+}
+
+/* ------------------------------------------------------------- interning */
+
+uint32_t zo_intern(zo_oracle *z, int t, const char *id) {
+  Type *ty = &z->types[t];
+  int64_t f = sm_find(&ty->objs, id);
+  if (f >= 0) return (uint32_t)f;
+  if (ty->n_objs == ty->cap_objs) {
+    ty->cap_objs = ty->cap_objs ? ty->cap_objs * 2 : 64;
+    ty->obj_names = realloc(ty->obj_names, sizeof(char *) * ty->cap_objs);
+  }
+  char *k = strdup(id);
+  ty->obj_names[ty->n_objs] = k;
+  sm_put(&ty->objs, k, ty->n_objs);
+  return ty->n_objs++;
+}
+int64_t zo_find_object(const zo_oracle *z, int t, const char *id) {
+  if (t < 0 || t >= z->n_types) return -1;
+  return sm_find(&z->types[t].objs, id);
+}
+const char *zo_object_name(const zo_oracle *z, int t, uint32_t id) {
+  if (t < 0 || t >= z->n_types || id >= z->types[t].n_objs) return NULL;
+  return z->types[t].obj_names[id];
+}
+
+/* ------------------------------------------------------------- mutations */
+
+static int allowed_subject(const zo_oracle *z, int rel, int stype, int srel, int has_exp) {
+  const Slot *s = &z->slots[rel];
+  for (int i = 0; i < s->n_allowed; i++)
+    if (s->allowed[i].stype == stype && s->allowed[i].srel == srel) {
+      if (has_exp && !s->allowed[i].expiry) continue;
+      return 1;
+    }
+  return 0;
+}
+static void log_push(zo_oracle *z, Tuple t) {
+  if (z->n_log == z->cap_log) {
+    z->cap_log = z->cap_log ? z->cap_log * 2 : 1024;
+    z->log = realloc(z->log, sizeof(Tuple) * z->cap_log);
+  }
+  z->log[z->n_log++] = t;
+  z->dirty = 1;
+}
+static int same_key(const Tuple *a, const Tuple *b) {
+  return a->rel == b->rel && a->res == b->res && a->stype == b->stype && a->srel == b->srel && a->subj == b->subj;
+}
+
+int zo_write(zo_oracle *z, int op, int rel, uint32_t res, int stype, uint32_t subj, int srel, int64_t exp) {
+  if (rel < 0 || rel >= z->n_slots || z->slots[rel].is_perm) { set_err(z, "not a relation"); return -1; }
+  if (stype < 0 || stype >= z->n_types) { set_err(z, "unknown subject type"); return -1; }
+  if (op != ZO_OP_DELETE && !allowed_subject(z, rel, stype, srel, exp != 0)) {
+    set_err(z, "subject %s%s not allowed on %s#%s", z->types[stype].name,
+            srel == ZO_SREL_WILDCARD ? ":*" : (srel == ZO_SREL_NONE ? "" : "#rel"),
+            z->types[z->slots[rel].type].name, z->slots[rel].name);
+    return -1;
+  }
+  Tuple t = {.res = res, .subj = srel == ZO_SREL_WILDCARD ? 0 : subj, .exp = (uint32_t)exp,
+             .rel = (uint16_t)rel, .stype = (uint16_t)stype, .srel = (uint16_t)srel};
+  uint64_t at = z->n_log;
+  for (uint64_t i = 0; i < z->n_log; i++)
+    if (same_key(&z->log[i], &t)) { at = i; break; }
+  if (op == ZO_OP_DELETE) {
+    if (at < z->n_log) { z->log[at] = z->log[--z->n_log]; z->dirty = 1; }
+    return 0;
+  }
+  if (at < z->n_log) {
+    if (op == ZO_OP_CREATE) { set_err(z, "relationship already exists"); return -2; }
+    z->log[at] = t;
+    z->dirty = 1;
+    return 0;
+  }
+  log_push(z, t);
+  return 0;
+}
+
+typedef struct { char rt[128], rid[1100], rel[128], st[128], sid[1100], srel[128]; } RelParts;
+
+static int split_rel(const char *s, RelParts *p) {
+  /* ^(type):(id)#(rel)@(stype):(sid)(#(srel))?$  -- non-greedy like rules.go:1050 */
+  const char *c = strchr(s, ':');
+  if (!c) return -1;
+  const char *h = strchr(c + 1, '#');
+  if (!h) return -1;
+  const char *a = strchr(h + 1, '@');
+  if (!a) return -1;
+  const char *c2 = strchr(a + 1, ':');
+  if (!c2) return -1;
+  const char *h2 = strchr(c2 + 1, '#');
+  size_t n;
+#define CP(dst, b, e) n = (size_t)((e) - (b)); if (n >= sizeof(dst)) return -1; memcpy(dst, b, n); dst[n] = 0;
+  CP(p->rt, s, c);
+  CP(p->rid, c + 1, h);
+  CP(p->rel, h + 1, a);
+  CP(p->st, a + 1, c2);
+  if (h2) { CP(p->sid, c2 + 1, h2); CP(p->srel, h2 + 1, h2 + 1 + strlen(h2 + 1)); }
+  else { CP(p->sid, c2 + 1, c2 + 1 + strlen(c2 + 1)); p->srel[0] = 0; }
+#undef CP
+  return 0;
+}
+
+int zo_write_str(zo_oracle *z, int op, const char *rel, int64_t exp) {
+  RelParts p;
+  if (split_rel(rel, &p) != 0) { set_err(z, "malformed relationship '%s'", rel); return -1; }
+  int rt = zo_type_id(z, p.rt), st = zo_type_id(z, p.st);
+  if (rt < 0 || st < 0) { set_err(z, "unknown type in '%s'", rel); return -1; }
+  int rs = zo_slot_id(z, rt, p.rel);
+  if (rs < 0) { set_err(z, "unknown relation in '%s'", rel); return -1; }
+  int srel = ZO_SREL_NONE;
+  uint32_t sid = 0;
+  if (strcmp(p.sid, "*") == 0) srel = ZO_SREL_WILDCARD;
+  else {
+    if (p.srel[0] && strcmp(p.srel, "...") != 0) {
+      srel = zo_slot_id(z, st, p.srel);
+      if (srel < 0) { set_err(z, "unknown subject relation in '%s'", rel); return -1; }
+    }
+    sid = zo_intern(z, st, p.sid);
+  }
+  return zo_write(z, op, rs, zo_intern(z, rt, p.rid), st, sid, srel, exp);
+}
+
+int zo_add_bulk(zo_oracle *z, int rel, int stype, int srel, const uint32_t *res, const uint32_t *subj, uint64_t n) {
+  if (rel < 0 || rel >= z->n_slots || z->slots[rel].is_perm) { set_err(z, "not a relation"); return -1; }
+  if (!allowed_subject(z, rel, stype, srel, 0)) { set_err(z, "subject type not allowed on relation"); return -1; }
+  if (z->n_log + n > z->cap_log) {
+    z->cap_log = z->n_log + n;
+    z->log = realloc(z->log, sizeof(Tuple) * z->cap_log);
+  }
+  for (uint64_t i = 0; i < n; i++) {
+    Tuple t = {.res = res[i], .subj = srel == ZO_SREL_WILDCARD ? 0 : subj[i], .exp = 0,
+               .rel = (uint16_t)rel, .stype = (uint16_t)stype, .srel = (uint16_t)srel};
+    z->log[z->n_log++] = t;
+  }
+  z->dirty = 1;
+  return 0;
+}
+uint64_t zo_num_tuples(const zo_oracle *z) { return z->n_log; }
+
+/* ----------------------------------------------------------------- index */
+
+static int row_cmp(const void *a, const void *b) {
+  const Tuple *x = a, *y = b;
+  if (x->stype != y->stype) return x->stype < y->stype ? -1 : 1;
+  if (x->srel != y->srel) return x->srel < y->srel ? -1 : 1;
+  if (x->subj != y->subj) return x->subj < y->subj ? -1 : 1;
+  return 0;
+}
+static int u32_cmp(const void *a, const void *b) {
+  uint32_t x = *(const uint32_t *)a, y = *(const uint32_t *)b;
+  return x < y ? -1 : x > y;
+}
+
+static void freeze(zo_oracle *z) {
+  if (!z->dirty) return;
+  for (int s = 0; s < z->n_slots; s++) {
+    free(z->slots[s].row);
+    z->slots[s].row = NULL;
+    z->slots[s].nrow = 0;
+  }
+  for (uint64_t i = 0; i < z->n_log; i++) {
+    Slot *s = &z->slots[z->log[i].rel];
+    if (z->log[i].res + 1 > s->nrow) s->nrow = z->log[i].res + 1;
+  }
+  for (int s = 0; s < z->n_slots; s++)
+    if (z->slots[s].nrow) z->slots[s].row = calloc((size_t)z->slots[s].nrow + 2, sizeof(uint64_t));
+  for (uint64_t i = 0; i < z->n_log; i++) z->slots[z->log[i].rel].row[z->log[i].res + 1]++;
+  uint64_t base = 0;
+  for (int s = 0; s < z->n_slots; s++) {
+    Slot *sl = &z->slots[s];
+    if (!sl->nrow) continue;
+    uint64_t acc = base;
+    for (uint32_t r = 0; r <= sl->nrow; r++) { /* row[r+1] holds count(r) */
+      uint64_t c = sl->row[r + 1];
+      sl->row[r] = acc; /* exclusive start of r, but shifted: fix below */
+      acc += c;
+    }
+    /* after loop row[r] = start(r) for r in [0,nrow], row[nrow] = end; row[nrow+1] spare */
+    base = acc;
+  }
+  free(z->sorted);
+  z->sorted = malloc(sizeof(Tuple) * (z->n_log ? z->n_log : 1));
+  /* scatter with a moving cursor kept in row[] then restore */
+  uint64_t **cur = calloc(z->n_slots, sizeof *cur);
+  for (int s = 0; s < z->n_slots; s++)
+    if (z->slots[s].nrow) {
+      cur[s] = malloc(sizeof(uint64_t) * z->slots[s].nrow);
+      memcpy(cur[s], z->slots[s].row, sizeof(uint64_t) * z->slots[s].nrow);
+    }
+  for (uint64_t i = 0; i < z->n_log; i++) {
+    const Tuple *t = &z->log[i];
+    z->sorted[cur[t->rel][t->res]++] = *t;
+  }
+  for (int s = 0; s < z->n_slots; s++) free(cur[s]);
+  free(cur);
+  z->n_sorted = z->n_log;
+  /* sort rows; bulk loads may carry duplicates (TOUCH semantics): mark and drop */
+  int dup = 0;
+  for (int s = 0; s < z->n_slots; s++) {
+    Slot *sl = &z->slots[s];
+    for (uint32_t r = 0; r < sl->nrow; r++) {
+      uint64_t b = sl->row[r], e = sl->row[r + 1];
+      if (e - b > 1) {
+        qsort(z->sorted + b, e - b, sizeof(Tuple), row_cmp);
+        for (uint64_t i = b + 1; i < e; i++)
+          if (same_key(&z->sorted[i], &z->sorted[i - 1])) dup = 1;
+      }
+    }
+  }
+  if (dup) { /* compact the log to unique keys and rebuild once */
+    uint64_t w = 0;
+    for (uint64_t i = 0; i < z->n_sorted; i++)
+      if (i + 1 == z->n_sorted || !same_key(&z->sorted[i], &z->sorted[i + 1])) z->log[w++] = z->sorted[i];
+    z->n_log = w;
+    freeze(z);
+    return;
+  }
+  /* resource id lists per type (objects that are the resource of >= 1 tuple) */
+  for (int t = 0; t < z->n_types; t++) {
+    Type *ty = &z->types[t];
+    free(ty->res_ids);
+    ty->res_ids = NULL;
+    ty->n_res_ids = 0;
+    uint64_t cap = 0;
+    for (int i = 0; i < ty->n_slots; i++) {
+      Slot *sl = &z->slots[ty->slots[i]];
+      for (uint32_t r = 0; r < sl->nrow; r++)
+        if (sl->row[r + 1] > sl->row[r]) {
+          if (ty->n_res_ids == cap) {
+            cap = cap ? cap * 2 : 256;
+            ty->res_ids = realloc(ty->res_ids, sizeof(uint32_t) * cap);
+          }
+          ty->res_ids[ty->n_res_ids++] = r;
+        }
+    }
+    if (ty->n_res_ids > 1) {
+      qsort(ty->res_ids, ty->n_res_ids, sizeof(uint32_t), u32_cmp);
+      uint64_t w = 1;
+      for (uint64_t i = 1; i < ty->n_res_ids; i++)
+        if (ty->res_ids[i] != ty->res_ids[w - 1]) ty->res_ids[w++] = ty->res_ids[i];
+      ty->n_res_ids = w;
+    }
+  }
+  z->dirty = 0;
+}
+
+/* ----------------------------------------------------------------- check */
+
+typedef struct {
+  const zo_oracle *z;
+  int stype;
+  uint32_t subj;
+  int srel;
+  uint32_t now;
+  int count_bytes; /* canonical B(q): no short circuit */
+  uint64_t bytes;
+} Ctx;
+
+static inline int live(const Tuple *t, uint32_t now) { return t->exp == 0 || t->exp > now; }
+static inline int v_or(int a, int b) { return (a == V_T || b == V_T) ? V_T : ((a == V_E || b == V_E) ? V_E : V_F); }
+static inline int v_and(int a, int b) { return (a == V_F || b == V_F) ? V_F : ((a == V_E || b == V_E) ? V_E : V_T); }
+static inline int v_not(int a) { return a == V_T ? V_F : (a == V_F ? V_T : V_E); }
+
+static int check_slot(Ctx *c, int slot, uint32_t obj, int depth);
+
+static int find_exact(const Tuple *row, uint64_t n, int stype, int srel, uint32_t subj, uint64_t *probes) {
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) {
+    uint64_t mid = (lo + hi) / 2;
+    const Tuple *t = &row[mid];
+    if (probes) ++*probes;
+    int cmp = t->stype != stype ? (t->stype < stype ? -1 : 1)
+              : t->srel != srel ? (t->srel < srel ? -1 : 1)
+              : t->subj != subj ? (t->subj < subj ? -1 : 1) : 0;
+    if (cmp == 0) return (int)mid;
+    if (cmp < 0) lo = mid + 1; else hi = mid;
+  }
+  return -1;
+}
+
+static int eval_relation(Ctx *c, int rel, uint32_t obj, int depth) {
+  const Slot *sl = &c->z->slots[rel];
+  if (c->count_bytes) c->bytes += 8;
+  if (obj >= sl->nrow) return V_F;
+  const Tuple *row = c->z->sorted + sl->row[obj];
+  uint64_t n = sl->row[obj + 1] - sl->row[obj];
+  int r = V_F;
+  if (c->srel == ZO_SREL_NONE) {
+    if (c->count_bytes) { /* probe(v) = ceil(log2(deg_direct+1)) reads */
+      uint64_t d = 0;
+      for (uint64_t i = 0; i < n; i++) d += row[i].srel == ZO_SREL_NONE;
+      uint64_t p = 0;
+      while ((1ull << p) < d + 1) p++;
+      c->bytes += 4 * p;
+    }
+    int i = find_exact(row, n, c->stype, ZO_SREL_NONE, c->subj, NULL);
+    if (i >= 0 && live(&row[i], c->now)) { if (!c->count_bytes) return V_T; r = V_T; }
+    i = find_exact(row, n, c->stype, ZO_SREL_WILDCARD, 0, NULL);
+    if (i >= 0 && live(&row[i], c->now)) { if (!c->count_bytes) return V_T; r = V_T; }
+  }
+  for (uint64_t i = 0; i < n; i++) {
+    const Tuple *t = &row[i];
+    if (t->srel == ZO_SREL_NONE || t->srel == ZO_SREL_WILDCARD || !live(t, c->now)) continue;
+    if (c->count_bytes) c->bytes += 4;
+    int v = depth + 1 > ZO_MAX_DEPTH ? V_E : check_slot(c, t->srel, t->subj, depth + 1);
+    r = v_or(r, v);
+    if (r == V_T && !c->count_bytes) return V_T;
+  }
+  return r;
+}
+
+static int eval_expr(Ctx *c, const Expr *e, int type, uint32_t obj, int depth) {
+  switch (e->op) {
+    case E_NIL: return V_F;
+    case E_REF: return check_slot(c, e->slot, obj, depth);
+    case E_ARROW: {
+      const Slot *sl = &c->z->slots[e->slot];
+      if (c->count_bytes) c->bytes += 8;
+      if (obj >= sl->nrow) return V_F;
+      const Tuple *row = c->z->sorted + sl->row[obj];
+      uint64_t n = sl->row[obj + 1] - sl->row[obj];
+      int r = V_F;
+      for (uint64_t i = 0; i < n; i++) {
+        const Tuple *t = &row[i];
+        if (t->srel == ZO_SREL_WILDCARD || !live(t, c->now)) continue;
+        int tgt = slot_by_name_id(c->z, t->stype, e->name_id);
+        if (tgt < 0) continue;
+        if (c->count_bytes) c->bytes += 4;
+        int v = depth + 1 > ZO_MAX_DEPTH ? V_E : check_slot(c, tgt, t->subj, depth + 1);
+        r = v_or(r, v);
+        if (r == V_T && !c->count_bytes) return V_T;
+      }
+      return r;
+    }
+    case E_UNION: {
+      int a = eval_expr(c, e->l, type, obj, depth);
+      if (a == V_T && !c->count_bytes) return V_T;
+      return v_or(a, eval_expr(c, e->r, type, obj, depth));
+    }
+    case E_INTER: {
+      int a = eval_expr(c, e->l, type, obj, depth);
+      if (a == V_F && !c->count_bytes) return V_F;
+      return v_and(a, eval_expr(c, e->r, type, obj, depth));
+    }
+    case E_EXCL: {
+      int a = eval_expr(c, e->l, type, obj, depth);
+      if (a == V_F && !c->count_bytes) return V_F;
+      return v_and(a, v_not(eval_expr(c, e->r, type, obj, depth)));
+    }
+  }
+  return V_F;
+}
+
+static int check_slot(Ctx *c, int slot, uint32_t obj, int depth) {
+  const Slot *sl = &c->z->slots[slot];
+  if (c->srel == slot && c->subj == obj) return V_T; /* userset subject is a member of itself */
+  if (!sl->is_perm) return eval_relation(c, slot, obj, depth);
+  return eval_expr(c, sl->expr, sl->type, obj, depth);
+}
+
+static int check_one(const zo_oracle *z, const zo_check_item *it, int64_t now, uint64_t *bytes) {
+  if (it->perm >= z->n_slots || it->stype >= z->n_types) return ZO_ERROR;
+  if (it->srel != ZO_SREL_NONE && (it->srel >= z->n_slots || z->slots[it->srel].type != it->stype)) return ZO_ERROR;
+  Ctx c = {.z = z, .stype = it->stype, .subj = it->subj, .srel = it->srel, .now = (uint32_t)now,
+           .count_bytes = bytes != NULL};
+  int v = check_slot(&c, it->perm, it->res, 0);
+  if (bytes) *bytes += 17 + c.bytes;
+  return v == V_T ? ZO_HAS_PERMISSION : (v == V_E ? ZO_ERROR : ZO_NO_PERMISSION);
+}
+
+int zo_check(zo_oracle *z, const zo_check_item *it, int64_t now) {
+  freeze(z);
+  return check_one(z, it, now, NULL);
+}
+
+int zo_check_str(zo_oracle *z, const char *rt, const char *rid, const char *perm, const char *st,
+                 const char *sid, const char *srel, int64_t now) {
+  int t = zo_type_id(z, rt), s = zo_type_id(z, st);
+  if (t < 0 || s < 0) { set_err(z, "unknown object type"); return ZO_ERROR; }
+  int p = zo_slot_id(z, t, perm);
+  if (p < 0) { set_err(z, "unknown permission %s#%s", rt, perm); return ZO_ERROR; }
+  int sr = ZO_SREL_NONE;
+  if (srel && srel[0] && strcmp(srel, "...") != 0) {
+    sr = zo_slot_id(z, s, srel);
+    if (sr < 0) { set_err(z, "unknown subject relation %s#%s", st, srel); return ZO_ERROR; }
+  }
+  int64_t r = zo_find_object(z, t, rid), u = zo_find_object(z, s, sid);
+  /* Objects never written cannot be related to anything, but R#P@R#P is still a
+   * member of itself: two unknown names of one type that are the same string get
+   * the same sentinel id. */
+  uint32_t rsent = 0xFFFFFFFFu, usent = (r < 0 && t == s && strcmp(rid, sid) == 0) ? 0xFFFFFFFFu : 0xFFFFFFFEu;
+  zo_check_item it = {.res = r < 0 ? rsent : (uint32_t)r, .subj = u < 0 ? usent : (uint32_t)u,
+                      .perm = (uint16_t)p, .stype = (uint16_t)s, .srel = (uint16_t)sr};
+  return zo_check(z, &it, now);
+}
+
+typedef struct {
+  const zo_oracle *z;
+  const zo_check_item *items;
+  uint8_t *out;
+  uint64_t n;
+  int64_t now;
+  uint64_t *next; /* shared work counter */
+} Job;
+
+static void *bulk_worker(void *p) {
+  Job *j = p;
+  for (;;) {
+    uint64_t b = __atomic_fetch_add(j->next, 1024, __ATOMIC_RELAXED);
+    if (b >= j->n) break;
+    uint64_t e = b + 1024 < j->n ? b + 1024 : j->n;
+    for (uint64_t i = b; i < e; i++) j->out[i] = (uint8_t)check_one(j->z, &j->items[i], j->now, NULL);
+  }
+  return NULL;
+}
+
+int zo_check_bulk(zo_oracle *z, const zo_check_item *items, uint64_t n, uint8_t *out, int nthreads, int64_t now) {
+  freeze(z);
+  if (nthreads <= 0) nthreads = (int)sysconf(_SC_NPROCESSORS_ONLN);
+  if (nthreads > 256) nthreads = 256;
+  uint64_t next = 0;
+  Job j = {z, items, out, n, now, &next};
+  if (nthreads == 1 || n < 2048) { bulk_worker(&j); return 0; }
+  pthread_t th[256];
+  for (int i = 0; i < nthreads; i++) pthread_create(&th[i], NULL, bulk_worker, &j);
+  for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
+  return 0;
+}
+
+uint64_t zo_check_bytes(zo_oracle *z, const zo_check_item *items, uint64_t n, int64_t now) {
+  freeze(z);
+  uint64_t b = 0;
+  for (uint64_t i = 0; i < n; i++) check_one(z, &items[i], now, &b);
+  return b;
+}
+
+/* ------------------------------------------------------- LookupResources */
+
+int zo_lookup_resources(zo_oracle *z, int rt, int perm, int stype, uint32_t subj, int srel, int64_t now,
+                        uint32_t *out, uint64_t cap, uint64_t *n_out) {
+  freeze(z);
+  if (rt < 0 || rt >= z->n_types || perm < 0 || perm >= z->n_slots || z->slots[perm].type != rt) {
+    set_err(z, "unknown resource type or permission");
+    return -1;
+  }
+  const Type *ty = &z->types[rt];
+  uint64_t k = 0;
+  for (uint64_t i = 0; i < ty->n_res_ids; i++) {
+    uint32_t r = ty->res_ids[i];
+    /* the resource must have a LIVE relationship */
+    int alive = 0;
+    for (int s = 0; s < ty->n_slots && !alive; s++) {
+      const Slot *sl = &z->slots[ty->slots[s]];
+      if (r >= sl->nrow) continue;
+      for (uint64_t e = sl->row[r]; e < sl->row[r + 1] && !alive; e++) alive = live(&z->sorted[e], (uint32_t)now);
+    }
+    if (!alive) continue;
+    zo_check_item it = {.res = r, .subj = subj, .perm = (uint16_t)perm, .stype = (uint16_t)stype, .srel = (uint16_t)srel};
+    if (check_one(z, &it, now, NULL) == ZO_HAS_PERMISSION) {
+      if (k < cap) out[k] = r;
+      k++;
+    }
+  }
+  *n_out = k;
+  return k > cap ? -7 : 0;
+}
+
+/* ------------------------------------------------------ ReadRelationships */
+
+static int line_cmp(const void *a, const void *b) { return strcmp(*(char *const *)a, *(char *const *)b); }
+
+int64_t zo_read_str(zo_oracle *z, const char *rt, const char *rid, const char *rel, const char *st,
+                    const char *sid, const char *srel, int64_t now, char *buf, size_t cap, size_t *need) {
+  freeze(z);
+  char **lines = NULL;
+  int64_t n = 0;
+  size_t total = 0;
+  for (uint64_t i = 0; i < z->n_sorted; i++) {
+    const Tuple *t = &z->sorted[i];
+    if (!live(t, (uint32_t)now)) continue;
+    const Slot *sl = &z->slots[t->rel];
+    const char *trt = z->types[sl->type].name;
+    const char *trid = zo_object_name(z, sl->type, t->res);
+    const char *tst = z->types[t->stype].name;
+    const char *tsid = t->srel == ZO_SREL_WILDCARD ? "*" : zo_object_name(z, t->stype, t->subj);
+    const char *tsrel = (t->srel == ZO_SREL_NONE || t->srel == ZO_SREL_WILDCARD) ? "" : z->slots[t->srel].name;
+    char num1[16], num2[16];
+    if (!trid) { snprintf(num1, sizeof num1, "%u", t->res); trid = num1; }
+    if (!tsid) { snprintf(num2, sizeof num2, "%u", t->subj); tsid = num2; }
+    if (rt && rt[0] && strcmp(rt, trt)) continue;
+    if (rid && rid[0] && strcmp(rid, trid)) continue;
+    if (rel && rel[0] && strcmp(rel, sl->name)) continue;
+    if (st && st[0] && strcmp(st, tst)) continue;
+    if (sid && sid[0] && strcmp(sid, tsid)) continue;
+    if (srel && srel[0] && strcmp(srel, tsrel)) continue;
+    char *line = NULL;
+    int len = asprintf(&line, "%s:%s#%s@%s:%s%s%s\n", trt, trid, sl->name, tst, tsid, tsrel[0] ? "#" : "", tsrel);
+    lines = realloc(lines, sizeof(char *) * (n + 1));
+    lines[n++] = line;
+    total += (size_t)len;
+  }
+  if (n > 1) qsort(lines, (size_t)n, sizeof(char *), line_cmp);
+  if (need) *need = total + 1;
+  int64_t ret = n;
+  if (total + 1 > cap) ret = -7;
+  else {
+    size_t w = 0;
+    for (int64_t i = 0; i < n; i++) { size_t l = strlen(lines[i]); memcpy(buf + w, lines[i], l); w += l; }
+    buf[w] = 0;
+  }
+  for (int64_t i = 0; i < n; i++) free(lines[i]);
+  free(lines);
+  return ret;
+}
