@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- Mchecks/sec of batched CheckPermission (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3] [--impl reference]
+
+A "step" is one pass of the hot path (CheckBulkPermissions) over one batch of
+synthetic checks of the named workload. Prints ONE JSON line.
+
+  value     whole-job Mchecks/s, inputs resident in HBM when the timed region starts
+            (zg_check_bulk_device on device buffers, CUDA events on the launch stream,
+            max over ranks)
+  e2e       the same metric through the reference-facing C ABI call zg_check_bulk with
+            pinned HOST buffers: H2D of the 16 B items and D2H of the 1 B answers are
+            inside the timed region
+  roofline  algorithmic bytes of the check kernel (counted by the instrumented kernel
+            variant) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the CPU oracle (a port: the reference's engine is a Go module that
+            cannot be built here) on a bounded sample, rank 0, N=1
+
+Multi-GPU (--gpus N under torchrun): the store (<= 1.6 GB) is REPLICATED on every GPU
+and each rank answers its own batch: no data-path collective, "scaling": "weak".
+--impl reference: the oracle on all host threads, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Mchecks/sec (batched CheckPermission)"
+UNIT = "Mchecks/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="zgpu", choices=["zgpu", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg2", "cfg2-zipf", "cfg3", "cfg4"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="checks in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def workload_config(w, args, world):
+    return {
+        "workload": f"{w.name}: {w.note}",
+        "tuples": w.n_tuples(),
+        "batch": w.n_checks(),
+        "global_batch": w.n_checks() * world,
+        "parallelism": f"replicas x{world} (store replicated, checks sharded, no collective)" if world > 1 else "1 GPU",
+        "l2": "L2 flushed (256 MiB write) between timed steps; per-step CUDA events exclude the flush",
+        "scale": args.scale,
+    }
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """dram bytes per launch of check_kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(workload)
+    return None
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_arm(args, rank, world):
+    """--impl reference: the oracle port, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    import numpy as np
+
+    from oracle.pyoracle import CHECK_DTYPE, Oracle
+    from spicedb_kubeapi_proxy_b200 import workloads
+
+    w = workloads.by_name(args.workload, args.scale)
+    o = Oracle(w.schema)
+    w.load_into(o)
+    items = w.check_items(o, CHECK_DTYPE)
+    cores = os.cpu_count() or 1
+    o.check_bulk(items[:256])  # builds the index (not timed)
+    t = time.perf_counter()
+    o.check_bulk(items[:4096], nthreads=cores)
+    rate = 4096 / max(time.perf_counter() - t, 1e-6)
+    budget_s = 120.0 / max(args.steps + args.warmup, 1)
+    n = args.cpu_sample or int(min(items.size, max(2048, rate * min(budget_s, 8.0))))
+    sample = items[:n]
+    for _ in range(args.warmup):
+        o.check_bulk(sample, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.check_bulk(sample, nthreads=cores)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt / 1e6
+    desc = f"first {n} checks of the {w.name} batch per step, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(w, args, 1),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                         "note": "C oracle restating SpiceDB v1.47.1 check semantics; the reference's own engine is an "
+                                 "un-vendored Go module and no Go toolchain exists on this box"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank, local_rank, world = dist_env()
+    if args.impl == "reference":
+        cpu_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+
+    import zgpu
+    from spicedb_kubeapi_proxy_b200 import workloads
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path in libzgpu)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w = workloads.by_name(args.workload, args.scale)
+    eng = zgpu.Engine(w.schema, device=local_rank)
+    w.load_into(eng)
+    t0 = time.perf_counter()
+    eng.publish()
+    publish_s = time.perf_counter() - t0
+    items = w.check_items(eng, zgpu.CHECK_DTYPE)
+    if world > 1:  # each rank answers its own batch (weak scaling): rank-specific permutation
+        items = items[np.random.default_rng(1000 + rank).permutation(items.size)]
+    n = items.size
+
+    d_items = torch.from_numpy(items.view(np.uint8).copy()).cuda()
+    d_out = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        eng.check_bulk_device(d_items.data_ptr(), n, d_out.data_ptr(), stream.cuda_stream)
+
+    # algorithmic bytes of one launch, from the instrumented kernel variant (not timed)
+    alg_bytes = eng.count_alg_bytes(items)
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step_device()
+    torch.cuda.synchronize()
+    launches0 = eng.stats()["launches"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in evs:
+        flush.zero_()  # evict the store and the batch from L2; outside the event pair
+        a.record(stream)
+        step_device()
+        b.record(stream)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    launches = eng.stats()["launches"] - launches0
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    value = n * world * args.steps / (dev_ms_max / 1e3) / 1e6
+
+    # ---- e2e: the public C ABI call with pinned host buffers, copies inside the timed region
+    pin_in = zgpu._lib.PinnedArray(n, zgpu.CHECK_DTYPE)
+    pin_out = zgpu._lib.PinnedArray(n, np.uint8)
+    pin_in.array[:] = items
+    for _ in range(2):
+        eng.check_bulk_ptr(pin_in.ptr, n, pin_out.ptr)
+    e2e_steps = max(3, min(args.steps, 10))
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.check_bulk_ptr(pin_in.ptr, n, pin_out.ptr)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n * world * e2e_steps / float(t.item()) / 1e6
+    clocks = sampler.stop() if rank == 0 else None
+    host_answers = pin_out.array.copy()
+    assert np.array_equal(host_answers, d_out.cpu().numpy()), "host and device entry points disagree"
+
+    # ---- CPU baseline: oracle on a bounded sample (rank 0, N=1), also a live parity check
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.pyoracle import Oracle
+
+        o = Oracle(w.schema)
+        w.load_into(o)
+        cores = os.cpu_count() or 1
+        o.check_bulk(items[:256])
+        tq = time.perf_counter()
+        o.check_bulk(items[:2048], nthreads=cores)
+        rate = 2048 / max(time.perf_counter() - tq, 1e-6)
+        ns = args.cpu_sample or int(min(n, max(4096, rate * 15.0)))
+        tq = time.perf_counter()
+        want = o.check_bulk(items[:ns], nthreads=cores)
+        dt = time.perf_counter() - tq
+        mism = int((want != host_answers[:ns]).sum())
+        cpu = {"value": ns / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {ns} checks of the same batch, {cores} threads, {dt:.1f} s",
+               "parity_mismatches_vs_gpu": mism}
+        if mism:
+            raise SystemExit(f"PARITY FAILURE: {mism} of {ns} answers differ from the oracle")
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        kernel_ms = dev_ms_max / args.steps
+        achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+        traffic = ncu_traffic(w.name)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "impl": "zgpu",
+            "config": workload_config(w, args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n,
+                    "steps": e2e_steps, "api": "zg_check_bulk (C ABI, pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "zg::check_kernel<false>",
+                         "alg_bytes_per_launch": int(alg_bytes), "alg_bytes_per_check": alg_bytes / n,
+                         "kernel_ms": kernel_ms,
+                         "note": "algorithmic bytes counted by the instrumented kernel variant: 16 B item + 1 B answer "
+                                 "+ 4 B per row offset, probe and edge actually needed (short circuit included)"},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "has_fraction": float((host_answers == 2).mean()),
+            "publish_s": publish_s,
+        }
+        print(json.dumps(out), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,227 @@
+/*
+ * zgpu.h -- C ABI of libzgpu.so: a B200-native (sm_100a) batched Zanzibar
+ * permission-check engine that drops in behind the reference proxy's
+ * v1.PermissionsServiceClient boundary (authzed/spicedb-kubeapi-proxy,
+ * pkg/proxy/options.go:81-82,371-377).
+ *
+ * Every entry point is what a cgo shim implementing v1.PermissionsServiceClient
+ * would bind (INTEGRATION.md shows that shim). Plain pointers and sizes only; the
+ * caller owns every buffer, the library copies what it keeps and never retains a
+ * caller pointer past return; nothing throws or aborts across this boundary.
+ *
+ * Reference interface each group replaces (file:line in /root/reference):
+ *   zg_check_bulk*              CheckBulkPermissions   pkg/authz/check.go:41-69,
+ *                                                      pkg/authz/postfilter.go:127-178
+ *                               CheckPermission        pkg/authz/watch.go:50-67
+ *   zg_lookup_resources*        LookupResources stream pkg/authz/lookups.go:49-88
+ *   zg_write_relationships      WriteRelationships     pkg/authz/distributedtx/activity.go:54-76
+ *   zg_delete_relationships     DeleteRelationships    (v1 API; filter semantics update.go:207-271)
+ *   zg_read_relationships       ReadRelationships      pkg/authz/distributedtx/activity.go:128-171
+ *   zg_engine_create/load_schema embedded SpiceDB ctor pkg/spicedb/spicedb.go:18-57
+ *
+ * Return codes: 0 = OK, negative = error (message: zg_last_error).
+ */
+#ifndef ZGPU_H
+#define ZGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZG_OK 0
+#define ZG_EINVAL (-1)   /* bad argument / schema violation                      */
+#define ZG_EEXIST (-2)   /* CREATE of an existing relationship                   */
+#define ZG_ENOSCHEMA (-3)
+#define ZG_ECUDA (-4)    /* CUDA error: the call fails closed                     */
+#define ZG_EPRECOND (-5) /* a WriteRelationships precondition did not hold       */
+#define ZG_ENOSNAPSHOT (-6) /* nothing published yet                             */
+#define ZG_E2BIG (-7)    /* output buffer too small; required size reported      */
+#define ZG_ENOMEM (-8)
+
+/* v1.CheckPermissionResponse.Permissionship (authzed-go v1.6.0); per-item codes */
+#define ZG_NO_PERMISSION 1
+#define ZG_HAS_PERMISSION 2
+#define ZG_CONDITIONAL 3 /* never produced: caveats are out of scope              */
+#define ZG_ITEM_ERROR 255 /* per-item error (depth > 50, unknown permission ...)  */
+
+#define ZG_SREL_NONE 0xFFFFu     /* subject has no relation ("" or "...")          */
+#define ZG_SREL_WILDCARD 0xFFFEu /* stored relationship whose subject is type:*   */
+#define ZG_NO_OBJECT 0xFFFFFFFFu /* object id of a name that was never written    */
+
+#define ZG_OP_TOUCH 0  /* v1.RelationshipUpdate_OPERATION_TOUCH  */
+#define ZG_OP_CREATE 1 /* v1.RelationshipUpdate_OPERATION_CREATE */
+#define ZG_OP_DELETE 2 /* v1.RelationshipUpdate_OPERATION_DELETE */
+
+#define ZG_PRECOND_MUST_MATCH 1     /* v1.Precondition_OPERATION_MUST_MATCH     */
+#define ZG_PRECOND_MUST_NOT_MATCH 2 /* v1.Precondition_OPERATION_MUST_NOT_MATCH */
+
+#define ZG_MAX_DEPTH 50 /* pkg/spicedb/spicedb.go:33 WithDispatchMaxDepth(50) */
+
+typedef struct zg_engine zg_engine;
+
+/* zg_config.flags: build schema/store/snapshot on the host only (CPU unit tests of
+ * the host logic). Every hot-path call on such an engine FAILS with ZG_ECUDA:
+ * there is no CPU evaluation path in this library. */
+#define ZG_FLAG_HOST_ONLY 1u
+
+typedef struct {
+  int32_t device;            /* CUDA device ordinal; -1 = current device          */
+  uint32_t flags;            /* ZG_FLAG_*                                         */
+  uint64_t subquery_capacity; /* 0 = default; sub-queries buffered per pass       */
+  uint32_t work_budget;      /* 0 = default; expansion rounds per 32-check batch
+                                before unresolved checks report ZG_ITEM_ERROR
+                                (the analogue of a request deadline)              */
+  uint32_t reserved;
+} zg_config;
+
+/* One interned check: 16 bytes in, 1 byte out. Object ids are dense per type. */
+typedef struct {
+  uint32_t res;   /* resource object id (type implied by perm)                    */
+  uint32_t subj;  /* subject object id                                            */
+  uint16_t perm;  /* slot id of the permission OR relation being checked          */
+  uint16_t stype; /* subject type id                                              */
+  uint16_t srel;  /* subject relation slot id, or ZG_SREL_NONE                    */
+  uint16_t flags; /* 0                                                            */
+} zg_check;
+
+/* One interned relationship (pkg/rules/rules.go:1050 grammar, interned). */
+typedef struct {
+  uint32_t res;
+  uint32_t subj;  /* ignored when srel == ZG_SREL_WILDCARD                        */
+  uint16_t rel;   /* slot id of the relation (implies resource type)              */
+  uint16_t stype;
+  uint16_t srel;  /* slot id, ZG_SREL_NONE or ZG_SREL_WILDCARD                    */
+  uint16_t flags; /* 0                                                            */
+} zg_tuple;
+
+typedef struct {
+  zg_tuple t;
+  uint32_t expires_at; /* unix seconds, 0 = never (OptionalExpiresAt)             */
+  uint32_t op;         /* ZG_OP_*                                                 */
+} zg_update;
+
+/* String forms: what the Go shim passes straight from the v1 protobuf messages. */
+typedef struct {
+  const char *res_type, *res_id, *relation; /* relation or permission name        */
+  const char *subj_type, *subj_id, *subj_rel; /* subj_rel NULL/""/"..." = none     */
+} zg_rel_str;
+
+typedef struct {
+  zg_rel_str rel;
+  uint32_t expires_at;
+  uint32_t op;
+} zg_update_str;
+
+/* v1.RelationshipFilter (pkg/authz/update.go:207-271): NULL/"" = unset field.   */
+typedef struct {
+  const char *res_type, *res_id, *relation;
+  const char *subj_type, *subj_id, *subj_rel;
+} zg_filter_str;
+
+typedef struct {
+  uint32_t op; /* ZG_PRECOND_* */
+  zg_filter_str filter;
+} zg_precondition_str;
+
+typedef struct {
+  uint64_t checks;          /* checks answered since creation                     */
+  uint64_t launches;        /* kernels launched since creation                    */
+  uint64_t passes;          /* sub-query passes beyond the first                  */
+  uint64_t tuples;          /* relationships in the published snapshot            */
+  uint64_t snapshot_bytes;  /* device bytes of the published snapshot             */
+  uint64_t revision;        /* increments on every publish                        */
+  uint64_t last_alg_bytes;  /* algorithmic bytes of the last counted call         */
+  double last_kernel_ms;    /* device time of the last hot-path call              */
+} zg_stats;
+
+/* ---- lifecycle --------------------------------------------------------- */
+int zg_engine_create(const zg_config *cfg, zg_engine **out);
+void zg_engine_destroy(zg_engine *e);
+/* Thread-local message of the last failing call on this thread. */
+const char *zg_last_error(void);
+
+/* ---- schema (SpiceDB schema DSL subset; pkg/spicedb/bootstrap.yaml) ----- */
+int zg_load_schema(zg_engine *e, const char *dsl, size_t len);
+int zg_num_types(const zg_engine *e);
+int zg_num_slots(const zg_engine *e);
+int zg_type_id(const zg_engine *e, const char *type_name);            /* -1 unknown */
+int zg_slot_id(const zg_engine *e, int type_id, const char *name);    /* -1 unknown */
+int zg_slot_type(const zg_engine *e, int slot);
+int zg_slot_is_permission(const zg_engine *e, int slot);
+const char *zg_slot_name(const zg_engine *e, int slot);
+const char *zg_type_name(const zg_engine *e, int type_id);
+
+/* ---- object interning (string id <-> dense per-type u32) ---------------- */
+uint32_t zg_intern_object(zg_engine *e, int type_id, const char *object_id);
+uint32_t zg_find_object(const zg_engine *e, int type_id, const char *object_id); /* ZG_NO_OBJECT */
+/* Copies the name into buf (NUL terminated); returns its length or ZG_E2BIG/ZG_EINVAL. */
+int zg_object_name(const zg_engine *e, int type_id, uint32_t id, char *buf, size_t cap);
+
+/* ---- relationship store -------------------------------------------------- */
+/* Bulk TOUCH of interned relationships (expires may be NULL). Not visible to
+ * checks until zg_publish. */
+int zg_load_tuples(zg_engine *e, const zg_tuple *t, const uint32_t *expires, uint64_t n);
+/* Transactional CREATE/TOUCH/DELETE; all-or-nothing. Not visible until publish. */
+int zg_apply_updates(zg_engine *e, const zg_update *u, uint64_t n);
+/* Builds the CSR snapshot in HBM and makes it the one every later check sees. */
+int zg_publish(zg_engine *e);
+uint64_t zg_num_tuples(const zg_engine *e);
+/* Clock used for expiration; 0 = wall clock (default). */
+void zg_set_clock(zg_engine *e, int64_t unix_seconds);
+
+/* v1 WriteRelationships: validate, check preconditions, apply, publish. The
+ * write is visible to every check that starts after return (FullyConsistent). */
+int zg_write_relationships(zg_engine *e, const zg_update_str *updates, uint64_t n,
+                           const zg_precondition_str *pre, uint64_t n_pre);
+/* v1 DeleteRelationships by filter; *n_deleted may be NULL. */
+int zg_delete_relationships(zg_engine *e, const zg_filter_str *filter,
+                            const zg_precondition_str *pre, uint64_t n_pre, uint64_t *n_deleted);
+/* v1 ReadRelationships: matching live relationships as "type:id#rel@stype:sid[#srel]\n"
+ * lines, sorted. Returns 0 or ZG_E2BIG (*need = bytes required incl. NUL). */
+int zg_read_relationships(zg_engine *e, const zg_filter_str *filter, char *buf, size_t cap,
+                          size_t *need, uint64_t *n_out);
+
+/* ---- the hot path -------------------------------------------------------- */
+/* CheckBulkPermissions: out[i] answers items[i] (same length, same order:
+ * pkg/authz/check.go:54-57). HOST buffers; copies are inside the call. */
+int zg_check_bulk(zg_engine *e, const zg_check *items, uint64_t n, uint8_t *out);
+/* Same with DEVICE buffers on the given cudaStream_t (NULL = default stream);
+ * asynchronous when the schema needs no sub-query pass. */
+int zg_check_bulk_device(zg_engine *e, const zg_check *d_items, uint64_t n, uint8_t *d_out,
+                         void *cuda_stream);
+/* String form of CheckBulkPermissions / CheckPermission (n = 1). */
+int zg_check_bulk_str(zg_engine *e, const zg_rel_str *items, uint64_t n, uint8_t *out);
+
+/* LookupResources: ids (ascending) of every object of res_type with HAS_PERMISSION.
+ * Returns 0, or ZG_E2BIG with *n_out = required capacity. */
+int zg_lookup_resources(zg_engine *e, uint16_t res_type, uint16_t perm, uint16_t stype,
+                        uint32_t subj, uint16_t srel, uint32_t *out_ids, uint64_t cap,
+                        uint64_t *n_out);
+/* String form: resource object ids as '\n'-separated lines. */
+int zg_lookup_resources_str(zg_engine *e, const char *res_type, const char *perm,
+                            const char *subj_type, const char *subj_id, const char *subj_rel,
+                            char *buf, size_t cap, size_t *need, uint64_t *n_out);
+
+/* Pinned host memory for request/response buffers: zg_check_bulk copies straight
+ * from/to such buffers (no staging memcpy). */
+void *zg_host_alloc(size_t bytes);
+void zg_host_free(void *p);
+
+/* Test hook: copies row (relation slot, resource id, edge class k) of the last
+ * BUILT snapshot (host copy) into out. Returns 0 / ZG_E2BIG (*n_out = size). */
+int zg_debug_row(zg_engine *e, uint16_t rel_slot, uint32_t res, uint32_t cls, uint32_t *out,
+                 uint64_t cap, uint64_t *n_out);
+
+/* ---- measurement --------------------------------------------------------- */
+int zg_stats_get(zg_engine *e, zg_stats *out);
+/* Runs the batch through the instrumented kernel variant and returns the
+ * ALGORITHMIC bytes it needed (DESIGN.md "Algorithmic bytes"); not for timing. */
+int zg_count_alg_bytes(zg_engine *e, const zg_check *items, uint64_t n, uint64_t *bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -401,6 +401,22 @@ static int add_slot(zo_oracle *z, int type, const char *name, int is_perm) {
   return z->n_slots++;
 }
 
+/* permission p = ... p ... on the SAME object would recurse forever: reject */
+static int ref_cycle(const zo_oracle *z, const Expr *e, int *state) {
+  if (!e) return 0;
+  if (e->op == E_REF && z->slots[e->slot].is_perm) {
+    if (state[e->slot] == 1) return 1;
+    if (state[e->slot] == 0) {
+      state[e->slot] = 1;
+      if (ref_cycle(z, z->slots[e->slot].expr, state)) return 1;
+      state[e->slot] = 2;
+    }
+    return 0;
+  }
+  if (e->op == E_REF || e->op == E_ARROW || e->op == E_NIL) return 0;
+  return ref_cycle(z, e->l, state) || ref_cycle(z, e->r, state);
+}
+
 static int parse_schema(zo_oracle *z, const char *text) {
   Lex L = {.s = text, .z = z};
   PendingPerm *pp = NULL;
@@ -513,6 +529,20 @@ static int parse_schema(zo_oracle *z, const char *text) {
     pe_free(pp[i].pe);
   }
   free(pp);
+  if (ok) {
+    int *state = calloc((size_t)z->n_slots + 1, sizeof(int));
+    for (int s = 0; ok && s < z->n_slots; s++)
+      if (z->slots[s].is_perm && state[s] == 0) {
+        state[s] = 1;
+        if (ref_cycle(z, z->slots[s].expr, state)) {
+          set_err(z, "permission %s#%s refers to itself on the same object", z->types[z->slots[s].type].name,
+                  z->slots[s].name);
+          ok = 0;
+        }
+        state[s] = 2;
+      }
+    free(state);
+  }
   return ok ? 0 : -1;
 }
 

@@ -1,0 +1,382 @@
+"""ctypes binding of libzgpu.so (include/zgpu.h). No torch types cross this boundary."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+
+NO_PERMISSION, HAS_PERMISSION, ITEM_ERROR = 1, 2, 255
+SREL_NONE, SREL_WILDCARD = 0xFFFF, 0xFFFE
+NO_OBJECT = 0xFFFFFFFF
+OP_TOUCH, OP_CREATE, OP_DELETE = 0, 1, 2
+PRECOND_MUST_MATCH, PRECOND_MUST_NOT_MATCH = 1, 2
+E2BIG = -7
+
+CHECK_DTYPE = np.dtype(
+    [("res", "<u4"), ("subj", "<u4"), ("perm", "<u2"), ("stype", "<u2"), ("srel", "<u2"), ("flags", "<u2")]
+)
+TUPLE_DTYPE = np.dtype(
+    [("res", "<u4"), ("subj", "<u4"), ("rel", "<u2"), ("stype", "<u2"), ("srel", "<u2"), ("flags", "<u2")]
+)
+
+
+class ZgpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"zgpu error {code}: {msg}")
+        self.code = code
+
+
+class _Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("subquery_capacity", C.c_uint64),
+                ("work_budget", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class _RelStr(C.Structure):
+    _fields_ = [(n, C.c_char_p) for n in ("res_type", "res_id", "relation", "subj_type", "subj_id", "subj_rel")]
+
+
+class _UpdateStr(C.Structure):
+    _fields_ = [("rel", _RelStr), ("expires_at", C.c_uint32), ("op", C.c_uint32)]
+
+
+class _Precond(C.Structure):
+    _fields_ = [("op", C.c_uint32), ("filter", _RelStr)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [("checks", C.c_uint64), ("launches", C.c_uint64), ("passes", C.c_uint64), ("tuples", C.c_uint64),
+                ("snapshot_bytes", C.c_uint64), ("revision", C.c_uint64), ("last_alg_bytes", C.c_uint64),
+                ("last_kernel_ms", C.c_double)]
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libzgpu.so")
+
+
+def build_library(force: bool = False) -> str:
+    """nvcc-compile csrc/ into libzgpu.so for sm_100a (cross-compiles without a GPU)."""
+    so = library_path()
+    csrc = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cc", ".h", ".cuh"))]
+    srcs.append(os.path.join(_ROOT, "include", "zgpu.h"))
+    stale = not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        if not os.path.exists("/usr/local/cuda/bin/nvcc"):
+            if os.path.exists(so):
+                return so
+            raise ZgpuError(-4, "libzgpu.so is missing and nvcc is not available to build it")
+        r = subprocess.run(["make", "-C", csrc], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise ZgpuError(-4, "building libzgpu.so failed:\n" + r.stdout[-2000:] + r.stderr[-4000:])
+    return so
+
+
+_LIB = None
+
+_SIGS = {
+    "zg_engine_create": (C.c_int, [C.POINTER(_Config), C.POINTER(C.c_void_p)]),
+    "zg_engine_destroy": (None, [C.c_void_p]),
+    "zg_last_error": (C.c_char_p, []),
+    "zg_load_schema": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
+    "zg_num_types": (C.c_int, [C.c_void_p]),
+    "zg_num_slots": (C.c_int, [C.c_void_p]),
+    "zg_type_id": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "zg_slot_id": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p]),
+    "zg_slot_type": (C.c_int, [C.c_void_p, C.c_int]),
+    "zg_slot_is_permission": (C.c_int, [C.c_void_p, C.c_int]),
+    "zg_slot_name": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "zg_type_name": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "zg_intern_object": (C.c_uint32, [C.c_void_p, C.c_int, C.c_char_p]),
+    "zg_find_object": (C.c_uint32, [C.c_void_p, C.c_int, C.c_char_p]),
+    "zg_object_name": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_char_p, C.c_size_t]),
+    "zg_load_tuples": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "zg_apply_updates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "zg_publish": (C.c_int, [C.c_void_p]),
+    "zg_num_tuples": (C.c_uint64, [C.c_void_p]),
+    "zg_set_clock": (None, [C.c_void_p, C.c_int64]),
+    "zg_write_relationships": (C.c_int, [C.c_void_p, C.POINTER(_UpdateStr), C.c_uint64, C.POINTER(_Precond), C.c_uint64]),
+    "zg_delete_relationships": (C.c_int, [C.c_void_p, C.POINTER(_RelStr), C.POINTER(_Precond), C.c_uint64,
+                                          C.POINTER(C.c_uint64)]),
+    "zg_read_relationships": (C.c_int, [C.c_void_p, C.POINTER(_RelStr), C.c_char_p, C.c_size_t,
+                                        C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]),
+    "zg_check_bulk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "zg_check_bulk_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "zg_check_bulk_str": (C.c_int, [C.c_void_p, C.POINTER(_RelStr), C.c_uint64, C.c_void_p]),
+    "zg_lookup_resources": (C.c_int, [C.c_void_p, C.c_uint16, C.c_uint16, C.c_uint16, C.c_uint32, C.c_uint16,
+                                      C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "zg_lookup_resources_str": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p,
+                                          C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]),
+    "zg_debug_row": (C.c_int, [C.c_void_p, C.c_uint16, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
+                               C.POINTER(C.c_uint64)]),
+    "zg_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "zg_host_free": (None, [C.c_void_p]),
+    "zg_stats_get": (C.c_int, [C.c_void_p, C.POINTER(_Stats)]),
+    "zg_count_alg_bytes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+}
+
+
+def exported_symbols():
+    """Names include/zgpu.h declares; tests assert the .so exports each of them."""
+    return sorted(_SIGS)
+
+
+def lib():
+    """Loads libzgpu.so. There is NO fallback: a missing library is an error."""
+    global _LIB
+    if _LIB is None:
+        so = build_library()
+        L = C.CDLL(so)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)  # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def _b(s):
+    if s is None:
+        return None
+    return s.encode() if isinstance(s, str) else s
+
+
+def _relstr(rt, rid, rel, st, sid, srel):
+    return _RelStr(_b(rt), _b(rid), _b(rel), _b(st), _b(sid), _b(srel or ""))
+
+
+def split_rel(rel: str):
+    """'type:id#rel@stype:sid[#srel]' (pkg/rules/rules.go:1050 grammar) -> 6-tuple."""
+    left, right = rel.split("@", 1)
+    rt, rest = left.split(":", 1)
+    rid, r = rest.rsplit("#", 1)
+    st, srest = right.split(":", 1)
+    sid, _, srel = srest.partition("#")
+    return rt, rid, r, st, sid, srel
+
+
+class PinnedArray:
+    """numpy view over zg_host_alloc memory (freed with the object)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * self.dtype.itemsize
+        self._L = lib()
+        self.ptr = self._L.zg_host_alloc(max(n, 1))
+        if not self.ptr:
+            raise ZgpuError(-8, "zg_host_alloc failed")
+        buf = (C.c_uint8 * max(n, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            self._L.zg_host_free(self.ptr)
+            self.ptr = None
+
+
+class Engine:
+    """One zg_engine: schema + relationship store + published CSR snapshot in HBM."""
+
+    def __init__(self, schema: str | None = None, device: int = -1, subquery_capacity: int = 0, work_budget: int = 0,
+                 host_only: bool = False):
+        """host_only=True builds schema/store/snapshot without a GPU (CPU unit tests of
+        the host logic); every check/lookup on such an engine raises ZgpuError."""
+        self._L = lib()
+        cfg = _Config(device, 1 if host_only else 0, subquery_capacity, work_budget, 0)
+        h = C.c_void_p()
+        rc = self._L.zg_engine_create(C.byref(cfg), C.byref(h))
+        if rc:
+            raise ZgpuError(rc, self._L.zg_last_error().decode())
+        self._h = h
+        if schema is not None:
+            self.load_schema(schema)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.zg_engine_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc:
+            raise ZgpuError(rc, self._L.zg_last_error().decode())
+
+    # -- schema ---------------------------------------------------------------
+    def load_schema(self, text: str):
+        b = _b(text)
+        self._ck(self._L.zg_load_schema(self._h, b, len(b)))
+
+    def type_id(self, name):
+        return self._L.zg_type_id(self._h, _b(name))
+
+    def slot_id(self, type_name, rel):
+        return self._L.zg_slot_id(self._h, self.type_id(type_name), _b(rel))
+
+    def slot_table(self):
+        L, h = self._L, self._h
+        return [
+            (s, L.zg_type_name(h, L.zg_slot_type(h, s)).decode(), L.zg_slot_name(h, s).decode(),
+             bool(L.zg_slot_is_permission(h, s)))
+            for s in range(L.zg_num_slots(h))
+        ]
+
+    def intern(self, type_name, object_id):
+        return self._L.zg_intern_object(self._h, self.type_id(type_name), _b(object_id))
+
+    def find(self, type_name, object_id):
+        return self._L.zg_find_object(self._h, self.type_id(type_name), _b(object_id))
+
+    # -- store ----------------------------------------------------------------
+    def load_tuples(self, tuples: np.ndarray, expires: np.ndarray | None = None):
+        t = np.ascontiguousarray(tuples, dtype=TUPLE_DTYPE)
+        ex = None if expires is None else np.ascontiguousarray(expires, dtype=np.uint32)
+        self._ck(self._L.zg_load_tuples(self._h, t.ctypes.data, None if ex is None else ex.ctypes.data, t.size))
+
+    def add_bulk(self, type_name, rel, subj_type, res, subj, srel=None, wildcard=False):
+        """Bulk TOUCH of relationships sharing (relation, subject type, subject relation)."""
+        res = np.ascontiguousarray(res, dtype=np.uint32)
+        t = np.zeros(res.size, dtype=TUPLE_DTYPE)
+        t["res"] = res
+        t["subj"] = 0 if wildcard else np.ascontiguousarray(subj, dtype=np.uint32)
+        t["rel"] = self.slot_id(type_name, rel)
+        t["stype"] = self.type_id(subj_type)
+        t["srel"] = SREL_WILDCARD if wildcard else (SREL_NONE if srel is None else self.slot_id(subj_type, srel))
+        self.load_tuples(t)
+
+    def publish(self):
+        self._ck(self._L.zg_publish(self._h))
+
+    def num_tuples(self):
+        return self._L.zg_num_tuples(self._h)
+
+    def set_clock(self, unix_seconds: int):
+        self._L.zg_set_clock(self._h, int(unix_seconds))
+
+    def write_relationships(self, updates, preconditions=()):
+        """updates: [(op, 'type:id#rel@stype:sid[#srel]', expires_at)];
+        preconditions: [(op, {filter fields})]"""
+        n = len(updates)
+        arr = (_UpdateStr * max(n, 1))()
+        keep = []
+        for i, (op, rel, exp) in enumerate(updates):
+            parts = [_b(x) for x in split_rel(rel)]
+            keep.append(parts)
+            arr[i] = _UpdateStr(_RelStr(*parts), int(exp), int(op))
+        pre = (_Precond * max(len(preconditions), 1))()
+        for i, (op, f) in enumerate(preconditions):
+            pre[i] = _Precond(int(op), self._filter(f))
+        self._ck(self._L.zg_write_relationships(self._h, arr, n, pre, len(preconditions)))
+
+    @staticmethod
+    def _filter(f):
+        return _RelStr(_b(f.get("res_type", "")), _b(f.get("res_id", "")), _b(f.get("rel", "")),
+                       _b(f.get("subj_type", "")), _b(f.get("subj_id", "")), _b(f.get("subj_rel", "")))
+
+    def delete_relationships(self, flt: dict, preconditions=()):
+        pre = (_Precond * max(len(preconditions), 1))()
+        for i, (op, f) in enumerate(preconditions):
+            pre[i] = _Precond(int(op), self._filter(f))
+        n = C.c_uint64(0)
+        f = self._filter(flt)
+        self._ck(self._L.zg_delete_relationships(self._h, C.byref(f), pre, len(preconditions), C.byref(n)))
+        return n.value
+
+    def read_relationships(self, **flt):
+        f = self._filter(flt)
+        cap = 1 << 16
+        while True:
+            buf = C.create_string_buffer(cap)
+            need, n = C.c_size_t(0), C.c_uint64(0)
+            rc = self._L.zg_read_relationships(self._h, C.byref(f), buf, cap, C.byref(need), C.byref(n))
+            if rc == E2BIG:
+                cap = need.value + 16
+                continue
+            self._ck(rc)
+            return [l for l in buf.value.decode().split("\n") if l]
+
+    # -- hot path ---------------------------------------------------------------
+    def check_bulk(self, items: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """CheckBulkPermissions on interned items (HOST buffers; copies inside the call)."""
+        items = np.ascontiguousarray(items, dtype=CHECK_DTYPE)
+        if out is None:
+            out = np.empty(items.size, dtype=np.uint8)
+        self._ck(self._L.zg_check_bulk(self._h, items.ctypes.data, items.size, out.ctypes.data))
+        return out
+
+    def check_bulk_ptr(self, items_ptr: int, n: int, out_ptr: int):
+        """Raw HOST pointers (e.g. pinned buffers from PinnedArray)."""
+        self._ck(self._L.zg_check_bulk(self._h, items_ptr, n, out_ptr))
+
+    def check_bulk_device(self, d_items_ptr: int, n: int, d_out_ptr: int, stream: int = 0):
+        """DEVICE pointers (e.g. torch tensors' data_ptr()) on a cudaStream_t handle."""
+        self._ck(self._L.zg_check_bulk_device(self._h, d_items_ptr, n, d_out_ptr, stream))
+
+    def check_bulk_str(self, rels) -> np.ndarray:
+        n = len(rels)
+        arr = (_RelStr * max(n, 1))()
+        keep = []
+        for i, r in enumerate(rels):
+            parts = [_b(x) for x in (split_rel(r) if isinstance(r, str) else r)]
+            keep.append(parts)
+            arr[i] = _RelStr(*parts)
+        out = np.empty(n, dtype=np.uint8)
+        self._ck(self._L.zg_check_bulk_str(self._h, arr, n, out.ctypes.data))
+        return out
+
+    def lookup_resources_ids(self, res_type, perm, subj_type, subj, srel=None) -> np.ndarray:
+        sr = SREL_NONE if srel is None else self.slot_id(subj_type, srel)
+        cap = 1 << 12
+        while True:
+            out = np.empty(cap, dtype=np.uint32)
+            n = C.c_uint64(0)
+            rc = self._L.zg_lookup_resources(self._h, self.type_id(res_type), self.slot_id(res_type, perm),
+                                             self.type_id(subj_type), int(subj), sr, out.ctypes.data, cap, C.byref(n))
+            if rc == E2BIG:
+                cap = int(n.value)
+                continue
+            self._ck(rc)
+            return out[: n.value].copy()
+
+    def lookup_resources_str(self, res_type, perm, subj_type, subj_id, subj_rel=""):
+        cap = 1 << 16
+        while True:
+            buf = C.create_string_buffer(cap)
+            need, n = C.c_size_t(0), C.c_uint64(0)
+            rc = self._L.zg_lookup_resources_str(self._h, _b(res_type), _b(perm), _b(subj_type), _b(subj_id),
+                                                 _b(subj_rel or ""), buf, cap, C.byref(need), C.byref(n))
+            if rc == E2BIG:
+                cap = need.value + 16
+                continue
+            self._ck(rc)
+            return [l for l in buf.value.decode().split("\n") if l]
+
+    def debug_row(self, type_name, rel, res, cls=0) -> np.ndarray:
+        cap = 1 << 10
+        while True:
+            out = np.empty(cap, dtype=np.uint32)
+            n = C.c_uint64(0)
+            rc = self._L.zg_debug_row(self._h, self.slot_id(type_name, rel), int(res), int(cls), out.ctypes.data, cap,
+                                      C.byref(n))
+            if rc == E2BIG:
+                cap = int(n.value)
+                continue
+            self._ck(rc)
+            return out[: n.value].copy()
+
+    # -- measurement ------------------------------------------------------------
+    def stats(self) -> dict:
+        s = _Stats()
+        self._ck(self._L.zg_stats_get(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in _Stats._fields_}
+
+    def count_alg_bytes(self, items: np.ndarray) -> int:
+        items = np.ascontiguousarray(items, dtype=CHECK_DTYPE)
+        b = C.c_uint64(0)
+        self._ck(self._L.zg_count_alg_bytes(self._h, items.ctypes.data, items.size, C.byref(b)))
+        return b.value

@@ -1,0 +1,658 @@
+// capi.cu -- the C ABI declared in include/zgpu.h. Thin glue: argument checks,
+// string <-> id resolution, locking; the work is in store.cc and device.cu.
+#include <algorithm>
+#include <cstring>
+#include <ctime>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/zgpu.h"
+#include "device.h"
+#include "schema.h"
+#include "store.h"
+
+using namespace zg;
+
+struct zg_engine {
+  std::mutex mu;  // one writer or one hot-path call at a time (round 1: coarse)
+  Schema schema;
+  bool has_schema = false;
+  Store store;
+  Device dev;
+  int64_t clock = 0;
+  uint64_t revision = 0;
+  bool dirty = false;  // store changed since the last publish
+  bool host_only = false;
+  HostSnapshot last_built;  // kept only for zg_debug_row / host-only engines
+  bool keep_built = false;
+};
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+extern "C" const char* zg_last_error(void) { return g_err.c_str(); }
+
+static uint32_t now_of(const zg_engine* e) {
+  return static_cast<uint32_t>(e->clock ? e->clock : static_cast<int64_t>(time(nullptr)));
+}
+static bool none_rel(const char* s) { return !s || !*s || std::strcmp(s, "...") == 0; }
+
+extern "C" int zg_engine_create(const zg_config* cfg, zg_engine** out) {
+  if (!out) return fail(ZG_EINVAL, "out is NULL");
+  *out = nullptr;
+  zg_engine* e = new (std::nothrow) zg_engine();
+  if (!e) return fail(ZG_ENOMEM, "out of memory");
+  if (cfg && (cfg->flags & ZG_FLAG_HOST_ONLY)) {
+    e->host_only = true;
+    e->keep_built = true;
+    *out = e;
+    return ZG_OK;
+  }
+  std::string err = e->dev.init(cfg ? cfg->device : -1, cfg ? cfg->subquery_capacity : 0, cfg ? cfg->work_budget : 0);
+  if (!err.empty()) {
+    delete e;
+    return fail(ZG_ECUDA, err);
+  }
+  *out = e;
+  return ZG_OK;
+}
+extern "C" void zg_engine_destroy(zg_engine* e) { delete e; }
+
+extern "C" int zg_load_schema(zg_engine* e, const char* dsl, size_t len) {
+  if (!e || !dsl) return fail(ZG_EINVAL, "NULL argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  Schema s;
+  std::string err = s.parse(std::string(dsl, len));
+  if (!err.empty()) return fail(ZG_EINVAL, err);
+  e->schema = std::move(s);
+  e->has_schema = true;
+  e->store.reset(&e->schema);
+  e->dev.snap.reset();
+  e->dirty = true;
+  return ZG_OK;
+}
+
+#define NEED_SCHEMA(e, ret)              \
+  if (!(e) || !(e)->has_schema) {        \
+    g_err = "no schema loaded";          \
+    return ret;                          \
+  }
+
+extern "C" int zg_num_types(const zg_engine* e) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  return static_cast<int>(e->schema.types.size());
+}
+extern "C" int zg_num_slots(const zg_engine* e) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  return static_cast<int>(e->schema.slots.size());
+}
+extern "C" int zg_type_id(const zg_engine* e, const char* n) {
+  NEED_SCHEMA(e, -1);
+  return n ? e->schema.type_id(n) : -1;
+}
+extern "C" int zg_slot_id(const zg_engine* e, int t, const char* n) {
+  NEED_SCHEMA(e, -1);
+  return n ? e->schema.slot_id(t, n) : -1;
+}
+extern "C" int zg_slot_type(const zg_engine* e, int s) {
+  NEED_SCHEMA(e, -1);
+  return s >= 0 && s < static_cast<int>(e->schema.slots.size()) ? e->schema.slots[s].type : -1;
+}
+extern "C" int zg_slot_is_permission(const zg_engine* e, int s) {
+  NEED_SCHEMA(e, -1);
+  return s >= 0 && s < static_cast<int>(e->schema.slots.size()) ? e->schema.slots[s].is_perm : -1;
+}
+extern "C" const char* zg_slot_name(const zg_engine* e, int s) {
+  NEED_SCHEMA(e, nullptr);
+  return s >= 0 && s < static_cast<int>(e->schema.slots.size()) ? e->schema.slots[s].name.c_str() : nullptr;
+}
+extern "C" const char* zg_type_name(const zg_engine* e, int t) {
+  NEED_SCHEMA(e, nullptr);
+  return t >= 0 && t < static_cast<int>(e->schema.types.size()) ? e->schema.types[t].name.c_str() : nullptr;
+}
+
+extern "C" uint32_t zg_intern_object(zg_engine* e, int t, const char* id) {
+  NEED_SCHEMA(e, ZG_NO_OBJECT);
+  if (!id || !*id || t < 0 || t >= static_cast<int>(e->schema.types.size())) return ZG_NO_OBJECT;
+  std::lock_guard<std::mutex> g(e->mu);
+  return e->store.intern(t, id);
+}
+extern "C" uint32_t zg_find_object(const zg_engine* e, int t, const char* id) {
+  NEED_SCHEMA(e, ZG_NO_OBJECT);
+  if (!id) return ZG_NO_OBJECT;
+  std::lock_guard<std::mutex> g(const_cast<zg_engine*>(e)->mu);
+  return e->store.find(t, id);
+}
+extern "C" int zg_object_name(const zg_engine* e, int t, uint32_t id, char* buf, size_t cap) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  std::lock_guard<std::mutex> g(const_cast<zg_engine*>(e)->mu);
+  const std::string* n = e->store.name(t, id);
+  if (!n) return fail(ZG_EINVAL, "object has no name");
+  if (n->size() + 1 > cap) return ZG_E2BIG;
+  std::memcpy(buf, n->c_str(), n->size() + 1);
+  return static_cast<int>(n->size());
+}
+
+extern "C" int zg_load_tuples(zg_engine* e, const zg_tuple* t, const uint32_t* expires, uint64_t n) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if (!t && n) return fail(ZG_EINVAL, "NULL tuples");
+  std::lock_guard<std::mutex> g(e->mu);
+  std::string err = e->store.load(t, expires, n);
+  if (!err.empty()) return fail(ZG_EINVAL, err);
+  e->dirty = true;
+  return ZG_OK;
+}
+extern "C" int zg_apply_updates(zg_engine* e, const zg_update* u, uint64_t n) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if (!u && n) return fail(ZG_EINVAL, "NULL updates");
+  std::lock_guard<std::mutex> g(e->mu);
+  int code = ZG_OK;
+  std::string err = e->store.apply(u, n, &code);
+  if (!err.empty()) return fail(code, err);
+  e->dirty = true;
+  return ZG_OK;
+}
+
+static int publish_locked(zg_engine* e) {
+  HostSnapshot h = e->store.build();
+  if (!h.err.empty()) return fail(ZG_EINVAL, h.err);
+  if (e->host_only) {
+    ++e->revision;
+    e->last_built = std::move(h);
+    e->dirty = false;
+    return ZG_OK;
+  }
+  std::string err = e->dev.publish(h, e->schema, ++e->revision);
+  if (!err.empty()) return fail(ZG_ECUDA, err);
+  if (e->keep_built) e->last_built = std::move(h);
+  e->dirty = false;
+  return ZG_OK;
+}
+extern "C" int zg_publish(zg_engine* e) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  std::lock_guard<std::mutex> g(e->mu);
+  return publish_locked(e);
+}
+extern "C" uint64_t zg_num_tuples(const zg_engine* e) {
+  if (!e || !e->has_schema) return 0;
+  std::lock_guard<std::mutex> g(const_cast<zg_engine*>(e)->mu);
+  std::vector<uint64_t> idx;
+  Store::Filter f;
+  e->store.match(f, 0, &idx);  // also folds duplicates of bulk loads
+  return e->store.size();
+}
+extern "C" void zg_set_clock(zg_engine* e, int64_t t) {
+  if (e) e->clock = t;
+}
+
+// ---- string resolution ---------------------------------------------------------------
+
+static std::string rel_text(const zg_rel_str& r) {
+  auto s = [](const char* x) { return std::string(x ? x : ""); };
+  return s(r.res_type) + ":" + s(r.res_id) + "#" + s(r.relation) + "@" + s(r.subj_type) + ":" + s(r.subj_id) +
+         (none_rel(r.subj_rel) ? "" : "#" + s(r.subj_rel));
+}
+
+// Resolve a relationship to WRITE (interns objects). Returns "" or an error.
+static std::string resolve_write(zg_engine* e, const zg_rel_str& r, zg_tuple* t) {
+  const Schema& sc = e->schema;
+  if (!r.res_type || !r.res_id || !r.relation || !r.subj_type || !r.subj_id) return "relationship has NULL fields";
+  int rt = sc.type_id(r.res_type), st = sc.type_id(r.subj_type);
+  if (rt < 0) return std::string("object definition `") + r.res_type + "` not found";
+  if (st < 0) return std::string("object definition `") + r.subj_type + "` not found";
+  int rel = sc.slot_id(rt, r.relation);
+  if (rel < 0 || sc.slots[rel].is_perm)
+    return std::string("relation `") + r.relation + "` not found under definition `" + r.res_type + "`";
+  if (!*r.res_id || !*r.subj_id) return "empty object id";
+  t->rel = static_cast<uint16_t>(rel);
+  t->stype = static_cast<uint16_t>(st);
+  t->flags = 0;
+  t->srel = kNone;
+  if (std::strcmp(r.subj_id, "*") == 0) {
+    if (!none_rel(r.subj_rel)) return "wildcard subjects cannot have a relation";
+    t->srel = kWildcard;
+    t->subj = 0;
+  } else {
+    if (!none_rel(r.subj_rel)) {
+      int sr = sc.slot_id(st, r.subj_rel);
+      if (sr < 0) return std::string("relation `") + r.subj_rel + "` not found under definition `" + r.subj_type + "`";
+      t->srel = static_cast<uint16_t>(sr);
+    }
+    t->subj = e->store.intern(st, r.subj_id);
+  }
+  t->res = e->store.intern(rt, r.res_id);
+  return "";
+}
+
+static Store::Filter resolve_filter(const zg_engine* e, const zg_filter_str& f, std::string* err) {
+  const Schema& sc = e->schema;
+  Store::Filter o;
+  auto set = [](const char* s) { return s && *s; };
+  if (set(f.res_type)) {
+    o.res_type = sc.type_id(f.res_type);
+    if (o.res_type < 0) {
+      *err = std::string("object definition `") + f.res_type + "` not found";
+      return o;
+    }
+  }
+  if (set(f.res_id)) {
+    if (o.res_type < 0) {
+      *err = "resource id filter needs a resource type";
+      return o;
+    }
+    o.has_res = true;
+    o.res = e->store.find(o.res_type, f.res_id);
+    if (o.res == ZG_NO_OBJECT) o.impossible = true;
+  }
+  if (set(f.relation)) {
+    if (o.res_type < 0) {
+      *err = "relation filter needs a resource type";
+      return o;
+    }
+    o.rel = sc.slot_id(o.res_type, f.relation);
+    if (o.rel < 0) {
+      *err = std::string("relation `") + f.relation + "` not found under definition `" + f.res_type + "`";
+      return o;
+    }
+  }
+  if (set(f.subj_type)) {
+    o.subj_type = sc.type_id(f.subj_type);
+    if (o.subj_type < 0) {
+      *err = std::string("object definition `") + f.subj_type + "` not found";
+      return o;
+    }
+  }
+  if (set(f.subj_id)) {
+    if (o.subj_type < 0) {
+      *err = "subject id filter needs a subject type";
+      return o;
+    }
+    if (std::strcmp(f.subj_id, "*") == 0) {
+      o.subj_wildcard = true;
+    } else {
+      o.has_subj = true;
+      o.subj = e->store.find(o.subj_type, f.subj_id);
+      if (o.subj == ZG_NO_OBJECT) o.impossible = true;
+    }
+  }
+  if (set(f.subj_rel)) {
+    if (o.subj_type < 0) {
+      *err = "subject relation filter needs a subject type";
+      return o;
+    }
+    o.has_srel = true;
+    if (std::strcmp(f.subj_rel, "...") == 0) {
+      o.srel = kNone;
+    } else {
+      int sr = sc.slot_id(o.subj_type, f.subj_rel);
+      if (sr < 0) o.impossible = true;
+      else o.srel = static_cast<uint16_t>(sr);
+    }
+  }
+  return o;
+}
+
+static int check_preconditions(zg_engine* e, const zg_precondition_str* pre, uint64_t n_pre) {
+  std::vector<uint64_t> idx;
+  for (uint64_t i = 0; i < n_pre; ++i) {
+    std::string err;
+    Store::Filter f = resolve_filter(e, pre[i].filter, &err);
+    if (!err.empty()) return fail(ZG_EINVAL, "precondition " + std::to_string(i) + ": " + err);
+    e->store.match(f, now_of(e), &idx);
+    const bool any = !idx.empty();
+    if (pre[i].op == ZG_PRECOND_MUST_MATCH && !any)
+      return fail(ZG_EPRECOND, "precondition " + std::to_string(i) + " (MUST_MATCH) failed");
+    if (pre[i].op == ZG_PRECOND_MUST_NOT_MATCH && any)
+      return fail(ZG_EPRECOND, "precondition " + std::to_string(i) + " (MUST_NOT_MATCH) failed");
+    if (pre[i].op != ZG_PRECOND_MUST_MATCH && pre[i].op != ZG_PRECOND_MUST_NOT_MATCH)
+      return fail(ZG_EINVAL, "unknown precondition operation");
+  }
+  return ZG_OK;
+}
+
+extern "C" int zg_write_relationships(zg_engine* e, const zg_update_str* ups, uint64_t n, const zg_precondition_str* pre,
+                                      uint64_t n_pre) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if ((!ups && n) || (!pre && n_pre)) return fail(ZG_EINVAL, "NULL argument");
+  if (n > 1000)  // pkg/spicedb/spicedb.go:34 WithMaximumUpdatesPerWrite(1000)
+    return fail(ZG_EINVAL, "update count of " + std::to_string(n) + " is greater than maximum allowed of 1000");
+  if (n_pre > 1000)  // pkg/spicedb/spicedb.go:35
+    return fail(ZG_EINVAL, "precondition count is greater than maximum allowed of 1000");
+  std::lock_guard<std::mutex> g(e->mu);
+  std::vector<zg_update> u(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    if (ups[i].op == ZG_OP_DELETE) {
+      // deleting a relationship whose objects were never written is a no-op, not an error
+      const zg_rel_str& r = ups[i].rel;
+      const Schema& sc = e->schema;
+      int rt = r.res_type ? sc.type_id(r.res_type) : -1, st = r.subj_type ? sc.type_id(r.subj_type) : -1;
+      int rel = rt >= 0 && r.relation ? sc.slot_id(rt, r.relation) : -1;
+      if (rt < 0 || st < 0 || rel < 0 || sc.slots[rel].is_perm || !r.res_id || !r.subj_id)
+        return fail(ZG_EINVAL, "update " + std::to_string(i) + ": malformed relationship " + rel_text(r));
+    }
+    std::string err = resolve_write(e, ups[i].rel, &u[i].t);
+    if (!err.empty()) return fail(ZG_EINVAL, "update " + std::to_string(i) + " (" + rel_text(ups[i].rel) + "): " + err);
+    u[i].expires_at = ups[i].expires_at;
+    u[i].op = ups[i].op;
+    // two updates of one relationship in a single write are rejected by SpiceDB
+    for (uint64_t j = 0; j < i; ++j)
+      if (key_of(u[j].t) == key_of(u[i].t))
+        return fail(ZG_EINVAL, "found more than one update with relationship " + rel_text(ups[i].rel));
+  }
+  int rc = check_preconditions(e, pre, n_pre);
+  if (rc) return rc;
+  int code = ZG_OK;
+  std::string err = e->store.apply(u.data(), n, &code);
+  if (!err.empty()) return fail(code, err);
+  return publish_locked(e);
+}
+
+extern "C" int zg_delete_relationships(zg_engine* e, const zg_filter_str* filter, const zg_precondition_str* pre,
+                                       uint64_t n_pre, uint64_t* n_deleted) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if (!filter || (!pre && n_pre)) return fail(ZG_EINVAL, "NULL argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  std::string err;
+  Store::Filter f = resolve_filter(e, *filter, &err);
+  if (!err.empty()) return fail(ZG_EINVAL, err);
+  int rc = check_preconditions(e, pre, n_pre);
+  if (rc) return rc;
+  std::vector<uint64_t> idx;
+  e->store.match(f, 0, &idx);  // expired relationships are deleted too
+  std::vector<zg_update> u(idx.size());
+  for (size_t i = 0; i < idx.size(); ++i) {
+    u[i].t = e->store.tuples[idx[i]];
+    u[i].expires_at = 0;
+    u[i].op = ZG_OP_DELETE;
+  }
+  int code = ZG_OK;
+  err = e->store.apply(u.data(), u.size(), &code);
+  if (!err.empty()) return fail(code, err);
+  if (n_deleted) *n_deleted = idx.size();
+  return publish_locked(e);
+}
+
+static std::string tuple_text(const zg_engine* e, const zg_tuple& t) {
+  const Schema& sc = e->schema;
+  const SlotInfo& rel = sc.slots[t.rel];
+  auto obj = [&](int type, uint32_t id) {
+    const std::string* n = e->store.name(type, id);
+    return n ? *n : std::to_string(id);
+  };
+  std::string s = sc.types[rel.type].name + ":" + obj(rel.type, t.res) + "#" + rel.name + "@" + sc.types[t.stype].name + ":";
+  if (t.srel == kWildcard) return s + "*";
+  s += obj(t.stype, t.subj);
+  if (t.srel != kNone) s += "#" + sc.slots[t.srel].name;
+  return s;
+}
+
+extern "C" int zg_read_relationships(zg_engine* e, const zg_filter_str* filter, char* buf, size_t cap, size_t* need,
+                                     uint64_t* n_out) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if (!filter) return fail(ZG_EINVAL, "NULL filter");
+  std::lock_guard<std::mutex> g(e->mu);
+  std::string err;
+  Store::Filter f = resolve_filter(e, *filter, &err);
+  if (!err.empty()) return fail(ZG_EINVAL, err);
+  std::vector<uint64_t> idx;
+  e->store.match(f, now_of(e), &idx);
+  std::vector<std::string> lines;
+  lines.reserve(idx.size());
+  for (uint64_t i : idx) lines.push_back(tuple_text(e, e->store.tuples[i]));
+  std::sort(lines.begin(), lines.end());
+  size_t total = 1;
+  for (const auto& l : lines) total += l.size() + 1;
+  if (need) *need = total;
+  if (n_out) *n_out = lines.size();
+  if (total > cap || !buf) return ZG_E2BIG;
+  size_t w = 0;
+  for (const auto& l : lines) {
+    std::memcpy(buf + w, l.data(), l.size());
+    w += l.size();
+    buf[w++] = '\n';
+  }
+  buf[w] = 0;
+  return ZG_OK;
+}
+
+// ---- hot path ------------------------------------------------------------------------
+
+static int ensure_published(zg_engine* e) {
+  if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
+  if (e->dirty || !e->dev.snap) return publish_locked(e);
+  return ZG_OK;
+}
+
+extern "C" int zg_check_bulk(zg_engine* e, const zg_check* items, uint64_t n, uint8_t* out) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if ((!items || !out) && n) return fail(ZG_EINVAL, "NULL argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
+  if (!e->dev.snap) return fail(ZG_ENOSNAPSHOT, "no snapshot published (call zg_publish)");
+  e->dev.now = now_of(e);
+  std::string err;
+  int rc = e->dev.check_host(items, n, out, &err);
+  return rc ? fail(rc, err) : ZG_OK;
+}
+
+extern "C" int zg_check_bulk_device(zg_engine* e, const zg_check* d_items, uint64_t n, uint8_t* d_out, void* stream) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if ((!d_items || !d_out) && n) return fail(ZG_EINVAL, "NULL argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
+  e->dev.now = now_of(e);
+  std::string err;
+  int rc = e->dev.check_device(d_items, n, d_out, static_cast<cudaStream_t>(stream), true, nullptr, &err);
+  return rc ? fail(rc, err) : ZG_OK;
+}
+
+extern "C" int zg_count_alg_bytes(zg_engine* e, const zg_check* items, uint64_t n, uint64_t* bytes) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if (!items || !bytes) return fail(ZG_EINVAL, "NULL argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
+  e->dev.now = now_of(e);
+  std::string err;
+  void *d_in = nullptr, *d_out = nullptr;
+  if (cudaMalloc(&d_in, n * sizeof(zg_check)) != cudaSuccess || cudaMalloc(&d_out, n ? n : 1) != cudaSuccess) {
+    if (d_in) cudaFree(d_in);
+    return fail(ZG_ENOMEM, "out of device memory");
+  }
+  cudaMemcpy(d_in, items, n * sizeof(zg_check), cudaMemcpyHostToDevice);
+  uint64_t b = 0;
+  int rc = e->dev.check_device(static_cast<zg_check*>(d_in), n, static_cast<uint8_t*>(d_out), nullptr, true, &b, &err);
+  cudaFree(d_in);
+  cudaFree(d_out);
+  if (rc) return fail(rc, err);
+  *bytes = b;
+  return ZG_OK;
+}
+
+// Resolve a CHECK item without interning anything (query strings must not grow the store).
+static void resolve_check(const zg_engine* e, const zg_rel_str& r, zg_check* c) {
+  const Schema& sc = e->schema;
+  c->res = ZG_NO_OBJECT;
+  c->subj = ZG_NO_OBJECT - 1;
+  c->perm = kNone;  // invalid -> ZG_ITEM_ERROR
+  c->stype = 0;
+  c->srel = kNone;
+  c->flags = 0;
+  if (!r.res_type || !r.res_id || !r.relation || !r.subj_type || !r.subj_id) return;
+  int rt = sc.type_id(r.res_type), st = sc.type_id(r.subj_type);
+  if (rt < 0 || st < 0) return;
+  int perm = sc.slot_id(rt, r.relation);
+  if (perm < 0) return;
+  if (!none_rel(r.subj_rel)) {
+    int sr = sc.slot_id(st, r.subj_rel);
+    if (sr < 0) return;
+    c->srel = static_cast<uint16_t>(sr);
+  }
+  c->stype = static_cast<uint16_t>(st);
+  c->res = e->store.find(rt, r.res_id);
+  uint32_t su = e->store.find(st, r.subj_id);
+  // two never-written names that are the same object must still compare equal
+  if (su == ZG_NO_OBJECT) su = (c->res == ZG_NO_OBJECT && rt == st && std::strcmp(r.res_id, r.subj_id) == 0)
+                                   ? ZG_NO_OBJECT : ZG_NO_OBJECT - 1;
+  c->subj = su;
+  c->perm = static_cast<uint16_t>(perm);
+}
+
+extern "C" int zg_check_bulk_str(zg_engine* e, const zg_rel_str* items, uint64_t n, uint8_t* out) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if ((!items || !out) && n) return fail(ZG_EINVAL, "NULL argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  int rc = ensure_published(e);
+  if (rc) return rc;
+  std::vector<zg_check> c(n);
+  for (uint64_t i = 0; i < n; ++i) resolve_check(e, items[i], &c[i]);
+  e->dev.now = now_of(e);
+  std::string err;
+  rc = e->dev.check_host(c.data(), n, out, &err);
+  return rc ? fail(rc, err) : ZG_OK;
+}
+
+static int lookup_locked(zg_engine* e, uint16_t res_type, uint16_t perm, uint16_t stype, uint32_t subj, uint16_t srel,
+                         std::vector<uint32_t>* ids) {
+  const Schema& sc = e->schema;
+  if (res_type >= sc.types.size() || perm >= sc.slots.size() || sc.slots[perm].type != res_type)
+    return fail(ZG_EINVAL, "unknown resource type or permission");
+  if (stype >= sc.types.size() || (srel != kNone && (srel >= sc.slots.size() || sc.slots[srel].type != stype)))
+    return fail(ZG_EINVAL, "unknown subject type or relation");
+  zg_check proto{};
+  proto.subj = subj;
+  proto.perm = perm;
+  proto.stype = stype;
+  proto.srel = srel;
+  e->dev.now = now_of(e);
+  std::string err;
+  int rc = e->dev.lookup(res_type, proto, ids, &err);
+  if (rc) return fail(rc, err);
+  // a userset subject res_type:x#perm is a member of itself even without relationships
+  if (srel == perm && stype == res_type && subj < ZG_NO_OBJECT - 1 &&
+      !std::binary_search(ids->begin(), ids->end(), subj))
+    ids->insert(std::upper_bound(ids->begin(), ids->end(), subj), subj);
+  return ZG_OK;
+}
+
+extern "C" int zg_lookup_resources(zg_engine* e, uint16_t res_type, uint16_t perm, uint16_t stype, uint32_t subj,
+                                   uint16_t srel, uint32_t* out_ids, uint64_t cap, uint64_t* n_out) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if (!n_out) return fail(ZG_EINVAL, "NULL n_out");
+  std::lock_guard<std::mutex> g(e->mu);
+  if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
+  if (!e->dev.snap) return fail(ZG_ENOSNAPSHOT, "no snapshot published (call zg_publish)");
+  std::vector<uint32_t> ids;
+  int rc = lookup_locked(e, res_type, perm, stype, subj, srel, &ids);
+  if (rc) return rc;
+  *n_out = ids.size();
+  if (ids.size() > cap || (!out_ids && !ids.empty())) return ZG_E2BIG;
+  if (!ids.empty()) std::memcpy(out_ids, ids.data(), ids.size() * 4);
+  return ZG_OK;
+}
+
+extern "C" int zg_lookup_resources_str(zg_engine* e, const char* res_type, const char* perm, const char* subj_type,
+                                       const char* subj_id, const char* subj_rel, char* buf, size_t cap, size_t* need,
+                                       uint64_t* n_out) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if (!res_type || !perm || !subj_type || !subj_id) return fail(ZG_EINVAL, "NULL argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  int rc = ensure_published(e);
+  if (rc) return rc;
+  const Schema& sc = e->schema;
+  int rt = sc.type_id(res_type), st = sc.type_id(subj_type);
+  if (rt < 0) return fail(ZG_EINVAL, std::string("object definition `") + res_type + "` not found");
+  if (st < 0) return fail(ZG_EINVAL, std::string("object definition `") + subj_type + "` not found");
+  int p = sc.slot_id(rt, perm);
+  if (p < 0) return fail(ZG_EINVAL, std::string("relation/permission `") + perm + "` not found under definition `" + res_type + "`");
+  uint16_t sr = kNone;
+  if (!none_rel(subj_rel)) {
+    int s = sc.slot_id(st, subj_rel);
+    if (s < 0) return fail(ZG_EINVAL, std::string("relation `") + subj_rel + "` not found under definition `" + subj_type + "`");
+    sr = static_cast<uint16_t>(s);
+  }
+  uint32_t su = e->store.find(st, subj_id);
+  std::vector<uint32_t> ids;
+  rc = lookup_locked(e, static_cast<uint16_t>(rt), static_cast<uint16_t>(p), static_cast<uint16_t>(st),
+                     su == ZG_NO_OBJECT ? ZG_NO_OBJECT - 1 : su, sr, &ids);
+  if (rc) return rc;
+  std::vector<std::string> names;
+  for (uint32_t id : ids) {
+    const std::string* n = e->store.name(rt, id);
+    names.push_back(n ? *n : std::to_string(id));
+  }
+  // never-written userset subject that names itself
+  if (su == ZG_NO_OBJECT && sr == p && st == rt) names.push_back(subj_id);
+  size_t total = 1;
+  for (const auto& n : names) total += n.size() + 1;
+  if (need) *need = total;
+  if (n_out) *n_out = names.size();
+  if (total > cap || !buf) return ZG_E2BIG;
+  size_t w = 0;
+  for (const auto& n : names) {
+    std::memcpy(buf + w, n.data(), n.size());
+    w += n.size();
+    buf[w++] = '\n';
+  }
+  buf[w] = 0;
+  return ZG_OK;
+}
+
+extern "C" int zg_stats_get(zg_engine* e, zg_stats* out) {
+  if (!e || !out) return fail(ZG_EINVAL, "NULL argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  if (!e->host_only) e->dev.finish_timing();
+  std::memset(out, 0, sizeof *out);
+  out->checks = e->dev.checks;
+  out->launches = e->dev.launches;
+  out->passes = e->dev.passes;
+  out->revision = e->revision;
+  out->last_alg_bytes = e->dev.last_alg_bytes;
+  out->last_kernel_ms = e->dev.last_ms;
+  if (e->dev.snap) {
+    out->tuples = e->dev.snap->n_tuples;
+    out->snapshot_bytes = e->dev.snap->bytes;
+  }
+  return ZG_OK;
+}
+
+extern "C" int zg_debug_row(zg_engine* e, uint16_t rel_slot, uint32_t res, uint32_t cls, uint32_t* out, uint64_t cap,
+                            uint64_t* n_out) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if (!n_out) return fail(ZG_EINVAL, "NULL n_out");
+  std::lock_guard<std::mutex> g(e->mu);
+  e->keep_built = true;
+  if (e->last_built.rels.empty() && !e->schema.rel_slots.empty()) {
+    e->last_built = e->store.build();
+    if (!e->last_built.err.empty()) return fail(ZG_EINVAL, e->last_built.err);
+  }
+  const Schema& sc = e->schema;
+  if (rel_slot >= sc.slots.size() || sc.slots[rel_slot].is_perm) return fail(ZG_EINVAL, "not a relation");
+  const DRel& r = e->last_built.rels[sc.slots[rel_slot].rel_index];
+  *n_out = 0;
+  if (cls >= r.ncls) return fail(ZG_EINVAL, "class out of range");
+  if (res >= r.nres) return ZG_OK;
+  uint64_t idx = r.row_base + uint64_t(res) * r.ncls + cls;
+  uint32_t b = e->last_built.row_ptr[idx], en = e->last_built.row_ptr[idx + 1];
+  *n_out = en - b;
+  if (en - b > cap) return ZG_E2BIG;
+  for (uint32_t i = b; i < en; ++i) out[i - b] = e->last_built.col[i];
+  return ZG_OK;
+}
+
+extern "C" void* zg_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    g_err = "cudaMallocHost failed";
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void zg_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}

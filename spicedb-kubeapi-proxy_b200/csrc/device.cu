@@ -1,0 +1,378 @@
+// device.cu -- snapshot upload and the launch sequences of the hot path.
+//
+// Call graph it replaces in the reference:
+//   CheckBulkPermissions (pkg/authz/check.go:48, postfilter.go:134) -> check_*()
+//   LookupResources      (pkg/authz/lookups.go:65)                    -> lookup()
+#include "device.h"
+
+#include <algorithm>
+#include <cstring>
+
+#include "kernels.cuh"
+
+namespace zg {
+
+#define ZG_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      if (err) *err = std::string(#expr) + ": " + cudaGetErrorString(_e);               \
+      return ZG_ECUDA;                                                                  \
+    }                                                                                   \
+  } while (0)
+
+bool DevBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return true;
+  release();
+  size_t want = std::max<size_t>(bytes, 256);
+  if (cudaMalloc(&p, want) != cudaSuccess) {
+    p = nullptr;
+    cap = 0;
+    cudaGetLastError();
+    return false;
+  }
+  cap = want;
+  return true;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+Snapshot::~Snapshot() {
+  row_ptr.release();
+  col.release();
+  exp.release();
+  prog.release();
+  for (auto& r : resources) r.release();
+}
+
+Device::~Device() {
+  if (stream) cudaStreamSynchronize(stream);
+  snap.reset();
+  spill_.release();
+  ctrl_.release();
+  for (auto* v : {&q_, &parent_, &jobs_, &val_})
+    for (auto& b : *v) b.release();
+  stage_in_.release();
+  stage_out_.release();
+  lk_jobs_.release();
+  lk_codes_.release();
+  lk_ids_.release();
+  if (pin_in_) cudaFreeHost(pin_in_);
+  if (pin_out_) cudaFreeHost(pin_out_);
+  if (ev0_) cudaEventDestroy(ev0_);
+  if (ev1_) cudaEventDestroy(ev1_);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+static size_t smem_bytes(uint32_t prog_bytes) {
+  return prog_bytes + static_cast<size_t>(kWarpsPerBlock) * kStackCap * sizeof(uint4);
+}
+
+std::string Device::init(int dev, uint64_t subq_cap, uint32_t budget) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+           " (libzgpu has no CPU fallback)";
+  if (dev < 0) {
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  }
+  if (dev >= count) return "CUDA device ordinal out of range";
+  if ((e = cudaSetDevice(dev)) != cudaSuccess) return std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+  device = dev;
+  cudaDeviceProp prop{};
+  if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess)
+    return std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+  sm_count_ = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+  cudaEventCreate(&ev0_);
+  cudaEventCreate(&ev1_);
+  if (subq_cap) subq_cap_ = subq_cap;
+  if (budget) budget_ = budget;
+  if (!ctrl_.ensure(64)) return "out of device memory";
+  cudaMemset(ctrl_.p, 0, 64);
+  return "";
+}
+
+std::string Device::publish(const HostSnapshot& h, const Schema& sc, uint64_t revision) {
+  cudaSetDevice(device);
+  auto s = std::make_shared<Snapshot>();
+  std::vector<uint8_t> blob = sc.blob(h.rels);
+  auto up = [&](DevBuf& b, const void* src, size_t bytes) -> bool {
+    if (!b.ensure(bytes ? bytes : 16)) return false;
+    if (bytes && cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess) return false;
+    s->bytes += bytes;
+    return true;
+  };
+  bool ok = up(s->row_ptr, h.row_ptr.data(), h.row_ptr.size() * 4) && up(s->col, h.col.data(), h.col.size() * 4) &&
+            up(s->prog, blob.data(), blob.size());
+  if (ok && sc.has_expiry) ok = up(s->exp, h.exp.data(), h.exp.size() * 4);
+  s->resources.resize(h.resources.size());
+  s->n_resources.resize(h.resources.size());
+  for (size_t t = 0; ok && t < h.resources.size(); ++t) {
+    s->n_resources[t] = h.resources[t].size();
+    ok = up(s->resources[t], h.resources[t].data(), h.resources[t].size() * 4);
+  }
+  if (!ok || cudaStreamSynchronize(stream) != cudaSuccess) {
+    std::string m = std::string("snapshot upload failed: ") + cudaGetErrorString(cudaGetLastError());
+    return m;
+  }
+  s->prog_bytes = static_cast<uint32_t>(blob.size());
+  s->max_leaves = sc.max_leaves;
+  s->has_nonpure = sc.has_nonpure;
+  s->n_tuples = h.n_tuples;
+  s->revision = revision;
+
+  // occupancy for this program size (dynamic shared memory = program + warp stacks)
+  size_t sm = smem_bytes(s->prog_bytes);
+  if (sm > 200 * 1024) return "schema program too large for shared memory";
+  cudaFuncSetAttribute(check_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+  cudaFuncSetAttribute(check_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+  int occ = 0, occ_c = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, check_kernel<false>, kThreads, sm);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, check_kernel<true>, kThreads, sm);
+  if (occ < 1 || occ_c < 1) return "check kernel cannot be resident (occupancy 0)";
+  blocks_per_sm_ = occ;
+  blocks_per_sm_count_ = occ_c;
+  size_t warps = static_cast<size_t>(sm_count_) * std::max(occ, occ_c) * kWarpsPerBlock;
+  if (!spill_.ensure(warps * spill_cap_ * sizeof(uint4))) return "out of device memory (spill areas)";
+  // readers that already hold the old snapshot keep it alive until they finish
+  snap = s;
+  return "";
+}
+
+int Device::run_pass(const Snapshot& s, const zg_check* jobs, uint64_t njobs, uint8_t* val, bool final_codes, bool raw,
+                     zg_check* subq, uint32_t* subq_parent, cudaStream_t st, bool count, std::string* err) {
+  KParams p{};
+  p.row_ptr = s.row_ptr.as<uint32_t>();
+  p.col = s.col.as<uint32_t>();
+  p.exp = s.exp.p ? s.exp.as<uint32_t>() : nullptr;
+  p.prog = s.prog.as<uint8_t>();
+  p.prog_bytes = s.prog_bytes;
+  p.jobs = jobs;
+  p.njobs = njobs;
+  p.val = val;
+  p.final_codes = final_codes;
+  unsigned long long* ctrl = ctrl_.as<unsigned long long>();
+  p.next = ctrl;
+  p.subq_count = ctrl + 1;
+  p.alg_bytes = ctrl + 2;
+  p.flags = reinterpret_cast<uint32_t*>(ctrl + 3);
+  p.spill = spill_.as<uint4>();
+  p.spill_cap = spill_cap_;
+  p.subq = subq;
+  p.subq_parent = subq_parent;
+  p.subq_cap = subq ? subq_cap_ : 0;
+  p.now = now;
+  p.budget = budget_;
+  p.raw_items = raw;
+  ZG_CUDA(cudaMemsetAsync(ctrl, 0, 16, st));  // next, subq_count
+  const int per_sm = count ? blocks_per_sm_count_ : blocks_per_sm_;
+  uint64_t want = (njobs + kThreads - 1) / kThreads;
+  int grid = static_cast<int>(std::min<uint64_t>(want, static_cast<uint64_t>(sm_count_) * per_sm));
+  if (grid < 1) grid = 1;
+  size_t sm = smem_bytes(s.prog_bytes);
+  if (count) check_kernel<true><<<grid, kThreads, sm, st>>>(p);
+  else check_kernel<false><<<grid, kThreads, sm, st>>>(p);
+  ZG_CUDA(cudaGetLastError());
+  ++launches;
+  return ZG_OK;
+}
+
+void Device::finish_timing() {
+  if (!timing_pending_) return;
+  if (cudaEventSynchronize(ev1_) == cudaSuccess) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess) last_ms = ms;
+  }
+  timing_pending_ = false;
+}
+
+int Device::check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cudaStream_t st, bool raw_items,
+                         uint64_t* count_bytes, std::string* err) {
+  std::shared_ptr<Snapshot> s = snap;
+  if (!s) {
+    if (err) *err = "no snapshot published (call zg_publish after loading relationships)";
+    return ZG_ENOSNAPSHOT;
+  }
+  if (n == 0) return ZG_OK;
+  ZG_CUDA(cudaSetDevice(device));
+  if (!st) st = stream;
+  const bool count = count_bytes != nullptr;
+  unsigned long long* ctrl = ctrl_.as<unsigned long long>();
+  ZG_CUDA(cudaMemsetAsync(ctrl + 2, 0, 16, st));  // alg_bytes, flags
+  cudaEventRecord(ev0_, st);
+  const uint32_t L = s->max_leaves;
+  int rc = ZG_OK;
+  if (!s->has_nonpure) {
+    // every slot is a relation or a pure union: one job per check, answered in one launch
+    rc = run_pass(*s, d_items, n, d_out, true, raw_items, nullptr, nullptr, st, count, err);
+    if (rc) return rc;
+  } else {
+    if (n * L >= (1ull << 32)) {
+      if (err) *err = "batch too large for one call (n * leaves >= 2^32)";
+      return ZG_EINVAL;
+    }
+    std::vector<uint64_t> nq;  // queries per pass level
+    auto level = [&](size_t lv) {
+      if (q_.size() <= lv) {
+        q_.resize(lv + 1);
+        parent_.resize(lv + 1);
+        jobs_.resize(lv + 1);
+        val_.resize(lv + 1);
+      }
+    };
+    const zg_check* queries = d_items;
+    uint64_t cur = n;
+    bool raw = raw_items;
+    for (size_t lv = 0; cur > 0; ++lv) {
+      if (lv > ZG_MAX_DEPTH + 1) {
+        if (err) *err = "sub-query passes exceeded the depth cap";
+        return ZG_ECUDA;
+      }
+      level(lv + 1);
+      nq.push_back(cur);
+      if (!jobs_[lv].ensure(cur * L * sizeof(zg_check)) || !val_[lv].ensure(cur * L + 4) ||
+          !q_[lv + 1].ensure(subq_cap_ * sizeof(zg_check)) || !parent_[lv + 1].ensure(subq_cap_ * 4)) {
+        if (err) *err = "out of device memory (pass buffers)";
+        return ZG_ENOMEM;
+      }
+      const unsigned blk = 256;
+      prep_jobs_kernel<<<static_cast<unsigned>((cur + blk - 1) / blk), blk, 0, st>>>(
+          s->prog.as<uint8_t>(), queries, cur, L, jobs_[lv].as<zg_check>(), raw ? 1 : 0);
+      ++launches;
+      rc = run_pass(*s, jobs_[lv].as<zg_check>(), cur * L, val_[lv].as<uint8_t>(), false, false,
+                    q_[lv + 1].as<zg_check>(), parent_[lv + 1].as<uint32_t>(), st, count, err);
+      if (rc) return rc;
+      unsigned long long host_ctrl[4];
+      ZG_CUDA(cudaMemcpyAsync(host_ctrl, ctrl, sizeof host_ctrl, cudaMemcpyDeviceToHost, st));
+      ZG_CUDA(cudaStreamSynchronize(st));
+      const uint32_t flags = static_cast<uint32_t>(host_ctrl[3] & 0xFFFFFFFFu);
+      if (flags & 2u) {
+        if (err) *err = "sub-query buffer overflow: raise zg_config.subquery_capacity";
+        return ZG_ENOMEM;
+      }
+      cur = host_ctrl[1];
+      queries = q_[lv + 1].as<zg_check>();
+      raw = false;
+      if (cur) ++passes;
+    }
+    for (size_t lv = nq.size(); lv-- > 0;) {
+      const unsigned blk = 256;
+      const uint64_t m = nq[lv];
+      fold_kernel<<<static_cast<unsigned>((m + blk - 1) / blk), blk, 0, st>>>(
+          s->prog.as<uint8_t>(), lv == 0 ? d_items : q_[lv].as<zg_check>(), m, L, val_[lv].as<uint8_t>(),
+          lv == 0 ? d_out : nullptr, lv == 0 ? nullptr : parent_[lv].as<uint32_t>(),
+          lv == 0 ? nullptr : val_[lv - 1].as<uint8_t>());
+      ++launches;
+    }
+    ZG_CUDA(cudaGetLastError());
+  }
+  cudaEventRecord(ev1_, st);
+  timing_pending_ = true;
+  checks += n;
+  if (count) {
+    unsigned long long host_ctrl[4];
+    ZG_CUDA(cudaMemcpyAsync(host_ctrl, ctrl, sizeof host_ctrl, cudaMemcpyDeviceToHost, st));
+    ZG_CUDA(cudaStreamSynchronize(st));
+    *count_bytes = host_ctrl[2];
+    last_alg_bytes = host_ctrl[2];
+  }
+  return ZG_OK;
+}
+
+int Device::check_host(const zg_check* items, uint64_t n, uint8_t* out, std::string* err) {
+  if (n == 0) return ZG_OK;
+  ZG_CUDA(cudaSetDevice(device));
+  if (!stage_in_.ensure(n * sizeof(zg_check)) || !stage_out_.ensure(n)) {
+    if (err) *err = "out of device memory (staging)";
+    return ZG_ENOMEM;
+  }
+  // Pinned caller buffers (zg_host_alloc) are copied straight from/to; pageable
+  // ones go through the engine's pinned staging area.
+  cudaPointerAttributes a{};
+  const bool in_pinned = cudaPointerGetAttributes(&a, items) == cudaSuccess && a.type == cudaMemoryTypeHost;
+  const bool out_pinned = cudaPointerGetAttributes(&a, out) == cudaSuccess && a.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  const void* src = items;
+  if (!in_pinned) {
+    if (pin_in_cap_ < n * sizeof(zg_check)) {
+      if (pin_in_) cudaFreeHost(pin_in_);
+      pin_in_cap_ = 0;
+      ZG_CUDA(cudaMallocHost(&pin_in_, n * sizeof(zg_check)));
+      pin_in_cap_ = n * sizeof(zg_check);
+    }
+    std::memcpy(pin_in_, items, n * sizeof(zg_check));
+    src = pin_in_;
+  }
+  void* dst = out;
+  if (!out_pinned) {
+    if (pin_out_cap_ < n) {
+      if (pin_out_) cudaFreeHost(pin_out_);
+      pin_out_cap_ = 0;
+      ZG_CUDA(cudaMallocHost(&pin_out_, n));
+      pin_out_cap_ = n;
+    }
+    dst = pin_out_;
+  }
+  ZG_CUDA(cudaMemcpyAsync(stage_in_.p, src, n * sizeof(zg_check), cudaMemcpyHostToDevice, stream));
+  int rc = check_device(stage_in_.as<zg_check>(), n, stage_out_.as<uint8_t>(), stream, true, nullptr, err);
+  if (rc) return rc;
+  ZG_CUDA(cudaMemcpyAsync(dst, stage_out_.p, n, cudaMemcpyDeviceToHost, stream));
+  uint32_t flags = 0;
+  ZG_CUDA(cudaMemcpyAsync(&flags, ctrl_.as<unsigned long long>() + 3, 4, cudaMemcpyDeviceToHost, stream));
+  ZG_CUDA(cudaStreamSynchronize(stream));
+  if (flags & 1u) {
+    if (err) *err = "expansion stack overflow (per-warp spill area exhausted)";
+    return ZG_ENOMEM;
+  }
+  if (!out_pinned) std::memcpy(out, pin_out_, n);
+  return ZG_OK;
+}
+
+int Device::lookup(uint16_t res_type, const zg_check& proto, std::vector<uint32_t>* ids, std::string* err) {
+  ids->clear();
+  std::shared_ptr<Snapshot> s = snap;
+  if (!s) {
+    if (err) *err = "no snapshot published";
+    return ZG_ENOSNAPSHOT;
+  }
+  if (res_type >= s->resources.size()) {
+    if (err) *err = "unknown resource type";
+    return ZG_EINVAL;
+  }
+  const uint64_t n = s->n_resources[res_type];
+  if (n == 0) return ZG_OK;
+  ZG_CUDA(cudaSetDevice(device));
+  const size_t count_off = (n * 4 + 7) & ~size_t(7);  // the result count lives after the ids
+  if (!lk_jobs_.ensure(n * sizeof(zg_check)) || !lk_codes_.ensure(n) || !lk_ids_.ensure(count_off + 8)) {
+    if (err) *err = "out of device memory (lookup)";
+    return ZG_ENOMEM;
+  }
+  const unsigned blk = 256, grid = static_cast<unsigned>((n + blk - 1) / blk);
+  const uint32_t* cand = s->resources[res_type].as<uint32_t>();
+  lookup_fill_kernel<<<grid, blk, 0, stream>>>(cand, n, proto, lk_jobs_.as<zg_check>());
+  ++launches;
+  int rc = check_device(lk_jobs_.as<zg_check>(), n, lk_codes_.as<uint8_t>(), stream, true, nullptr, err);
+  if (rc) return rc;
+  unsigned long long* d_count = reinterpret_cast<unsigned long long*>(lk_ids_.as<uint8_t>() + count_off);
+  ZG_CUDA(cudaMemsetAsync(d_count, 0, 8, stream));
+  lookup_compact_kernel<<<grid, blk, 0, stream>>>(cand, lk_codes_.as<uint8_t>(), n, lk_ids_.as<uint32_t>(), n, d_count,
+                                                  reinterpret_cast<uint32_t*>(ctrl_.as<unsigned long long>() + 3));
+  ++launches;
+  unsigned long long cnt = 0;
+  ZG_CUDA(cudaMemcpyAsync(&cnt, d_count, 8, cudaMemcpyDeviceToHost, stream));
+  ZG_CUDA(cudaStreamSynchronize(stream));
+  ids->resize(cnt);
+  if (cnt) {
+    ZG_CUDA(cudaMemcpyAsync(ids->data(), lk_ids_.p, cnt * 4, cudaMemcpyDeviceToHost, stream));
+    ZG_CUDA(cudaStreamSynchronize(stream));
+    std::sort(ids->begin(), ids->end());
+  }
+  return ZG_OK;
+}
+
+}  // namespace zg

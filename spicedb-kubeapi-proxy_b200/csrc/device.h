@@ -1,0 +1,79 @@
+// device.h -- device-side state of one engine: the published CSR snapshot in HBM,
+// scratch buffers, and the launch sequences of the hot path.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/zgpu.h"
+#include "schema.h"
+#include "store.h"
+
+namespace zg {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  // grow-only; returns false on allocation failure
+  bool ensure(size_t bytes);
+  void release();
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+// Immutable once published; shared_ptr keeps it alive for in-flight readers.
+struct Snapshot {
+  DevBuf row_ptr, col, exp, prog;
+  std::vector<DevBuf> resources;  // per type
+  std::vector<uint64_t> n_resources;
+  uint32_t prog_bytes = 0;
+  uint32_t max_leaves = 1;
+  bool has_nonpure = false;
+  uint64_t n_tuples = 0, bytes = 0, revision = 0;
+  ~Snapshot();
+};
+
+class Device {
+ public:
+  ~Device();
+  std::string init(int device, uint64_t subq_cap, uint32_t budget);
+  std::string publish(const HostSnapshot& h, const Schema& sc, uint64_t revision);
+
+  // d_items / d_out are device pointers. count_bytes != nullptr selects the
+  // instrumented kernel variant. Returns ZG_* and fills err.
+  int check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cudaStream_t st, bool raw_items,
+                   uint64_t* count_bytes, std::string* err);
+  int check_host(const zg_check* items, uint64_t n, uint8_t* out, std::string* err);
+  int lookup(uint16_t res_type, const zg_check& proto, std::vector<uint32_t>* ids, std::string* err);
+
+  std::shared_ptr<Snapshot> snap;
+  cudaStream_t stream = nullptr;
+  int device = 0;
+  uint64_t launches = 0, passes = 0, checks = 0;
+  double last_ms = 0;
+  uint32_t now = 0;  // clock for expiration, set by the caller before each hot-path call
+  uint64_t last_alg_bytes = 0;
+
+ private:
+  int run_pass(const Snapshot& s, const zg_check* jobs, uint64_t njobs, uint8_t* val, bool final_codes, bool raw,
+               zg_check* subq, uint32_t* subq_parent, cudaStream_t st, bool count, std::string* err);
+  int sm_count_ = 0, blocks_per_sm_ = 0, blocks_per_sm_count_ = 0;
+  uint32_t spill_cap_ = 4096, budget_ = 1u << 22;
+  uint64_t subq_cap_ = 1ull << 22;
+  DevBuf spill_, ctrl_;  // ctrl: [0] next, [1] subq_count, [2] alg_bytes, then flags u32
+  std::vector<DevBuf> q_, parent_, jobs_, val_;  // per pass level
+  DevBuf stage_in_, stage_out_, lk_jobs_, lk_codes_, lk_ids_;
+  void* pin_in_ = nullptr;
+  void* pin_out_ = nullptr;
+  size_t pin_in_cap_ = 0, pin_out_cap_ = 0;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  bool timing_pending_ = false;
+
+ public:
+  void finish_timing();
+};
+
+}  // namespace zg

@@ -1,0 +1,552 @@
+// kernels.cuh -- sm_100a CUDA kernels of the permission-check hot path.
+//
+// What this replaces in the reference: the per-item graph evaluation that
+// CheckBulkPermissions / CheckPermission / LookupResources trigger inside the
+// embedded SpiceDB (call sites pkg/authz/check.go:48, postfilter.go:134,
+// watch.go:50, lookups.go:65; engine config pkg/spicedb/spicedb.go:25-56).
+//
+// Execution model (DESIGN.md "Kernels"):
+//   * persistent grid, one CTA slot per SM x occupancy; every WARP owns a private
+//     LIFO of edge RANGES in shared memory (spilling to a per-warp HBM area) and
+//     pulls batches of 32 checks from a global counter;
+//   * one iteration pops ranges worth <= 32 edges, assigns one edge per lane
+//     (coalesced reads of each CSR segment), and every lane visits its child node:
+//     row offsets (one 4-byte load per class + 1), binary-search probe of the
+//     sorted direct-subject segment, ballot/popc-compacted push of the userset and
+//     arrow ranges it found;
+//   * found / error state is two warp-uniform 32-bit masks; a found check's
+//     remaining ranges are dropped when popped (short circuit);
+//   * no tensor cores, no floating point: HBM/L2-bound integer traversal.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/zgpu.h"
+#include "schema.h"
+
+namespace zg {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr int kStackCap = 128;        // range items per warp in shared memory
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr uint16_t kJobIsUnit = 0x8000;  // zg_check.flags: perm field is a unit id
+constexpr uint16_t kJobDepthMask = 0x00FF;
+
+// job value bits
+constexpr uint8_t kValT = 1, kValE = 2;
+
+struct KParams {
+  const uint32_t* row_ptr;
+  const uint32_t* col;
+  const uint32_t* exp;  // nullptr unless the schema uses expiration
+  const uint8_t* prog;
+  uint32_t prog_bytes;
+  const zg_check* jobs;
+  unsigned long long njobs;
+  uint8_t* val;  // per job: final codes (final_codes=1) or kValT|kValE bits
+  int final_codes;
+  unsigned long long* next;  // batch counter (zeroed before launch)
+  uint4* spill;              // per-warp spill areas
+  uint32_t spill_cap;        // items per warp
+  // sub-queries raised when an edge leads into a non-pure permission
+  zg_check* subq;
+  uint32_t* subq_parent;
+  unsigned long long* subq_count;
+  unsigned long long subq_cap;
+  uint32_t* flags;  // bit0: spill overflow, bit1: sub-query overflow, bit2: budget hit
+  uint32_t now;
+  uint32_t budget;
+  int raw_items;  // jobs are caller-supplied zg_check items: flags are ignored
+  unsigned long long* alg_bytes;  // COUNT variant only
+};
+
+struct Prog {
+  const DHeader* h;
+  const DSlot* slots;
+  const DUnit* units;
+  const DOp* ops;
+  const DRel* rels;
+  const DCls* cls;
+  const uint16_t* tgts;
+  const uint16_t* members;
+  const DTree* trees;
+  const DTreeOp* tree_ops;
+  const uint16_t* leaf_units;
+};
+
+__device__ __forceinline__ Prog make_prog(const uint8_t* b) {
+  Prog p;
+  p.h = reinterpret_cast<const DHeader*>(b);
+  p.slots = reinterpret_cast<const DSlot*>(b + p.h->off_slots);
+  p.units = reinterpret_cast<const DUnit*>(b + p.h->off_units);
+  p.ops = reinterpret_cast<const DOp*>(b + p.h->off_ops);
+  p.rels = reinterpret_cast<const DRel*>(b + p.h->off_rels);
+  p.cls = reinterpret_cast<const DCls*>(b + p.h->off_cls);
+  p.tgts = reinterpret_cast<const uint16_t*>(b + p.h->off_tgts);
+  p.members = reinterpret_cast<const uint16_t*>(b + p.h->off_members);
+  p.trees = reinterpret_cast<const DTree*>(b + p.h->off_trees);
+  p.tree_ops = reinterpret_cast<const DTreeOp*>(b + p.h->off_tree_ops);
+  p.leaf_units = reinterpret_cast<const uint16_t*>(b + p.h->off_leaf_units);
+  return p;
+}
+
+// range item: x = begin, y = end (edge indices into col), z = meta, w unused
+//   meta: bits 0-4 job slot, 5-10 depth of the children, 11 class has expiry,
+//         16-31 slot the children are visited at
+__device__ __forceinline__ uint32_t make_meta(uint32_t jslot, uint32_t depth, bool expiry, uint32_t tslot) {
+  return jslot | (depth << 5) | (expiry ? (1u << 11) : 0u) | (tslot << 16);
+}
+
+template <bool COUNT>
+struct WarpCtx {
+  uint4* stack;
+  uint4* spill;
+  int top, spill_top;
+  uint32_t spill_cap;
+  unsigned found, err;  // warp-uniform, indexed by job slot
+  uint32_t my_subj, my_ss;  // this lane's own job: subject id, stype<<16 | srel
+  unsigned long long bytes;
+  bool fatal;
+  unsigned lane;
+};
+
+template <bool COUNT>
+__device__ __forceinline__ void spill_half(WarpCtx<COUNT>& c) {
+  constexpr int H = kStackCap / 2;
+  if (c.spill_top + H > static_cast<int>(c.spill_cap)) {
+    c.fatal = true;
+    c.top = 0;
+    return;
+  }
+  for (int i = c.lane; i < H; i += 32) c.spill[c.spill_top + i] = c.stack[i];
+  __syncwarp();
+  int rest = c.top - H;  // <= H: read [H, top) and write [0, rest) never overlap
+  uint4 t0, t1;
+  int i0 = c.lane, i1 = c.lane + 32;
+  if (i0 < rest) t0 = c.stack[H + i0];
+  if (i1 < rest) t1 = c.stack[H + i1];
+  __syncwarp();
+  if (i0 < rest) c.stack[i0] = t0;
+  if (i1 < rest) c.stack[i1] = t1;
+  __syncwarp();
+  c.spill_top += H;
+  c.top = rest;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void refill(WarpCtx<COUNT>& c) {
+  constexpr int H = kStackCap / 2;
+  int n = c.spill_top < H ? c.spill_top : H;
+  for (int i = c.lane; i < n; i += 32) c.stack[i] = c.spill[c.spill_top - n + i];
+  __syncwarp();
+  c.spill_top -= n;
+  c.top = n;
+}
+
+// Warp-collective push: lanes with want=true append their item in lane order.
+template <bool COUNT>
+__device__ __forceinline__ void push(WarpCtx<COUNT>& c, bool want, const uint4& item) {
+  unsigned m = __ballot_sync(kFull, want);
+  if (!m || c.fatal) return;
+  int cnt = __popc(m);
+  if (c.top + cnt > kStackCap) spill_half(c);
+  if (c.fatal) return;
+  if (want) c.stack[c.top + __popc(m & ((1u << c.lane) - 1u))] = item;
+  c.top += cnt;
+  __syncwarp();
+}
+
+// Binary search of the sorted direct-subject segment col[lo, hi) for sid.
+template <bool COUNT>
+__device__ __forceinline__ bool probe(const KParams& p, WarpCtx<COUNT>& c, uint32_t lo, uint32_t hi, uint32_t sid,
+                                      bool expiry) {
+  while (lo < hi) {
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    uint32_t v = __ldg(p.col + mid);
+    if (COUNT) c.bytes += 4;
+    if (v == sid) {
+      if (expiry) {
+        uint32_t e = __ldg(p.exp + mid);
+        if (COUNT) c.bytes += 4;
+        return e == 0 || e > p.now;
+      }
+      return true;
+    }
+    if (v < sid) lo = mid + 1; else hi = mid;
+  }
+  return false;
+}
+
+// Warp-collective node visit: every lane may carry one (job slot, object, unit).
+// Evaluates the unit's REL / ARROW ops at the object: membership-of-itself test,
+// direct and wildcard probes, and pushes the userset / arrow edge ranges.
+template <bool COUNT>
+__device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<COUNT>& c, bool active,
+                                      uint32_t jslot, uint32_t obj, uint32_t unit, uint32_t depth) {
+  const uint32_t sid = __shfl_sync(kFull, c.my_subj, jslot & 31);
+  const uint32_t ss = __shfl_sync(kFull, c.my_ss, jslot & 31);
+  const uint32_t stype = ss >> 16, srel = ss & 0xFFFFu;
+  bool hit = false;
+  int nops = 0, ob = 0;
+  if (active) {
+    const DUnit u = pr.units[unit];
+    if (srel != kNone && sid == obj)
+      for (int m = u.mem_begin; m < u.mem_end; ++m) hit = hit || pr.members[m] == srel;
+    if (!hit) {
+      ob = u.op_begin;
+      nops = u.op_end - u.op_begin;
+    }
+  }
+  const int maxops = __reduce_max_sync(kFull, nops);
+  for (int i = 0; i < maxops; ++i) {
+    DOp op{};
+    DRel rel{};
+    int ncls = 0;
+    unsigned long long ridx = 0;
+    if (i < nops && !hit) {
+      op = pr.ops[ob + i];
+      rel = pr.rels[op.rel];
+      if (obj < rel.nres) {
+        ncls = rel.ncls;
+        ridx = rel.row_base + static_cast<unsigned long long>(obj) * rel.ncls;
+      }
+    }
+    const int maxcls = __reduce_max_sync(kFull, ncls);
+    uint32_t lo = 0;
+    if (ncls) {
+      lo = __ldg(p.row_ptr + ridx);
+      if (COUNT) c.bytes += 4;
+    }
+    for (int k = 0; k < maxcls; ++k) {
+      bool want = false;
+      uint4 item = make_uint4(0, 0, 0, 0);
+      uint32_t hi = lo;
+      if (k < ncls) {
+        hi = __ldg(p.row_ptr + ridx + k + 1);
+        if (COUNT) c.bytes += 4;
+        if (hi > lo && !hit) {
+          const DCls cl = pr.cls[rel.cls_begin + k];
+          const bool expiry = (cl.flags & CF_EXPIRY) != 0;
+          uint32_t tslot = kNone;
+          if (op.kind == OP_REL) {
+            if (cl.sslot == kNone) {
+              if (srel == kNone && stype == cl.stype) hit = probe(p, c, lo, hi, sid, expiry);
+            } else if (cl.sslot == kWildcard) {
+              if (srel == kNone && stype == cl.stype) {
+                if (expiry) {
+                  uint32_t e = __ldg(p.exp + lo);
+                  if (COUNT) c.bytes += 4;
+                  hit = e == 0 || e > p.now;
+                } else {
+                  hit = true;
+                }
+              }
+            } else {
+              tslot = cl.sslot;
+            }
+          } else {
+            tslot = pr.tgts[op.tgt_begin + k];
+          }
+          if (tslot != kNone && !hit) {
+            want = true;
+            item = make_uint4(lo, hi, make_meta(jslot, depth + 1, expiry, tslot), 0);
+          }
+        }
+      }
+      push(c, want, item);
+      lo = hi;
+    }
+  }
+  c.found |= __reduce_or_sync(kFull, hit ? (1u << jslot) : 0u);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kThreads) check_kernel(const KParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  for (uint32_t i = threadIdx.x; i < p.prog_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(p.prog)[i];
+  __syncthreads();
+  const Prog pr = make_prog(smem);
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpCtx<COUNT> c;
+  c.lane = lane;
+  c.stack = reinterpret_cast<uint4*>(smem + p.prog_bytes) + warp * kStackCap;
+  c.spill = p.spill + (static_cast<size_t>(blockIdx.x) * kWarpsPerBlock + warp) * p.spill_cap;
+  c.spill_cap = p.spill_cap;
+  c.bytes = 0;
+  const uint32_t n_slots = pr.h->n_slots, n_types = pr.h->n_types, n_units = pr.h->n_units;
+
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(p.next, 32ull);
+    base = __shfl_sync(kFull, base, 0);
+    if (base >= p.njobs) break;
+    const unsigned long long q = base + lane;
+    bool valid = q < p.njobs, bad = false;
+    uint32_t obj = 0, unit = 0, depth = 0;
+    c.my_subj = 0;
+    c.my_ss = (0u << 16) | kNone;
+    if (valid) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.jobs) + q);
+      if (COUNT) c.bytes += 17;
+      obj = raw.x;
+      c.my_subj = raw.y;
+      const uint32_t perm = raw.z & 0xFFFFu, stype = raw.z >> 16;
+      const uint32_t srel = raw.w & 0xFFFFu, fl = p.raw_items ? 0u : raw.w >> 16;
+      c.my_ss = (stype << 16) | srel;
+      depth = fl & kJobDepthMask;
+      if (stype >= n_types || (srel != kNone && (srel >= n_slots || pr.slots[srel].type != stype))) bad = true;
+      if (fl & kJobIsUnit) {
+        unit = perm;
+        if (unit == kNone) valid = false;  // padding job: value stays 0
+        else if (unit >= n_units) bad = true;
+      } else if (perm >= n_slots || pr.slots[perm].kind == SK_NONPURE) {
+        bad = true;  // non-pure permissions reach this kernel as leaf-unit jobs
+      } else {
+        unit = pr.slots[perm].unit;
+      }
+    }
+    c.found = 0;
+    c.err = __ballot_sync(kFull, valid && bad);
+    c.top = 0;
+    c.spill_top = 0;
+    c.fatal = false;
+    const unsigned live_jobs = __ballot_sync(kFull, valid && !bad);
+
+    visit(p, pr, c, valid && !bad, lane, obj, unit, depth);
+
+    uint32_t iters = 0;
+    for (;;) {
+      if (!c.fatal && c.top == 0) {
+        if (c.spill_top == 0) break;
+        refill(c);
+      }
+      if ((c.found & live_jobs) == live_jobs) break;  // every check already answered
+      if (++iters > p.budget || c.fatal) {
+        if (lane == 0) atomicOr(p.flags, c.fatal ? 1u : 4u);
+        c.err |= live_jobs & ~c.found;
+        break;
+      }
+      // ---- pop ranges worth <= 32 edges from the top of the stack
+      const int n = c.top < 32 ? c.top : 32;
+      uint4 it = make_uint4(0, 0, 0, 0);
+      if (static_cast<int>(lane) < n) it = c.stack[c.top - 1 - lane];
+      const bool dead = (c.found >> (it.z & 31)) & 1u;
+      const uint32_t len = (static_cast<int>(lane) < n && !dead) ? it.y - it.x : 0u;
+      uint32_t incl = len;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t v = __shfl_up_sync(kFull, incl, d);
+        if (static_cast<int>(lane) >= d) incl += v;
+      }
+      const uint32_t excl = incl - len;
+      const unsigned fullm = __ballot_sync(kFull, static_cast<int>(lane) < n && incl <= 32u);
+      const int nfull = __popc(fullm);  // prefix of fully consumed items
+      uint32_t total = __shfl_sync(kFull, incl, 31);
+      if (total > 32u) total = 32u;
+      __syncwarp();
+      if (static_cast<int>(lane) == nfull && static_cast<int>(lane) < n)  // partially consumed item stays on top
+        c.stack[c.top - 1 - lane].x = it.x + (32u - excl);
+      c.top -= nfull;
+      __syncwarp();
+      // ---- lane k takes edge k: owner item j = #items with incl <= k
+      int j = 0;
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        const int probe_lane = j + step - 1;
+        const uint32_t v = __shfl_sync(kFull, incl, probe_lane & 31);
+        if (probe_lane < 32 && v <= lane) j += step;
+      }
+      const uint32_t jb = __shfl_sync(kFull, it.x, j & 31);
+      const uint32_t jmeta = __shfl_sync(kFull, it.z, j & 31);
+      const uint32_t jexcl = __shfl_sync(kFull, excl, j & 31);
+      bool active = lane < total;
+      uint32_t child = 0;
+      const uint32_t jslot = jmeta & 31u, cdepth = (jmeta >> 5) & 63u, tslot = jmeta >> 16;
+      const uint32_t sq_subj = __shfl_sync(kFull, c.my_subj, jslot);
+      const uint32_t sq_ss = __shfl_sync(kFull, c.my_ss, jslot);
+      if (active) {
+        const uint32_t e = jb + (lane - jexcl);
+        child = __ldg(p.col + e);
+        if (COUNT) c.bytes += 4;
+        if (jmeta & (1u << 11)) {
+          const uint32_t ex = __ldg(p.exp + e);
+          if (COUNT) c.bytes += 4;
+          active = ex == 0 || ex > p.now;
+        }
+      }
+      // the 51st hop is an error (pkg/spicedb/spicedb.go:33)
+      const bool too_deep = active && cdepth > ZG_MAX_DEPTH;
+      c.err |= __reduce_or_sync(kFull, too_deep ? (1u << jslot) : 0u);
+      active = active && !too_deep;
+      uint32_t cunit = 0;
+      if (active) {
+        const DSlot s = pr.slots[tslot];
+        if (s.kind == SK_NONPURE) {
+          // defer: Check(child#tslot @ S) becomes a sub-query of the next pass
+          const unsigned long long at = atomicAdd(p.subq_count, 1ull);
+          if (at < p.subq_cap) {
+            zg_check sq;
+            sq.res = child;
+            sq.subj = sq_subj;
+            sq.perm = static_cast<uint16_t>(tslot);
+            sq.stype = static_cast<uint16_t>(sq_ss >> 16);
+            sq.srel = static_cast<uint16_t>(sq_ss & 0xFFFFu);
+            sq.flags = static_cast<uint16_t>(cdepth);
+            p.subq[at] = sq;
+            p.subq_parent[at] = static_cast<uint32_t>(base + jslot);
+          } else {
+            atomicOr(p.flags, 2u);
+          }
+          active = false;
+        } else {
+          cunit = s.unit;
+        }
+      }
+      visit(p, pr, c, active, jslot, child, cunit, cdepth);
+    }
+
+    if (q < p.njobs) {
+      const bool t = (c.found >> lane) & 1u, e = (c.err >> lane) & 1u;
+      uint8_t v;
+      if (p.final_codes) v = t ? ZG_HAS_PERMISSION : (e ? ZG_ITEM_ERROR : ZG_NO_PERMISSION);
+      else v = t ? kValT : (e ? kValE : 0);
+      p.val[q] = v;
+    }
+  }
+  if (COUNT) {
+    unsigned long long b = c.bytes;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) b += __shfl_xor_sync(kFull, b, d);
+    if (lane == 0 && b) atomicAdd(p.alg_bytes, b);
+  }
+}
+
+// ---- general mode: queries -> leaf-unit jobs, and the boolean fold ------------------
+
+// jobs[q*L + l] for l < L. Pure / relation slots use one job; non-pure slots one per
+// leaf unit of their tree. Unused positions are padding (unit = kNone).
+__global__ void prep_jobs_kernel(const uint8_t* prog, const zg_check* queries, unsigned long long n, uint32_t L,
+                                 zg_check* jobs, int raw_items) {
+  const Prog pr = make_prog(prog);
+  unsigned long long q = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+  if (q >= n) return;
+  const zg_check it = queries[q];
+  const uint16_t depth = raw_items ? 0 : (it.flags & kJobDepthMask);
+  uint32_t nl = 0;
+  const uint16_t* leaf = nullptr;
+  uint16_t single = kNone;
+  if (it.perm < pr.h->n_slots) {
+    const DSlot s = pr.slots[it.perm];
+    if (s.kind == SK_NONPURE) {
+      const DTree t = pr.trees[s.unit];
+      nl = t.n_leaves;
+      leaf = pr.leaf_units + t.leaf_begin;
+    } else {
+      nl = 1;
+      single = s.unit;
+    }
+  }
+  for (uint32_t l = 0; l < L; ++l) {
+    zg_check j = it;
+    j.perm = l < nl ? (leaf ? leaf[l] : single) : kNone;
+    j.flags = static_cast<uint16_t>(depth | kJobIsUnit);
+    jobs[q * L + l] = j;
+  }
+}
+
+__device__ __forceinline__ uint32_t kleene_or(uint32_t a, uint32_t b) {  // 0 F, 1 T, 2 E
+  return (a == 1 || b == 1) ? 1u : ((a == 2 || b == 2) ? 2u : 0u);
+}
+__device__ __forceinline__ uint32_t kleene_and(uint32_t a, uint32_t b) {
+  return (a == 0 || b == 0) ? 0u : ((a == 2 || b == 2) ? 2u : 1u);
+}
+
+// Evaluates each query's boolean tree over its leaf-job values. final: write the
+// v1 code to out[q]; otherwise OR the value into the parent job of the previous pass.
+__global__ void fold_kernel(const uint8_t* prog, const zg_check* queries, unsigned long long n, uint32_t L,
+                            const uint8_t* val, uint8_t* out, const uint32_t* parent, uint8_t* parent_val) {
+  const Prog pr = make_prog(prog);
+  unsigned long long q = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+  if (q >= n) return;
+  const zg_check it = queries[q];
+  uint32_t r = 2;  // invalid query -> error
+  const bool ok = it.perm < pr.h->n_slots && it.stype < pr.h->n_types &&
+                  (it.srel == kNone || (it.srel < pr.h->n_slots && pr.slots[it.srel].type == it.stype));
+  if (ok) {
+    const DSlot s = pr.slots[it.perm];
+    auto leafval = [&](uint32_t l) -> uint32_t {
+      const uint8_t v = val[q * L + l];
+      return (v & kValT) ? 1u : ((v & kValE) ? 2u : 0u);
+    };
+    if (s.kind != SK_NONPURE) {
+      r = leafval(0);
+    } else {
+      const DTree t = pr.trees[s.unit];
+      unsigned long long st = 0;  // 2-bit entries
+      int sp = 0;
+      for (int i = t.op_begin; i < t.op_end; ++i) {
+        const DTreeOp o = pr.tree_ops[i];
+        if (o.kind == T_LEAF) {
+          st |= static_cast<unsigned long long>(leafval(o.arg)) << (2 * sp);
+          ++sp;
+        } else if (o.kind == T_TRIVIAL) {
+          const uint32_t v = (it.srel == o.arg && it.subj == it.res) ? 1u : 0u;
+          st |= static_cast<unsigned long long>(v) << (2 * sp);
+          ++sp;
+        } else {
+          const uint32_t b = (st >> (2 * (sp - 1))) & 3u, a = (st >> (2 * (sp - 2))) & 3u;
+          uint32_t v;
+          if (o.kind == T_OR) v = kleene_or(a, b);
+          else if (o.kind == T_AND) v = kleene_and(a, b);
+          else v = kleene_and(a, b == 1 ? 0u : (b == 0 ? 1u : 2u));
+          sp -= 2;
+          st &= ~(0xFull << (2 * sp));
+          st |= static_cast<unsigned long long>(v) << (2 * sp);
+          ++sp;
+        }
+      }
+      r = st & 3u;
+    }
+  }
+  if (out) {
+    out[q] = r == 1 ? ZG_HAS_PERMISSION : (r == 2 ? ZG_ITEM_ERROR : ZG_NO_PERMISSION);
+  } else if (r) {
+    const uint32_t pj = parent[q];
+    const uint32_t bits = r == 1 ? kValT : kValE;
+    atomicOr(reinterpret_cast<unsigned int*>(parent_val + (pj & ~3u)), bits << (8 * (pj & 3u)));
+  }
+}
+
+// ---- LookupResources helpers ---------------------------------------------------------
+
+__global__ void lookup_fill_kernel(const uint32_t* cand, unsigned long long n, zg_check proto, zg_check* jobs) {
+  unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  proto.res = cand[i];
+  jobs[i] = proto;
+}
+
+// ids of candidates whose code is HAS, compacted with ballot + popc; order is
+// restored by the caller (results are a set: pkg/authz/lookups.go:129).
+__global__ void lookup_compact_kernel(const uint32_t* cand, const uint8_t* codes, unsigned long long n, uint32_t* out,
+                                      unsigned long long cap, unsigned long long* count, uint32_t* flags) {
+  unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+  const bool has = i < n && codes[i] == ZG_HAS_PERMISSION;
+  const bool bad = i < n && codes[i] == ZG_ITEM_ERROR;
+  const unsigned m = __ballot_sync(kFull, has);
+  if (__any_sync(kFull, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, 8u);
+  if (!m) return;
+  unsigned long long base = 0;
+  const unsigned lane = threadIdx.x & 31;
+  if (lane == 0) base = atomicAdd(count, static_cast<unsigned long long>(__popc(m)));
+  base = __shfl_sync(kFull, base, 0);
+  if (has) {
+    const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
+    if (at < cap) out[at] = cand[i];
+  }
+}
+
+}  // namespace zg

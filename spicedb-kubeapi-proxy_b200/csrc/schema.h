@@ -1,0 +1,145 @@
+// schema.h -- SpiceDB schema DSL subset -> flat device program.
+//
+// The reference configures its engine with schema text (pkg/spicedb/bootstrap.yaml:1-38,
+// pkg/spicedb/spicedb.go:19-24). This compiler turns that text into the tables the
+// CUDA kernels walk:
+//   * every relation becomes a "data relation" with one EDGE CLASS per allowed
+//     subject kind (type, type#rel, type:*): subject type and child slot are static
+//     per class, so an edge is a bare u32 object id;
+//   * every permission whose (same-object-inlined) expression is a pure union
+//     becomes a UNIT: a short list of REL / ARROW ops evaluated as reachability;
+//   * permissions containing & or - become a TREE: a postfix boolean program over
+//     leaf units, evaluated after the reachability pass (DESIGN.md "Boolean
+//     structure").
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace zg {
+
+constexpr uint16_t kNone = 0xFFFF;      // ZG_SREL_NONE
+constexpr uint16_t kWildcard = 0xFFFE;  // ZG_SREL_WILDCARD
+constexpr int kMaxClasses = 8;          // edge classes per relation
+constexpr int kMaxLeaves = 32;          // leaf units per non-pure permission
+
+// ---- device-visible PODs (copied verbatim into the program blob) -------------
+enum SlotKind : uint16_t { SK_RELATION = 0, SK_PURE = 1, SK_NONPURE = 2 };
+enum OpKind : uint16_t { OP_REL = 0, OP_ARROW = 1 };
+enum TreeOpKind : uint16_t { T_LEAF = 0, T_TRIVIAL = 1, T_OR = 2, T_AND = 3, T_ANDNOT = 4 };
+enum ClsFlags : uint16_t { CF_EXPIRY = 1 };
+
+struct DSlot {   // per slot (relation or permission)
+  uint16_t kind;        // SlotKind
+  uint16_t unit;        // SK_RELATION / SK_PURE: unit id ; SK_NONPURE: tree id
+  uint16_t type;
+  uint16_t pad;
+};
+struct DUnit {   // pure-union program evaluated at one object
+  uint16_t op_begin, op_end;    // into ops[]
+  uint16_t mem_begin, mem_end;  // into members[]: slots inlined into this unit
+};
+struct DOp {
+  uint16_t kind;       // OpKind
+  uint16_t rel;        // data relation index
+  uint16_t tgt_begin;  // OP_ARROW: tgts[tgt_begin + class] = child slot or kNone
+  uint16_t pad;
+};
+struct DRel {    // data relation: rows of (object x class)
+  uint64_t row_base;   // index into row_ptr pool of (object 0, class 0)
+  uint32_t nres;       // objects covered
+  uint16_t ncls;
+  uint16_t cls_begin;  // into classes[]
+};
+struct DCls {
+  uint16_t stype;
+  uint16_t sslot;      // kNone (direct), kWildcard, or subject relation slot
+  uint16_t flags;      // ClsFlags
+  uint16_t pad;
+};
+struct DTree {   // postfix boolean program of a non-pure permission
+  uint16_t op_begin, op_end;     // into tree_ops[]
+  uint16_t leaf_begin, n_leaves; // leaf_units[leaf_begin + i] = unit id
+};
+struct DTreeOp {
+  uint16_t kind;  // TreeOpKind
+  uint16_t arg;   // T_LEAF: leaf index ; T_TRIVIAL: slot
+};
+struct DHeader {  // first bytes of the blob; offsets in bytes from blob start
+  uint32_t magic, total_bytes;
+  uint32_t n_types, n_slots, n_units, n_ops, n_rels, n_cls, n_trees, n_tree_ops;
+  uint32_t off_slots, off_units, off_ops, off_rels, off_cls, off_tgts, off_members;
+  uint32_t off_trees, off_tree_ops, off_leaf_units, off_reach;
+  uint32_t max_leaves;   // job stride L in general mode (1 if no non-pure slot)
+  uint32_t has_nonpure;
+  uint32_t has_expiry;
+  uint32_t reach_words;  // u32 words per slot in reach[] (bit t: subjects of type t reachable)
+};
+
+// ---- host-side model -----------------------------------------------------------
+struct ClassInfo {
+  uint16_t stype;
+  uint16_t sslot;
+  bool expiry;
+};
+struct Expr {
+  enum Kind { NIL, REF, ARROW, UNION, INTER, EXCL } kind = NIL;
+  int slot = -1;   // REF: slot ; ARROW: tupleset relation slot
+  int name = -1;   // ARROW: name id of the computed permission
+  int l = -1, r = -1;
+};
+struct SlotInfo {
+  std::string name;
+  int name_id = -1;
+  uint16_t type = 0;
+  bool is_perm = false;
+  std::vector<ClassInfo> classes;  // relations
+  int expr = -1;                   // permissions: root in Schema::exprs
+  int rel_index = -1;              // relations: data relation index
+  uint16_t kind = SK_RELATION;
+  int unit = -1, tree = -1;
+};
+struct TypeInfo {
+  std::string name;
+  std::vector<int> slots;
+};
+
+class Schema {
+ public:
+  // Returns empty string on success, else the error message.
+  std::string parse(const std::string& text);
+
+  int type_id(const std::string& n) const;
+  int slot_id(int type, const std::string& n) const;
+  int slot_by_name_id(int type, int name_id) const;
+  int class_of(int rel_slot, uint16_t stype, uint16_t sslot) const;  // -1 if not allowed
+
+  std::vector<TypeInfo> types;
+  std::vector<SlotInfo> slots;
+  std::vector<std::string> names;
+  std::vector<Expr> exprs;
+  std::vector<int> rel_slots;  // data relation index -> slot
+  bool use_expiration = false;
+
+  // compiled tables
+  std::vector<DSlot> d_slots;
+  std::vector<DUnit> d_units;
+  std::vector<DOp> d_ops;
+  std::vector<DCls> d_cls;
+  std::vector<uint16_t> d_tgts, d_members, d_leaf_units;
+  std::vector<DTree> d_trees;
+  std::vector<DTreeOp> d_tree_ops;
+  std::vector<uint32_t> d_reach;
+  uint32_t reach_words = 1;
+  uint32_t max_leaves = 1;
+  bool has_nonpure = false, has_expiry = false;
+
+  // Serialises the program; DRel rows (row_base, nres) come from the store.
+  std::vector<uint8_t> blob(const std::vector<DRel>& rels) const;
+
+ private:
+  std::string compile();
+  int name_id(const std::string& n);
+};
+
+}  // namespace zg

@@ -1,0 +1,303 @@
+// store.cc -- see store.h.
+#include "store.h"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+namespace zg {
+
+void Store::reset(const Schema* s) {
+  schema = s;
+  tuples.clear();
+  expires.clear();
+  objs_.assign(s ? s->types.size() : 0, TypeObjs{});
+  index_.clear();
+  indexed_ = true;
+  live_ = 0;
+}
+
+uint32_t Store::intern(int type, const std::string& id) {
+  TypeObjs& t = objs_[type];
+  auto it = t.ids.find(id);
+  if (it != t.ids.end()) return it->second;
+  // keep string ids and bulk numeric ids in one id space
+  uint32_t nid = std::max<uint32_t>(static_cast<uint32_t>(t.names.size()), t.n_numeric);
+  t.names.resize(nid + 1);
+  t.names[nid] = id;
+  t.ids.emplace(id, nid);
+  return nid;
+}
+uint32_t Store::find(int type, const std::string& id) const {
+  if (type < 0 || type >= static_cast<int>(objs_.size())) return ZG_NO_OBJECT;
+  auto it = objs_[type].ids.find(id);
+  return it == objs_[type].ids.end() ? ZG_NO_OBJECT : it->second;
+}
+const std::string* Store::name(int type, uint32_t id) const {
+  if (type < 0 || type >= static_cast<int>(objs_.size())) return nullptr;
+  const TypeObjs& t = objs_[type];
+  if (id >= t.names.size() || t.names[id].empty()) return nullptr;  // numeric-only object
+  return &t.names[id];
+}
+
+std::string Store::validate(const zg_tuple& t, bool has_expiry) const {
+  const Schema& sc = *schema;
+  if (t.rel >= sc.slots.size() || sc.slots[t.rel].is_perm) return "relationship does not name a relation";
+  if (t.stype >= sc.types.size()) return "unknown subject type";
+  int k = sc.class_of(t.rel, t.stype, t.srel);
+  if (k < 0) {
+    const SlotInfo& r = sc.slots[t.rel];
+    std::string what = sc.types[t.stype].name;
+    if (t.srel == kWildcard) what += ":*";
+    else if (t.srel != kNone) what += t.srel < sc.slots.size() ? "#" + sc.slots[t.srel].name : "#?";
+    return "subjects of type " + what + " are not allowed on relation " + sc.types[r.type].name + "#" + r.name;
+  }
+  if (has_expiry && !sc.slots[t.rel].classes[k].expiry)
+    return "relation " + sc.types[sc.slots[t.rel].type].name + "#" + sc.slots[t.rel].name +
+           " does not allow expiration for this subject type";
+  if (t.res == ZG_NO_OBJECT || (t.srel != kWildcard && t.subj == ZG_NO_OBJECT)) return "invalid object id";
+  return "";
+}
+
+std::string Store::load(const zg_tuple* t, const uint32_t* ex, uint64_t n) {
+  // validate per distinct (rel, stype, srel, has_exp) combination: cache the last one
+  uint64_t last = ~0ull;
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t sig = (uint64_t(t[i].rel) << 33) | (uint64_t(t[i].stype) << 17) | (uint64_t(t[i].srel) << 1) |
+                   (ex && ex[i] ? 1u : 0u);
+    if (sig != last || t[i].res == ZG_NO_OBJECT || t[i].subj == ZG_NO_OBJECT) {
+      std::string err = validate(t[i], ex && ex[i]);
+      if (!err.empty()) return "relationship " + std::to_string(i) + ": " + err;
+      last = sig;
+    }
+  }
+  size_t base = tuples.size();
+  tuples.resize(base + n);
+  expires.resize(base + n);
+  for (uint64_t i = 0; i < n; ++i) {
+    zg_tuple x = t[i];
+    x.flags = 0;
+    if (x.srel == kWildcard) x.subj = 0;
+    tuples[base + i] = x;
+    expires[base + i] = ex ? ex[i] : 0;
+    TypeObjs& rt = objs_[schema->slots[x.rel].type];
+    if (x.res + 1 > rt.n_numeric) rt.n_numeric = x.res + 1;
+    if (x.srel != kWildcard) {
+      TypeObjs& st = objs_[x.stype];
+      if (x.subj + 1 > st.n_numeric) st.n_numeric = x.subj + 1;
+    }
+  }
+  live_ += n;  // upper bound until duplicates are folded by ensure_index()/build()
+  indexed_ = false;
+  return "";
+}
+
+void Store::ensure_index() {
+  if (indexed_) return;
+  index_.clear();
+  index_.reserve(tuples.size() * 2);
+  live_ = 0;
+  for (uint64_t i = 0; i < tuples.size(); ++i) {
+    if (tuples[i].flags & 1) continue;
+    auto res = index_.emplace(key_of(tuples[i]), i);
+    if (!res.second) {  // later TOUCH wins
+      tuples[res.first->second].flags |= 1;
+      res.first->second = i;
+    } else {
+      ++live_;
+    }
+  }
+  indexed_ = true;
+}
+
+std::string Store::apply(const zg_update* u, uint64_t n, int* code) {
+  *code = ZG_EINVAL;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (u[i].op > ZG_OP_DELETE) return "update " + std::to_string(i) + ": unknown operation";
+    if (u[i].op == ZG_OP_DELETE) {
+      if (u[i].t.rel >= schema->slots.size() || schema->slots[u[i].t.rel].is_perm) return "update names no relation";
+      continue;
+    }
+    std::string err = validate(u[i].t, u[i].expires_at != 0);
+    if (!err.empty()) return "update " + std::to_string(i) + ": " + err;
+  }
+  ensure_index();
+  // CREATE must not collide with an existing relationship or with an earlier update
+  for (uint64_t i = 0; i < n; ++i)
+    if (u[i].op == ZG_OP_CREATE) {
+      zg_tuple t = u[i].t;
+      if (index_.count(key_of(t))) {
+        *code = ZG_EEXIST;
+        return "update " + std::to_string(i) + ": relationship already exists";
+      }
+    }
+  for (uint64_t i = 0; i < n; ++i) {
+    zg_tuple t = u[i].t;
+    t.flags = 0;
+    if (t.srel == kWildcard) t.subj = 0;
+    Key k = key_of(t);
+    auto it = index_.find(k);
+    if (u[i].op == ZG_OP_DELETE) {
+      if (it != index_.end()) {
+        tuples[it->second].flags |= 1;
+        index_.erase(it);
+        --live_;
+      }
+      continue;
+    }
+    if (it != index_.end()) {
+      expires[it->second] = u[i].expires_at;
+      continue;
+    }
+    index_.emplace(k, tuples.size());
+    tuples.push_back(t);
+    expires.push_back(u[i].expires_at);
+    ++live_;
+    TypeObjs& rt = objs_[schema->slots[t.rel].type];
+    if (t.res + 1 > rt.n_numeric) rt.n_numeric = t.res + 1;
+    if (t.srel != kWildcard) {
+      TypeObjs& st = objs_[t.stype];
+      if (t.subj + 1 > st.n_numeric) st.n_numeric = t.subj + 1;
+    }
+  }
+  // compact tombstones when they dominate
+  if (tuples.size() > 1024 && live_ * 2 < tuples.size()) {
+    size_t w = 0;
+    for (size_t i = 0; i < tuples.size(); ++i)
+      if (!(tuples[i].flags & 1)) {
+        tuples[w] = tuples[i];
+        expires[w] = expires[i];
+        ++w;
+      }
+    tuples.resize(w);
+    expires.resize(w);
+    indexed_ = false;
+    ensure_index();
+  }
+  *code = ZG_OK;
+  return "";
+}
+
+void Store::match(const Filter& f, uint32_t now, std::vector<uint64_t>* idx) const {
+  idx->clear();
+  if (f.impossible) return;
+  const_cast<Store*>(this)->ensure_index();
+  for (uint64_t i = 0; i < tuples.size(); ++i) {
+    const zg_tuple& t = tuples[i];
+    if (t.flags & 1) continue;
+    if (expires[i] != 0 && expires[i] <= now) continue;
+    if (f.res_type >= 0 && schema->slots[t.rel].type != f.res_type) continue;
+    if (f.has_res && t.res != f.res) continue;
+    if (f.rel >= 0 && t.rel != f.rel) continue;
+    if (f.subj_type >= 0 && t.stype != f.subj_type) continue;
+    if (f.subj_wildcard && t.srel != kWildcard) continue;
+    if (f.has_subj && (t.srel == kWildcard || t.subj != f.subj)) continue;
+    if (f.has_srel && t.srel != f.srel) continue;
+    idx->push_back(i);
+  }
+}
+
+HostSnapshot Store::build() const {
+  const Schema& sc = *schema;
+  HostSnapshot h;
+  const size_t nt = sc.types.size();
+  h.n_objects.resize(nt);
+  for (size_t t = 0; t < nt; ++t)
+    h.n_objects[t] = std::max<uint32_t>(static_cast<uint32_t>(objs_[t].names.size()), objs_[t].n_numeric);
+
+  uint64_t pool = 0;
+  uint16_t cls_begin = 0;
+  for (int rs : sc.rel_slots) {
+    const SlotInfo& s = sc.slots[rs];
+    DRel r{};
+    r.row_base = pool;
+    r.nres = h.n_objects[s.type];
+    r.ncls = static_cast<uint16_t>(s.classes.size());
+    r.cls_begin = cls_begin;
+    cls_begin = static_cast<uint16_t>(cls_begin + r.ncls);
+    pool += uint64_t(r.nres) * r.ncls;
+    h.rels.push_back(r);
+  }
+  h.row_ptr.assign(pool + 1, 0);
+  const bool with_exp = sc.has_expiry;
+
+  // class lookup table per data relation
+  auto row_index = [&](const zg_tuple& t) -> uint64_t {
+    const DRel& r = h.rels[sc.slots[t.rel].rel_index];
+    int k = sc.class_of(t.rel, t.stype, t.srel);
+    return r.row_base + uint64_t(t.res) * r.ncls + static_cast<uint64_t>(k);
+  };
+
+  std::vector<std::vector<uint8_t>> seen(nt);
+  for (size_t t = 0; t < nt; ++t) seen[t].assign(h.n_objects[t], 0);
+  uint64_t n_live = 0;
+  for (size_t i = 0; i < tuples.size(); ++i) {
+    const zg_tuple& t = tuples[i];
+    if (t.flags & 1) continue;
+    ++h.row_ptr[row_index(t) + 1];
+    seen[sc.slots[t.rel].type][t.res] = 1;
+    ++n_live;
+  }
+  for (uint64_t i = 0; i < pool; ++i) h.row_ptr[i + 1] += h.row_ptr[i];
+  if (n_live >= 0xFFFFFFF0ull) {
+    h.err = "more than 2^32 relationships in one snapshot";
+    return h;
+  }
+  h.col.resize(n_live);
+  if (with_exp) h.exp.resize(n_live);
+  {
+    std::vector<uint32_t> cur(h.row_ptr.begin(), h.row_ptr.end() - 1);
+    for (size_t i = 0; i < tuples.size(); ++i) {
+      const zg_tuple& t = tuples[i];
+      if (t.flags & 1) continue;
+      uint32_t pos = cur[row_index(t)]++;
+      h.col[pos] = t.srel == kWildcard ? 0u : t.subj;
+      if (with_exp) h.exp[pos] = expires[i];
+    }
+  }
+  // sort each (object, class) row; fold duplicates (bulk loads are TOUCH: last wins)
+  bool dup = false;
+  std::vector<std::pair<uint32_t, uint32_t>> tmp;
+  for (uint64_t r = 0; r < pool; ++r) {
+    uint32_t b = h.row_ptr[r], e = h.row_ptr[r + 1];
+    if (e - b < 2) continue;
+    if (!with_exp) {
+      std::sort(h.col.begin() + b, h.col.begin() + e);
+    } else {
+      tmp.resize(e - b);
+      for (uint32_t i = b; i < e; ++i) tmp[i - b] = {h.col[i], h.exp[i]};
+      std::stable_sort(tmp.begin(), tmp.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+      for (uint32_t i = b; i < e; ++i) {
+        h.col[i] = tmp[i - b].first;
+        h.exp[i] = tmp[i - b].second;
+      }
+    }
+    for (uint32_t i = b + 1; i < e && !dup; ++i) dup = h.col[i] == h.col[i - 1];
+  }
+  if (dup) {
+    std::vector<uint32_t> nrow(pool + 1, 0);
+    uint32_t w = 0;
+    for (uint64_t r = 0; r < pool; ++r) {
+      uint32_t b = h.row_ptr[r], e = h.row_ptr[r + 1];
+      nrow[r] = w;
+      for (uint32_t i = b; i < e; ++i) {
+        if (i + 1 < e && h.col[i + 1] == h.col[i]) continue;  // keep the last of a run
+        h.col[w] = h.col[i];
+        if (with_exp) h.exp[w] = h.exp[i];
+        ++w;
+      }
+    }
+    nrow[pool] = w;
+    h.row_ptr.swap(nrow);
+    h.col.resize(w);
+    if (with_exp) h.exp.resize(w);
+  }
+  h.n_tuples = h.col.size();
+  h.resources.resize(nt);
+  for (size_t t = 0; t < nt; ++t)
+    for (uint32_t i = 0; i < seen[t].size(); ++i)
+      if (seen[t][i]) h.resources[t].push_back(i);
+  return h;
+}
+
+}  // namespace zg

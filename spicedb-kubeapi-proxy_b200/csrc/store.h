@@ -1,0 +1,95 @@
+// store.h -- host side of the relationship store: object interning, the mutable
+// relationship set (what WriteRelationships / DeleteRelationships act on,
+// pkg/authz/distributedtx/activity.go:54-76) and the CSR snapshot builder whose
+// output the engine uploads to HBM.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/zgpu.h"
+#include "schema.h"
+
+namespace zg {
+
+struct Key {
+  uint64_t hi, lo;  // hi = rel<<32 | stype<<16 | srel ; lo = res<<32 | subj
+  bool operator==(const Key& o) const { return hi == o.hi && lo == o.lo; }
+};
+struct KeyHash {
+  size_t operator()(const Key& k) const {
+    uint64_t x = k.hi * 0x9E3779B97F4A7C15ull ^ (k.lo + 0xD6E8FEB86659FD93ull);
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 29;
+    return static_cast<size_t>(x);
+  }
+};
+inline Key key_of(const zg_tuple& t) {
+  return Key{(uint64_t(t.rel) << 32) | (uint64_t(t.stype) << 16) | t.srel,
+             (uint64_t(t.res) << 32) | (t.srel == kWildcard ? 0u : t.subj)};
+}
+
+// CSR snapshot in host memory, ready to upload. Layout: DESIGN.md "Data layout in HBM".
+struct HostSnapshot {
+  std::vector<uint32_t> row_ptr;  // pool: per data relation, nres x ncls offsets, +1 sentinel
+  std::vector<uint32_t> col;      // subject object ids, sorted within (object, class)
+  std::vector<uint32_t> exp;      // parallel to col when the schema uses expiration, else empty
+  std::vector<DRel> rels;
+  std::vector<std::vector<uint32_t>> resources;  // per type: ids that are the resource of >= 1 relationship
+  std::vector<uint32_t> n_objects;               // per type
+  uint64_t n_tuples = 0;
+  std::string err;  // non-empty: build failed
+};
+
+class Store {
+ public:
+  void reset(const Schema* s);
+
+  uint32_t intern(int type, const std::string& id);
+  uint32_t find(int type, const std::string& id) const;  // ZG_NO_OBJECT
+  const std::string* name(int type, uint32_t id) const;
+
+  // Returns "" or an error message; `code` receives the ZG_* code.
+  std::string validate(const zg_tuple& t, bool has_expiry) const;
+  std::string load(const zg_tuple* t, const uint32_t* expires, uint64_t n);
+  std::string apply(const zg_update* u, uint64_t n, int* code);
+
+  // Live relationships matching a filter (unset field = -1 / ZG_NO_OBJECT-1 sentinel via has_*).
+  struct Filter {
+    int res_type = -1;
+    bool has_res = false;
+    uint32_t res = 0;
+    int rel = -1;  // slot
+    int subj_type = -1;
+    bool has_subj = false;
+    uint32_t subj = 0;
+    bool subj_wildcard = false;
+    bool has_srel = false;
+    uint16_t srel = kNone;
+    bool impossible = false;  // names an object/relation that does not exist
+  };
+  void match(const Filter& f, uint32_t now, std::vector<uint64_t>* idx) const;
+
+  HostSnapshot build() const;
+  uint64_t size() const { return live_; }
+
+  const Schema* schema = nullptr;
+  std::vector<zg_tuple> tuples;  // flags bit0 = dead (tombstone)
+  std::vector<uint32_t> expires; // parallel to tuples (always sized like tuples)
+
+ private:
+  void ensure_index();
+  struct TypeObjs {
+    std::unordered_map<std::string, uint32_t> ids;
+    std::vector<std::string> names;
+    uint32_t n_numeric = 0;  // max numeric id seen in bulk loads + 1
+  };
+  std::vector<TypeObjs> objs_;
+  std::unordered_map<Key, uint64_t, KeyHash> index_;
+  bool indexed_ = true;  // index_ covers every live tuple
+  uint64_t live_ = 0;
+};
+
+}  // namespace zg

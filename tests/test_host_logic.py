@@ -1,0 +1,194 @@
+"""CPU-only tests of the product's HOST logic (no GPU, no compute calls):
+the C ABI library loads and exports every symbol include/zgpu.h declares, the schema
+compiler agrees with the oracle's slot numbering, the CSR snapshot builder lays rows
+out as documented, and the relationship store implements the v1 write / read /
+delete / precondition contract the reference relies on
+(pkg/authz/distributedtx/activity.go:54-76,128-171; pkg/authz/update.go:207-271)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import randgen
+import zgpu
+from oracle.pyoracle import Oracle
+from spicedb_kubeapi_proxy_b200 import _lib, workloads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "zgpu.h")).read()
+    declared = set(re.findall(r"\b(zg_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed from include/zgpu.h"
+    L = ctypes.CDLL(zgpu.build_library())
+    for name in sorted(declared):
+        assert hasattr(L, name), f"libzgpu.so does not export {name}"
+    # the python binding binds exactly the declared set
+    assert set(_lib.exported_symbols()) == declared
+
+
+def test_no_cpu_fallback_on_hot_path():
+    e = zgpu.Engine(workloads.CFG2_SCHEMA, host_only=True)
+    e.add_bulk("pod", "viewer", "user", [1, 2], [3, 4])
+    e.publish()
+    items = np.zeros(2, dtype=zgpu.CHECK_DTYPE)
+    with pytest.raises(zgpu.ZgpuError, match="no CPU fallback"):
+        e.check_bulk(items)
+    with pytest.raises(zgpu.ZgpuError, match="no CPU fallback"):
+        e.lookup_resources_ids("pod", "view", "user", 3)
+    with pytest.raises(zgpu.ZgpuError, match="no CPU fallback"):
+        e.check_bulk_str(["pod:a#view@user:b"])
+
+
+def test_engine_create_without_gpu_fails_loudly():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(zgpu.ZgpuError, match="no CUDA device"):
+        zgpu.Engine(workloads.CFG2_SCHEMA)
+
+
+@pytest.mark.parametrize("schema", [workloads.BOOTSTRAP_SCHEMA, workloads.CFG3_SCHEMA, workloads.CFG4_SCHEMA]
+                         + list(randgen.FIXED_SCHEMAS.values()))
+def test_slot_numbering_matches_oracle(schema):
+    e, o = zgpu.Engine(schema, host_only=True), Oracle(schema)
+    assert e.slot_table() == o.slot_table()
+    for t in ("user", "group", "namespace", "document", "nope"):
+        assert e.type_id(t) == o.type_id(t)
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_random_schemas_compile_like_the_oracle(seed):
+    import random
+
+    schema, _ = randgen.random_schema(random.Random(seed))
+    e, o = zgpu.Engine(schema, host_only=True), Oracle(schema)
+    assert e.slot_table() == o.slot_table()
+
+
+BAD_SCHEMAS = {
+    "definition a { relation r: nope }": "unknown subject type",
+    "definition a { relation r: a#zz }": "does not exist",
+    "definition a { permission p = q }": "unknown relation or permission",
+    "definition a { relation r: a  permission p = p2->x  permission p2 = r }": "needs a relation on the left",
+    "definition a { relation r: a with somecaveat }": "caveats are not supported",
+    "caveat c(x int) { x > 1 }": "caveats are not supported",
+    "definition a { permission p = p }": "refers to itself",
+    "definition a { relation r: a  relation r: a }": "duplicate",
+    "definition a {": "expected",
+    "definition a { relation r: a  permission p = r.all(p) }": "only .any",
+}
+
+
+@pytest.mark.parametrize("text,msg", list(BAD_SCHEMAS.items()))
+def test_schema_errors(text, msg):
+    with pytest.raises(zgpu.ZgpuError, match=msg):
+        zgpu.Engine(text, host_only=True)
+    with pytest.raises(Exception):
+        Oracle(text)
+
+
+def test_operator_precedence_matches_oracle_and_mini():
+    """'+' binds tightest, then '&', then '-' (SpiceDB DSL); same in all three parsers."""
+    from oracle.mini_oracle import parse_schema
+
+    s = "definition user {} definition d { relation a: user relation b: user relation c: user " \
+        "permission p = a - b + c  permission q = a & b + c  permission r = a + b - c & a }"
+    d = parse_schema(s)["d"]["permissions"]
+    assert d["p"] == ("-", ("ref", "a"), ("+", ("ref", "b"), ("ref", "c")))
+    assert d["q"] == ("&", ("ref", "a"), ("+", ("ref", "b"), ("ref", "c")))
+    assert d["r"] == ("-", ("+", ("ref", "a"), ("ref", "b")), ("&", ("ref", "c"), ("ref", "a")))
+    zgpu.Engine(s, host_only=True)
+
+
+def test_csr_rows_match_numpy_reference():
+    w = workloads.cfg3(scale=0.002)
+    e = zgpu.Engine(w.schema, host_only=True)
+    w.load_into(e)
+    e.publish()
+    g = w.groups[0]  # group#member@user -> class 0 of (user | group#member)
+    for grp in np.unique(g.res)[:50]:
+        want = np.unique(g.subj[g.res == grp])
+        assert np.array_equal(e.debug_row("group", "member", int(grp), 0), want)
+        assert e.debug_row("group", "member", int(grp), 1).size == 0
+    t = w.groups[1]  # team#member@group#member -> class 0 of (group#member | user)
+    for team in np.unique(t.res)[:20]:
+        assert np.array_equal(e.debug_row("team", "member", int(team), 0), np.unique(t.subj[t.res == team]))
+    # duplicates in bulk loads fold (TOUCH semantics)
+    e2 = zgpu.Engine(workloads.CFG2_SCHEMA, host_only=True)
+    e2.add_bulk("pod", "viewer", "user", [5, 5, 5, 1], [9, 9, 2, 7])
+    e2.publish()
+    assert list(e2.debug_row("pod", "viewer", 5)) == [2, 9]
+    assert e2.num_tuples() == 3
+
+
+def test_write_read_delete_preconditions():
+    C = zgpu.client
+    e = zgpu.Engine(workloads.BOOTSTRAP_SCHEMA, host_only=True)
+    cl = C.PermissionsClient(workloads.BOOTSTRAP_SCHEMA, engine=e)
+    up = lambda op, rel, exp=0: C.RelationshipUpdate(op, C.Relationship.parse(rel, exp))
+    cl.WriteRelationships(C.WriteRelationshipsRequest([
+        up(C.OPERATION_CREATE, "namespace:ns1#creator@user:paul"),
+        up(C.OPERATION_CREATE, "namespace:ns1#cluster@cluster:cluster"),
+        up(C.OPERATION_TOUCH, "pod:ns1/p1#viewer@user:app"),
+    ]))
+    read = lambda **f: sorted(r.relationship.text() for r in cl.ReadRelationships(
+        C.ReadRelationshipsRequest(C.RelationshipFilter(**f))))
+    assert read(resource_type="namespace") == ["namespace:ns1#cluster@cluster:cluster", "namespace:ns1#creator@user:paul"]
+    assert read(resource_type="pod", optional_resource_id="ns1/p1", optional_relation="viewer") == ["pod:ns1/p1#viewer@user:app"]
+    assert read(resource_type="namespace", optional_subject_filter=C.SubjectFilter("user", "paul")) == \
+        ["namespace:ns1#creator@user:paul"]
+    assert read(resource_type="pod", optional_resource_id="never-written") == []
+    # CREATE of an existing relationship fails the whole write (nothing applied)
+    with pytest.raises(C.RpcError, match="ALREADY_EXISTS"):
+        cl.WriteRelationships(C.WriteRelationshipsRequest([
+            up(C.OPERATION_TOUCH, "namespace:ns2#creator@user:chani"),
+            up(C.OPERATION_CREATE, "namespace:ns1#creator@user:paul")]))
+    assert read(resource_type="namespace", optional_resource_id="ns2") == []
+    # preconditions (pkg/authz/distributedtx/workflow.go:147-182 builds MUST_NOT_MATCH ones)
+    pre_absent = C.Precondition(C.PRECONDITION_MUST_NOT_MATCH, C.RelationshipFilter(
+        "namespace", "ns1", "cluster", C.SubjectFilter("cluster", "cluster")))
+    with pytest.raises(C.RpcError, match="FAILED_PRECONDITION"):
+        cl.WriteRelationships(C.WriteRelationshipsRequest([up(C.OPERATION_TOUCH, "namespace:ns1#viewer@user:x")], [pre_absent]))
+    assert read(resource_type="namespace", optional_relation="viewer") == []
+    pre_present = C.Precondition(C.PRECONDITION_MUST_MATCH, pre_absent.filter)
+    cl.WriteRelationships(C.WriteRelationshipsRequest([up(C.OPERATION_TOUCH, "namespace:ns1#viewer@user:x")], [pre_present]))
+    assert read(resource_type="namespace", optional_relation="viewer") == ["namespace:ns1#viewer@user:x"]
+    # schema validation of writes
+    with pytest.raises(C.RpcError, match="INVALID_ARGUMENT"):
+        cl.WriteRelationships(C.WriteRelationshipsRequest([up(C.OPERATION_TOUCH, "namespace:ns1#viewer@cluster:c")]))
+    with pytest.raises(C.RpcError, match="INVALID_ARGUMENT"):
+        cl.WriteRelationships(C.WriteRelationshipsRequest([up(C.OPERATION_TOUCH, "namespace:ns1#view@user:u")]))
+    with pytest.raises(C.RpcError, match="INVALID_ARGUMENT"):  # expiration only where the schema allows it
+        cl.WriteRelationships(C.WriteRelationshipsRequest([up(C.OPERATION_TOUCH, "namespace:ns1#viewer@user:u", 99)]))
+    cl.WriteRelationships(C.WriteRelationshipsRequest([up(C.OPERATION_TOUCH, "workflow:w#idempotency_key@activity:a", 2_000_000_000)]))
+    e.set_clock(1_999_999_999)
+    assert read(resource_type="workflow") == ["workflow:w#idempotency_key@activity:a"]
+    e.set_clock(2_000_000_000)
+    assert read(resource_type="workflow") == []  # expired relationships are invisible
+    # DELETE update + delete by filter
+    cl.WriteRelationships(C.WriteRelationshipsRequest([up(C.OPERATION_DELETE, "namespace:ns1#viewer@user:x")]))
+    assert read(resource_type="namespace", optional_relation="viewer") == []
+    n = cl.DeleteRelationships(C.DeleteRelationshipsRequest(C.RelationshipFilter("namespace", "ns1")))
+    assert n == 2 and read(resource_type="namespace") == []
+    # more than 1000 updates per write is rejected (pkg/spicedb/spicedb.go:34)
+    with pytest.raises(C.RpcError, match="INVALID_ARGUMENT"):
+        cl.WriteRelationships(C.WriteRelationshipsRequest(
+            [up(C.OPERATION_TOUCH, f"pod:p{i}#viewer@user:u") for i in range(1001)]))
+
+
+def test_workload_generators_are_deterministic_and_sized():
+    a, b = workloads.cfg3(scale=0.001), workloads.cfg3(scale=0.001)
+    assert all(np.array_equal(x.res, y.res) and np.array_equal(x.subj, y.subj) for x, y in zip(a.groups, b.groups))
+    assert np.array_equal(a.checks[0].res, b.checks[0].res)
+    w1 = workloads.cfg1()
+    assert 400 < w1.n_tuples() < 600 and w1.n_checks() == 1000
+    w4 = workloads.cfg4(scale=0.0005)
+    rels = {(g.res_type, g.rel, g.subj_type, g.srel, g.wildcard) for g in w4.groups}
+    assert ("document", "viewer", "user", None, True) in rels and ("folder", "parent", "folder", None, False) in rels
+    o = Oracle(w4.schema)
+    w4.load_into(o)  # every generated relationship is valid under the schema
