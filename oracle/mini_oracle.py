@@ -210,5 +210,7 @@ class MiniOracle:
         return {F: NO, T: HAS, E: ERR}[v]
 
     def lookup_resources(self, rt, perm, st, sid, srel="", now=0):
-        cands = sorted({rid for (t, rid, rl) in self.rows if t == rt and self._live(t, rid, rl, now)})
-        return [r for r in cands if self.check(rt, r, perm, st, sid, srel, now) == HAS]
+        cands = {rid for (t, rid, rl) in self.rows if t == rt and self._live(t, rid, rl, now)}
+        if srel not in ("", "...", None) and st == rt and srel == perm:
+            cands.add(sid)  # a userset subject rt:x#perm is a member of itself
+        return [r for r in sorted(cands) if self.check(rt, r, perm, st, sid, srel, now) == HAS]

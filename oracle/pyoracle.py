@@ -203,7 +203,10 @@ class Oracle:
         u = self._L.zo_find_object(self._h, self.type_id(subj_type), _b(subj_id))
         ids = self.lookup_resources_ids(res_type, perm, subj_type, 0xFFFFFFFE if u < 0 else u,
                                         subj_rel or None, now)
-        return [self.object_name(res_type, int(i)) for i in ids]
+        names = [self.object_name(res_type, int(i)) for i in ids]
+        if u < 0 and subj_rel and subj_type == res_type and subj_rel == perm:
+            names.append(subj_id)  # never-written userset subject that names itself
+        return names
 
     def read(self, res_type="", res_id="", rel="", subj_type="", subj_id="", subj_rel="", now=0):
         cap = 1 << 16

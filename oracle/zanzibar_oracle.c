@@ -1029,8 +1029,18 @@ int zo_lookup_resources(zo_oracle *z, int rt, int perm, int stype, uint32_t subj
   }
   const Type *ty = &z->types[rt];
   uint64_t k = 0;
+  /* A userset subject rt:x#perm is a member of itself even with no relationships
+   * (SpiceDB LookupResources yields the subject's own object when type and
+   * permission coincide); merged in id order below. */
+  int self = (srel == perm && stype == rt && subj < 0xFFFFFFFEu);
+  int self_done = !self;
   for (uint64_t i = 0; i < ty->n_res_ids; i++) {
     uint32_t r = ty->res_ids[i];
+    if (!self_done && subj <= r) {
+      if (subj < r) { if (k < cap) out[k] = subj; k++; }
+      self_done = 1; /* if subj == r the normal path below reports it (Check is HAS) */
+      if (subj == r) { if (k < cap) out[k] = r; k++; continue; }
+    }
     /* the resource must have a LIVE relationship */
     int alive = 0;
     for (int s = 0; s < ty->n_slots && !alive; s++) {
@@ -1045,6 +1055,7 @@ int zo_lookup_resources(zo_oracle *z, int rt, int perm, int stype, uint32_t subj
       k++;
     }
   }
+  if (!self_done) { if (k < cap) out[k] = subj; k++; }
   *n_out = k;
   return k > cap ? -7 : 0;
 }

@@ -465,7 +465,7 @@ extern "C" int zg_count_alg_bytes(zg_engine* e, const zg_check* items, uint64_t 
   }
   cudaMemcpy(d_in, items, n * sizeof(zg_check), cudaMemcpyHostToDevice);
   uint64_t b = 0;
-  int rc = e->dev.check_device(static_cast<zg_check*>(d_in), n, static_cast<uint8_t*>(d_out), nullptr, true, &b, &err);
+  int rc = e->dev.check_device(static_cast<zg_check*>(d_in), n, static_cast<uint8_t*>(d_out), e->dev.stream, true, &b, &err);
   cudaFree(d_in);
   cudaFree(d_out);
   if (rc) return fail(rc, err);

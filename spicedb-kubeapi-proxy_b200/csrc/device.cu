@@ -63,6 +63,7 @@ Device::~Device() {
   if (pin_out_) cudaFreeHost(pin_out_);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
+  if (last_done_) cudaEventDestroy(last_done_);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -90,6 +91,7 @@ std::string Device::init(int dev, uint64_t subq_cap, uint32_t budget) {
     return std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
   cudaEventCreate(&ev0_);
   cudaEventCreate(&ev1_);
+  cudaEventCreateWithFlags(&last_done_, cudaEventDisableTiming);
   if (subq_cap) subq_cap_ = subq_cap;
   if (budget) budget_ = budget;
   if (!ctrl_.ensure(64)) return "out of device memory";
@@ -200,7 +202,10 @@ int Device::check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cu
   }
   if (n == 0) return ZG_OK;
   ZG_CUDA(cudaSetDevice(device));
-  if (!st) st = stream;
+  // st == NULL is the caller's legacy default stream, not the engine's own stream.
+  // Scratch (ctrl_, spill_, pass buffers) is shared by every call: order this call
+  // after the previous one even when they were enqueued on different streams.
+  if (have_last_) ZG_CUDA(cudaStreamWaitEvent(st, last_done_, 0));
   const bool count = count_bytes != nullptr;
   unsigned long long* ctrl = ctrl_.as<unsigned long long>();
   ZG_CUDA(cudaMemsetAsync(ctrl + 2, 0, 16, st));  // alg_bytes, flags
@@ -272,6 +277,8 @@ int Device::check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cu
     ZG_CUDA(cudaGetLastError());
   }
   cudaEventRecord(ev1_, st);
+  cudaEventRecord(last_done_, st);
+  have_last_ = true;
   timing_pending_ = true;
   checks += n;
   if (count) {

@@ -69,7 +69,8 @@ class Device {
   void* pin_in_ = nullptr;
   void* pin_out_ = nullptr;
   size_t pin_in_cap_ = 0, pin_out_cap_ = 0;
-  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, last_done_ = nullptr;
+  bool have_last_ = false;
   bool timing_pending_ = false;
 
  public:

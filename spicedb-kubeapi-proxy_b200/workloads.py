@@ -215,7 +215,11 @@ def cfg3(seed=3, scale=1.0, batch=1 << 20) -> Workload:
     r = _rng(seed)
     n_users, n_groups = max(int(1_000_000 * scale), 32), max(int(100_000 * scale), 16)
     n_teams, n_ns = max(int(10_000 * scale), 8), max(int(100_000 * scale), 16)
-    n_gm, n_tm, n_nv = max(int(8_000_000 * scale), 128), max(int(1_000_000 * scale), 32), max(int(1_000_000 * scale), 32)
+    # fan-outs (80 users/group, 100 groups/team, 10 teams/namespace at full size) shrink with
+    # the populations, so scaled-down graphs keep a mix of reachable and unreachable pairs
+    gpt = max(2, min(100, n_groups // 100))
+    tpn = max(2, min(10, n_teams // 10))
+    n_gm, n_tm, n_nv = max(int(8_000_000 * scale), 128), n_teams * gpt, n_ns * tpn
     gm_g = r.integers(0, n_groups, n_gm, dtype=np.uint32)
     gm_u = r.integers(0, n_users, n_gm, dtype=np.uint32)
     tm_t = r.integers(0, n_teams, n_tm, dtype=np.uint32)
