@@ -66,6 +66,9 @@ typedef struct zg_engine zg_engine;
  * the host logic). Every hot-path call on such an engine FAILS with ZG_ECUDA:
  * there is no CPU evaluation path in this library. */
 #define ZG_FLAG_HOST_ONLY 1u
+/* Forward expansion only: every direct probe is a binary search of the resource's row
+ * (no direction-optimised probes from the subject's reverse rows). For A/B measurement. */
+#define ZG_FLAG_FORWARD_ONLY 2u
 
 typedef struct {
   int32_t device;            /* CUDA device ordinal; -1 = current device          */

@@ -183,11 +183,11 @@ class Engine:
     """One zg_engine: schema + relationship store + published CSR snapshot in HBM."""
 
     def __init__(self, schema: str | None = None, device: int = -1, subquery_capacity: int = 0, work_budget: int = 0,
-                 host_only: bool = False):
+                 host_only: bool = False, forward_only: bool = False):
         """host_only=True builds schema/store/snapshot without a GPU (CPU unit tests of
         the host logic); every check/lookup on such an engine raises ZgpuError."""
         self._L = lib()
-        cfg = _Config(device, 1 if host_only else 0, subquery_capacity, work_budget, 0)
+        cfg = _Config(device, (1 if host_only else 0) | (2 if forward_only else 0), subquery_capacity, work_budget, 0)
         h = C.c_void_p()
         rc = self._L.zg_engine_create(C.byref(cfg), C.byref(h))
         if rc:

@@ -58,6 +58,7 @@ extern "C" int zg_engine_create(const zg_config* cfg, zg_engine** out) {
     delete e;
     return fail(ZG_ECUDA, err);
   }
+  if (cfg && (cfg->flags & ZG_FLAG_FORWARD_ONLY)) e->dev.invert = false;
   *out = e;
   return ZG_OK;
 }

@@ -6,6 +6,7 @@
 #include "device.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.cuh"
@@ -44,6 +45,8 @@ Snapshot::~Snapshot() {
   col.release();
   exp.release();
   prog.release();
+  rrow_ptr.release();
+  rcol.release();
   for (auto& r : resources) r.release();
 }
 
@@ -68,10 +71,11 @@ Device::~Device() {
 }
 
 static size_t smem_bytes(uint32_t prog_bytes) {
-  return prog_bytes + static_cast<size_t>(kWarpsPerBlock) * kStackCap * sizeof(uint4);
+  return prog_bytes + static_cast<size_t>(kWarpsPerBlock) * kWarpSmem;
 }
 
 std::string Device::init(int dev, uint64_t subq_cap, uint32_t budget) {
+  if (const char* v = std::getenv("ZGPU_NO_INVERT")) invert = !(*v && *v != '0');
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)
@@ -102,7 +106,7 @@ std::string Device::init(int dev, uint64_t subq_cap, uint32_t budget) {
 std::string Device::publish(const HostSnapshot& h, const Schema& sc, uint64_t revision) {
   cudaSetDevice(device);
   auto s = std::make_shared<Snapshot>();
-  std::vector<uint8_t> blob = sc.blob(h.rels);
+  std::vector<uint8_t> blob = sc.blob(h.rels, h.cls);
   auto up = [&](DevBuf& b, const void* src, size_t bytes) -> bool {
     if (!b.ensure(bytes ? bytes : 16)) return false;
     if (bytes && cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess) return false;
@@ -110,7 +114,8 @@ std::string Device::publish(const HostSnapshot& h, const Schema& sc, uint64_t re
     return true;
   };
   bool ok = up(s->row_ptr, h.row_ptr.data(), h.row_ptr.size() * 4) && up(s->col, h.col.data(), h.col.size() * 4) &&
-            up(s->prog, blob.data(), blob.size());
+            up(s->prog, blob.data(), blob.size()) && up(s->rrow_ptr, h.rrow_ptr.data(), h.rrow_ptr.size() * 4) &&
+            up(s->rcol, h.rcol.data(), h.rcol.size() * 4);
   if (ok && sc.has_expiry) ok = up(s->exp, h.exp.data(), h.exp.size() * 4);
   s->resources.resize(h.resources.size());
   s->n_resources.resize(h.resources.size());
@@ -152,6 +157,9 @@ int Device::run_pass(const Snapshot& s, const zg_check* jobs, uint64_t njobs, ui
   p.row_ptr = s.row_ptr.as<uint32_t>();
   p.col = s.col.as<uint32_t>();
   p.exp = s.exp.p ? s.exp.as<uint32_t>() : nullptr;
+  p.rrow_ptr = s.rrow_ptr.as<uint32_t>();
+  p.rcol = s.rcol.as<uint32_t>();
+  p.invert = invert ? 1 : 0;
   p.prog = s.prog.as<uint8_t>();
   p.prog_bytes = s.prog_bytes;
   p.jobs = jobs;

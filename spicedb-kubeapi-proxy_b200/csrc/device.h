@@ -26,7 +26,7 @@ struct DevBuf {
 
 // Immutable once published; shared_ptr keeps it alive for in-flight readers.
 struct Snapshot {
-  DevBuf row_ptr, col, exp, prog;
+  DevBuf row_ptr, col, exp, prog, rrow_ptr, rcol;
   std::vector<DevBuf> resources;  // per type
   std::vector<uint64_t> n_resources;
   uint32_t prog_bytes = 0;
@@ -54,6 +54,7 @@ class Device {
   int device = 0;
   uint64_t launches = 0, passes = 0, checks = 0;
   double last_ms = 0;
+  bool invert = true;  // direction-optimised probes (ZG_FLAG_FORWARD_ONLY / ZGPU_NO_INVERT=1 disable)
   uint32_t now = 0;  // clock for expiration, set by the caller before each hot-path call
   uint64_t last_alg_bytes = 0;
 
@@ -61,7 +62,7 @@ class Device {
   int run_pass(const Snapshot& s, const zg_check* jobs, uint64_t njobs, uint8_t* val, bool final_codes, bool raw,
                zg_check* subq, uint32_t* subq_parent, cudaStream_t st, bool count, std::string* err);
   int sm_count_ = 0, blocks_per_sm_ = 0, blocks_per_sm_count_ = 0;
-  uint32_t spill_cap_ = 4096, budget_ = 1u << 22;
+  uint32_t spill_cap_ = 4096, budget_ = 1u << 20;
   uint64_t subq_cap_ = 1ull << 22;
   DevBuf spill_, ctrl_;  // ctrl: [0] next, [1] subq_count, [2] alg_bytes, then flags u32
   std::vector<DevBuf> q_, parent_, jobs_, val_;  // per pass level

@@ -30,6 +30,8 @@ namespace zg {
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kStackCap = 128;        // range items per warp in shared memory
+constexpr int kRsetCap = 16;          // reverse-row entries kept per check (subject's direct memberships)
+constexpr size_t kWarpSmem = kStackCap * sizeof(uint4) + kRsetCap * 32 * sizeof(unsigned long long);
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint16_t kJobIsUnit = 0x8000;  // zg_check.flags: perm field is a unit id
 constexpr uint16_t kJobDepthMask = 0x00FF;
@@ -41,6 +43,9 @@ struct KParams {
   const uint32_t* row_ptr;
   const uint32_t* col;
   const uint32_t* exp;  // nullptr unless the schema uses expiration
+  const uint32_t* rrow_ptr;  // reverse CSR (subject -> resources) per edge class
+  const uint32_t* rcol;
+  int invert;  // answer direct probes from the subject's reverse rows when they are small
   const uint8_t* prog;
   uint32_t prog_bytes;
   const zg_check* jobs;
@@ -74,6 +79,9 @@ struct Prog {
   const DTree* trees;
   const DTreeOp* tree_ops;
   const uint16_t* leaf_units;
+  const DTypeInv* type_inv;
+  const uint16_t* inv_cls;
+  const DStep* steps;
 };
 
 __device__ __forceinline__ Prog make_prog(const uint8_t* b) {
@@ -89,12 +97,18 @@ __device__ __forceinline__ Prog make_prog(const uint8_t* b) {
   p.trees = reinterpret_cast<const DTree*>(b + p.h->off_trees);
   p.tree_ops = reinterpret_cast<const DTreeOp*>(b + p.h->off_tree_ops);
   p.leaf_units = reinterpret_cast<const uint16_t*>(b + p.h->off_leaf_units);
+  p.type_inv = reinterpret_cast<const DTypeInv*>(b + p.h->off_type_inv);
+  p.inv_cls = reinterpret_cast<const uint16_t*>(b + p.h->off_inv_cls);
+  p.steps = reinterpret_cast<const DStep*>(b + p.h->off_steps);
   return p;
 }
 
 // range item: x = begin, y = end (edge indices into col), z = meta, w unused
 //   meta: bits 0-4 job slot, 5-10 depth of the children, 11 class has expiry,
-//         16-31 slot the children are visited at
+//         12 LEAF-SCAN (children can only be matched against the subject's reverse-row
+//         set: the warp scans the range cooperatively), 16-31 slot of the children
+constexpr uint32_t kMetaLeafScan = 1u << 12;
+constexpr uint32_t kLeafScanMin = 16;  // shorter ranges are probed per lane instead
 __device__ __forceinline__ uint32_t make_meta(uint32_t jslot, uint32_t depth, bool expiry, uint32_t tslot) {
   return jslot | (depth << 5) | (expiry ? (1u << 11) : 0u) | (tslot << 16);
 }
@@ -107,6 +121,11 @@ struct WarpCtx {
   uint32_t spill_cap;
   unsigned found, err;  // warp-uniform, indexed by job slot
   uint32_t my_subj, my_ss;  // this lane's own job: subject id, stype<<16 | srel
+  // Direction-optimised probes: rset[i * 32 + job] = (class << 32 | resource) for every
+  // direct relationship of the job's subject (its reverse rows), when there are <= kRsetCap.
+  unsigned long long* rset;
+  uint32_t my_rcnt;   // entries of this lane's own job
+  unsigned inv_mask;  // jobs whose reverse rows fit
   unsigned long long bytes;
   bool fatal;
   unsigned lane;
@@ -189,81 +208,80 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
   const uint32_t ss = __shfl_sync(kFull, c.my_ss, jslot & 31);
   const uint32_t stype = ss >> 16, srel = ss & 0xFFFFu;
   bool hit = false;
-  int nops = 0, ob = 0;
+  int nsteps = 0, sb = 0;
   if (active) {
     const DUnit u = pr.units[unit];
     if (srel != kNone && sid == obj)
       for (int m = u.mem_begin; m < u.mem_end; ++m) hit = hit || pr.members[m] == srel;
     if (!hit) {
-      ob = u.op_begin;
-      nops = u.op_end - u.op_begin;
+      sb = u.step_begin;
+      nsteps = u.step_end - u.step_begin;
     }
   }
-  const int maxops = __reduce_max_sync(kFull, nops);
-  for (int i = 0; i < maxops; ++i) {
-    DOp op{};
-    DRel rel{};
-    int ncls = 0;
-    unsigned long long ridx = 0;
-    if (i < nops && !hit) {
-      op = pr.ops[ob + i];
-      rel = pr.rels[op.rel];
-      if (obj < rel.nres) {
-        ncls = rel.ncls;
-        ridx = rel.row_base + static_cast<unsigned long long>(obj) * rel.ncls;
-      }
-    }
-    const int maxcls = __reduce_max_sync(kFull, ncls);
-    uint32_t lo = 0;
-    if (ncls) {
-      lo = __ldg(p.row_ptr + ridx);
-      if (COUNT) c.bytes += 4;
-    }
-    for (int k = 0; k < maxcls; ++k) {
-      bool want = false;
-      uint4 item = make_uint4(0, 0, 0, 0);
-      uint32_t hi = lo;
-      if (k < ncls) {
-        hi = __ldg(p.row_ptr + ridx + k + 1);
-        if (COUNT) c.bytes += 4;
-        if (hi > lo && !hit) {
-          const DCls cl = pr.cls[rel.cls_begin + k];
-          const bool expiry = (cl.flags & CF_EXPIRY) != 0;
-          uint32_t tslot = kNone;
-          if (op.kind == OP_REL) {
-            if (cl.sslot == kNone) {
-              if (srel == kNone && stype == cl.stype) hit = probe(p, c, lo, hi, sid, expiry);
-            } else if (cl.sslot == kWildcard) {
-              if (srel == kNone && stype == cl.stype) {
-                if (expiry) {
-                  uint32_t e = __ldg(p.exp + lo);
-                  if (COUNT) c.bytes += 4;
-                  hit = e == 0 || e > p.now;
-                } else {
-                  hit = true;
-                }
-              }
+  const bool inverted = (c.inv_mask >> (jslot & 31)) & 1u;
+  const uint32_t rcnt = __shfl_sync(kFull, c.my_rcnt, jslot & 31);
+  const int maxsteps = __reduce_max_sync(kFull, nsteps);
+  for (int i = 0; i < maxsteps; ++i) {
+    bool want = false;
+    uint4 item = make_uint4(0, 0, 0, 0);
+    if (i < nsteps && !hit) {
+      const DStep st = pr.steps[sb + i];
+      const bool expiry = (st.flags & CF_EXPIRY) != 0;
+      const bool subject_fits = srel == kNone && stype == st.stype;
+      if (st.kind == ST_DIRECT && subject_fits && inverted && (st.flags & CF_INVERT)) {
+        // direction-optimised probe: is (class, obj) among the subject's own memberships?
+        const unsigned long long key = (static_cast<unsigned long long>(st.gc) << 32) | obj;
+        for (uint32_t r = 0; r < rcnt; ++r) hit = hit || c.rset[r * 32 + (jslot & 31)] == key;
+      } else if ((st.kind == ST_PUSH || subject_fits) && obj < st.nres) {
+        const unsigned long long ridx = st.row_base + static_cast<unsigned long long>(obj) * st.ncls;
+        const uint32_t lo = __ldg(p.row_ptr + ridx), hi = __ldg(p.row_ptr + ridx + 1);
+        if (COUNT) c.bytes += 8;
+        if (hi > lo) {
+          if (st.kind == ST_DIRECT) {
+            hit = probe(p, c, lo, hi, sid, expiry);
+          } else if (st.kind == ST_WILD) {
+            if (expiry) {
+              const uint32_t e = __ldg(p.exp + lo);
+              if (COUNT) c.bytes += 4;
+              hit = e == 0 || e > p.now;
             } else {
-              tslot = cl.sslot;
+              hit = true;
+            }
+          } else if ((st.flags & kStepTargetLeaf) && inverted && !expiry && depth + 1 <= ZG_MAX_DEPTH) {
+            // Every child of this range could only be answered by "is (class, child) one of
+            // the subject's memberships": intersect the subject's reverse-row set with the
+            // sorted range instead of visiting each child (meet in the middle). Long ranges
+            // are scanned by the whole warp (coalesced); short ones are probed right here.
+            if (hi - lo >= kLeafScanMin) {
+              if (rcnt) {  // no memberships at all: nothing in the range can match
+                want = true;
+                item = make_uint4(lo, hi, make_meta(jslot, depth + 1, false, st.tslot) | kMetaLeafScan, 0);
+              }
+            } else
+            for (uint32_t r = 0; r < rcnt && !hit; ++r) {
+              const unsigned long long key = c.rset[r * 32 + (jslot & 31)];
+              const uint32_t kgc = static_cast<uint32_t>(key >> 32);
+              bool mine = kgc == st.tgc;
+              if (st.tgc == kNone) {
+                const DUnit tu = pr.units[st.tunit];
+                for (int q = tu.step_begin; q < tu.step_end; ++q) mine = mine || pr.steps[q].gc == kgc;
+              }
+              if (mine) hit = probe(p, c, lo, hi, static_cast<uint32_t>(key), false);
             }
           } else {
-            tslot = pr.tgts[op.tgt_begin + k];
-          }
-          if (tslot != kNone && !hit) {
             want = true;
-            item = make_uint4(lo, hi, make_meta(jslot, depth + 1, expiry, tslot), 0);
+            item = make_uint4(lo, hi, make_meta(jslot, depth + 1, expiry, st.tslot), 0);
           }
         }
       }
-      push(c, want, item);
-      lo = hi;
     }
+    push(c, want, item);
   }
   c.found |= __reduce_or_sync(kFull, hit ? (1u << jslot) : 0u);
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(kThreads) check_kernel(const KParams p) {
+__global__ void __launch_bounds__(kThreads, 4) check_kernel(const KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   for (uint32_t i = threadIdx.x; i < p.prog_bytes / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(p.prog)[i];
@@ -272,7 +290,9 @@ __global__ void __launch_bounds__(kThreads) check_kernel(const KParams p) {
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpCtx<COUNT> c;
   c.lane = lane;
-  c.stack = reinterpret_cast<uint4*>(smem + p.prog_bytes) + warp * kStackCap;
+  uint8_t* wsm = smem + p.prog_bytes + warp * kWarpSmem;
+  c.stack = reinterpret_cast<uint4*>(wsm);
+  c.rset = reinterpret_cast<unsigned long long*>(wsm + kStackCap * sizeof(uint4));
   c.spill = p.spill + (static_cast<size_t>(blockIdx.x) * kWarpsPerBlock + warp) * p.spill_cap;
   c.spill_cap = p.spill_cap;
   c.bytes = 0;
@@ -308,6 +328,42 @@ __global__ void __launch_bounds__(kThreads) check_kernel(const KParams p) {
         unit = pr.slots[perm].unit;
       }
     }
+    // ---- direction-optimised probes: load the subject's reverse rows (its direct
+    // memberships) when the check can fan out and they are few
+    {
+      bool inv = p.invert && valid && !bad && (c.my_ss & 0xFFFFu) == kNone && (pr.units[unit].flags & UF_EXPANSIVE);
+      uint32_t rcnt = 0;
+      int ib = 0, ncl = 0;
+      if (inv) {
+        const DTypeInv ti = pr.type_inv[c.my_ss >> 16];
+        ib = ti.begin;
+        ncl = ti.end - ti.begin;
+      }
+      const int maxcl = __reduce_max_sync(kFull, ncl);
+      for (int i = 0; i < maxcl; ++i) {
+        if (inv && i < ncl) {
+          const uint32_t gc = pr.inv_cls[ib + i];
+          const DCls cl = pr.cls[gc];
+          if (!(cl.flags & CF_EMPTY) && c.my_subj < cl.nsubj) {
+            const uint32_t b = __ldg(p.rrow_ptr + cl.rrow_base + c.my_subj);
+            const uint32_t e = __ldg(p.rrow_ptr + cl.rrow_base + c.my_subj + 1);
+            if (COUNT) c.bytes += 8;
+            if (rcnt + (e - b) > static_cast<uint32_t>(kRsetCap)) {
+              inv = false;  // too many memberships: this check probes forward
+            } else {
+              for (uint32_t x = b; x < e; ++x) {
+                c.rset[rcnt * 32 + lane] = (static_cast<unsigned long long>(gc) << 32) | __ldg(p.rcol + x);
+                ++rcnt;
+              }
+              if (COUNT) c.bytes += 4ull * (e - b);
+            }
+          }
+        }
+      }
+      c.inv_mask = __ballot_sync(kFull, inv);
+      c.my_rcnt = rcnt;
+      __syncwarp();
+    }
     c.found = 0;
     c.err = __ballot_sync(kFull, valid && bad);
     c.top = 0;
@@ -329,10 +385,54 @@ __global__ void __launch_bounds__(kThreads) check_kernel(const KParams p) {
         c.err |= live_jobs & ~c.found;
         break;
       }
-      // ---- pop ranges worth <= 32 edges from the top of the stack
-      const int n = c.top < 32 ? c.top : 32;
+      // ---- LEAF-SCAN item on top: the whole warp intersects the sorted range with the
+      // job's reverse-row set (both ascending): coalesced reads, no per-child visit
+      {
+        const uint4 top_it = c.stack[c.top - 1];
+        if (top_it.z & kMetaLeafScan) {
+          const uint32_t js = top_it.z & 31u;
+          --c.top;
+          if (!((c.found >> js) & 1u)) {
+            const uint32_t rc = __shfl_sync(kFull, c.my_rcnt, js);
+            const DUnit tu = pr.units[pr.slots[top_it.z >> 16].unit];
+            unsigned long long key = 0;
+            bool mine = false;
+            if (lane < rc) {
+              key = c.rset[lane * 32 + js];
+              const uint32_t kgc = static_cast<uint32_t>(key >> 32);
+              for (int q = tu.step_begin; q < tu.step_end; ++q) mine = mine || pr.steps[q].gc == kgc;
+            }
+            const uint32_t kobj = mine ? static_cast<uint32_t>(key) : 0xFFFFFFFFu;
+            bool hitm = false;
+            for (uint32_t e0 = top_it.x; e0 < top_it.y; e0 += 32) {
+              const uint32_t e = e0 + lane;
+              const uint32_t child = e < top_it.y ? __ldg(p.col + e) : 0xFFFFFFFEu;
+              if (COUNT && e < top_it.y) c.bytes += 4;
+              const uint32_t last = top_it.y - e0 < 32u ? top_it.y - e0 - 1u : 31u;
+              const uint32_t cmin = __shfl_sync(kFull, child, 0), cmax = __shfl_sync(kFull, child, last);
+              unsigned km = __ballot_sync(kFull, mine && kobj >= cmin && kobj <= cmax);
+              while (km) {  // usually empty: a 32-child window rarely contains a membership
+                const int l = __ffs(km) - 1;
+                km &= km - 1;
+                const uint32_t k = __shfl_sync(kFull, kobj, l);  // unconditional: every lane takes part
+                hitm = hitm || child == k;
+              }
+            }
+            if (__any_sync(kFull, hitm)) c.found |= 1u << js;
+          }
+          continue;
+        }
+      }
+      // ---- pop ranges worth <= 32 edges from the top of the stack (up to the next
+      // LEAF-SCAN item, which is handled on its own)
+      int n = c.top < 32 ? c.top : 32;
       uint4 it = make_uint4(0, 0, 0, 0);
       if (static_cast<int>(lane) < n) it = c.stack[c.top - 1 - lane];
+      {
+        const unsigned lsm = __ballot_sync(kFull, static_cast<int>(lane) < n && (it.z & kMetaLeafScan));
+        if (lsm) n = __ffs(lsm) - 1;
+      }
+      if (static_cast<int>(lane) >= n) it = make_uint4(0, 0, 0, 0);
       const bool dead = (c.found >> (it.z & 31)) & 1u;
       const uint32_t len = (static_cast<int>(lane) < n && !dead) ? it.y - it.x : 0u;
       uint32_t incl = len;

@@ -462,6 +462,12 @@ std::string Schema::compile() {
     du.mem_begin = static_cast<uint16_t>(d_members.size());
     for (int m : u.members) d_members.push_back(static_cast<uint16_t>(m));
     du.mem_end = static_cast<uint16_t>(d_members.size());
+    du.flags = 0;
+    for (const auto& o : u.ops) {
+      if (o.kind == OP_ARROW) du.flags |= UF_EXPANSIVE;
+      for (const auto& c : slots[o.rel_slot].classes)
+        if (c.sslot != kNone && c.sslot != kWildcard) du.flags |= UF_EXPANSIVE;
+    }
     d_units.push_back(du);
     if (d_ops.size() > 0xFFF0 || d_tgts.size() > 0xFFF0 || d_members.size() > 0xFFF0 || d_units.size() > 0x7FF0)
       throw std::runtime_error("schema too large for the device program");
@@ -532,12 +538,23 @@ std::string Schema::compile() {
   }
 
   for (int rs : rel_slots)
-    for (const auto& c : slots[rs].classes)
-      d_cls.push_back(DCls{c.stype, c.sslot, static_cast<uint16_t>(c.expiry ? CF_EXPIRY : 0), 0});
+    for (const auto& c : slots[rs].classes) {
+      uint16_t fl = c.expiry ? CF_EXPIRY : 0;
+      if (c.sslot == kNone && !c.expiry) fl |= CF_INVERT;
+      d_cls.push_back(DCls{c.stype, c.sslot, fl, static_cast<uint16_t>(slots[rs].rel_index), 0, 0, 0});
+    }
+  d_type_inv.assign(types.size(), DTypeInv{0, 0});
+  d_inv_cls.clear();
+  for (size_t t = 0; t < types.size(); ++t) {
+    d_type_inv[t].begin = static_cast<uint16_t>(d_inv_cls.size());
+    for (size_t c = 0; c < d_cls.size(); ++c)
+      if ((d_cls[c].flags & CF_INVERT) && d_cls[c].stype == t) d_inv_cls.push_back(static_cast<uint16_t>(c));
+    d_type_inv[t].end = static_cast<uint16_t>(d_inv_cls.size());
+  }
   return "";
 }
 
-std::vector<uint8_t> Schema::blob(const std::vector<DRel>& rels) const {
+std::vector<uint8_t> Schema::blob(const std::vector<DRel>& rels, const std::vector<DCls>& cls) const {
   DHeader h{};
   h.magic = 0x5A47504Du;  // "ZGPM"
   h.n_types = static_cast<uint32_t>(types.size());
@@ -559,16 +576,72 @@ std::vector<uint8_t> Schema::blob(const std::vector<DRel>& rels) const {
     if (bytes) std::memcpy(out.data() + at, p, bytes);
     *off = static_cast<uint32_t>(at);
   };
+  // flatten every unit into steps for THIS snapshot (empty classes vanish)
+  std::vector<DUnit> units = d_units;
+  std::vector<DStep> steps;
+  for (auto& u : units) {
+    u.step_begin = static_cast<uint16_t>(steps.size());
+    for (int oi = u.op_begin; oi < u.op_end; ++oi) {
+      const DOp& op = d_ops[oi];
+      const DRel& r = rels[op.rel];
+      for (uint16_t k = 0; k < r.ncls; ++k) {
+        const DCls& c = cls[r.cls_begin + k];
+        if (c.flags & CF_EMPTY) continue;
+        DStep st{};
+        st.row_base = r.row_base + k;
+        st.nres = r.nres;
+        st.ncls = r.ncls;
+        st.flags = c.flags;
+        st.gc = static_cast<uint16_t>(r.cls_begin + k);
+        st.stype = c.stype;
+        st.tslot = kNone;
+        if (op.kind == OP_REL) {
+          if (c.sslot == kNone) st.kind = ST_DIRECT;
+          else if (c.sslot == kWildcard) st.kind = ST_WILD;
+          else {
+            st.kind = ST_PUSH;
+            st.tslot = c.sslot;
+          }
+        } else {
+          st.kind = ST_PUSH;
+          st.tslot = d_tgts[op.tgt_begin + k];
+          if (st.tslot == kNone) continue;
+        }
+        steps.push_back(st);
+      }
+    }
+    u.step_end = static_cast<uint16_t>(steps.size());
+    bool leaf = u.step_end > u.step_begin;
+    for (int i = u.step_begin; i < u.step_end; ++i)
+      leaf = leaf && steps[i].kind == ST_DIRECT && (steps[i].flags & CF_INVERT);
+    if (leaf) u.flags |= UF_LEAF_INV;
+  }
+  for (auto& st : steps) {
+    if (st.kind != ST_PUSH) continue;
+    st.tunit = kNone;
+    st.tgc = kNone;
+    if (d_slots[st.tslot].kind == SK_NONPURE) continue;
+    st.tunit = d_slots[st.tslot].unit;
+    const DUnit& tu = units[st.tunit];
+    if (tu.flags & UF_LEAF_INV) {
+      st.flags |= kStepTargetLeaf;
+      if (tu.step_end - tu.step_begin == 1) st.tgc = steps[tu.step_begin].gc;
+    }
+  }
+  h.n_steps = static_cast<uint32_t>(steps.size());
   put(rels.data(), rels.size() * sizeof(DRel), &h.off_rels);  // first: needs 8-byte alignment
+  put(steps.data(), steps.size() * sizeof(DStep), &h.off_steps);
+  put(cls.data(), cls.size() * sizeof(DCls), &h.off_cls);  // 8-byte aligned members
   put(d_slots.data(), d_slots.size() * sizeof(DSlot), &h.off_slots);
-  put(d_units.data(), d_units.size() * sizeof(DUnit), &h.off_units);
+  put(units.data(), units.size() * sizeof(DUnit), &h.off_units);
   put(d_ops.data(), d_ops.size() * sizeof(DOp), &h.off_ops);
-  put(d_cls.data(), d_cls.size() * sizeof(DCls), &h.off_cls);
   put(d_tgts.data(), d_tgts.size() * 2, &h.off_tgts);
   put(d_members.data(), d_members.size() * 2, &h.off_members);
   put(d_trees.data(), d_trees.size() * sizeof(DTree), &h.off_trees);
   put(d_tree_ops.data(), d_tree_ops.size() * sizeof(DTreeOp), &h.off_tree_ops);
   put(d_leaf_units.data(), d_leaf_units.size() * 2, &h.off_leaf_units);
+  put(d_type_inv.data(), d_type_inv.size() * sizeof(DTypeInv), &h.off_type_inv);
+  put(d_inv_cls.data(), d_inv_cls.size() * 2, &h.off_inv_cls);
   h.off_reach = 0;
   out.resize((out.size() + 15) & ~size_t(15));
   h.total_bytes = static_cast<uint32_t>(out.size());

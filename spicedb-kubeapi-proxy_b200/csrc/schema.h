@@ -27,7 +27,17 @@ constexpr int kMaxLeaves = 32;          // leaf units per non-pure permission
 enum SlotKind : uint16_t { SK_RELATION = 0, SK_PURE = 1, SK_NONPURE = 2 };
 enum OpKind : uint16_t { OP_REL = 0, OP_ARROW = 1 };
 enum TreeOpKind : uint16_t { T_LEAF = 0, T_TRIVIAL = 1, T_OR = 2, T_AND = 3, T_ANDNOT = 4 };
-enum ClsFlags : uint16_t { CF_EXPIRY = 1 };
+enum ClsFlags : uint16_t {
+  CF_EXPIRY = 1,  // relationships of this class may carry an expiration
+  CF_EMPTY = 2,   // no relationship of this class in the whole snapshot (set at publish)
+  CF_INVERT = 4,  // direct class whose probes may be answered from the subject's reverse row
+};
+enum UnitFlags : uint16_t {
+  UF_EXPANSIVE = 1,  // unit can push userset / arrow ranges
+  UF_LEAF_INV = 2,   // in this snapshot every step is an invertible direct probe: a visit can
+                     // only answer "is (class, obj) one of the subject's own memberships"
+};
+constexpr uint16_t kStepTargetLeaf = 0x100;  // DStep.flags: children are UF_LEAF_INV visits
 
 struct DSlot {   // per slot (relation or permission)
   uint16_t kind;        // SlotKind
@@ -38,6 +48,25 @@ struct DSlot {   // per slot (relation or permission)
 struct DUnit {   // pure-union program evaluated at one object
   uint16_t op_begin, op_end;    // into ops[]
   uint16_t mem_begin, mem_end;  // into members[]: slots inlined into this unit
+  uint16_t flags;               // UnitFlags
+  uint16_t step_begin, step_end;  // into steps[]: the unit flattened for this snapshot
+  uint16_t pad;
+};
+// One edge class a unit touches, with everything the visit needs in one 24-byte record.
+// Built at publish: classes that are empty in the snapshot produce no step at all.
+enum StepKind : uint16_t { ST_DIRECT = 0, ST_WILD = 1, ST_PUSH = 2 };
+struct DStep {
+  uint64_t row_base;  // row_ptr index of (object 0, this class): rel.row_base + k
+  uint32_t nres;      // objects covered by the relation's row table
+  uint16_t ncls;      // row stride
+  uint16_t kind;      // StepKind
+  uint16_t stype;     // ST_DIRECT / ST_WILD: subject type that can match
+  uint16_t tslot;     // ST_PUSH: slot the children are visited at
+  uint16_t flags;     // ClsFlags (CF_EXPIRY, CF_INVERT) | kStepTargetLeaf
+  uint16_t gc;        // global class id (key of the subject's reverse-row set)
+  uint16_t tunit;     // ST_PUSH: unit of tslot (kNone when tslot is a non-pure permission)
+  uint16_t tgc;       // kStepTargetLeaf: the single class of the target unit, or kNone if several
+  uint32_t pad;
 };
 struct DOp {
   uint16_t kind;       // OpKind
@@ -55,7 +84,13 @@ struct DCls {
   uint16_t stype;
   uint16_t sslot;      // kNone (direct), kWildcard, or subject relation slot
   uint16_t flags;      // ClsFlags
-  uint16_t pad;
+  uint16_t rel;        // data relation index this class belongs to
+  uint32_t nsubj;      // reverse CSR: subject objects covered (1 for a wildcard class)
+  uint32_t pad;
+  uint64_t rrow_base;  // reverse CSR: index into rrow_ptr of (subject 0) for this class
+};
+struct DTypeInv {  // per subject type: the invertible direct classes (inv_cls[begin, end))
+  uint16_t begin, end;
 };
 struct DTree {   // postfix boolean program of a non-pure permission
   uint16_t op_begin, op_end;     // into tree_ops[]
@@ -70,6 +105,7 @@ struct DHeader {  // first bytes of the blob; offsets in bytes from blob start
   uint32_t n_types, n_slots, n_units, n_ops, n_rels, n_cls, n_trees, n_tree_ops;
   uint32_t off_slots, off_units, off_ops, off_rels, off_cls, off_tgts, off_members;
   uint32_t off_trees, off_tree_ops, off_leaf_units, off_reach;
+  uint32_t off_type_inv, off_inv_cls, off_steps, n_steps;
   uint32_t max_leaves;   // job stride L in general mode (1 if no non-pure slot)
   uint32_t has_nonpure;
   uint32_t has_expiry;
@@ -135,7 +171,10 @@ class Schema {
   bool has_nonpure = false, has_expiry = false;
 
   // Serialises the program; DRel rows (row_base, nres) come from the store.
-  std::vector<uint8_t> blob(const std::vector<DRel>& rels) const;
+  // cls: per-class dynamic data from the store (rrow_base, CF_EMPTY), same order as d_cls.
+  std::vector<uint8_t> blob(const std::vector<DRel>& rels, const std::vector<DCls>& cls) const;
+  std::vector<DTypeInv> d_type_inv;
+  std::vector<uint16_t> d_inv_cls;
 
  private:
   std::string compile();

@@ -293,6 +293,40 @@ HostSnapshot Store::build() const {
     if (with_exp) h.exp.resize(w);
   }
   h.n_tuples = h.col.size();
+
+  // ---- reverse CSR (subject -> resources), per edge class; built from the deduplicated
+  // forward rows in ascending resource order, so every reverse row comes out sorted
+  h.cls = sc.d_cls;
+  uint64_t rpool = 0;
+  for (auto& c : h.cls) {
+    c.rrow_base = rpool;
+    c.nsubj = c.sslot == kWildcard ? 1u : h.n_objects[c.stype];
+    rpool += c.nsubj;
+    c.flags |= CF_EMPTY;
+  }
+  h.rrow_ptr.assign(rpool + 1, 0);
+  h.rcol.resize(h.col.size());
+  for (int pass = 0; pass < 2; ++pass) {
+    std::vector<uint32_t> cur;
+    if (pass == 1) {
+      for (uint64_t i = 0; i < rpool; ++i) h.rrow_ptr[i + 1] += h.rrow_ptr[i];
+      cur.assign(h.rrow_ptr.begin(), h.rrow_ptr.end() - 1);
+    }
+    for (const DRel& r : h.rels)
+      for (uint32_t res = 0; res < r.nres; ++res)
+        for (uint32_t k = 0; k < r.ncls; ++k) {
+          const uint64_t idx = r.row_base + uint64_t(res) * r.ncls + k;
+          const uint32_t b = h.row_ptr[idx], e = h.row_ptr[idx + 1];
+          if (b == e) continue;
+          DCls& c = h.cls[r.cls_begin + k];
+          c.flags &= static_cast<uint16_t>(~CF_EMPTY);
+          for (uint32_t i = b; i < e; ++i) {
+            const uint64_t ridx = c.rrow_base + (c.sslot == kWildcard ? 0u : h.col[i]);
+            if (pass == 0) ++h.rrow_ptr[ridx + 1];
+            else h.rcol[cur[ridx]++] = res;
+          }
+        }
+  }
   h.resources.resize(nt);
   for (size_t t = 0; t < nt; ++t)
     for (uint32_t i = 0; i < seen[t].size(); ++i)

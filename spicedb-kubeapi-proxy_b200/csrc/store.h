@@ -37,6 +37,9 @@ struct HostSnapshot {
   std::vector<uint32_t> col;      // subject object ids, sorted within (object, class)
   std::vector<uint32_t> exp;      // parallel to col when the schema uses expiration, else empty
   std::vector<DRel> rels;
+  std::vector<DCls> cls;          // schema classes + rrow_base / CF_EMPTY for this snapshot
+  std::vector<uint32_t> rrow_ptr; // reverse CSR: per class, one row per SUBJECT object (+1 sentinel)
+  std::vector<uint32_t> rcol;     // resource object ids, ascending within a row
   std::vector<std::vector<uint32_t>> resources;  // per type: ids that are the resource of >= 1 relationship
   std::vector<uint32_t> n_objects;               // per type
   uint64_t n_tuples = 0;

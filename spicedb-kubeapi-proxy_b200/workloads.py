@@ -265,12 +265,22 @@ def cfg4(seed=4, scale=1.0, batch=1 << 20) -> Workload:
     gm_g, gm_u = ints(G, 0.18 * N), None
     gm_u = ints(U, gm_g.size)
     groups.append(RelGroup("group", "member", "user", gm_g, gm_u))
-    # nested groups, acyclic: parent id > child id
-    child = ints(max(G - 1, 1), 0.02 * N)
-    parent = _u32(child + 1 + (r.random(child.size) * (G - 1 - child)).astype(np.uint32))
-    parent = np.minimum(parent, G - 1).astype(np.uint32)
-    keep = parent > child
-    groups.append(RelGroup("group", "member", "group", parent[keep], child[keep], srel="member"))
+    # nested groups, three tiers (ids ascending by tier): tier-1 groups (25 %) include 1-2
+    # tier-0 groups, tier-2 groups (5 %) include 1-2 tier-1 groups. Acyclic, depth <= 2,
+    # path multiplicity <= 4: forward evaluation without result caching
+    # (pkg/spicedb/spicedb.go:44-46) is exponential in the multiplicity of deeper DAGs.
+    t0, t1 = int(G * 0.70), int(G * 0.95)
+    par, chi = [], []
+    for lo, hi, clo, chi_hi in ((t0, t1, 0, t0), (t1, G, t0, t1)):
+        if hi > lo and chi_hi > clo:
+            ids = np.arange(lo, hi, dtype=np.int64)
+            for _rep in range(2):
+                take = ids if _rep == 0 else ids[r.random(ids.size) < 0.5]
+                par.append(take)
+                chi.append(r.integers(clo, chi_hi, take.size))
+    if par:
+        groups.append(RelGroup("group", "member", "group", _u32(np.concatenate(par)), _u32(np.concatenate(chi)),
+                               srel="member"))
     groups.append(RelGroup("org", "member", "user", ints(O, 0.02 * N), ints(U, nz(0.02 * N, 4))))
     groups.append(RelGroup("org", "member", "group", ints(O, 0.005 * N), ints(G, nz(0.005 * N, 4)), srel="member"))
     # folders: 6 levels, level l parents live in level l-1 (ids ascending by level)

@@ -200,13 +200,17 @@ def test_bulk_contract_and_edge_cases(zg):
     assert np.array_equal(e.check_bulk(items[perm]), e.check_bulk(items)[perm])
 
 
-@pytest.mark.parametrize("name,scale", [("cfg1", 1.0), ("cfg2", 0.01), ("cfg2-zipf", 0.01), ("cfg3", 0.002), ("cfg4", 0.0005)])
-def test_baseline_configs_scaled_bit_exact(zg, name, scale):
+@pytest.mark.parametrize("forward_only", [False, True])
+@pytest.mark.parametrize("name,scale", [("cfg1", 1.0), ("cfg2", 0.01), ("cfg2-zipf", 0.01), ("cfg3", 0.002), ("cfg3", 0.01),
+                                        ("cfg4", 0.0005), ("cfg4", 0.002)])
+def test_baseline_configs_scaled_bit_exact(zg, name, scale, forward_only):
+    """Both probe strategies (direction-optimised from the subject's reverse rows, and
+    forward-only binary search) must agree with the oracle bit for bit."""
     from oracle.pyoracle import Oracle
     from spicedb_kubeapi_proxy_b200 import workloads
 
     w = workloads.by_name(name, scale)
-    e, o = zg.Engine(w.schema), Oracle(w.schema)
+    e, o = zg.Engine(w.schema, forward_only=forward_only), Oracle(w.schema)
     w.load_into(e), w.load_into(o)
     e.publish()
     items = w.check_items(e, zg.CHECK_DTYPE)
