@@ -105,10 +105,9 @@ __device__ __forceinline__ Prog make_prog(const uint8_t* b) {
 
 // range item: x = begin, y = end (edge indices into col), z = meta, w unused
 //   meta: bits 0-4 job slot, 5-10 depth of the children, 11 class has expiry,
-//         12 LEAF-SCAN (children can only be matched against the subject's reverse-row
-//         set: the warp scans the range cooperatively), 16-31 slot of the children
-constexpr uint32_t kMetaLeafScan = 1u << 12;
-constexpr uint32_t kLeafScanMin = 16;  // shorter ranges are probed per lane instead
+//         12 LEAF (children can only be matched against the subject's reverse-row set:
+//         w = class index | keys done << 8; popped as (range, key) pairs), 16-31 child slot
+constexpr uint32_t kMetaLeaf = 1u << 12;
 __device__ __forceinline__ uint32_t make_meta(uint32_t jslot, uint32_t depth, bool expiry, uint32_t tslot) {
   return jslot | (depth << 5) | (expiry ? (1u << 11) : 0u) | (tslot << 16);
 }
@@ -124,7 +123,7 @@ struct WarpCtx {
   // Direction-optimised probes: rset[i * 32 + job] = (class << 32 | resource) for every
   // direct relationship of the job's subject (its reverse rows), when there are <= kRsetCap.
   unsigned long long* rset;
-  uint32_t my_rcnt;   // entries of this lane's own job
+  unsigned long long my_cst;  // class boundaries of this lane's own job (see cst_at)
   unsigned inv_mask;  // jobs whose reverse rows fit
   unsigned long long bytes;
   bool fatal;
@@ -198,14 +197,23 @@ __device__ __forceinline__ bool probe(const KParams& p, WarpCtx<COUNT>& c, uint3
   return false;
 }
 
+// Boundaries of a job's reverse-row set per invertible class of its subject type:
+// 5 bits each (0..16), boundary i at bit 5*i; class i owns entries [b_i, b_{i+1}).
+__device__ __forceinline__ uint32_t cst_at(unsigned long long cst, uint32_t i) {
+  return static_cast<uint32_t>(cst >> (5u * i)) & 31u;
+}
+constexpr int kMaxInvClasses = 11;
+
 // Warp-collective node visit: every lane may carry one (job slot, object, unit).
-// Evaluates the unit's REL / ARROW ops at the object: membership-of-itself test,
-// direct and wildcard probes, and pushes the userset / arrow edge ranges.
+// Evaluates the unit's steps at the object: membership-of-itself test, direct and
+// wildcard probes (from the subject's reverse-row set when the job is inverted, else a
+// binary search of the row), and pushes the userset / arrow edge ranges.
 template <bool COUNT>
 __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<COUNT>& c, bool active,
                                       uint32_t jslot, uint32_t obj, uint32_t unit, uint32_t depth) {
   const uint32_t sid = __shfl_sync(kFull, c.my_subj, jslot & 31);
   const uint32_t ss = __shfl_sync(kFull, c.my_ss, jslot & 31);
+  const unsigned long long cst = __shfl_sync(kFull, c.my_cst, jslot & 31);
   const uint32_t stype = ss >> 16, srel = ss & 0xFFFFu;
   bool hit = false;
   int nsteps = 0, sb = 0;
@@ -219,7 +227,6 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
     }
   }
   const bool inverted = (c.inv_mask >> (jslot & 31)) & 1u;
-  const uint32_t rcnt = __shfl_sync(kFull, c.my_rcnt, jslot & 31);
   const int maxsteps = __reduce_max_sync(kFull, nsteps);
   for (int i = 0; i < maxsteps; ++i) {
     bool want = false;
@@ -229,9 +236,10 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
       const bool expiry = (st.flags & CF_EXPIRY) != 0;
       const bool subject_fits = srel == kNone && stype == st.stype;
       if (st.kind == ST_DIRECT && subject_fits && inverted && (st.flags & CF_INVERT)) {
-        // direction-optimised probe: is (class, obj) among the subject's own memberships?
-        const unsigned long long key = (static_cast<unsigned long long>(st.gc) << 32) | obj;
-        for (uint32_t r = 0; r < rcnt; ++r) hit = hit || c.rset[r * 32 + (jslot & 31)] == key;
+        // direction-optimised probe: is obj among the subject's memberships of this class?
+        const uint32_t kb = cst_at(cst, st.tinv), ke = cst_at(cst, st.tinv + 1u);
+        for (uint32_t r = kb; r < ke; ++r)
+          hit = hit || static_cast<uint32_t>(c.rset[r * 32 + (jslot & 31)]) == obj;
       } else if ((st.kind == ST_PUSH || subject_fits) && obj < st.nres) {
         const unsigned long long ridx = st.row_base + static_cast<unsigned long long>(obj) * st.ncls;
         const uint32_t lo = __ldg(p.row_ptr + ridx), hi = __ldg(p.row_ptr + ridx + 1);
@@ -248,25 +256,20 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
               hit = true;
             }
           } else if ((st.flags & kStepTargetLeaf) && inverted && !expiry && depth + 1 <= ZG_MAX_DEPTH) {
-            // Every child of this range could only be answered by "is (class, child) one of
-            // the subject's memberships": intersect the subject's reverse-row set with the
-            // sorted range instead of visiting each child (meet in the middle). Long ranges
-            // are scanned by the whole warp (coalesced); short ones are probed right here.
-            if (hi - lo >= kLeafScanMin) {
-              if (rcnt) {  // no memberships at all: nothing in the range can match
-                want = true;
-                item = make_uint4(lo, hi, make_meta(jslot, depth + 1, false, st.tslot) | kMetaLeafScan, 0);
+            // Children of this range can only be answered by "is the child one of the
+            // subject's memberships of class tinv": meet in the middle. nk memberships
+            // against hi-lo children: no membership -> nothing can match; fewer children
+            // than memberships -> visit the children; else a LEAF item whose (range, key)
+            // pairs are binary-searched one per lane.
+            // (a child class for another subject type can never match this subject)
+            const uint32_t nk = stype == st.tstype ? cst_at(cst, st.tinv + 1u) - cst_at(cst, st.tinv) : 0u;
+            if (nk) {
+              want = true;
+              item = make_uint4(lo, hi, make_meta(jslot, depth + 1, false, st.tslot), 0);
+              if (hi - lo >= nk) {
+                item.z |= kMetaLeaf;
+                item.w = st.tinv;  // bits 0-7: class index, bits 8-15: keys already done
               }
-            } else
-            for (uint32_t r = 0; r < rcnt && !hit; ++r) {
-              const unsigned long long key = c.rset[r * 32 + (jslot & 31)];
-              const uint32_t kgc = static_cast<uint32_t>(key >> 32);
-              bool mine = kgc == st.tgc;
-              if (st.tgc == kNone) {
-                const DUnit tu = pr.units[st.tunit];
-                for (int q = tu.step_begin; q < tu.step_end; ++q) mine = mine || pr.steps[q].gc == kgc;
-              }
-              if (mine) hit = probe(p, c, lo, hi, static_cast<uint32_t>(key), false);
             }
           } else {
             want = true;
@@ -329,15 +332,20 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const KParams p) {
       }
     }
     // ---- direction-optimised probes: load the subject's reverse rows (its direct
-    // memberships) when the check can fan out and they are few
+    // memberships, class by class) when the check can fan out and they are few
     {
       bool inv = p.invert && valid && !bad && (c.my_ss & 0xFFFFu) == kNone && (pr.units[unit].flags & UF_EXPANSIVE);
       uint32_t rcnt = 0;
+      unsigned long long cst = 0;
       int ib = 0, ncl = 0;
       if (inv) {
         const DTypeInv ti = pr.type_inv[c.my_ss >> 16];
         ib = ti.begin;
         ncl = ti.end - ti.begin;
+        if (ncl > kMaxInvClasses) {
+          inv = false;
+          ncl = 0;
+        }
       }
       const int maxcl = __reduce_max_sync(kFull, ncl);
       for (int i = 0; i < maxcl; ++i) {
@@ -358,10 +366,11 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const KParams p) {
               if (COUNT) c.bytes += 4ull * (e - b);
             }
           }
+          cst |= static_cast<unsigned long long>(rcnt) << (5u * (i + 1));
         }
       }
       c.inv_mask = __ballot_sync(kFull, inv);
-      c.my_rcnt = rcnt;
+      c.my_cst = cst;
       __syncwarp();
     }
     c.found = 0;
@@ -385,56 +394,28 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const KParams p) {
         c.err |= live_jobs & ~c.found;
         break;
       }
-      // ---- LEAF-SCAN item on top: the whole warp intersects the sorted range with the
-      // job's reverse-row set (both ascending): coalesced reads, no per-child visit
-      {
-        const uint4 top_it = c.stack[c.top - 1];
-        if (top_it.z & kMetaLeafScan) {
-          const uint32_t js = top_it.z & 31u;
-          --c.top;
-          if (!((c.found >> js) & 1u)) {
-            const uint32_t rc = __shfl_sync(kFull, c.my_rcnt, js);
-            const DUnit tu = pr.units[pr.slots[top_it.z >> 16].unit];
-            unsigned long long key = 0;
-            bool mine = false;
-            if (lane < rc) {
-              key = c.rset[lane * 32 + js];
-              const uint32_t kgc = static_cast<uint32_t>(key >> 32);
-              for (int q = tu.step_begin; q < tu.step_end; ++q) mine = mine || pr.steps[q].gc == kgc;
-            }
-            const uint32_t kobj = mine ? static_cast<uint32_t>(key) : 0xFFFFFFFFu;
-            bool hitm = false;
-            for (uint32_t e0 = top_it.x; e0 < top_it.y; e0 += 32) {
-              const uint32_t e = e0 + lane;
-              const uint32_t child = e < top_it.y ? __ldg(p.col + e) : 0xFFFFFFFEu;
-              if (COUNT && e < top_it.y) c.bytes += 4;
-              const uint32_t last = top_it.y - e0 < 32u ? top_it.y - e0 - 1u : 31u;
-              const uint32_t cmin = __shfl_sync(kFull, child, 0), cmax = __shfl_sync(kFull, child, last);
-              unsigned km = __ballot_sync(kFull, mine && kobj >= cmin && kobj <= cmax);
-              while (km) {  // usually empty: a 32-child window rarely contains a membership
-                const int l = __ffs(km) - 1;
-                km &= km - 1;
-                const uint32_t k = __shfl_sync(kFull, kobj, l);  // unconditional: every lane takes part
-                hitm = hitm || child == k;
-              }
-            }
-            if (__any_sync(kFull, hitm)) c.found |= 1u << js;
-          }
-          continue;
-        }
-      }
-      // ---- pop ranges worth <= 32 edges from the top of the stack (up to the next
-      // LEAF-SCAN item, which is handled on its own)
+      // ---- pop work worth <= 32 lanes from the top of the stack. The top item decides
+      // the mode: EDGE items contribute one lane per edge (child visit), LEAF items one
+      // lane per (range, membership key) pair (binary search). Items of the other kind
+      // wait for a later iteration.
       int n = c.top < 32 ? c.top : 32;
       uint4 it = make_uint4(0, 0, 0, 0);
       if (static_cast<int>(lane) < n) it = c.stack[c.top - 1 - lane];
+      const bool leaf_mode = (__shfl_sync(kFull, it.z, 0) & kMetaLeaf) != 0;
       {
-        const unsigned lsm = __ballot_sync(kFull, static_cast<int>(lane) < n && (it.z & kMetaLeafScan));
-        if (lsm) n = __ffs(lsm) - 1;
+        const unsigned other = __ballot_sync(kFull, static_cast<int>(lane) < n && ((it.z & kMetaLeaf) != 0) != leaf_mode);
+        if (other) n = __ffs(other) - 1;
       }
       if (static_cast<int>(lane) >= n) it = make_uint4(0, 0, 0, 0);
       const bool dead = (c.found >> (it.z & 31)) & 1u;
-      const uint32_t len = (static_cast<int>(lane) < n && !dead) ? it.y - it.x : 0u;
+      uint32_t len = 0;
+      if (leaf_mode) {
+        const unsigned long long icst = __shfl_sync(kFull, c.my_cst, it.z & 31);
+        const uint32_t tinv = it.w & 0xFFu, kdone = it.w >> 8;
+        if (static_cast<int>(lane) < n && !dead) len = cst_at(icst, tinv + 1u) - cst_at(icst, tinv) - kdone;
+      } else if (static_cast<int>(lane) < n && !dead) {
+        len = it.y - it.x;
+      }
       uint32_t incl = len;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -447,11 +428,13 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const KParams p) {
       uint32_t total = __shfl_sync(kFull, incl, 31);
       if (total > 32u) total = 32u;
       __syncwarp();
-      if (static_cast<int>(lane) == nfull && static_cast<int>(lane) < n)  // partially consumed item stays on top
-        c.stack[c.top - 1 - lane].x = it.x + (32u - excl);
+      if (static_cast<int>(lane) == nfull && static_cast<int>(lane) < n) {  // partially consumed item stays on top
+        if (leaf_mode) c.stack[c.top - 1 - lane].w = it.w + ((32u - excl) << 8);
+        else c.stack[c.top - 1 - lane].x = it.x + (32u - excl);
+      }
       c.top -= nfull;
       __syncwarp();
-      // ---- lane k takes edge k: owner item j = #items with incl <= k
+      // ---- lane k takes work unit k: owner item j = #items with incl <= k
       int j = 0;
 #pragma unroll
       for (int step = 16; step >= 1; step >>= 1) {
@@ -463,8 +446,20 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const KParams p) {
       const uint32_t jmeta = __shfl_sync(kFull, it.z, j & 31);
       const uint32_t jexcl = __shfl_sync(kFull, excl, j & 31);
       bool active = lane < total;
-      uint32_t child = 0;
       const uint32_t jslot = jmeta & 31u, cdepth = (jmeta >> 5) & 63u, tslot = jmeta >> 16;
+      if (leaf_mode) {
+        const uint32_t je = __shfl_sync(kFull, it.y, j & 31);
+        const uint32_t jw = __shfl_sync(kFull, it.w, j & 31);
+        const unsigned long long jcst = __shfl_sync(kFull, c.my_cst, jslot);
+        bool hit = false;
+        if (active) {
+          const uint32_t r = cst_at(jcst, jw & 0xFFu) + (jw >> 8) + (lane - jexcl);
+          hit = probe(p, c, jb, je, static_cast<uint32_t>(c.rset[r * 32 + jslot]), false);
+        }
+        c.found |= __reduce_or_sync(kFull, hit ? (1u << jslot) : 0u);
+        continue;
+      }
+      uint32_t child = 0;
       const uint32_t sq_subj = __shfl_sync(kFull, c.my_subj, jslot);
       const uint32_t sq_ss = __shfl_sync(kFull, c.my_ss, jslot);
       if (active) {

@@ -616,16 +616,22 @@ std::vector<uint8_t> Schema::blob(const std::vector<DRel>& rels, const std::vect
       leaf = leaf && steps[i].kind == ST_DIRECT && (steps[i].flags & CF_INVERT);
     if (leaf) u.flags |= UF_LEAF_INV;
   }
+  std::vector<uint16_t> inv_pos(cls.size(), kNone);  // class -> index in its type's invertible list
+  for (const auto& ti : d_type_inv)
+    for (uint16_t i = ti.begin; i < ti.end; ++i) inv_pos[d_inv_cls[i]] = static_cast<uint16_t>(i - ti.begin);
   for (auto& st : steps) {
+    st.tinv = st.kind == ST_DIRECT ? inv_pos[st.gc] : kNone;
     if (st.kind != ST_PUSH) continue;
     st.tunit = kNone;
     st.tgc = kNone;
     if (d_slots[st.tslot].kind == SK_NONPURE) continue;
     st.tunit = d_slots[st.tslot].unit;
     const DUnit& tu = units[st.tunit];
-    if (tu.flags & UF_LEAF_INV) {
+    if ((tu.flags & UF_LEAF_INV) && tu.step_end - tu.step_begin == 1) {
       st.flags |= kStepTargetLeaf;
-      if (tu.step_end - tu.step_begin == 1) st.tgc = steps[tu.step_begin].gc;
+      st.tgc = steps[tu.step_begin].gc;
+      st.tinv = inv_pos[st.tgc];
+      st.tstype = steps[tu.step_begin].stype;
     }
   }
   h.n_steps = static_cast<uint32_t>(steps.size());

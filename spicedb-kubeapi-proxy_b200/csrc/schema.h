@@ -65,8 +65,10 @@ struct DStep {
   uint16_t flags;     // ClsFlags (CF_EXPIRY, CF_INVERT) | kStepTargetLeaf
   uint16_t gc;        // global class id (key of the subject's reverse-row set)
   uint16_t tunit;     // ST_PUSH: unit of tslot (kNone when tslot is a non-pure permission)
-  uint16_t tgc;       // kStepTargetLeaf: the single class of the target unit, or kNone if several
-  uint32_t pad;
+  uint16_t tgc;       // kStepTargetLeaf: the single class of the target unit
+  uint16_t tinv;      // ST_DIRECT: index of gc among its subject type's invertible classes;
+                      // kStepTargetLeaf: the same for tgc
+  uint16_t tstype;    // kStepTargetLeaf: subject type the target class accepts
 };
 struct DOp {
   uint16_t kind;       // OpKind
