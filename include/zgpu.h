@@ -138,6 +138,8 @@ typedef struct {
   uint64_t revision;        /* increments on every publish                        */
   uint64_t last_alg_bytes;  /* algorithmic bytes of the last counted call         */
   double last_kernel_ms;    /* device time of the last hot-path call              */
+  uint64_t coalesced_launches; /* launches that answered more than one concurrent caller */
+  uint64_t coalesced_requests; /* zg_check_bulk calls answered by those launches         */
 } zg_stats;
 
 /* ---- lifecycle --------------------------------------------------------- */

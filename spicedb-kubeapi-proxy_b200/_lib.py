@@ -51,7 +51,7 @@ class _Precond(C.Structure):
 class _Stats(C.Structure):
     _fields_ = [("checks", C.c_uint64), ("launches", C.c_uint64), ("passes", C.c_uint64), ("tuples", C.c_uint64),
                 ("snapshot_bytes", C.c_uint64), ("revision", C.c_uint64), ("last_alg_bytes", C.c_uint64),
-                ("last_kernel_ms", C.c_double)]
+                ("last_kernel_ms", C.c_double), ("coalesced_launches", C.c_uint64), ("coalesced_requests", C.c_uint64)]
 
 
 def library_path() -> str:

@@ -1,6 +1,7 @@
 // capi.cu -- the C ABI declared in include/zgpu.h. Thin glue: argument checks,
 // string <-> id resolution, locking; the work is in store.cc and device.cu.
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
 #include <ctime>
 #include <mutex>
@@ -15,8 +16,31 @@
 
 using namespace zg;
 
+// Coalescing batcher ("group commit") for zg_check_bulk. The proxy calls the boundary
+// from one goroutine per rule check (pkg/authz/check.go:77-93) and per list request
+// (pkg/authz/postfilter.go:127-134): many concurrent, mostly small calls. The first
+// caller to arrive becomes the leader; while its launch is in flight later callers
+// queue, and the next leader answers ALL of them with one launch sequence. No timer:
+// batching is driven purely by arrivals during the previous launch.
+struct BatchReq {
+  const zg_check* items;
+  uint64_t n;
+  uint8_t* out;
+  int rc = ZG_OK;
+  std::string err;
+  bool done = false;
+};
+struct Batcher {
+  std::mutex m;
+  std::condition_variable cv;
+  std::vector<BatchReq*> queue;
+  bool leader_active = false;
+  static constexpr uint64_t kMaxItemsPerLaunch = 1ull << 24;
+};
+
 struct zg_engine {
-  std::mutex mu;  // one writer or one hot-path call at a time (round 1: coarse)
+  std::mutex mu;  // one writer or one hot-path launch sequence at a time
+  Batcher batcher;
   Schema schema;
   bool has_schema = false;
   Store store;
@@ -429,16 +453,63 @@ static int ensure_published(zg_engine* e) {
   return ZG_OK;
 }
 
+// Runs one group of queued requests under the engine lock.
+static void run_group(zg_engine* e, std::vector<BatchReq*>& group) {
+  std::lock_guard<std::mutex> g(e->mu);
+  int rc = ZG_OK;
+  std::string err;
+  if (e->host_only) {
+    rc = ZG_ECUDA;
+    err = "host-only engine: no CUDA device, and libzgpu has no CPU fallback";
+  } else if (!e->dev.snap) {
+    rc = ZG_ENOSNAPSHOT;
+    err = "no snapshot published (call zg_publish)";
+  } else {
+    e->dev.now = now_of(e);
+    std::vector<Device::HostReq> reqs;
+    reqs.reserve(group.size());
+    for (BatchReq* r : group) reqs.push_back({r->items, r->n, r->out});
+    rc = e->dev.check_host_multi(reqs, &err);
+  }
+  for (BatchReq* r : group) {
+    r->rc = rc;
+    r->err = err;
+  }
+}
+
 extern "C" int zg_check_bulk(zg_engine* e, const zg_check* items, uint64_t n, uint8_t* out) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if ((!items || !out) && n) return fail(ZG_EINVAL, "NULL argument");
-  std::lock_guard<std::mutex> g(e->mu);
-  if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
-  if (!e->dev.snap) return fail(ZG_ENOSNAPSHOT, "no snapshot published (call zg_publish)");
-  e->dev.now = now_of(e);
-  std::string err;
-  int rc = e->dev.check_host(items, n, out, &err);
-  return rc ? fail(rc, err) : ZG_OK;
+  if (n == 0) return ZG_OK;
+  Batcher& b = e->batcher;
+  BatchReq me{items, n, out};
+  std::unique_lock<std::mutex> lk(b.m);
+  b.queue.push_back(&me);
+  while (!me.done) {
+    if (b.leader_active) {
+      b.cv.wait(lk);
+      continue;
+    }
+    // become the leader: take as many queued requests as fit one launch (mine included,
+    // it is somewhere in the queue), answer them, then hand leadership back
+    b.leader_active = true;
+    std::vector<BatchReq*> group;
+    uint64_t total = 0;
+    size_t take = 0;
+    while (take < b.queue.size() && (group.empty() || total + b.queue[take]->n <= Batcher::kMaxItemsPerLaunch)) {
+      total += b.queue[take]->n;
+      group.push_back(b.queue[take++]);
+    }
+    b.queue.erase(b.queue.begin(), b.queue.begin() + static_cast<long>(take));
+    lk.unlock();
+    run_group(e, group);
+    lk.lock();
+    for (BatchReq* r : group) r->done = true;
+    b.leader_active = false;
+    b.cv.notify_all();
+  }
+  lk.unlock();
+  return me.rc ? fail(me.rc, me.err) : ZG_OK;
 }
 
 extern "C" int zg_check_bulk_device(zg_engine* e, const zg_check* d_items, uint64_t n, uint8_t* d_out, void* stream) {
@@ -614,6 +685,8 @@ extern "C" int zg_stats_get(zg_engine* e, zg_stats* out) {
   out->revision = e->revision;
   out->last_alg_bytes = e->dev.last_alg_bytes;
   out->last_kernel_ms = e->dev.last_ms;
+  out->coalesced_launches = e->dev.coalesced_launches;
+  out->coalesced_requests = e->dev.coalesced_requests;
   if (e->dev.snap) {
     out->tuples = e->dev.snap->n_tuples;
     out->snapshot_bytes = e->dev.snap->bytes;

@@ -348,6 +348,54 @@ int Device::check_host(const zg_check* items, uint64_t n, uint8_t* out, std::str
   return ZG_OK;
 }
 
+int Device::check_host_multi(const std::vector<HostReq>& reqs, std::string* err) {
+  if (reqs.size() == 1) return check_host(reqs[0].items, reqs[0].n, reqs[0].out, err);
+  uint64_t total = 0;
+  for (const auto& r : reqs) total += r.n;
+  if (total == 0) return ZG_OK;
+  ZG_CUDA(cudaSetDevice(device));
+  if (!stage_in_.ensure(total * sizeof(zg_check)) || !stage_out_.ensure(total)) {
+    if (err) *err = "out of device memory (staging)";
+    return ZG_ENOMEM;
+  }
+  if (pin_in_cap_ < total * sizeof(zg_check)) {
+    if (pin_in_) cudaFreeHost(pin_in_);
+    pin_in_cap_ = 0;
+    ZG_CUDA(cudaMallocHost(&pin_in_, total * sizeof(zg_check)));
+    pin_in_cap_ = total * sizeof(zg_check);
+  }
+  if (pin_out_cap_ < total) {
+    if (pin_out_) cudaFreeHost(pin_out_);
+    pin_out_cap_ = 0;
+    ZG_CUDA(cudaMallocHost(&pin_out_, total));
+    pin_out_cap_ = total;
+  }
+  uint64_t off = 0;
+  for (const auto& r : reqs) {
+    std::memcpy(static_cast<zg_check*>(pin_in_) + off, r.items, r.n * sizeof(zg_check));
+    off += r.n;
+  }
+  ZG_CUDA(cudaMemcpyAsync(stage_in_.p, pin_in_, total * sizeof(zg_check), cudaMemcpyHostToDevice, stream));
+  int rc = check_device(stage_in_.as<zg_check>(), total, stage_out_.as<uint8_t>(), stream, true, nullptr, err);
+  if (rc) return rc;
+  ZG_CUDA(cudaMemcpyAsync(pin_out_, stage_out_.p, total, cudaMemcpyDeviceToHost, stream));
+  uint32_t flags = 0;
+  ZG_CUDA(cudaMemcpyAsync(&flags, ctrl_.as<unsigned long long>() + 3, 4, cudaMemcpyDeviceToHost, stream));
+  ZG_CUDA(cudaStreamSynchronize(stream));
+  if (flags & 1u) {
+    if (err) *err = "expansion stack overflow (per-warp spill area exhausted)";
+    return ZG_ENOMEM;
+  }
+  off = 0;
+  for (const auto& r : reqs) {
+    std::memcpy(r.out, static_cast<uint8_t*>(pin_out_) + off, r.n);
+    off += r.n;
+  }
+  ++coalesced_launches;
+  coalesced_requests += reqs.size();
+  return ZG_OK;
+}
+
 int Device::lookup(uint16_t res_type, const zg_check& proto, std::vector<uint32_t>* ids, std::string* err) {
   ids->clear();
   std::shared_ptr<Snapshot> s = snap;

@@ -47,12 +47,20 @@ class Device {
   int check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cudaStream_t st, bool raw_items,
                    uint64_t* count_bytes, std::string* err);
   int check_host(const zg_check* items, uint64_t n, uint8_t* out, std::string* err);
+  // Several callers' requests answered by ONE launch sequence (see Batcher in capi.cu).
+  struct HostReq {
+    const zg_check* items;
+    uint64_t n;
+    uint8_t* out;
+  };
+  int check_host_multi(const std::vector<HostReq>& reqs, std::string* err);
   int lookup(uint16_t res_type, const zg_check& proto, std::vector<uint32_t>* ids, std::string* err);
 
   std::shared_ptr<Snapshot> snap;
   cudaStream_t stream = nullptr;
   int device = 0;
   uint64_t launches = 0, passes = 0, checks = 0;
+  uint64_t coalesced_launches = 0, coalesced_requests = 0;  // batcher: launches that served > 1 caller
   double last_ms = 0;
   bool invert = true;  // direction-optimised probes (ZG_FLAG_FORWARD_ONLY / ZGPU_NO_INVERT=1 disable)
   uint32_t now = 0;  // clock for expiration, set by the caller before each hot-path call

@@ -301,3 +301,43 @@ def test_full_size_cfg3_properties(zg):
     assert np.array_equal(got[sample], o.check_bulk(items[sample]))
     st = e.stats()
     assert st["tuples"] == e.num_tuples() and st["launches"] >= 1
+
+
+def test_concurrent_callers_are_coalesced_and_exact(zg):
+    """The proxy calls the boundary from many goroutines at once (pkg/authz/check.go:77-93,
+    pkg/authz/postfilter.go:127-134). Concurrent zg_check_bulk calls must each get exactly
+    their own answers, in order, while the batcher folds them into shared launches."""
+    import threading
+
+    from oracle.pyoracle import Oracle
+    from spicedb_kubeapi_proxy_b200 import workloads
+
+    w = workloads.cfg4(scale=0.001)
+    e, o = zg.Engine(w.schema), Oracle(w.schema)
+    w.load_into(e), w.load_into(o)
+    e.publish()
+    items = w.check_items(e, zg.CHECK_DTYPE)
+    want = o.check_bulk(items)
+    errors = []
+
+    def client(tid):
+        rng = np.random.default_rng(tid)
+        try:
+            for _ in range(40):
+                lo = int(rng.integers(0, items.size - 1))
+                n = int(rng.integers(1, min(3000, items.size - lo)))  # 1-item and list-sized calls
+                got = e.check_bulk(items[lo:lo + n])
+                if not np.array_equal(got, want[lo:lo + n]):
+                    errors.append((tid, lo, n))
+        except Exception as ex:  # noqa: BLE001
+            errors.append((tid, repr(ex)))
+
+    before = e.stats()
+    threads = [threading.Thread(target=client, args=(t,)) for t in range(24)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors[:3]
+    st = e.stats()
+    assert st["checks"] > before["checks"]
+    # informational: how many calls shared a launch
+    print("coalesced", st["coalesced_requests"], "calls into", st["coalesced_launches"], "launches")
