@@ -135,6 +135,7 @@ def cpu_reference_arm(args, rank, world):
         return
     import numpy as np
 
+    import zgpu  # noqa: F401  only registers the package so the workload generators import; libzgpu.so is NOT loaded
     from oracle.pyoracle import CHECK_DTYPE, Oracle
     from spicedb_kubeapi_proxy_b200 import workloads
 
@@ -171,6 +172,9 @@ def cpu_reference_arm(args, rank, world):
 
 
 def main():
+    # keep stdout to the single JSON line (NCCL prints its version banner there at VERSION level)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     args = parse_args()
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
