@@ -47,6 +47,7 @@ Snapshot::~Snapshot() {
   prog.release();
   rrow_ptr.release();
   rcol.release();
+  type_bit_base.release();
   for (auto& r : resources) r.release();
 }
 
@@ -62,6 +63,10 @@ Device::~Device() {
   lk_jobs_.release();
   lk_codes_.release();
   lk_ids_.release();
+  rb_visited_.release();
+  rb_front_[0].release();
+  rb_front_[1].release();
+  rb_cand_.release();
   if (pin_in_) cudaFreeHost(pin_in_);
   if (pin_out_) cudaFreeHost(pin_out_);
   if (ev0_) cudaEventDestroy(ev0_);
@@ -76,6 +81,7 @@ static size_t smem_bytes(uint32_t prog_bytes) {
 
 std::string Device::init(int dev, uint64_t subq_cap, uint32_t budget) {
   if (const char* v = std::getenv("ZGPU_NO_INVERT")) invert = !(*v && *v != '0');
+  if (const char* v = std::getenv("ZGPU_NO_RBFS")) use_rbfs = !(*v && *v != '0');
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)
@@ -117,6 +123,13 @@ std::string Device::publish(const HostSnapshot& h, const Schema& sc, uint64_t re
             up(s->prog, blob.data(), blob.size()) && up(s->rrow_ptr, h.rrow_ptr.data(), h.rrow_ptr.size() * 4) &&
             up(s->rcol, h.rcol.data(), h.rcol.size() * 4);
   if (ok && sc.has_expiry) ok = up(s->exp, h.exp.data(), h.exp.size() * 4);
+  {
+    std::vector<unsigned long long> base(h.n_objects.size() + 1, 0);
+    for (size_t t = 0; t < h.n_objects.size(); ++t) base[t + 1] = base[t] + ((uint64_t(h.n_objects[t]) + 31) & ~31ull);
+    s->total_bits = base.back();
+    s->n_objects = h.n_objects;
+    if (ok) ok = up(s->type_bit_base, base.data(), base.size() * 8);
+  }
   s->resources.resize(h.resources.size());
   s->n_resources.resize(h.resources.size());
   for (size_t t = 0; ok && t < h.resources.size(); ++t) {
@@ -396,6 +409,61 @@ int Device::check_host_multi(const std::vector<HostReq>& reqs, std::string* err)
   return ZG_OK;
 }
 
+int Device::lookup_candidates(const Snapshot& s, uint16_t res_type, const zg_check& proto, uint64_t* n_cand, bool* overflow,
+                              std::string* err) {
+  *overflow = false;
+  *n_cand = 0;
+  const size_t vis_bytes = static_cast<size_t>((s.total_bits + 31) / 32) * 4 + 16;
+  if (!rb_visited_.ensure(vis_bytes) || !rb_front_[0].ensure(rb_cap_ * 8) || !rb_front_[1].ensure(rb_cap_ * 8) ||
+      !rb_cand_.ensure(rb_cap_ * 4)) {
+    *overflow = true;  // not enough memory for the BFS buffers: exhaustive scan instead
+    return ZG_OK;
+  }
+  unsigned long long* ctrl = ctrl_.as<unsigned long long>();  // [4] next_count, [5] cand_count; flags at ctrl+3
+  ZG_CUDA(cudaMemsetAsync(rb_visited_.p, 0, vis_bytes, stream));
+  ZG_CUDA(cudaMemsetAsync(ctrl + 3, 0, 24, stream));
+  const unsigned long long seed = (static_cast<unsigned long long>(proto.stype) << 32) | proto.subj;
+  ZG_CUDA(cudaMemcpyAsync(rb_front_[0].p, &seed, 8, cudaMemcpyHostToDevice, stream));
+  RbfsParams p{};
+  p.rrow_ptr = s.rrow_ptr.as<uint32_t>();
+  p.rcol = s.rcol.as<uint32_t>();
+  p.prog = s.prog.as<uint8_t>();
+  p.visited = rb_visited_.as<uint32_t>();
+  p.type_bit_base = s.type_bit_base.as<unsigned long long>();
+  p.want_type = res_type;
+  p.cand = rb_cand_.as<uint32_t>();
+  p.cand_count = ctrl + 5;
+  p.cand_cap = rb_cap_;
+  p.next_count = ctrl + 4;
+  p.next_cap = rb_cap_;
+  p.flags = reinterpret_cast<uint32_t*>(ctrl + 3);
+  unsigned long long n_in = 1;
+  int cur = 0;
+  for (int level = 0; n_in > 0; ++level) {
+    if (level > ZG_MAX_DEPTH + 1) break;  // deeper objects cannot be within the dispatch cap anyway
+    p.frontier = rb_front_[cur].as<unsigned long long>();
+    p.n_in = n_in;
+    p.next = rb_front_[cur ^ 1].as<unsigned long long>();
+    p.wildcard_level = (level == 0 && proto.srel == kNone) ? 1 : 0;
+    ZG_CUDA(cudaMemsetAsync(ctrl + 4, 0, 8, stream));
+    const unsigned blk = 256;
+    const unsigned long long threads = n_in * 32;
+    rbfs_expand_kernel<<<static_cast<unsigned>((threads + blk - 1) / blk), blk, 0, stream>>>(p);
+    ++launches;
+    unsigned long long host[3];
+    ZG_CUDA(cudaMemcpyAsync(host, ctrl + 3, sizeof host, cudaMemcpyDeviceToHost, stream));
+    ZG_CUDA(cudaStreamSynchronize(stream));
+    if (static_cast<uint32_t>(host[0]) & 16u) {
+      *overflow = true;
+      return ZG_OK;
+    }
+    n_in = host[1];
+    *n_cand = host[2];
+    cur ^= 1;
+  }
+  return ZG_OK;
+}
+
 int Device::lookup(uint16_t res_type, const zg_check& proto, std::vector<uint32_t>* ids, std::string* err) {
   ids->clear();
   std::shared_ptr<Snapshot> s = snap;
@@ -407,16 +475,34 @@ int Device::lookup(uint16_t res_type, const zg_check& proto, std::vector<uint32_
     if (err) *err = "unknown resource type";
     return ZG_EINVAL;
   }
-  const uint64_t n = s->n_resources[res_type];
-  if (n == 0) return ZG_OK;
   ZG_CUDA(cudaSetDevice(device));
+  if (have_last_) ZG_CUDA(cudaStreamWaitEvent(stream, last_done_, 0));
+  // candidates: reverse BFS from the subject (superset of the answer), else every resource of the type
+  uint64_t n = s->n_resources[res_type];
+  const uint32_t* cand = s->resources[res_type].as<uint32_t>();
+  if (n == 0) return ZG_OK;
+  if (use_rbfs && proto.stype < s->n_objects.size()) {
+    uint64_t nc = 0;
+    bool overflow = false;
+    int rc = lookup_candidates(*s, res_type, proto, &nc, &overflow, err);
+    if (rc) return rc;
+    if (!overflow) {
+      ++lookups_rbfs;
+      n = nc;
+      cand = rb_cand_.as<uint32_t>();
+      if (n == 0) return ZG_OK;
+    } else {
+      ++lookups_exhaustive;
+    }
+  } else {
+    ++lookups_exhaustive;
+  }
   const size_t count_off = (n * 4 + 7) & ~size_t(7);  // the result count lives after the ids
   if (!lk_jobs_.ensure(n * sizeof(zg_check)) || !lk_codes_.ensure(n) || !lk_ids_.ensure(count_off + 8)) {
     if (err) *err = "out of device memory (lookup)";
     return ZG_ENOMEM;
   }
   const unsigned blk = 256, grid = static_cast<unsigned>((n + blk - 1) / blk);
-  const uint32_t* cand = s->resources[res_type].as<uint32_t>();
   lookup_fill_kernel<<<grid, blk, 0, stream>>>(cand, n, proto, lk_jobs_.as<zg_check>());
   ++launches;
   int rc = check_device(lk_jobs_.as<zg_check>(), n, lk_codes_.as<uint8_t>(), stream, true, nullptr, err);

@@ -26,7 +26,9 @@ struct DevBuf {
 
 // Immutable once published; shared_ptr keeps it alive for in-flight readers.
 struct Snapshot {
-  DevBuf row_ptr, col, exp, prog, rrow_ptr, rcol;
+  DevBuf row_ptr, col, exp, prog, rrow_ptr, rcol, type_bit_base;
+  std::vector<uint32_t> n_objects;  // per type
+  uint64_t total_bits = 0;          // visited bitmap size for the reverse BFS
   std::vector<DevBuf> resources;  // per type
   std::vector<uint64_t> n_resources;
   uint32_t prog_bytes = 0;
@@ -60,7 +62,9 @@ class Device {
   cudaStream_t stream = nullptr;
   int device = 0;
   uint64_t launches = 0, passes = 0, checks = 0;
-  uint64_t coalesced_launches = 0, coalesced_requests = 0;  // batcher: launches that served > 1 caller
+  uint64_t coalesced_launches = 0, coalesced_requests = 0;
+  uint64_t lookups_rbfs = 0, lookups_exhaustive = 0;
+  bool use_rbfs = true;  // ZGPU_NO_RBFS=1: LookupResources checks every resource of the type  // batcher: launches that served > 1 caller
   double last_ms = 0;
   bool invert = true;  // direction-optimised probes (ZG_FLAG_FORWARD_ONLY / ZGPU_NO_INVERT=1 disable)
   uint32_t now = 0;  // clock for expiration, set by the caller before each hot-path call
@@ -75,6 +79,11 @@ class Device {
   DevBuf spill_, ctrl_;  // ctrl: [0] next, [1] subq_count, [2] alg_bytes, then flags u32
   std::vector<DevBuf> q_, parent_, jobs_, val_;  // per pass level
   DevBuf stage_in_, stage_out_, lk_jobs_, lk_codes_, lk_ids_;
+  DevBuf rb_visited_, rb_front_[2], rb_cand_;
+  uint64_t rb_cap_ = 1ull << 22;  // frontier / candidate capacity before falling back to the exhaustive scan
+  // Reverse-BFS candidates of type res_type for the subject in proto; *overflow -> use the exhaustive list.
+  int lookup_candidates(const Snapshot& s, uint16_t res_type, const zg_check& proto, uint64_t* n_cand, bool* overflow,
+                        std::string* err);
   void* pin_in_ = nullptr;
   void* pin_out_ = nullptr;
   size_t pin_in_cap_ = 0, pin_out_cap_ = 0;

@@ -82,6 +82,8 @@ struct Prog {
   const DTypeInv* type_inv;
   const uint16_t* inv_cls;
   const DStep* steps;
+  const DTypeInv* type_rcls;
+  const uint16_t* rcls;
 };
 
 __device__ __forceinline__ Prog make_prog(const uint8_t* b) {
@@ -100,6 +102,8 @@ __device__ __forceinline__ Prog make_prog(const uint8_t* b) {
   p.type_inv = reinterpret_cast<const DTypeInv*>(b + p.h->off_type_inv);
   p.inv_cls = reinterpret_cast<const uint16_t*>(b + p.h->off_inv_cls);
   p.steps = reinterpret_cast<const DStep*>(b + p.h->off_steps);
+  p.type_rcls = reinterpret_cast<const DTypeInv*>(b + p.h->off_type_rcls);
+  p.rcls = reinterpret_cast<const uint16_t*>(b + p.h->off_rcls);
   return p;
 }
 
@@ -612,6 +616,90 @@ __global__ void fold_kernel(const uint8_t* prog, const zg_check* queries, unsign
     const uint32_t pj = parent[q];
     const uint32_t bits = r == 1 ? kValT : kValE;
     atomicOr(reinterpret_cast<unsigned int*>(parent_val + (pj & ~3u)), bits << (8 * (pj & 3u)));
+  }
+}
+
+// ---- LookupResources: candidate generation by reverse BFS ----------------------------
+//
+// Every true result r of LookupResources(T, P, S) has a forward path r -> o1 -> ... -> ok
+// where each o(i+1) is the subject object of a relationship on o(i) and S is a direct (or
+// wildcard) subject on ok. Walking the reverse CSR from S therefore reaches a SUPERSET of
+// the results (relation names, expiry and & / - are ignored here); the check kernel then
+// verifies every candidate of type T, so the answer is exact for any schema.
+
+struct RbfsParams {
+  const uint32_t* rrow_ptr;
+  const uint32_t* rcol;
+  const uint8_t* prog;
+  const unsigned long long* frontier;  // (type << 32 | object)
+  unsigned long long n_in;
+  unsigned long long* next;            // output frontier
+  unsigned long long* next_count;
+  unsigned long long next_cap;
+  uint32_t* visited;                   // bitmap over all objects, bit = type_bit_base[type] + object
+  const unsigned long long* type_bit_base;
+  uint32_t want_type;                  // candidates of this type go to cand[]
+  uint32_t* cand;
+  unsigned long long* cand_count;
+  unsigned long long cand_cap;
+  uint32_t* flags;                     // bit 4: frontier / candidate overflow
+  int wildcard_level;                  // level 0: also take the wildcard classes of the subject's type
+};
+
+// One warp per frontier object: for every class whose subjects have the object's type,
+// read its reverse row (coalesced) and mark the resources.
+__global__ void __launch_bounds__(256) rbfs_expand_kernel(const RbfsParams p) {
+  const Prog pr = make_prog(p.prog);
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned long long w = (blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x) >> 5;
+  if (w >= p.n_in) return;
+  const unsigned long long item = p.frontier[w];
+  const uint32_t type = static_cast<uint32_t>(item >> 32), obj = static_cast<uint32_t>(item);
+  const DTypeInv tc = pr.type_rcls[type];
+  for (int ci = tc.begin; ci < tc.end; ++ci) {
+    const DCls cl = pr.cls[pr.rcls[ci]];
+    if (cl.flags & CF_EMPTY) continue;
+    uint32_t row = obj;
+    if (cl.sslot == kWildcard) {
+      if (!p.wildcard_level) continue;  // type:* only matches the original, relation-less subject
+      row = 0;
+    } else if (obj >= cl.nsubj) {
+      continue;
+    }
+    const uint32_t b = __ldg(p.rrow_ptr + cl.rrow_base + row), e = __ldg(p.rrow_ptr + cl.rrow_base + row + 1);
+    const unsigned long long bit_base = p.type_bit_base[cl.rtype];
+    for (uint32_t i0 = b; i0 < e; i0 += 32) {
+      const uint32_t i = i0 + lane;
+      bool fresh = false;
+      uint32_t r = 0;
+      if (i < e) {
+        r = __ldg(p.rcol + i);
+        const unsigned long long bit = bit_base + r;
+        const uint32_t mask = 1u << (bit & 31);
+        fresh = !(atomicOr(p.visited + (bit >> 5), mask) & mask);
+      }
+      const unsigned fm = __ballot_sync(kFull, fresh);
+      if (fm) {
+        unsigned long long at = 0;
+        if (lane == 0) at = atomicAdd(p.next_count, static_cast<unsigned long long>(__popc(fm)));
+        at = __shfl_sync(kFull, at, 0) + __popc(fm & ((1u << lane) - 1u));
+        if (fresh) {
+          if (at < p.next_cap) p.next[at] = (static_cast<unsigned long long>(cl.rtype) << 32) | r;
+          else atomicOr(p.flags, 16u);
+        }
+      }
+      const bool is_cand = fresh && cl.rtype == p.want_type;
+      const unsigned cm = __ballot_sync(kFull, is_cand);
+      if (cm) {
+        unsigned long long at = 0;
+        if (lane == 0) at = atomicAdd(p.cand_count, static_cast<unsigned long long>(__popc(cm)));
+        at = __shfl_sync(kFull, at, 0) + __popc(cm & ((1u << lane) - 1u));
+        if (is_cand) {
+          if (at < p.cand_cap) p.cand[at] = r;
+          else atomicOr(p.flags, 16u);
+        }
+      }
+    }
   }
 }
 

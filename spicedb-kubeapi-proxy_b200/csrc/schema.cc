@@ -541,7 +541,7 @@ std::string Schema::compile() {
     for (const auto& c : slots[rs].classes) {
       uint16_t fl = c.expiry ? CF_EXPIRY : 0;
       if (c.sslot == kNone && !c.expiry) fl |= CF_INVERT;
-      d_cls.push_back(DCls{c.stype, c.sslot, fl, static_cast<uint16_t>(slots[rs].rel_index), 0, 0, 0});
+      d_cls.push_back(DCls{c.stype, c.sslot, fl, static_cast<uint16_t>(slots[rs].rel_index), 0, slots[rs].type, 0, 0});
     }
   d_type_inv.assign(types.size(), DTypeInv{0, 0});
   d_inv_cls.clear();
@@ -550,6 +550,14 @@ std::string Schema::compile() {
     for (size_t c = 0; c < d_cls.size(); ++c)
       if ((d_cls[c].flags & CF_INVERT) && d_cls[c].stype == t) d_inv_cls.push_back(static_cast<uint16_t>(c));
     d_type_inv[t].end = static_cast<uint16_t>(d_inv_cls.size());
+  }
+  d_type_rcls.assign(types.size(), DTypeInv{0, 0});
+  d_rcls.clear();
+  for (size_t t = 0; t < types.size(); ++t) {
+    d_type_rcls[t].begin = static_cast<uint16_t>(d_rcls.size());
+    for (size_t c = 0; c < d_cls.size(); ++c)
+      if (d_cls[c].stype == t) d_rcls.push_back(static_cast<uint16_t>(c));
+    d_type_rcls[t].end = static_cast<uint16_t>(d_rcls.size());
   }
   return "";
 }
@@ -648,6 +656,8 @@ std::vector<uint8_t> Schema::blob(const std::vector<DRel>& rels, const std::vect
   put(d_leaf_units.data(), d_leaf_units.size() * 2, &h.off_leaf_units);
   put(d_type_inv.data(), d_type_inv.size() * sizeof(DTypeInv), &h.off_type_inv);
   put(d_inv_cls.data(), d_inv_cls.size() * 2, &h.off_inv_cls);
+  put(d_type_rcls.data(), d_type_rcls.size() * sizeof(DTypeInv), &h.off_type_rcls);
+  put(d_rcls.data(), d_rcls.size() * 2, &h.off_rcls);
   h.off_reach = 0;
   out.resize((out.size() + 15) & ~size_t(15));
   h.total_bytes = static_cast<uint32_t>(out.size());

@@ -88,7 +88,8 @@ struct DCls {
   uint16_t flags;      // ClsFlags
   uint16_t rel;        // data relation index this class belongs to
   uint32_t nsubj;      // reverse CSR: subject objects covered (1 for a wildcard class)
-  uint32_t pad;
+  uint16_t rtype;      // type of the resources of this class
+  uint16_t pad;
   uint64_t rrow_base;  // reverse CSR: index into rrow_ptr of (subject 0) for this class
 };
 struct DTypeInv {  // per subject type: the invertible direct classes (inv_cls[begin, end))
@@ -108,6 +109,7 @@ struct DHeader {  // first bytes of the blob; offsets in bytes from blob start
   uint32_t off_slots, off_units, off_ops, off_rels, off_cls, off_tgts, off_members;
   uint32_t off_trees, off_tree_ops, off_leaf_units, off_reach;
   uint32_t off_type_inv, off_inv_cls, off_steps, n_steps;
+  uint32_t off_type_rcls, off_rcls;  // per subject type: every class whose subjects have that type
   uint32_t max_leaves;   // job stride L in general mode (1 if no non-pure slot)
   uint32_t has_nonpure;
   uint32_t has_expiry;
@@ -175,8 +177,8 @@ class Schema {
   // Serialises the program; DRel rows (row_base, nres) come from the store.
   // cls: per-class dynamic data from the store (rrow_base, CF_EMPTY), same order as d_cls.
   std::vector<uint8_t> blob(const std::vector<DRel>& rels, const std::vector<DCls>& cls) const;
-  std::vector<DTypeInv> d_type_inv;
-  std::vector<uint16_t> d_inv_cls;
+  std::vector<DTypeInv> d_type_inv, d_type_rcls;
+  std::vector<uint16_t> d_inv_cls, d_rcls;
 
  private:
   std::string compile();

@@ -341,3 +341,40 @@ def test_concurrent_callers_are_coalesced_and_exact(zg):
     assert st["checks"] > before["checks"]
     # informational: how many calls shared a launch
     print("coalesced", st["coalesced_requests"], "calls into", st["coalesced_launches"], "launches")
+
+
+@pytest.mark.parametrize("name,scale", [("cfg2", 0.02), ("cfg3", 0.01), ("cfg4", 0.002)])
+def test_lookup_resources_reverse_bfs_equals_exhaustive_and_oracle(zg, name, scale, monkeypatch):
+    """LookupResources = reverse-BFS candidates (a superset) verified by the check kernel.
+    It must equal both the exhaustive scan of every resource of the type and the oracle's
+    definition (pkg/authz/lookups.go:49-88 consumes it as a set)."""
+    from oracle.pyoracle import Oracle
+    from spicedb_kubeapi_proxy_b200 import workloads
+
+    w = workloads.by_name(name, scale)
+    e = zg.Engine(w.schema)
+    monkeypatch.setenv("ZGPU_NO_RBFS", "1")
+    e_ex = zg.Engine(w.schema)
+    monkeypatch.delenv("ZGPU_NO_RBFS")
+    o = Oracle(w.schema)
+    for t in (e, e_ex, o):
+        w.load_into(t)
+    e.publish(), e_ex.publish()
+    rng = np.random.default_rng(11)
+    rt, perm, st, _ = w.lookups[0]
+    perms = [perm] + (["restricted_view", "edit"] if name == "cfg4" else [])
+    n_users = max(g.subj.max() for g in w.groups if g.subj_type == st and not g.wildcard) + 1
+    nonempty = 0
+    for p in perms:
+        for u in list(rng.integers(0, n_users, 12)) + [n_users + 5]:  # incl. a never-written subject
+            a = e.lookup_resources_ids(rt, p, st, int(u))
+            b = e_ex.lookup_resources_ids(rt, p, st, int(u))
+            c = o.lookup_resources_ids(rt, p, st, int(u))
+            assert np.array_equal(a, b) and np.array_equal(a, c), (name, p, u, a.size, b.size, c.size)
+            nonempty += a.size > 0
+    assert nonempty > 0
+    if name == "cfg4":  # userset subject: group:g#member
+        for g in rng.integers(0, 50, 4):
+            a = e.lookup_resources_ids("document", "view", "group", int(g), srel="member")
+            c = o.lookup_resources_ids("document", "view", "group", int(g), srel="member")
+            assert np.array_equal(a, c)
