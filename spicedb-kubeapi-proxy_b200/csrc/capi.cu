@@ -710,7 +710,7 @@ extern "C" int zg_debug_row(zg_engine* e, uint16_t rel_slot, uint32_t res, uint3
   *n_out = 0;
   if (cls >= r.ncls) return fail(ZG_EINVAL, "class out of range");
   if (res >= r.nres) return ZG_OK;
-  uint64_t idx = r.row_base + uint64_t(res) * r.ncls + cls;
+  uint64_t idx = r.row_base + uint64_t(res) * r.stride + cls;
   uint32_t b = e->last_built.row_ptr[idx], en = e->last_built.row_ptr[idx + 1];
   *n_out = en - b;
   if (en - b > cap) return ZG_E2BIG;

@@ -201,6 +201,28 @@ __device__ __forceinline__ bool probe(const KParams& p, WarpCtx<COUNT>& c, uint3
   return false;
 }
 
+// Two independent binary searches advanced in lock step (two loads in flight per lane).
+template <bool COUNT>
+__device__ __forceinline__ void probe2(const KParams& p, WarpCtx<COUNT>& c, uint32_t lo0, uint32_t hi0, uint32_t k0,
+                                       uint32_t lo1, uint32_t hi1, uint32_t k1, bool& hit0, bool& hit1) {
+  while (lo0 < hi0 || lo1 < hi1) {
+    const bool a0 = lo0 < hi0, a1 = lo1 < hi1;
+    const uint32_t m0 = lo0 + ((hi0 - lo0) >> 1), m1 = lo1 + ((hi1 - lo1) >> 1);
+    uint32_t v0 = 0, v1 = 0;
+    if (a0) v0 = __ldg(p.col + m0);
+    if (a1) v1 = __ldg(p.col + m1);
+    if (COUNT) c.bytes += 4u * (a0 + a1);
+    if (a0) {
+      if (v0 == k0) { hit0 = true; lo0 = hi0; }
+      else if (v0 < k0) lo0 = m0 + 1; else hi0 = m0;
+    }
+    if (a1) {
+      if (v1 == k1) { hit1 = true; lo1 = hi1; }
+      else if (v1 < k1) lo1 = m1 + 1; else hi1 = m1;
+    }
+  }
+}
+
 // Boundaries of a job's reverse-row set per invertible class of its subject type:
 // 5 bits each (0..16), boundary i at bit 5*i; class i owns entries [b_i, b_{i+1}).
 __device__ __forceinline__ uint32_t cst_at(unsigned long long cst, uint32_t i) {
@@ -427,42 +449,63 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const KParams p) {
         if (static_cast<int>(lane) >= d) incl += v;
       }
       const uint32_t excl = incl - len;
-      const unsigned fullm = __ballot_sync(kFull, static_cast<int>(lane) < n && incl <= 32u);
+      const uint32_t W = leaf_mode ? 64u : 32u;  // LEAF iterations run two pairs per lane
+      const unsigned fullm = __ballot_sync(kFull, static_cast<int>(lane) < n && incl <= W);
       const int nfull = __popc(fullm);  // prefix of fully consumed items
       uint32_t total = __shfl_sync(kFull, incl, 31);
-      if (total > 32u) total = 32u;
+      if (total > W) total = W;
       __syncwarp();
       if (static_cast<int>(lane) == nfull && static_cast<int>(lane) < n) {  // partially consumed item stays on top
-        if (leaf_mode) c.stack[c.top - 1 - lane].w = it.w + ((32u - excl) << 8);
-        else c.stack[c.top - 1 - lane].x = it.x + (32u - excl);
+        if (leaf_mode) c.stack[c.top - 1 - lane].w = it.w + ((W - excl) << 8);
+        else c.stack[c.top - 1 - lane].x = it.x + (W - excl);
       }
       c.top -= nfull;
       __syncwarp();
-      // ---- lane k takes work unit k: owner item j = #items with incl <= k
-      int j = 0;
+      // ---- lane k takes work unit k (and k + 32 in LEAF mode): owner item j = #items with incl <= k
+      auto owner = [&](uint32_t u) -> int {
+        int j = 0;
 #pragma unroll
-      for (int step = 16; step >= 1; step >>= 1) {
-        const int probe_lane = j + step - 1;
-        const uint32_t v = __shfl_sync(kFull, incl, probe_lane & 31);
-        if (probe_lane < 32 && v <= lane) j += step;
+        for (int step = 16; step >= 1; step >>= 1) {
+          const int probe_lane = j + step - 1;
+          const uint32_t v = __shfl_sync(kFull, incl, probe_lane & 31);
+          if (probe_lane < 32 && v <= u) j += step;
+        }
+        return j;
+      };
+      if (leaf_mode) {
+        uint32_t lo[2], hi[2], key[2], js[2];
+        bool act[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t u = lane + 32u * h;
+          const int j = owner(u);
+          lo[h] = __shfl_sync(kFull, it.x, j & 31);
+          hi[h] = __shfl_sync(kFull, it.y, j & 31);
+          const uint32_t jm = __shfl_sync(kFull, it.z, j & 31);
+          const uint32_t jw = __shfl_sync(kFull, it.w, j & 31);
+          const uint32_t jx = __shfl_sync(kFull, excl, j & 31);
+          js[h] = jm & 31u;
+          const unsigned long long jcst = __shfl_sync(kFull, c.my_cst, js[h]);
+          act[h] = u < total;
+          key[h] = 0;
+          if (act[h]) {
+            const uint32_t r = cst_at(jcst, jw & 0xFFu) + (jw >> 8) + (u - jx);
+            key[h] = static_cast<uint32_t>(c.rset[r * 32 + js[h]]);
+          } else {
+            hi[h] = lo[h];  // empty search
+          }
+        }
+        bool hit0 = false, hit1 = false;
+        probe2(p, c, lo[0], hi[0], key[0], lo[1], hi[1], key[1], hit0, hit1);
+        c.found |= __reduce_or_sync(kFull, (hit0 ? (1u << js[0]) : 0u) | (hit1 ? (1u << js[1]) : 0u));
+        continue;
       }
+      const int j = owner(lane);
       const uint32_t jb = __shfl_sync(kFull, it.x, j & 31);
       const uint32_t jmeta = __shfl_sync(kFull, it.z, j & 31);
       const uint32_t jexcl = __shfl_sync(kFull, excl, j & 31);
       bool active = lane < total;
       const uint32_t jslot = jmeta & 31u, cdepth = (jmeta >> 5) & 63u, tslot = jmeta >> 16;
-      if (leaf_mode) {
-        const uint32_t je = __shfl_sync(kFull, it.y, j & 31);
-        const uint32_t jw = __shfl_sync(kFull, it.w, j & 31);
-        const unsigned long long jcst = __shfl_sync(kFull, c.my_cst, jslot);
-        bool hit = false;
-        if (active) {
-          const uint32_t r = cst_at(jcst, jw & 0xFFu) + (jw >> 8) + (lane - jexcl);
-          hit = probe(p, c, jb, je, static_cast<uint32_t>(c.rset[r * 32 + jslot]), false);
-        }
-        c.found |= __reduce_or_sync(kFull, hit ? (1u << jslot) : 0u);
-        continue;
-      }
       uint32_t child = 0;
       const uint32_t sq_subj = __shfl_sync(kFull, c.my_subj, jslot);
       const uint32_t sq_ss = __shfl_sync(kFull, c.my_ss, jslot);

@@ -598,7 +598,7 @@ std::vector<uint8_t> Schema::blob(const std::vector<DRel>& rels, const std::vect
         DStep st{};
         st.row_base = r.row_base + k;
         st.nres = r.nres;
-        st.ncls = r.ncls;
+        st.ncls = static_cast<uint16_t>(r.stride);
         st.flags = c.flags;
         st.gc = static_cast<uint16_t>(r.cls_begin + k);
         st.stype = c.stype;

@@ -58,7 +58,7 @@ enum StepKind : uint16_t { ST_DIRECT = 0, ST_WILD = 1, ST_PUSH = 2 };
 struct DStep {
   uint64_t row_base;  // row_ptr index of (object 0, this class): rel.row_base + k
   uint32_t nres;      // objects covered by the relation's row table
-  uint16_t ncls;      // row stride
+  uint16_t ncls;      // row stride per object (all classes of the resource type)
   uint16_t kind;      // StepKind
   uint16_t stype;     // ST_DIRECT / ST_WILD: subject type that can match
   uint16_t tslot;     // ST_PUSH: slot the children are visited at
@@ -76,11 +76,14 @@ struct DOp {
   uint16_t tgt_begin;  // OP_ARROW: tgts[tgt_begin + class] = child slot or kNone
   uint16_t pad;
 };
-struct DRel {    // data relation: rows of (object x class)
-  uint64_t row_base;   // index into row_ptr pool of (object 0, class 0)
+struct DRel {    // data relation: rows of (object x class). All relations of one resource type
+                 // are interleaved per object, so one object's offsets share a sector or two.
+  uint64_t row_base;   // index into row_ptr pool of (object 0, class 0 of this relation)
   uint32_t nres;       // objects covered
-  uint16_t ncls;
+  uint16_t ncls;       // classes of this relation
   uint16_t cls_begin;  // into classes[]
+  uint32_t stride;     // classes of ALL relations of the resource type = row stride per object
+  uint32_t pad;
 };
 struct DCls {
   uint16_t stype;

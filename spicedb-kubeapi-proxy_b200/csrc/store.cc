@@ -205,17 +205,24 @@ HostSnapshot Store::build() const {
   for (size_t t = 0; t < nt; ++t)
     h.n_objects[t] = std::max<uint32_t>(static_cast<uint32_t>(objs_[t].names.size()), objs_[t].n_numeric);
 
-  uint64_t pool = 0;
+  // row table: per resource type, objects x (all classes of all relations of the type)
+  std::vector<uint32_t> type_ncls(nt, 0);
+  for (int rs : sc.rel_slots) type_ncls[sc.slots[rs].type] += static_cast<uint32_t>(sc.slots[rs].classes.size());
+  std::vector<uint64_t> type_base(nt + 1, 0);
+  for (size_t t = 0; t < nt; ++t) type_base[t + 1] = type_base[t] + uint64_t(h.n_objects[t]) * type_ncls[t];
+  const uint64_t pool = type_base[nt];
+  std::vector<uint32_t> type_used(nt, 0);
   uint16_t cls_begin = 0;
   for (int rs : sc.rel_slots) {
     const SlotInfo& s = sc.slots[rs];
     DRel r{};
-    r.row_base = pool;
+    r.row_base = type_base[s.type] + type_used[s.type];
     r.nres = h.n_objects[s.type];
     r.ncls = static_cast<uint16_t>(s.classes.size());
+    r.stride = type_ncls[s.type];
     r.cls_begin = cls_begin;
     cls_begin = static_cast<uint16_t>(cls_begin + r.ncls);
-    pool += uint64_t(r.nres) * r.ncls;
+    type_used[s.type] += r.ncls;
     h.rels.push_back(r);
   }
   h.row_ptr.assign(pool + 1, 0);
@@ -225,7 +232,7 @@ HostSnapshot Store::build() const {
   auto row_index = [&](const zg_tuple& t) -> uint64_t {
     const DRel& r = h.rels[sc.slots[t.rel].rel_index];
     int k = sc.class_of(t.rel, t.stype, t.srel);
-    return r.row_base + uint64_t(t.res) * r.ncls + static_cast<uint64_t>(k);
+    return r.row_base + uint64_t(t.res) * r.stride + static_cast<uint64_t>(k);
   };
 
   std::vector<std::vector<uint8_t>> seen(nt);
@@ -315,7 +322,7 @@ HostSnapshot Store::build() const {
     for (const DRel& r : h.rels)
       for (uint32_t res = 0; res < r.nres; ++res)
         for (uint32_t k = 0; k < r.ncls; ++k) {
-          const uint64_t idx = r.row_base + uint64_t(res) * r.ncls + k;
+          const uint64_t idx = r.row_base + uint64_t(res) * r.stride + k;
           const uint32_t b = h.row_ptr[idx], e = h.row_ptr[idx + 1];
           if (b == e) continue;
           DCls& c = h.cls[r.cls_begin + k];
