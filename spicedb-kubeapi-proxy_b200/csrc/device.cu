@@ -56,6 +56,7 @@ Device::~Device() {
   snap.reset();
   spill_.release();
   ctrl_.release();
+  memo_.release();
   for (auto* v : {&q_, &parent_, &jobs_, &val_})
     for (auto& b : *v) b.release();
   stage_in_.release();
@@ -159,6 +160,8 @@ std::string Device::publish(const HostSnapshot& h, const Schema& sc, uint64_t re
   blocks_per_sm_count_ = occ_c;
   size_t warps = static_cast<size_t>(sm_count_) * std::max(occ, occ_c) * kWarpsPerBlock;
   if (!spill_.ensure(warps * spill_cap_ * sizeof(uint4))) return "out of device memory (spill areas)";
+  if (const char* v = std::getenv("ZGPU_MEMO_AFTER")) memo_after_ = static_cast<uint32_t>(std::atoi(v));
+  if (!memo_.ensure(warps * memo_entries_ * sizeof(unsigned long long))) memo_entries_ = 0;  // optional
   // readers that already hold the old snapshot keep it alive until they finish
   snap = s;
   return "";
@@ -192,6 +195,9 @@ int Device::run_pass(const Snapshot& s, const zg_check* jobs, uint64_t njobs, ui
   p.now = now;
   p.budget = budget_;
   p.raw_items = raw;
+  p.memo = memo_.as<unsigned long long>();
+  p.memo_entries = memo_.p ? memo_entries_ : 0;
+  p.memo_after = memo_after_;
   ZG_CUDA(cudaMemsetAsync(ctrl, 0, 16, st));  // next, subq_count
   const int per_sm = count ? blocks_per_sm_count_ : blocks_per_sm_;
   uint64_t want = (njobs + kThreads - 1) / kThreads;

@@ -76,7 +76,8 @@ class Device {
   int sm_count_ = 0, blocks_per_sm_ = 0, blocks_per_sm_count_ = 0;
   uint32_t spill_cap_ = 4096, budget_ = 1u << 20;
   uint64_t subq_cap_ = 1ull << 22;
-  DevBuf spill_, ctrl_;  // ctrl: [0] next, [1] subq_count, [2] alg_bytes, then flags u32
+  DevBuf spill_, ctrl_, memo_;
+  uint32_t memo_entries_ = 8192, memo_after_ = 2048;  // ctrl: [0] next, [1] subq_count, [2] alg_bytes, then flags u32
   std::vector<DevBuf> q_, parent_, jobs_, val_;  // per pass level
   DevBuf stage_in_, stage_out_, lk_jobs_, lk_codes_, lk_ids_;
   DevBuf rb_visited_, rb_front_[2], rb_cand_;

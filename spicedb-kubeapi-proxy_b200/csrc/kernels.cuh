@@ -64,6 +64,11 @@ struct KParams {
   uint32_t now;
   uint32_t budget;
   int raw_items;  // jobs are caller-supplied zg_check items: flags are ignored
+  // Per-warp lossy memo of (job, slot, object, depth) child visits, switched on only for
+  // batches that run long (DAG-shaped data multiplies paths; see DESIGN.md "Path memo").
+  unsigned long long* memo;
+  uint32_t memo_entries;  // per warp, power of two (0 = disabled)
+  uint32_t memo_after;    // iterations before the memo is switched on for a batch
   unsigned long long* alg_bytes;  // COUNT variant only
 };
 
@@ -409,6 +414,8 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const KParams p) {
     visit(p, pr, c, valid && !bad, lane, obj, unit, depth);
 
     uint32_t iters = 0;
+    bool use_memo = false;
+    unsigned long long* memo = p.memo + (static_cast<size_t>(blockIdx.x) * kWarpsPerBlock + warp) * p.memo_entries;
     for (;;) {
       if (!c.fatal && c.top == 0) {
         if (c.spill_top == 0) break;
@@ -419,6 +426,13 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const KParams p) {
         if (lane == 0) atomicOr(p.flags, c.fatal ? 1u : 4u);
         c.err |= live_jobs & ~c.found;
         break;
+      }
+      if (!use_memo && p.memo_entries && iters > p.memo_after) {
+        // this batch is expanding far more than usual: path multiplicity. Remember child
+        // visits from here on; an identical (job, slot, object, depth) visit is skipped.
+        for (uint32_t i = lane; i < p.memo_entries; i += 32) memo[i] = 0ull;
+        __syncwarp();
+        use_memo = true;
       }
       // ---- pop work worth <= 32 lanes from the top of the stack. The top item decides
       // the mode: EDGE items contribute one lane per edge (child visit), LEAF items one
@@ -523,6 +537,17 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const KParams p) {
       const bool too_deep = active && cdepth > ZG_MAX_DEPTH;
       c.err |= __reduce_or_sync(kFull, too_deep ? (1u << jslot) : 0u);
       active = active && !too_deep;
+      if (use_memo && active) {
+        // exact key (a visit at another depth has another hop budget, so depth is part of it);
+        // direct-mapped and lossy: a lost entry only costs a repeated visit
+        const unsigned long long key = (1ull << 59) | (static_cast<unsigned long long>(jslot) << 54) |
+                                       (static_cast<unsigned long long>(cdepth) << 48) |
+                                       (static_cast<unsigned long long>(tslot) << 32) | child;
+        unsigned long long hsh = key * 0x9E3779B97F4A7C15ull;
+        const uint32_t at = static_cast<uint32_t>(hsh >> 40) & (p.memo_entries - 1u);
+        if (memo[at] == key) active = false;
+        else memo[at] = key;
+      }
       uint32_t cunit = 0;
       if (active) {
         const DSlot s = pr.slots[tslot];

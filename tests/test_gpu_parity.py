@@ -378,3 +378,74 @@ def test_lookup_resources_reverse_bfs_equals_exhaustive_and_oracle(zg, name, sca
             a = e.lookup_resources_ids("document", "view", "group", int(g), srel="member")
             c = o.lookup_resources_ids("document", "view", "group", int(g), srel="member")
             assert np.array_equal(a, c)
+
+
+def _layered_dag(layers, width, fan, seed):
+    """group layers: every group of layer l includes `fan` random groups of layer l+1 (as
+    group#member usersets); users sit in the last layer. Path multiplicity ~ fan**layers."""
+    rng = np.random.default_rng(seed)
+    par, chi = [], []
+    for l in range(layers - 1):
+        for g in range(width):
+            for c in rng.choice(width, size=fan, replace=False):
+                par.append(l * width + g)
+                chi.append((l + 1) * width + int(c))
+    last = (layers - 1) * width
+    gm_g = np.repeat(np.arange(last, last + width), 2)
+    gm_u = rng.integers(0, 64, gm_g.size)
+    return np.array(par, np.uint32), np.array(chi, np.uint32), gm_g.astype(np.uint32), gm_u.astype(np.uint32)
+
+
+NEST = "definition user {}\ndefinition group { relation member: user | group#member }\n"
+
+
+def test_path_memo_keeps_dag_blowup_exact(zg, monkeypatch):
+    """Cache-off forward evaluation multiplies work by the number of PATHS. With the memo
+    switched on early the GPU must still equal the oracle bit for bit (moderate DAG the
+    oracle can finish), i.e. skipping repeated (job, slot, object, depth) visits is exact."""
+    from oracle.pyoracle import Oracle
+
+    par, chi, gm_g, gm_u = _layered_dag(layers=7, width=8, fan=3, seed=1)  # ~3^6 = 729 paths / check
+    monkeypatch.setenv("ZGPU_MEMO_AFTER", "4")
+    e = zg.Engine(NEST)
+    monkeypatch.delenv("ZGPU_MEMO_AFTER")
+    e_plain, o = zg.Engine(NEST), Oracle(NEST)
+    for t in (e, e_plain, o):
+        t.add_bulk("group", "member", "group", par, chi, srel="member")
+        t.add_bulk("group", "member", "user", gm_g, gm_u)
+    e.publish(), e_plain.publish()
+    items = np.zeros(8 * 80, dtype=zg.CHECK_DTYPE)
+    items["res"] = np.repeat(np.arange(8), 80)  # top-layer groups
+    items["subj"] = np.tile(np.arange(80), 8)   # users 64..79 are members of nothing
+    items["perm"], items["stype"], items["srel"] = e.slot_id("group", "member"), e.type_id("user"), 0xFFFF
+    want = o.check_bulk(items)
+    assert np.array_equal(e.check_bulk(items), want)
+    assert np.array_equal(e_plain.check_bulk(items), want)
+    assert 0.05 < (want == 2).mean() < 0.999
+
+
+def test_path_memo_bounds_work_on_deep_dags(zg):
+    """3^14 = 4.8 M paths per check: far beyond what path enumeration finishes inside the work
+    budget, but only 15 x 8 distinct (object, depth) nodes. Ground truth is plain
+    reachability (numpy); the engine must answer every check, without budget errors."""
+    L, Wd = 15, 8
+    par, chi, gm_g, gm_u = _layered_dag(layers=L, width=Wd, fan=3, seed=2)
+    e = zg.Engine(NEST)
+    e.add_bulk("group", "member", "group", par, chi, srel="member")
+    e.add_bulk("group", "member", "user", gm_g, gm_u)
+    e.publish()
+    n = L * Wd
+    reach = np.zeros((n, 80), dtype=bool)
+    reach[gm_g, gm_u] = True
+    for l in range(L - 2, -1, -1):  # propagate memberships up the layers
+        for p_, c_ in zip(par, chi):
+            if p_ // Wd == l:
+                reach[p_] |= reach[c_]
+    items = np.zeros(Wd * 80, dtype=zg.CHECK_DTYPE)
+    items["res"] = np.repeat(np.arange(Wd), 80)
+    items["subj"] = np.tile(np.arange(80), Wd)
+    items["perm"], items["stype"], items["srel"] = e.slot_id("group", "member"), e.type_id("user"), 0xFFFF
+    got = e.check_bulk(items)
+    want = np.where(reach[items["res"], items["subj"]], 2, 1)
+    assert not (got == 255).any(), "work budget hit: the path memo did not bound the expansion"
+    assert np.array_equal(got, want)
