@@ -55,7 +55,8 @@ class _Stats(C.Structure):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libzgpu.so")
+    # ZGPU_LIB selects an alternative build of the same sources (tuning experiments)
+    return os.environ.get("ZGPU_LIB") or os.path.join(_HERE, "libzgpu.so")
 
 
 def build_library(force: bool = False) -> str:
@@ -65,6 +66,8 @@ def build_library(force: bool = False) -> str:
     srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cc", ".h", ".cuh"))]
     srcs.append(os.path.join(_ROOT, "include", "zgpu.h"))
     stale = not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if os.environ.get("ZGPU_LIB"):
+        stale = force = False  # explicitly chosen library: use as is
     if force or stale:
         if not os.path.exists("/usr/local/cuda/bin/nvcc"):
             if os.path.exists(so):

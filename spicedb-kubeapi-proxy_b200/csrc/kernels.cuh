@@ -29,9 +29,13 @@ namespace zg {
 
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
+#ifndef ZG_MIN_BLOCKS
+#define ZG_MIN_BLOCKS 4
+#endif
+constexpr int kMinBlocks = ZG_MIN_BLOCKS;  // resident CTAs per SM the register budget is tuned for
 constexpr int kStackCap = 128;        // range items per warp in shared memory
 constexpr int kRsetCap = 16;          // reverse-row entries kept per check (subject's direct memberships)
-constexpr size_t kWarpSmem = kStackCap * sizeof(uint4) + kRsetCap * 32 * sizeof(unsigned long long);
+constexpr size_t kWarpSmem = kStackCap * sizeof(uint4) + kRsetCap * 32 * sizeof(uint32_t);
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint16_t kJobIsUnit = 0x8000;  // zg_check.flags: perm field is a unit id
 constexpr uint16_t kJobDepthMask = 0x00FF;
@@ -129,9 +133,10 @@ struct WarpCtx {
   uint32_t spill_cap;
   unsigned found, err;  // warp-uniform, indexed by job slot
   uint32_t my_subj, my_ss;  // this lane's own job: subject id, stype<<16 | srel
-  // Direction-optimised probes: rset[i * 32 + job] = (class << 32 | resource) for every
-  // direct relationship of the job's subject (its reverse rows), when there are <= kRsetCap.
-  unsigned long long* rset;
+  // Direction-optimised probes: rset[i * 32 + job] = resource id of every direct relationship
+  // of the job's subject (its reverse rows), grouped by class (boundaries in my_cst), when
+  // there are <= kRsetCap.
+  uint32_t* rset;
   unsigned long long my_cst;  // class boundaries of this lane's own job (see cst_at)
   unsigned inv_mask;  // jobs whose reverse rows fit
   unsigned long long bytes;
@@ -270,7 +275,7 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
         // direction-optimised probe: is obj among the subject's memberships of this class?
         const uint32_t kb = cst_at(cst, st.tinv), ke = cst_at(cst, st.tinv + 1u);
         for (uint32_t r = kb; r < ke; ++r)
-          hit = hit || static_cast<uint32_t>(c.rset[r * 32 + (jslot & 31)]) == obj;
+          hit = hit || c.rset[r * 32 + (jslot & 31)] == obj;
       } else if ((st.kind == ST_PUSH || subject_fits) && obj < st.nres) {
         const unsigned long long ridx = st.row_base + static_cast<unsigned long long>(obj) * st.ncls;
         const uint32_t lo = __ldg(p.row_ptr + ridx), hi = __ldg(p.row_ptr + ridx + 1);
@@ -315,7 +320,7 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(kThreads, 4) check_kernel(const KParams p) {
+__global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   for (uint32_t i = threadIdx.x; i < p.prog_bytes / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(p.prog)[i];
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const KParams p) {
   c.lane = lane;
   uint8_t* wsm = smem + p.prog_bytes + warp * kWarpSmem;
   c.stack = reinterpret_cast<uint4*>(wsm);
-  c.rset = reinterpret_cast<unsigned long long*>(wsm + kStackCap * sizeof(uint4));
+  c.rset = reinterpret_cast<uint32_t*>(wsm + kStackCap * sizeof(uint4));
   c.spill = p.spill + (static_cast<size_t>(blockIdx.x) * kWarpsPerBlock + warp) * p.spill_cap;
   c.spill_cap = p.spill_cap;
   c.bytes = 0;
@@ -391,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const KParams p) {
               inv = false;  // too many memberships: this check probes forward
             } else {
               for (uint32_t x = b; x < e; ++x) {
-                c.rset[rcnt * 32 + lane] = (static_cast<unsigned long long>(gc) << 32) | __ldg(p.rcol + x);
+                c.rset[rcnt * 32 + lane] = __ldg(p.rcol + x);
                 ++rcnt;
               }
               if (COUNT) c.bytes += 4ull * (e - b);
@@ -504,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const KParams p) {
           key[h] = 0;
           if (act[h]) {
             const uint32_t r = cst_at(jcst, jw & 0xFFu) + (jw >> 8) + (u - jx);
-            key[h] = static_cast<uint32_t>(c.rset[r * 32 + js[h]]);
+            key[h] = c.rset[r * 32 + js[h]];
           } else {
             hi[h] = lo[h];  // empty search
           }
