@@ -76,45 +76,29 @@ struct KParams {
   unsigned long long* alg_bytes;  // COUNT variant only
 };
 
+// View of the program blob. Only the base pointer is kept in registers; table addresses are
+// formed from the header offsets on use (sixteen live 64-bit pointers cost 32 registers).
 struct Prog {
-  const DHeader* h;
-  const DSlot* slots;
-  const DUnit* units;
-  const DOp* ops;
-  const DRel* rels;
-  const DCls* cls;
-  const uint16_t* tgts;
-  const uint16_t* members;
-  const DTree* trees;
-  const DTreeOp* tree_ops;
-  const uint16_t* leaf_units;
-  const DTypeInv* type_inv;
-  const uint16_t* inv_cls;
-  const DStep* steps;
-  const DTypeInv* type_rcls;
-  const uint16_t* rcls;
+  const uint8_t* b;
+  __device__ __forceinline__ const DHeader* hdr() const { return reinterpret_cast<const DHeader*>(b); }
+#define ZG_TABLE(name, type, field) \
+  __device__ __forceinline__ const type* name() const { return reinterpret_cast<const type*>(b + hdr()->field); }
+  ZG_TABLE(slots, DSlot, off_slots)
+  ZG_TABLE(units, DUnit, off_units)
+  ZG_TABLE(cls, DCls, off_cls)
+  ZG_TABLE(members, uint16_t, off_members)
+  ZG_TABLE(trees, DTree, off_trees)
+  ZG_TABLE(tree_ops, DTreeOp, off_tree_ops)
+  ZG_TABLE(leaf_units, uint16_t, off_leaf_units)
+  ZG_TABLE(type_inv, DTypeInv, off_type_inv)
+  ZG_TABLE(inv_cls, uint16_t, off_inv_cls)
+  ZG_TABLE(steps, DStep, off_steps)
+  ZG_TABLE(type_rcls, DTypeInv, off_type_rcls)
+  ZG_TABLE(rcls, uint16_t, off_rcls)
+#undef ZG_TABLE
 };
 
-__device__ __forceinline__ Prog make_prog(const uint8_t* b) {
-  Prog p;
-  p.h = reinterpret_cast<const DHeader*>(b);
-  p.slots = reinterpret_cast<const DSlot*>(b + p.h->off_slots);
-  p.units = reinterpret_cast<const DUnit*>(b + p.h->off_units);
-  p.ops = reinterpret_cast<const DOp*>(b + p.h->off_ops);
-  p.rels = reinterpret_cast<const DRel*>(b + p.h->off_rels);
-  p.cls = reinterpret_cast<const DCls*>(b + p.h->off_cls);
-  p.tgts = reinterpret_cast<const uint16_t*>(b + p.h->off_tgts);
-  p.members = reinterpret_cast<const uint16_t*>(b + p.h->off_members);
-  p.trees = reinterpret_cast<const DTree*>(b + p.h->off_trees);
-  p.tree_ops = reinterpret_cast<const DTreeOp*>(b + p.h->off_tree_ops);
-  p.leaf_units = reinterpret_cast<const uint16_t*>(b + p.h->off_leaf_units);
-  p.type_inv = reinterpret_cast<const DTypeInv*>(b + p.h->off_type_inv);
-  p.inv_cls = reinterpret_cast<const uint16_t*>(b + p.h->off_inv_cls);
-  p.steps = reinterpret_cast<const DStep*>(b + p.h->off_steps);
-  p.type_rcls = reinterpret_cast<const DTypeInv*>(b + p.h->off_type_rcls);
-  p.rcls = reinterpret_cast<const uint16_t*>(b + p.h->off_rcls);
-  return p;
-}
+__device__ __forceinline__ Prog make_prog(const uint8_t* b) { return Prog{b}; }
 
 // range item: x = begin, y = end (edge indices into col), z = meta, w unused
 //   meta: bits 0-4 job slot, 5-10 depth of the children, 11 class has expiry,
@@ -213,14 +197,14 @@ __device__ __forceinline__ bool probe(const KParams& p, WarpCtx<COUNT>& c, uint3
 
 // Two independent binary searches advanced in lock step (two loads in flight per lane).
 template <bool COUNT>
-__device__ __forceinline__ void probe2(const KParams& p, WarpCtx<COUNT>& c, uint32_t lo0, uint32_t hi0, uint32_t k0,
-                                       uint32_t lo1, uint32_t hi1, uint32_t k1, bool& hit0, bool& hit1) {
+__device__ __forceinline__ void probe2(const uint32_t* __restrict__ arr, WarpCtx<COUNT>& c, uint32_t lo0, uint32_t hi0,
+                                       uint32_t k0, uint32_t lo1, uint32_t hi1, uint32_t k1, bool& hit0, bool& hit1) {
   while (lo0 < hi0 || lo1 < hi1) {
     const bool a0 = lo0 < hi0, a1 = lo1 < hi1;
     const uint32_t m0 = lo0 + ((hi0 - lo0) >> 1), m1 = lo1 + ((hi1 - lo1) >> 1);
     uint32_t v0 = 0, v1 = 0;
-    if (a0) v0 = __ldg(p.col + m0);
-    if (a1) v1 = __ldg(p.col + m1);
+    if (a0) v0 = __ldg(arr + m0);
+    if (a1) v1 = __ldg(arr + m1);
     if (COUNT) c.bytes += 4u * (a0 + a1);
     if (a0) {
       if (v0 == k0) { hit0 = true; lo0 = hi0; }
@@ -254,9 +238,9 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
   bool hit = false;
   int nsteps = 0, sb = 0;
   if (active) {
-    const DUnit u = pr.units[unit];
+    const DUnit u = pr.units()[unit];
     if (srel != kNone && sid == obj)
-      for (int m = u.mem_begin; m < u.mem_end; ++m) hit = hit || pr.members[m] == srel;
+      for (int m = u.mem_begin; m < u.mem_end; ++m) hit = hit || pr.members()[m] == srel;
     if (!hit) {
       sb = u.step_begin;
       nsteps = u.step_end - u.step_begin;
@@ -268,7 +252,7 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
     bool want = false;
     uint4 item = make_uint4(0, 0, 0, 0);
     if (i < nsteps && !hit) {
-      const DStep st = pr.steps[sb + i];
+      const DStep st = pr.steps()[sb + i];
       const bool expiry = (st.flags & CF_EXPIRY) != 0;
       const bool subject_fits = srel == kNone && stype == st.stype;
       if (st.kind == ST_DIRECT && subject_fits && inverted && (st.flags & CF_INVERT)) {
@@ -303,8 +287,11 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
               want = true;
               item = make_uint4(lo, hi, make_meta(jslot, depth + 1, false, st.tslot), 0);
               if (hi - lo >= nk) {
-                item.z |= kMetaLeaf;
-                item.w = st.tinv;  // bits 0-7: class index, bits 8-15: keys already done
+                // LEAF item: x = this object, y = this (userset) class: each pair asks the
+                // REVERSE row of the membership key "is x among the resources that list key as a
+                // subject in class y". Reverse rows of a check's few keys are short and shared by
+                // all its ranges, so the probes stay in a handful of cache lines.
+                item = make_uint4(obj, st.gc, item.z | kMetaLeaf, st.tinv);  // w: class index | keys done << 8
               }
             }
           } else {
@@ -335,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
   c.spill = p.spill + (static_cast<size_t>(blockIdx.x) * kWarpsPerBlock + warp) * p.spill_cap;
   c.spill_cap = p.spill_cap;
   c.bytes = 0;
-  const uint32_t n_slots = pr.h->n_slots, n_types = pr.h->n_types, n_units = pr.h->n_units;
+  const uint32_t n_slots = pr.hdr()->n_slots, n_types = pr.hdr()->n_types, n_units = pr.hdr()->n_units;
 
   for (;;) {
     unsigned long long base = 0;
@@ -356,26 +343,26 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
       const uint32_t srel = raw.w & 0xFFFFu, fl = p.raw_items ? 0u : raw.w >> 16;
       c.my_ss = (stype << 16) | srel;
       depth = fl & kJobDepthMask;
-      if (stype >= n_types || (srel != kNone && (srel >= n_slots || pr.slots[srel].type != stype))) bad = true;
+      if (stype >= n_types || (srel != kNone && (srel >= n_slots || pr.slots()[srel].type != stype))) bad = true;
       if (fl & kJobIsUnit) {
         unit = perm;
         if (unit == kNone) valid = false;  // padding job: value stays 0
         else if (unit >= n_units) bad = true;
-      } else if (perm >= n_slots || pr.slots[perm].kind == SK_NONPURE) {
+      } else if (perm >= n_slots || pr.slots()[perm].kind == SK_NONPURE) {
         bad = true;  // non-pure permissions reach this kernel as leaf-unit jobs
       } else {
-        unit = pr.slots[perm].unit;
+        unit = pr.slots()[perm].unit;
       }
     }
     // ---- direction-optimised probes: load the subject's reverse rows (its direct
     // memberships, class by class) when the check can fan out and they are few
     {
-      bool inv = p.invert && valid && !bad && (c.my_ss & 0xFFFFu) == kNone && (pr.units[unit].flags & UF_EXPANSIVE);
+      bool inv = p.invert && valid && !bad && (c.my_ss & 0xFFFFu) == kNone && (pr.units()[unit].flags & UF_EXPANSIVE);
       uint32_t rcnt = 0;
       unsigned long long cst = 0;
       int ib = 0, ncl = 0;
       if (inv) {
-        const DTypeInv ti = pr.type_inv[c.my_ss >> 16];
+        const DTypeInv ti = pr.type_inv()[c.my_ss >> 16];
         ib = ti.begin;
         ncl = ti.end - ti.begin;
         if (ncl > kMaxInvClasses) {
@@ -386,8 +373,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
       const int maxcl = __reduce_max_sync(kFull, ncl);
       for (int i = 0; i < maxcl; ++i) {
         if (inv && i < ncl) {
-          const uint32_t gc = pr.inv_cls[ib + i];
-          const DCls cl = pr.cls[gc];
+          const uint32_t gc = pr.inv_cls()[ib + i];
+          const DCls cl = pr.cls()[gc];
           if (!(cl.flags & CF_EMPTY) && c.my_subj < cl.nsubj) {
             const uint32_t b = __ldg(p.rrow_ptr + cl.rrow_base + c.my_subj);
             const uint32_t e = __ldg(p.rrow_ptr + cl.rrow_base + c.my_subj + 1);
@@ -498,24 +485,29 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
         for (int h = 0; h < 2; ++h) {
           const uint32_t u = lane + 32u * h;
           const int j = owner(u);
-          lo[h] = __shfl_sync(kFull, it.x, j & 31);
-          hi[h] = __shfl_sync(kFull, it.y, j & 31);
+          const uint32_t jobj = __shfl_sync(kFull, it.x, j & 31);
+          const uint32_t jgc = __shfl_sync(kFull, it.y, j & 31);
           const uint32_t jm = __shfl_sync(kFull, it.z, j & 31);
           const uint32_t jw = __shfl_sync(kFull, it.w, j & 31);
           const uint32_t jx = __shfl_sync(kFull, excl, j & 31);
           js[h] = jm & 31u;
           const unsigned long long jcst = __shfl_sync(kFull, c.my_cst, js[h]);
           act[h] = u < total;
-          key[h] = 0;
+          key[h] = jobj;  // searched for in the reverse row of the membership key
+          lo[h] = hi[h] = 0;
           if (act[h]) {
             const uint32_t r = cst_at(jcst, jw & 0xFFu) + (jw >> 8) + (u - jx);
-            key[h] = c.rset[r * 32 + js[h]];
-          } else {
-            hi[h] = lo[h];  // empty search
+            const uint32_t member = c.rset[r * 32 + js[h]];
+            const DCls cl = pr.cls()[jgc];
+            if (member < cl.nsubj) {
+              lo[h] = __ldg(p.rrow_ptr + cl.rrow_base + member);
+              hi[h] = __ldg(p.rrow_ptr + cl.rrow_base + member + 1);
+              if (COUNT) c.bytes += 8;
+            }
           }
         }
         bool hit0 = false, hit1 = false;
-        probe2(p, c, lo[0], hi[0], key[0], lo[1], hi[1], key[1], hit0, hit1);
+        probe2(p.rcol, c, lo[0], hi[0], key[0], lo[1], hi[1], key[1], hit0, hit1);
         c.found |= __reduce_or_sync(kFull, (hit0 ? (1u << js[0]) : 0u) | (hit1 ? (1u << js[1]) : 0u));
         continue;
       }
@@ -555,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
       }
       uint32_t cunit = 0;
       if (active) {
-        const DSlot s = pr.slots[tslot];
+        const DSlot s = pr.slots()[tslot];
         if (s.kind == SK_NONPURE) {
           // defer: Check(child#tslot @ S) becomes a sub-query of the next pass
           const unsigned long long at = atomicAdd(p.subq_count, 1ull);
@@ -610,12 +602,12 @@ __global__ void prep_jobs_kernel(const uint8_t* prog, const zg_check* queries, u
   uint32_t nl = 0;
   const uint16_t* leaf = nullptr;
   uint16_t single = kNone;
-  if (it.perm < pr.h->n_slots) {
-    const DSlot s = pr.slots[it.perm];
+  if (it.perm < pr.hdr()->n_slots) {
+    const DSlot s = pr.slots()[it.perm];
     if (s.kind == SK_NONPURE) {
-      const DTree t = pr.trees[s.unit];
+      const DTree t = pr.trees()[s.unit];
       nl = t.n_leaves;
-      leaf = pr.leaf_units + t.leaf_begin;
+      leaf = pr.leaf_units() + t.leaf_begin;
     } else {
       nl = 1;
       single = s.unit;
@@ -645,10 +637,10 @@ __global__ void fold_kernel(const uint8_t* prog, const zg_check* queries, unsign
   if (q >= n) return;
   const zg_check it = queries[q];
   uint32_t r = 2;  // invalid query -> error
-  const bool ok = it.perm < pr.h->n_slots && it.stype < pr.h->n_types &&
-                  (it.srel == kNone || (it.srel < pr.h->n_slots && pr.slots[it.srel].type == it.stype));
+  const bool ok = it.perm < pr.hdr()->n_slots && it.stype < pr.hdr()->n_types &&
+                  (it.srel == kNone || (it.srel < pr.hdr()->n_slots && pr.slots()[it.srel].type == it.stype));
   if (ok) {
-    const DSlot s = pr.slots[it.perm];
+    const DSlot s = pr.slots()[it.perm];
     auto leafval = [&](uint32_t l) -> uint32_t {
       const uint8_t v = val[q * L + l];
       return (v & kValT) ? 1u : ((v & kValE) ? 2u : 0u);
@@ -656,11 +648,11 @@ __global__ void fold_kernel(const uint8_t* prog, const zg_check* queries, unsign
     if (s.kind != SK_NONPURE) {
       r = leafval(0);
     } else {
-      const DTree t = pr.trees[s.unit];
+      const DTree t = pr.trees()[s.unit];
       unsigned long long st = 0;  // 2-bit entries
       int sp = 0;
       for (int i = t.op_begin; i < t.op_end; ++i) {
-        const DTreeOp o = pr.tree_ops[i];
+        const DTreeOp o = pr.tree_ops()[i];
         if (o.kind == T_LEAF) {
           st |= static_cast<unsigned long long>(leafval(o.arg)) << (2 * sp);
           ++sp;
@@ -728,9 +720,9 @@ __global__ void __launch_bounds__(256) rbfs_expand_kernel(const RbfsParams p) {
   if (w >= p.n_in) return;
   const unsigned long long item = p.frontier[w];
   const uint32_t type = static_cast<uint32_t>(item >> 32), obj = static_cast<uint32_t>(item);
-  const DTypeInv tc = pr.type_rcls[type];
+  const DTypeInv tc = pr.type_rcls()[type];
   for (int ci = tc.begin; ci < tc.end; ++ci) {
-    const DCls cl = pr.cls[pr.rcls[ci]];
+    const DCls cl = pr.cls()[pr.rcls()[ci]];
     if (cl.flags & CF_EMPTY) continue;
     uint32_t row = obj;
     if (cl.sslot == kWildcard) {
