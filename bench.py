@@ -286,9 +286,11 @@ def main():
         want = o.check_bulk(items[:ns], nthreads=cores)
         dt = time.perf_counter() - tq
         mism = int((want != host_answers[:ns]).sum())
+        # SURVEY 8(d)'s canonical figure: forward evaluation, no short circuit (small sample)
+        canon = o.check_bytes(items[:2000]) / 2000.0
         cpu = {"value": ns / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"first {ns} checks of the same batch, {cores} threads, {dt:.1f} s",
-               "parity_mismatches_vs_gpu": mism}
+               "parity_mismatches_vs_gpu": mism, "canonical_forward_bytes_per_check": canon}
         if mism:
             raise SystemExit(f"PARITY FAILURE: {mism} of {ns} answers differ from the oracle")
 
