@@ -216,7 +216,8 @@ void *zg_host_alloc(size_t bytes);
 void zg_host_free(void *p);
 
 /* Test hook: copies row (relation slot, resource id, edge class k) of the last
- * BUILT snapshot (host copy) into out. Returns 0 / ZG_E2BIG (*n_out = size). */
+ * BUILT snapshot (host copy) into out; with bit 31 of cls set, the REVERSE row of that
+ * class for subject id `res`. Returns 0 / ZG_E2BIG (*n_out = size). */
 int zg_debug_row(zg_engine *e, uint16_t rel_slot, uint32_t res, uint32_t cls, uint32_t *out,
                  uint64_t cap, uint64_t *n_out);
 

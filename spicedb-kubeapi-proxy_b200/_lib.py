@@ -359,7 +359,10 @@ class Engine:
             self._ck(rc)
             return [l for l in buf.value.decode().split("\n") if l]
 
-    def debug_row(self, type_name, rel, res, cls=0) -> np.ndarray:
+    def debug_row(self, type_name, rel, res, cls=0, reverse=False) -> np.ndarray:
+        """Forward row (resource `res`, class) or, reverse=True, the reverse row of subject `res`."""
+        if reverse:
+            cls |= 0x80000000
         cap = 1 << 10
         while True:
             out = np.empty(cap, dtype=np.uint32)

@@ -708,6 +708,18 @@ extern "C" int zg_debug_row(zg_engine* e, uint16_t rel_slot, uint32_t res, uint3
   if (rel_slot >= sc.slots.size() || sc.slots[rel_slot].is_perm) return fail(ZG_EINVAL, "not a relation");
   const DRel& r = e->last_built.rels[sc.slots[rel_slot].rel_index];
   *n_out = 0;
+  if (cls & 0x80000000u) {  // reverse row: `res` is the SUBJECT id, result = resources listing it
+    cls &= 0x7FFFFFFFu;
+    if (cls >= r.ncls) return fail(ZG_EINVAL, "class out of range");
+    const DCls& c = e->last_built.cls[r.cls_begin + cls];
+    const uint32_t row = c.sslot == kWildcard ? 0u : res;
+    if (row >= c.nsubj) return ZG_OK;
+    uint32_t b = e->last_built.rrow_ptr[c.rrow_base + row], en = e->last_built.rrow_ptr[c.rrow_base + row + 1];
+    *n_out = en - b;
+    if (en - b > cap) return ZG_E2BIG;
+    for (uint32_t i = b; i < en; ++i) out[i - b] = e->last_built.rcol[i];
+    return ZG_OK;
+  }
   if (cls >= r.ncls) return fail(ZG_EINVAL, "class out of range");
   if (res >= r.nres) return ZG_OK;
   uint64_t idx = r.row_base + uint64_t(res) * r.stride + cls;

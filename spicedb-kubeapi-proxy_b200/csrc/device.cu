@@ -284,8 +284,16 @@ int Device::check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cu
       ZG_CUDA(cudaStreamSynchronize(st));
       const uint32_t flags = static_cast<uint32_t>(host_ctrl[3] & 0xFFFFFFFFu);
       if (flags & 2u) {
-        if (err) *err = "sub-query buffer overflow: raise zg_config.subquery_capacity";
-        return ZG_ENOMEM;
+        // more sub-queries than the pass buffer holds: checks are independent, so answer the
+        // batch in two halves (each raises about half as many) instead of failing the call
+        if (n < 2) {
+          if (err) *err = "sub-query buffer overflow on a single check: raise zg_config.subquery_capacity";
+          return ZG_ENOMEM;
+        }
+        const uint64_t half = n / 2;
+        int r1 = check_device(d_items, half, d_out, st, raw_items, nullptr, err);
+        if (r1) return r1;
+        return check_device(d_items + half, n - half, d_out + half, st, raw_items, nullptr, err);
       }
       cur = host_ctrl[1];
       queries = q_[lv + 1].as<zg_check>();

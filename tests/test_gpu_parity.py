@@ -449,3 +449,27 @@ def test_path_memo_bounds_work_on_deep_dags(zg):
     want = np.where(reach[items["res"], items["subj"]], 2, 1)
     assert not (got == 255).any(), "work budget hit: the path memo did not bound the expansion"
     assert np.array_equal(got, want)
+
+
+def test_subquery_buffer_overflow_splits_the_batch(zg):
+    """Edges into non-pure permissions raise sub-queries; when a pass raises more than the
+    buffer holds the batch is answered in halves (checks are independent) - same answers."""
+    from oracle.pyoracle import Oracle
+
+    rng = random.Random(77)
+    schema = randgen.FIXED_SCHEMAS["deep_nonpure"]
+    model = randgen.model_from_schema(schema)
+    rels = randgen.random_relationships(rng, model, n_obj=8, n_user=6, density=0.35)
+    checks = randgen.random_checks(rng, model, 1500, n_obj=8, n_user=6)
+    o = Oracle(schema)
+    small, big = zg.Engine(schema, subquery_capacity=48), zg.Engine(schema)
+    for r in rels:
+        o.touch(r)
+    for e in (small, big):
+        ups = [(zg._lib.OP_TOUCH, r, 0) for r in rels]
+        for i in range(0, len(ups), 1000):
+            e.write_relationships(ups[i:i + 1000])
+    want = np.array([o.check(*split_rel(q)) for q in checks], dtype=np.uint8)
+    assert np.array_equal(big.check_bulk_str(checks), want)
+    assert np.array_equal(small.check_bulk_str(checks), want)
+    assert big.stats()["passes"] > 0, "this schema must exercise sub-query passes"

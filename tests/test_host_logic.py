@@ -118,6 +118,11 @@ def test_csr_rows_match_numpy_reference():
     t = w.groups[1]  # team#member@group#member -> class 0 of (group#member | user)
     for team in np.unique(t.res)[:20]:
         assert np.array_equal(e.debug_row("team", "member", int(team), 0), np.unique(t.subj[t.res == team]))
+    # reverse CSR (subject -> resources), what the direction-optimised probes and LookupResources read
+    for u in np.unique(g.subj)[:50]:
+        assert np.array_equal(e.debug_row("group", "member", int(u), 0, reverse=True), np.unique(g.res[g.subj == u]))
+    for grp in np.unique(t.subj)[:20]:
+        assert np.array_equal(e.debug_row("team", "member", int(grp), 0, reverse=True), np.unique(t.res[t.subj == grp]))
     # duplicates in bulk loads fold (TOUCH semantics)
     e2 = zgpu.Engine(workloads.CFG2_SCHEMA, host_only=True)
     e2.add_bulk("pod", "viewer", "user", [5, 5, 5, 1], [9, 9, 2, 7])
@@ -179,6 +184,26 @@ def test_write_read_delete_preconditions():
     with pytest.raises(C.RpcError, match="INVALID_ARGUMENT"):
         cl.WriteRelationships(C.WriteRelationshipsRequest(
             [up(C.OPERATION_TOUCH, f"pod:p{i}#viewer@user:u") for i in range(1001)]))
+
+
+def test_interleaved_rows_and_wildcard_reverse_row():
+    """All relations of a type share one row table (object-major); wildcard classes keep one
+    reverse row listing every resource that carries the wildcard."""
+    w = workloads.cfg4(scale=0.0005)
+    e = zgpu.Engine(w.schema, host_only=True)
+    w.load_into(e)
+    e.publish()
+    by = {(g.res_type, g.rel, g.subj_type, g.srel, g.wildcard): g for g in w.groups}
+    dv = by[("document", "viewer", "user", None, False)]
+    dg = by[("document", "viewer", "group", "member", False)]
+    dw = by[("document", "viewer", "user", None, True)]
+    db = by[("document", "banned", "user", None, False)]
+    for d in np.unique(dv.res)[:40]:
+        assert np.array_equal(e.debug_row("document", "viewer", int(d), 0), np.unique(dv.subj[dv.res == d]))
+        assert np.array_equal(e.debug_row("document", "viewer", int(d), 1), np.unique(dg.subj[dg.res == d]))
+        assert e.debug_row("document", "viewer", int(d), 2).size == int((dw.res == d).any())
+        assert np.array_equal(e.debug_row("document", "banned", int(d), 0), np.unique(db.subj[db.res == d]))
+    assert np.array_equal(e.debug_row("document", "viewer", 0, 2, reverse=True), np.unique(dw.res))
 
 
 def test_workload_generators_are_deterministic_and_sized():
