@@ -102,9 +102,7 @@ __device__ __forceinline__ Prog make_prog(const uint8_t* b) { return Prog{b}; }
 
 // range item: x = begin, y = end (edge indices into col), z = meta, w unused
 //   meta: bits 0-4 job slot, 5-10 depth of the children, 11 class has expiry,
-//         12 LEAF (children can only be matched against the subject's reverse-row set:
-//         w = class index | keys done << 8; popped as (range, key) pairs), 16-31 child slot
-constexpr uint32_t kMetaLeaf = 1u << 12;
+//         16-31 slot the children are visited at
 __device__ __forceinline__ uint32_t make_meta(uint32_t jslot, uint32_t depth, bool expiry, uint32_t tslot) {
   return jslot | (depth << 5) | (expiry ? (1u << 11) : 0u) | (tslot << 16);
 }
@@ -277,21 +275,34 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
             }
           } else if ((st.flags & kStepTargetLeaf) && inverted && !expiry && depth + 1 <= ZG_MAX_DEPTH) {
             // Children of this range can only be answered by "is the child one of the
-            // subject's memberships of class tinv": meet in the middle. nk memberships
-            // against hi-lo children: no membership -> nothing can match; fewer children
-            // than memberships -> visit the children; else a LEAF item whose (range, key)
-            // pairs are binary-searched one per lane.
-            // (a child class for another subject type can never match this subject)
-            const uint32_t nk = stype == st.tstype ? cst_at(cst, st.tinv + 1u) - cst_at(cst, st.tinv) : 0u;
-            if (nk) {
+            // subject's memberships of class tinv": meet in the middle. No membership (or a
+            // child class for another subject type): nothing can match.
+            const uint32_t kb = cst_at(cst, st.tinv), ke = stype == st.tstype ? cst_at(cst, st.tinv + 1u) : kb;
+            if (ke - kb > hi - lo) {  // fewer children than memberships: visit the children
               want = true;
               item = make_uint4(lo, hi, make_meta(jslot, depth + 1, false, st.tslot), 0);
-              if (hi - lo >= nk) {
-                // LEAF item: x = this object, y = this (userset) class: each pair asks the
-                // REVERSE row of the membership key "is x among the resources that list key as a
-                // subject in class y". Reverse rows of a check's few keys are short and shared by
-                // all its ranges, so the probes stay in a handful of cache lines.
-                item = make_uint4(obj, st.gc, item.z | kMetaLeaf, st.tinv);  // w: class index | keys done << 8
+            } else {
+              // For each membership key ask ITS reverse row (short, and shared by every range
+              // of this check, so it stays in L1): "does this object list the key as a subject
+              // of class gc". Two searches are advanced together for memory-level parallelism.
+              const DCls cl = pr.cls()[st.gc];
+              for (uint32_t r = kb; r < ke && !hit; r += 2) {
+                uint32_t l0 = 0, h0 = 0, l1 = 0, h1 = 0;
+                const uint32_t m0 = c.rset[r * 32 + (jslot & 31)];
+                const uint32_t m1 = r + 1 < ke ? c.rset[(r + 1) * 32 + (jslot & 31)] : 0xFFFFFFFFu;
+                if (m0 < cl.nsubj) {
+                  l0 = __ldg(p.rrow_ptr + cl.rrow_base + m0);
+                  h0 = __ldg(p.rrow_ptr + cl.rrow_base + m0 + 1);
+                  if (COUNT) c.bytes += 8;
+                }
+                if (m1 < cl.nsubj) {
+                  l1 = __ldg(p.rrow_ptr + cl.rrow_base + m1);
+                  h1 = __ldg(p.rrow_ptr + cl.rrow_base + m1 + 1);
+                  if (COUNT) c.bytes += 8;
+                }
+                bool hit0 = false, hit1 = false;
+                probe2(p.rcol, c, l0, h0, obj, l1, h1, obj, hit0, hit1);
+                hit = hit0 || hit1;
               }
             }
           } else {
@@ -426,28 +437,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
         __syncwarp();
         use_memo = true;
       }
-      // ---- pop work worth <= 32 lanes from the top of the stack. The top item decides
-      // the mode: EDGE items contribute one lane per edge (child visit), LEAF items one
-      // lane per (range, membership key) pair (binary search). Items of the other kind
-      // wait for a later iteration.
-      int n = c.top < 32 ? c.top : 32;
+      // ---- pop ranges worth <= 32 edges from the top of the stack
+      const int n = c.top < 32 ? c.top : 32;
       uint4 it = make_uint4(0, 0, 0, 0);
       if (static_cast<int>(lane) < n) it = c.stack[c.top - 1 - lane];
-      const bool leaf_mode = (__shfl_sync(kFull, it.z, 0) & kMetaLeaf) != 0;
-      {
-        const unsigned other = __ballot_sync(kFull, static_cast<int>(lane) < n && ((it.z & kMetaLeaf) != 0) != leaf_mode);
-        if (other) n = __ffs(other) - 1;
-      }
-      if (static_cast<int>(lane) >= n) it = make_uint4(0, 0, 0, 0);
       const bool dead = (c.found >> (it.z & 31)) & 1u;
-      uint32_t len = 0;
-      if (leaf_mode) {
-        const unsigned long long icst = __shfl_sync(kFull, c.my_cst, it.z & 31);
-        const uint32_t tinv = it.w & 0xFFu, kdone = it.w >> 8;
-        if (static_cast<int>(lane) < n && !dead) len = cst_at(icst, tinv + 1u) - cst_at(icst, tinv) - kdone;
-      } else if (static_cast<int>(lane) < n && !dead) {
-        len = it.y - it.x;
-      }
+      const uint32_t len = (static_cast<int>(lane) < n && !dead) ? it.y - it.x : 0u;
       uint32_t incl = len;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -455,19 +450,16 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
         if (static_cast<int>(lane) >= d) incl += v;
       }
       const uint32_t excl = incl - len;
-      const uint32_t W = leaf_mode ? 64u : 32u;  // LEAF iterations run two pairs per lane
-      const unsigned fullm = __ballot_sync(kFull, static_cast<int>(lane) < n && incl <= W);
+      const unsigned fullm = __ballot_sync(kFull, static_cast<int>(lane) < n && incl <= 32u);
       const int nfull = __popc(fullm);  // prefix of fully consumed items
       uint32_t total = __shfl_sync(kFull, incl, 31);
-      if (total > W) total = W;
+      if (total > 32u) total = 32u;
       __syncwarp();
-      if (static_cast<int>(lane) == nfull && static_cast<int>(lane) < n) {  // partially consumed item stays on top
-        if (leaf_mode) c.stack[c.top - 1 - lane].w = it.w + ((W - excl) << 8);
-        else c.stack[c.top - 1 - lane].x = it.x + (W - excl);
-      }
+      if (static_cast<int>(lane) == nfull && static_cast<int>(lane) < n)  // partially consumed item stays on top
+        c.stack[c.top - 1 - lane].x = it.x + (32u - excl);
       c.top -= nfull;
       __syncwarp();
-      // ---- lane k takes work unit k (and k + 32 in LEAF mode): owner item j = #items with incl <= k
+      // ---- lane k takes edge k: owner item j = #items with incl <= k
       auto owner = [&](uint32_t u) -> int {
         int j = 0;
 #pragma unroll
@@ -478,39 +470,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
         }
         return j;
       };
-      if (leaf_mode) {
-        uint32_t lo[2], hi[2], key[2], js[2];
-        bool act[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t u = lane + 32u * h;
-          const int j = owner(u);
-          const uint32_t jobj = __shfl_sync(kFull, it.x, j & 31);
-          const uint32_t jgc = __shfl_sync(kFull, it.y, j & 31);
-          const uint32_t jm = __shfl_sync(kFull, it.z, j & 31);
-          const uint32_t jw = __shfl_sync(kFull, it.w, j & 31);
-          const uint32_t jx = __shfl_sync(kFull, excl, j & 31);
-          js[h] = jm & 31u;
-          const unsigned long long jcst = __shfl_sync(kFull, c.my_cst, js[h]);
-          act[h] = u < total;
-          key[h] = jobj;  // searched for in the reverse row of the membership key
-          lo[h] = hi[h] = 0;
-          if (act[h]) {
-            const uint32_t r = cst_at(jcst, jw & 0xFFu) + (jw >> 8) + (u - jx);
-            const uint32_t member = c.rset[r * 32 + js[h]];
-            const DCls cl = pr.cls()[jgc];
-            if (member < cl.nsubj) {
-              lo[h] = __ldg(p.rrow_ptr + cl.rrow_base + member);
-              hi[h] = __ldg(p.rrow_ptr + cl.rrow_base + member + 1);
-              if (COUNT) c.bytes += 8;
-            }
-          }
-        }
-        bool hit0 = false, hit1 = false;
-        probe2(p.rcol, c, lo[0], hi[0], key[0], lo[1], hi[1], key[1], hit0, hit1);
-        c.found |= __reduce_or_sync(kFull, (hit0 ? (1u << js[0]) : 0u) | (hit1 ? (1u << js[1]) : 0u));
-        continue;
-      }
       const int j = owner(lane);
       const uint32_t jb = __shfl_sync(kFull, it.x, j & 31);
       const uint32_t jmeta = __shfl_sync(kFull, it.z, j & 31);
