@@ -52,6 +52,14 @@ def parse_args():
     return ap.parse_args()
 
 
+def host_cores():
+    """Threads the CPU arm may really use: the scheduler affinity, not the machine's CPU count."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -98,7 +106,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
@@ -143,7 +151,7 @@ def cpu_reference_arm(args, rank, world):
     o = Oracle(w.schema)
     w.load_into(o)
     items = w.check_items(o, CHECK_DTYPE)
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     o.check_bulk(items[:256])  # builds the index (not timed)
     t = time.perf_counter()
     o.check_bulk(items[:4096], nthreads=cores)
@@ -218,14 +226,14 @@ def main():
     # algorithmic bytes of one launch, from the instrumented kernel variant (not timed)
     alg_bytes = eng.count_alg_bytes(items)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # samples clocks / throttle reasons from the warm-up to the end of the e2e leg
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
         step_device()
     torch.cuda.synchronize()
     launches0 = eng.stats()["launches"]
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
@@ -276,7 +284,7 @@ def main():
 
         o = Oracle(w.schema)
         w.load_into(o)
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         o.check_bulk(items[:256])
         tq = time.perf_counter()
         o.check_bulk(items[:2048], nthreads=cores)

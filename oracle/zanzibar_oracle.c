@@ -24,6 +24,7 @@
 
 #include <ctype.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1000,7 +1001,10 @@ static void *bulk_worker(void *p) {
 
 int zo_check_bulk(zo_oracle *z, const zo_check_item *items, uint64_t n, uint8_t *out, int nthreads, int64_t now) {
   freeze(z);
-  if (nthreads <= 0) nthreads = (int)sysconf(_SC_NPROCESSORS_ONLN);
+  if (nthreads <= 0) { /* the cores this process may run on, not the machine's CPU count */
+    cpu_set_t set;
+    nthreads = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : (int)sysconf(_SC_NPROCESSORS_ONLN);
+  }
   if (nthreads > 256) nthreads = 256;
   uint64_t next = 0;
   Job j = {z, items, out, n, now, &next};
