@@ -6,17 +6,20 @@
 // watch.go:50, lookups.go:65; engine config pkg/spicedb/spicedb.go:25-56).
 //
 // Execution model (DESIGN.md "Kernels"):
-//   * persistent grid, one CTA slot per SM x occupancy; every WARP owns a private
-//     LIFO of edge RANGES in shared memory (spilling to a per-warp HBM area) and
-//     pulls batches of 32 checks from a global counter;
-//   * one iteration pops ranges worth <= 32 edges, assigns one edge per lane
-//     (coalesced reads of each CSR segment), and every lane visits its child node:
-//     row offsets (one 4-byte load per class + 1), binary-search probe of the
-//     sorted direct-subject segment, ballot/popc-compacted push of the userset and
-//     arrow ranges it found;
-//   * found / error state is two warp-uniform 32-bit masks; a found check's
-//     remaining ranges are dropped when popped (short circuit);
-//   * no tensor cores, no floating point: HBM/L2-bound integer traversal.
+//   * persistent grid, 148 SMs x 4 CTAs x 8 warps; every WARP owns a private LIFO of edge
+//     RANGES in shared memory (spilling to a per-warp HBM area) and pulls batches of 32
+//     checks from a global counter;
+//   * admission loads each subject's reverse rows (its direct memberships) into a small
+//     per-check set in shared memory: direct probes become shared-memory compares, and a
+//     range whose children could only match directly is resolved by searching the
+//     memberships' short reverse rows instead of visiting the children (meet in the middle);
+//   * one iteration pops ranges worth <= 32 edges, assigns one edge per lane (coalesced reads
+//     of each CSR segment), and every lane visits its child node: two row offsets per
+//     non-empty edge class, ballot/popc-compacted push of the userset and arrow ranges;
+//   * found / error state is two warp-uniform 32-bit masks; a found check's remaining ranges
+//     are dropped when popped (short circuit); long-running batches switch on a lossy memo of
+//     (check, slot, object, depth) visits so DAG-shaped data stays polynomial;
+//   * no tensor cores, no floating point: memory-latency / issue-bound integer traversal.
 #pragma once
 #include <cuda_runtime.h>
 

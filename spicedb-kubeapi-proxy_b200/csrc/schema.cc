@@ -643,13 +643,12 @@ std::vector<uint8_t> Schema::blob(const std::vector<DRel>& rels, const std::vect
     }
   }
   h.n_steps = static_cast<uint32_t>(steps.size());
-  put(rels.data(), rels.size() * sizeof(DRel), &h.off_rels);  // first: needs 8-byte alignment
+  // (rels / ops / tgts stay on the host: the kernels only read the flattened steps)
+  h.off_rels = h.off_ops = h.off_tgts = 0;
   put(steps.data(), steps.size() * sizeof(DStep), &h.off_steps);
   put(cls.data(), cls.size() * sizeof(DCls), &h.off_cls);  // 8-byte aligned members
   put(d_slots.data(), d_slots.size() * sizeof(DSlot), &h.off_slots);
   put(units.data(), units.size() * sizeof(DUnit), &h.off_units);
-  put(d_ops.data(), d_ops.size() * sizeof(DOp), &h.off_ops);
-  put(d_tgts.data(), d_tgts.size() * 2, &h.off_tgts);
   put(d_members.data(), d_members.size() * 2, &h.off_members);
   put(d_trees.data(), d_trees.size() * sizeof(DTree), &h.off_trees);
   put(d_tree_ops.data(), d_tree_ops.size() * sizeof(DTreeOp), &h.off_tree_ops);
