@@ -49,6 +49,7 @@ Snapshot::~Snapshot() {
   rcol.release();
   type_bit_base.release();
   for (auto& r : resources) r.release();
+  for (auto& f : flat_cls) f.release();
 }
 
 Device::~Device() {
@@ -140,6 +141,34 @@ std::string Device::publish(const HostSnapshot& h, const Schema& sc, uint64_t re
   if (!ok || cudaStreamSynchronize(stream) != cudaSuccess) {
     std::string m = std::string("snapshot upload failed: ") + cudaGetErrorString(cudaGetLastError());
     return m;
+  }
+  // flat-union slots: LookupResources is the union of the subject's reverse rows
+  {
+    const size_t ns = sc.slots.size();
+    s->flat_cls.resize(ns);
+    s->flat_n.assign(ns, -1);
+    for (size_t sl = 0; ok && sl < ns; ++sl) {
+      if (sc.d_slots[sl].kind == SK_NONPURE) continue;
+      const DUnit& u = sc.d_units[sc.d_slots[sl].unit];
+      bool flat = true;
+      std::vector<FlatLookupClass> fc;
+      for (int oi = u.op_begin; oi < u.op_end && flat; ++oi) {
+        const DOp& op = sc.d_ops[oi];
+        if (op.kind != OP_REL) { flat = false; break; }
+        const DRel& r = h.rels[op.rel];
+        for (uint16_t k = 0; k < r.ncls; ++k) {
+          const DCls& c = h.cls[r.cls_begin + k];
+          if (c.flags & CF_EMPTY) continue;
+          if ((c.sslot != kNone && c.sslot != kWildcard) || (c.flags & CF_EXPIRY)) { flat = false; break; }
+          fc.push_back(FlatLookupClass{c.rrow_base, c.nsubj, c.stype, static_cast<uint16_t>(c.sslot == kWildcard)});
+        }
+      }
+      if (!flat) continue;
+      s->flat_n[sl] = static_cast<int>(fc.size());
+      ok = up(s->flat_cls[sl], fc.data(), fc.size() * sizeof(FlatLookupClass));
+    }
+    if (ok && cudaStreamSynchronize(stream) != cudaSuccess) ok = false;
+    if (!ok) return std::string("snapshot upload failed (flat lookup tables)");
   }
   s->prog_bytes = static_cast<uint32_t>(blob.size());
   s->max_leaves = sc.max_leaves;
@@ -491,6 +520,41 @@ int Device::lookup(uint16_t res_type, const zg_check& proto, std::vector<uint32_
   }
   ZG_CUDA(cudaSetDevice(device));
   if (have_last_) ZG_CUDA(cudaStreamWaitEvent(stream, last_done_, 0));
+  // flat union of direct relations and a relation-less subject: the answer is the union of
+  // the subject's reverse rows (classes of other subject types contribute nothing)
+  if (use_rbfs && proto.srel == kNone && proto.perm < s->flat_n.size() && s->flat_n[proto.perm] >= 0) {
+    const int nc = s->flat_n[proto.perm];
+    const uint64_t cap = rb_cap_;
+    if (!rb_cand_.ensure(cap * 4 + 8)) return ZG_ENOMEM;
+    // layout: [count u64][ids ...] so the count and the first ids come back in ONE copy
+    unsigned long long* d_count = rb_cand_.as<unsigned long long>();
+    uint32_t* d_ids = rb_cand_.as<uint32_t>() + 2;
+    lookup_flat_kernel<<<1, 32, 0, stream>>>(s->rrow_ptr.as<uint32_t>(), s->rcol.as<uint32_t>(),
+                                             s->flat_cls[proto.perm].as<FlatLookupClass>(), nc, proto.stype, proto.subj,
+                                             d_ids, cap, d_count);
+    ++launches;
+    constexpr uint64_t kFirst = 4094;
+    static thread_local std::vector<uint32_t> host;
+    host.resize(2 + kFirst);
+    ZG_CUDA(cudaMemcpyAsync(host.data(), rb_cand_.p, host.size() * 4, cudaMemcpyDeviceToHost, stream));
+    ZG_CUDA(cudaStreamSynchronize(stream));
+    unsigned long long cnt = 0;
+    std::memcpy(&cnt, host.data(), 8);
+    if (cnt <= cap) {
+      ++lookups_flat;
+      ids->resize(cnt);
+      const uint64_t first = std::min<uint64_t>(cnt, kFirst);
+      if (first) std::memcpy(ids->data(), host.data() + 2, first * 4);
+      if (cnt > first) {
+        ZG_CUDA(cudaMemcpyAsync(ids->data() + first, d_ids + first, (cnt - first) * 4, cudaMemcpyDeviceToHost, stream));
+        ZG_CUDA(cudaStreamSynchronize(stream));
+      }
+      std::sort(ids->begin(), ids->end());
+      ids->erase(std::unique(ids->begin(), ids->end()), ids->end());
+      return ZG_OK;
+    }
+    // more results than the buffer: fall through to the general path
+  }
   // candidates: reverse BFS from the subject (superset of the answer), else every resource of the type
   uint64_t n = s->n_resources[res_type];
   const uint32_t* cand = s->resources[res_type].as<uint32_t>();

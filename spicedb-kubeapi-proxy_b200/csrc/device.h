@@ -29,6 +29,10 @@ struct Snapshot {
   DevBuf row_ptr, col, exp, prog, rrow_ptr, rcol, type_bit_base;
   std::vector<uint32_t> n_objects;  // per type
   uint64_t total_bits = 0;          // visited bitmap size for the reverse BFS
+  // Per slot: device array of FlatLookupClass when the slot is a flat union of direct
+  // (non-expiring) relations; flat_n[slot] = -1 otherwise.
+  std::vector<DevBuf> flat_cls;
+  std::vector<int> flat_n;
   std::vector<DevBuf> resources;  // per type
   std::vector<uint64_t> n_resources;
   uint32_t prog_bytes = 0;
@@ -63,7 +67,7 @@ class Device {
   int device = 0;
   uint64_t launches = 0, passes = 0, checks = 0;
   uint64_t coalesced_launches = 0, coalesced_requests = 0;
-  uint64_t lookups_rbfs = 0, lookups_exhaustive = 0;
+  uint64_t lookups_rbfs = 0, lookups_exhaustive = 0, lookups_flat = 0;
   bool use_rbfs = true;  // ZGPU_NO_RBFS=1: LookupResources checks every resource of the type  // batcher: launches that served > 1 caller
   double last_ms = 0;
   bool invert = true;  // direction-optimised probes (ZG_FLAG_FORWARD_ONLY / ZGPU_NO_INVERT=1 disable)

@@ -730,6 +730,32 @@ __global__ void __launch_bounds__(256) rbfs_expand_kernel(const RbfsParams p) {
   }
 }
 
+// LookupResources when the permission is a flat union of direct relations (the reference's
+// own schema: `permission view = viewer + creator`, pkg/spicedb/bootstrap.yaml:13): the answer
+// is the union of the subject's reverse rows of those classes. One warp copies them out.
+struct FlatLookupClass {
+  unsigned long long rrow_base;
+  uint32_t nsubj;
+  uint16_t stype;     // subject type the class accepts
+  uint16_t wildcard;  // row 0 regardless of the subject id
+};
+__global__ void lookup_flat_kernel(const uint32_t* rrow_ptr, const uint32_t* rcol, const FlatLookupClass* cls, int ncls,
+                                   uint32_t stype, uint32_t subj, uint32_t* out, unsigned long long cap,
+                                   unsigned long long* count) {
+  const unsigned lane = threadIdx.x & 31;
+  unsigned long long w = 0;
+  for (int c = 0; c < ncls; ++c) {
+    if (cls[c].stype != stype) continue;  // relationships with another subject type cannot match
+    const uint32_t row = cls[c].wildcard ? 0u : subj;
+    if (row >= cls[c].nsubj) continue;
+    const uint32_t b = rrow_ptr[cls[c].rrow_base + row], e = rrow_ptr[cls[c].rrow_base + row + 1];
+    for (uint32_t i = b + lane; i < e; i += 32)
+      if (w + (i - b) < cap) out[w + (i - b)] = rcol[i];
+    w += e - b;
+  }
+  if (lane == 0) *count = w;
+}
+
 // ---- LookupResources helpers ---------------------------------------------------------
 
 __global__ void lookup_fill_kernel(const uint32_t* cand, unsigned long long n, zg_check proto, zg_check* jobs) {

@@ -473,3 +473,37 @@ def test_subquery_buffer_overflow_splits_the_batch(zg):
     assert np.array_equal(big.check_bulk_str(checks), want)
     assert np.array_equal(small.check_bulk_str(checks), want)
     assert big.stats()["passes"] > 0, "this schema must exercise sub-query passes"
+
+
+def test_many_direct_classes_and_flat_lookup(zg):
+    """A subject type with more invertible classes than the per-check set tracks (12 > 11)
+    falls back to forward probes; flat unions of direct relations answer LookupResources
+    straight from the reverse rows. Both must equal the oracle."""
+    from oracle.pyoracle import Oracle
+
+    rels = [f"r{i}" for i in range(13)]
+    schema = "definition user {}\ndefinition group { relation member: user | group#member }\ndefinition doc {\n" + \
+        "".join(f"  relation {r}: user | user:*\n" for r in rels) + \
+        "  relation g: group#member\n" + \
+        "  permission any = " + " + ".join(rels) + "\n  permission deep = any + g\n}\n"
+    rng = np.random.default_rng(3)
+    e, o = zg.Engine(schema), Oracle(schema)
+    for t in (e, o):
+        for r in rels:
+            n = 300
+            t.add_bulk("doc", r, "user", rng.integers(0, 200, n), rng.integers(0, 50, n))
+        t.add_bulk("doc", "r3", "user", [7, 9], [0, 0], wildcard=True)
+        t.add_bulk("doc", "g", "group", rng.integers(0, 200, 100), rng.integers(0, 10, 100), srel="member")
+        t.add_bulk("group", "member", "user", rng.integers(0, 10, 60), rng.integers(0, 50, 60))
+        rng = np.random.default_rng(3)  # same data for the second target
+    e.publish()
+    items = np.zeros(4000, dtype=zg.CHECK_DTYPE)
+    r2 = np.random.default_rng(4)
+    items["res"], items["subj"] = r2.integers(0, 205, 4000), r2.integers(0, 55, 4000)
+    items["stype"], items["srel"] = e.type_id("user"), 0xFFFF
+    for perm in ("any", "deep", "r3"):
+        items["perm"] = e.slot_id("doc", perm)
+        assert np.array_equal(e.check_bulk(items), o.check_bulk(items)), perm
+        for u in (0, 1, 17, 49, 54, 10**6):
+            assert np.array_equal(e.lookup_resources_ids("doc", perm, "user", u),
+                                  o.lookup_resources_ids("doc", perm, "user", u)), (perm, u)
