@@ -2,6 +2,7 @@
 // string <-> id resolution, locking; the work is in store.cc and device.cu.
 #include <algorithm>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <mutex>
@@ -184,6 +185,19 @@ extern "C" int zg_apply_updates(zg_engine* e, const zg_update* u, uint64_t n) {
 }
 
 static int publish_locked(zg_engine* e) {
+  if (!e->host_only) {
+    // default: build the CSR on the GPU (csrc/build.cu). ZGPU_HOST_BUILD=1 builds on the host
+    // and uploads; ZGPU_VERIFY_BUILD=1 does both and compares every array (tests).
+    const char* hb = std::getenv("ZGPU_HOST_BUILD");
+    const char* vb = std::getenv("ZGPU_VERIFY_BUILD");
+    if (!(hb && *hb && *hb != '0')) {
+      std::string err = e->dev.publish_gpu(e->store, e->schema, ++e->revision, vb && *vb && *vb != '0');
+      if (!err.empty()) return fail(ZG_ECUDA, err);
+      e->last_built = HostSnapshot();
+      e->dirty = false;
+      return ZG_OK;
+    }
+  }
   HostSnapshot h = e->store.build();
   if (!h.err.empty()) return fail(ZG_EINVAL, h.err);
   if (e->host_only) {

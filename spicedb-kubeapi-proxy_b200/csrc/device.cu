@@ -114,7 +114,6 @@ std::string Device::init(int dev, uint64_t subq_cap, uint32_t budget) {
 std::string Device::publish(const HostSnapshot& h, const Schema& sc, uint64_t revision) {
   cudaSetDevice(device);
   auto s = std::make_shared<Snapshot>();
-  std::vector<uint8_t> blob = sc.blob(h.rels, h.cls);
   auto up = [&](DevBuf& b, const void* src, size_t bytes) -> bool {
     if (!b.ensure(bytes ? bytes : 16)) return false;
     if (bytes && cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess) return false;
@@ -122,9 +121,75 @@ std::string Device::publish(const HostSnapshot& h, const Schema& sc, uint64_t re
     return true;
   };
   bool ok = up(s->row_ptr, h.row_ptr.data(), h.row_ptr.size() * 4) && up(s->col, h.col.data(), h.col.size() * 4) &&
-            up(s->prog, blob.data(), blob.size()) && up(s->rrow_ptr, h.rrow_ptr.data(), h.rrow_ptr.size() * 4) &&
-            up(s->rcol, h.rcol.data(), h.rcol.size() * 4);
+            up(s->rrow_ptr, h.rrow_ptr.data(), h.rrow_ptr.size() * 4) && up(s->rcol, h.rcol.data(), h.rcol.size() * 4);
   if (ok && sc.has_expiry) ok = up(s->exp, h.exp.data(), h.exp.size() * 4);
+  s->resources.resize(h.resources.size());
+  s->n_resources.resize(h.resources.size());
+  for (size_t t = 0; ok && t < h.resources.size(); ++t) {
+    s->n_resources[t] = h.resources[t].size();
+    ok = up(s->resources[t], h.resources[t].data(), h.resources[t].size() * 4);
+  }
+  if (!ok || cudaStreamSynchronize(stream) != cudaSuccess)
+    return std::string("snapshot upload failed: ") + cudaGetErrorString(cudaGetLastError());
+  s->n_tuples = h.n_tuples;
+  return finish_publish(s, h, sc, revision);
+}
+
+std::string Device::publish_gpu(const Store& store, const Schema& sc, uint64_t revision, bool verify) {
+  cudaSetDevice(device);
+  HostSnapshot lay = store.layout();
+  auto s = std::make_shared<Snapshot>();
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, stream);
+  std::string err = gpu_build_snapshot(store, sc, &lay, stream, s.get());
+  cudaEventRecord(e1, stream);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  last_build_ms = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (!err.empty()) return "GPU snapshot build failed: " + err;
+  if (verify) {
+    // test mode: the host builder must produce byte-identical arrays
+    HostSnapshot h = store.build();
+    if (!h.err.empty()) return h.err;
+    auto same = [&](const DevBuf& d, const std::vector<uint32_t>& v, const char* what) -> std::string {
+      std::vector<uint32_t> got(v.size());
+      if (!v.empty() && cudaMemcpy(got.data(), d.p, v.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return std::string("verify: cannot read ") + what;
+      for (size_t i = 0; i < v.size(); ++i)
+        if (got[i] != v[i])
+          return std::string("verify: ") + what + " differs at " + std::to_string(i) + " (gpu " + std::to_string(got[i]) +
+                 ", host " + std::to_string(v[i]) + ")";
+      return "";
+    };
+    if (h.n_tuples != s->n_tuples) return "verify: relationship count differs";
+    for (auto m : {same(s->row_ptr, h.row_ptr, "row_ptr"), same(s->col, h.col, "col"), same(s->rrow_ptr, h.rrow_ptr, "rrow_ptr"),
+                   same(s->rcol, h.rcol, "rcol"), sc.has_expiry ? same(s->exp, h.exp, "exp") : std::string()})
+      if (!m.empty()) return m;
+    for (size_t t = 0; t < h.resources.size(); ++t) {
+      if (h.resources[t].size() != s->n_resources[t]) return "verify: resource list size differs";
+      std::string m = same(s->resources[t], h.resources[t], "resources");
+      if (!m.empty()) return m;
+    }
+    for (size_t c = 0; c < h.cls.size(); ++c)
+      if (h.cls[c].flags != lay.cls[c].flags) return "verify: class emptiness differs";
+  }
+  return finish_publish(s, lay, sc, revision);
+}
+
+std::string Device::finish_publish(std::shared_ptr<Snapshot> s, const HostSnapshot& h, const Schema& sc, uint64_t revision) {
+  std::vector<uint8_t> blob = sc.blob(h.rels, h.cls);
+  auto up = [&](DevBuf& b, const void* src, size_t bytes) -> bool {
+    if (!b.ensure(bytes ? bytes : 16)) return false;
+    if (bytes && cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess) return false;
+    s->bytes += bytes;
+    return true;
+  };
+  bool ok = up(s->prog, blob.data(), blob.size());
   {
     std::vector<unsigned long long> base(h.n_objects.size() + 1, 0);
     for (size_t t = 0; t < h.n_objects.size(); ++t) base[t + 1] = base[t] + ((uint64_t(h.n_objects[t]) + 31) & ~31ull);
@@ -132,16 +197,8 @@ std::string Device::publish(const HostSnapshot& h, const Schema& sc, uint64_t re
     s->n_objects = h.n_objects;
     if (ok) ok = up(s->type_bit_base, base.data(), base.size() * 8);
   }
-  s->resources.resize(h.resources.size());
-  s->n_resources.resize(h.resources.size());
-  for (size_t t = 0; ok && t < h.resources.size(); ++t) {
-    s->n_resources[t] = h.resources[t].size();
-    ok = up(s->resources[t], h.resources[t].data(), h.resources[t].size() * 4);
-  }
-  if (!ok || cudaStreamSynchronize(stream) != cudaSuccess) {
-    std::string m = std::string("snapshot upload failed: ") + cudaGetErrorString(cudaGetLastError());
-    return m;
-  }
+  if (!ok || cudaStreamSynchronize(stream) != cudaSuccess)
+    return std::string("snapshot upload failed: ") + cudaGetErrorString(cudaGetLastError());
   // flat-union slots: LookupResources is the union of the subject's reverse rows
   {
     const size_t ns = sc.slots.size();
@@ -173,7 +230,6 @@ std::string Device::publish(const HostSnapshot& h, const Schema& sc, uint64_t re
   s->prog_bytes = static_cast<uint32_t>(blob.size());
   s->max_leaves = sc.max_leaves;
   s->has_nonpure = sc.has_nonpure;
-  s->n_tuples = h.n_tuples;
   s->revision = revision;
 
   // occupancy for this program size (dynamic shared memory = program + warp stacks)

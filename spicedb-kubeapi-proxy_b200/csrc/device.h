@@ -46,7 +46,10 @@ class Device {
  public:
   ~Device();
   std::string init(int device, uint64_t subq_cap, uint32_t budget);
-  std::string publish(const HostSnapshot& h, const Schema& sc, uint64_t revision);
+  std::string publish(const HostSnapshot& h, const Schema& sc, uint64_t revision);  // host-built arrays
+  // Builds the CSR on the GPU (build.cu); verify: also build on the host and compare every array.
+  std::string publish_gpu(const Store& store, const Schema& sc, uint64_t revision, bool verify);
+  double last_build_ms = 0;
 
   // d_items / d_out are device pointers. count_bytes != nullptr selects the
   // instrumented kernel variant. Returns ZG_* and fills err.
@@ -75,6 +78,7 @@ class Device {
   uint64_t last_alg_bytes = 0;
 
  private:
+  std::string finish_publish(std::shared_ptr<Snapshot> s, const HostSnapshot& lay, const Schema& sc, uint64_t revision);
   int run_pass(const Snapshot& s, const zg_check* jobs, uint64_t njobs, uint8_t* val, bool final_codes, bool raw,
                zg_check* subq, uint32_t* subq_parent, cudaStream_t st, bool count, std::string* err);
   int sm_count_ = 0, blocks_per_sm_ = 0, blocks_per_sm_count_ = 0;
@@ -99,5 +103,7 @@ class Device {
  public:
   void finish_timing();
 };
+
+std::string gpu_build_snapshot(const Store& store, const Schema& sc, HostSnapshot* lay, cudaStream_t st, Snapshot* s);
 
 }  // namespace zg

@@ -197,7 +197,7 @@ void Store::match(const Filter& f, uint32_t now, std::vector<uint64_t>* idx) con
   }
 }
 
-HostSnapshot Store::build() const {
+HostSnapshot Store::layout() const {
   const Schema& sc = *schema;
   HostSnapshot h;
   const size_t nt = sc.types.size();
@@ -206,25 +206,42 @@ HostSnapshot Store::build() const {
     h.n_objects[t] = std::max<uint32_t>(static_cast<uint32_t>(objs_[t].names.size()), objs_[t].n_numeric);
 
   // row table: per resource type, objects x (all classes of all relations of the type)
-  std::vector<uint32_t> type_ncls(nt, 0);
-  for (int rs : sc.rel_slots) type_ncls[sc.slots[rs].type] += static_cast<uint32_t>(sc.slots[rs].classes.size());
-  std::vector<uint64_t> type_base(nt + 1, 0);
-  for (size_t t = 0; t < nt; ++t) type_base[t + 1] = type_base[t] + uint64_t(h.n_objects[t]) * type_ncls[t];
-  const uint64_t pool = type_base[nt];
+  h.type_ncls.assign(nt, 0);
+  for (int rs : sc.rel_slots) h.type_ncls[sc.slots[rs].type] += static_cast<uint32_t>(sc.slots[rs].classes.size());
+  h.type_base.assign(nt + 1, 0);
+  for (size_t t = 0; t < nt; ++t) h.type_base[t + 1] = h.type_base[t] + uint64_t(h.n_objects[t]) * h.type_ncls[t];
+  h.pool = h.type_base[nt];
   std::vector<uint32_t> type_used(nt, 0);
   uint16_t cls_begin = 0;
   for (int rs : sc.rel_slots) {
     const SlotInfo& s = sc.slots[rs];
     DRel r{};
-    r.row_base = type_base[s.type] + type_used[s.type];
+    r.row_base = h.type_base[s.type] + type_used[s.type];
     r.nres = h.n_objects[s.type];
     r.ncls = static_cast<uint16_t>(s.classes.size());
-    r.stride = type_ncls[s.type];
+    r.stride = h.type_ncls[s.type];
     r.cls_begin = cls_begin;
     cls_begin = static_cast<uint16_t>(cls_begin + r.ncls);
     type_used[s.type] += r.ncls;
     h.rels.push_back(r);
   }
+  // reverse CSR: one row per SUBJECT object per class (one row for a wildcard class)
+  h.cls = sc.d_cls;
+  h.rpool = 0;
+  for (auto& c : h.cls) {
+    c.rrow_base = h.rpool;
+    c.nsubj = c.sslot == kWildcard ? 1u : h.n_objects[c.stype];
+    h.rpool += c.nsubj;
+    c.flags |= CF_EMPTY;  // cleared by the builder for every class that has a relationship
+  }
+  return h;
+}
+
+HostSnapshot Store::build() const {
+  const Schema& sc = *schema;
+  HostSnapshot h = layout();
+  const size_t nt = sc.types.size();
+  const uint64_t pool = h.pool;
   h.row_ptr.assign(pool + 1, 0);
   const bool with_exp = sc.has_expiry;
 
@@ -303,14 +320,7 @@ HostSnapshot Store::build() const {
 
   // ---- reverse CSR (subject -> resources), per edge class; built from the deduplicated
   // forward rows in ascending resource order, so every reverse row comes out sorted
-  h.cls = sc.d_cls;
-  uint64_t rpool = 0;
-  for (auto& c : h.cls) {
-    c.rrow_base = rpool;
-    c.nsubj = c.sslot == kWildcard ? 1u : h.n_objects[c.stype];
-    rpool += c.nsubj;
-    c.flags |= CF_EMPTY;
-  }
+  const uint64_t rpool = h.rpool;
   h.rrow_ptr.assign(rpool + 1, 0);
   h.rcol.resize(h.col.size());
   for (int pass = 0; pass < 2; ++pass) {

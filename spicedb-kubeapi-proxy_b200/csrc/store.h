@@ -43,6 +43,9 @@ struct HostSnapshot {
   std::vector<std::vector<uint32_t>> resources;  // per type: ids that are the resource of >= 1 relationship
   std::vector<uint32_t> n_objects;               // per type
   uint64_t n_tuples = 0;
+  uint64_t pool = 0, rpool = 0;            // entries of row_ptr / rrow_ptr (each has +1 sentinel)
+  std::vector<uint64_t> type_base;         // per type: first row_ptr index of its objects
+  std::vector<uint32_t> type_ncls;         // per type: row stride (classes of all its relations)
   std::string err;  // non-empty: build failed
 };
 
@@ -75,6 +78,9 @@ class Store {
   };
   void match(const Filter& f, uint32_t now, std::vector<uint64_t>* idx) const;
 
+  // Sizes and bases only (n_objects, rels, cls with rrow_base / nsubj and CF_EMPTY set on every
+  // class): what both the host builder and the GPU builder (build.cu) start from.
+  HostSnapshot layout() const;
   HostSnapshot build() const;
   uint64_t size() const { return live_; }
 
