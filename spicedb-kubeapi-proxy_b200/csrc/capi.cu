@@ -2,6 +2,7 @@
 // string <-> id resolution, locking; the work is in store.cc and device.cu.
 #include <algorithm>
 #include <condition_variable>
+#include <cctype>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
@@ -237,6 +238,18 @@ static std::string rel_text(const zg_rel_str& r) {
          (none_rel(r.subj_rel) ? "" : "#" + s(r.subj_rel));
 }
 
+// SpiceDB object-id validation (v1 API): 1..1024 characters of [a-zA-Z0-9/_|\-=+], or "*".
+static bool valid_object_id(const char* id) {
+  size_t n = std::strlen(id);
+  if (n == 0 || n > 1024) return false;
+  if (n == 1 && id[0] == '*') return true;
+  for (size_t i = 0; i < n; ++i) {
+    const unsigned char c = static_cast<unsigned char>(id[i]);
+    if (!(std::isalnum(c) || c == '/' || c == '_' || c == '|' || c == '-' || c == '=' || c == '+')) return false;
+  }
+  return true;
+}
+
 // Resolve a relationship to WRITE (interns objects). Returns "" or an error.
 static std::string resolve_write(zg_engine* e, const zg_rel_str& r, zg_tuple* t) {
   const Schema& sc = e->schema;
@@ -247,7 +260,9 @@ static std::string resolve_write(zg_engine* e, const zg_rel_str& r, zg_tuple* t)
   int rel = sc.slot_id(rt, r.relation);
   if (rel < 0 || sc.slots[rel].is_perm)
     return std::string("relation `") + r.relation + "` not found under definition `" + r.res_type + "`";
-  if (!*r.res_id || !*r.subj_id) return "empty object id";
+  if (!valid_object_id(r.res_id) || std::strcmp(r.res_id, "*") == 0)
+    return std::string("invalid resource object id `") + r.res_id + "`";
+  if (!valid_object_id(r.subj_id)) return std::string("invalid subject object id `") + r.subj_id + "`";
   t->rel = static_cast<uint16_t>(rel);
   t->stype = static_cast<uint16_t>(st);
   t->flags = 0;

@@ -180,6 +180,11 @@ def test_write_read_delete_preconditions():
     assert read(resource_type="namespace", optional_relation="viewer") == []
     n = cl.DeleteRelationships(C.DeleteRelationshipsRequest(C.RelationshipFilter("namespace", "ns1")))
     assert n == 2 and read(resource_type="namespace") == []
+    # object ids: 1..1024 chars of [a-zA-Z0-9/_|\-=+]; '/' is legal and used (ns/name, pkg/rules/rules.go:335-339)
+    cl.WriteRelationships(C.WriteRelationshipsRequest([up(C.OPERATION_TOUCH, "pod:" + "a" * 1024 + "#viewer@user:x_y|z-1=2+3")]))
+    for bad in ("pod:" + "a" * 1025 + "#viewer@user:u", "pod:has space#viewer@user:u", "pod:p#viewer@user:u!", "pod:*#viewer@user:u"):
+        with pytest.raises(C.RpcError, match="INVALID_ARGUMENT"):
+            cl.WriteRelationships(C.WriteRelationshipsRequest([up(C.OPERATION_TOUCH, bad)]))
     # more than 1000 updates per write is rejected (pkg/spicedb/spicedb.go:34)
     with pytest.raises(C.RpcError, match="INVALID_ARGUMENT"):
         cl.WriteRelationships(C.WriteRelationshipsRequest(
