@@ -16,6 +16,7 @@
 //   5. per type: objects that own >= 1 relationship (cub::DeviceSelect over row_ptr)
 // The host builder (store.cc) produces identical arrays; ZGPU_VERIFY_BUILD=1 compares them.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
 #include <cstring>
@@ -252,7 +253,7 @@ std::string gpu_build_snapshot(const Store& store, const Schema& sc, HostSnapsho
     owner_flag_kernel<<<(no + blk - 1) / blk, blk, 0, st>>>(s->row_ptr.as<uint32_t>(), lay->type_base[t], lay->type_ncls[t], no,
                                                             d_of.as<uint8_t>());
     size_t tb = 0;
-    cub::CountingInputIterator<uint32_t> ids(0);
+    thrust::counting_iterator<uint32_t> ids(0);
     cub::DeviceSelect::Flagged(nullptr, tb, ids, d_of.as<uint8_t>(), s->resources[t].as<uint32_t>(), d_num.as<uint32_t>(), no, st);
     if (!d_tmp.ensure(tb + 256)) return "out of device memory (select scratch)";
     tb = d_tmp.cap;
