@@ -31,8 +31,19 @@ def build() -> str:
     """Compile oracle/libzoracle.so if it is missing or stale."""
     so = os.path.join(_HERE, "libzoracle.so")
     srcs = [os.path.join(_HERE, f) for f in ("zanzibar_oracle.c", "zanzibar_oracle.h")]
-    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.run(["make", "-C", _HERE, "libzoracle.so"], check=True, capture_output=True)
+    def stale():
+        return not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+
+    if stale():
+        import fcntl
+
+        with open(os.path.join(_HERE, ".build.lock"), "w") as lock:  # ranks / workers importing at once
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if stale():
+                    subprocess.run(["make", "-C", _HERE, "libzoracle.so"], check=True, capture_output=True)
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return so
 
 

@@ -73,9 +73,19 @@ def build_library(force: bool = False) -> str:
             if os.path.exists(so):
                 return so
             raise ZgpuError(-4, "libzgpu.so is missing and nvcc is not available to build it")
-        r = subprocess.run(["make", "-C", csrc], capture_output=True, text=True)
-        if r.returncode != 0:
-            raise ZgpuError(-4, "building libzgpu.so failed:\n" + r.stdout[-2000:] + r.stderr[-4000:])
+        # several ranks (torchrun) or test workers may import at once: one builds, the others wait
+        import fcntl
+
+        with open(os.path.join(csrc, ".build.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                still_stale = not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+                if force or still_stale:
+                    r = subprocess.run(["make", "-C", csrc], capture_output=True, text=True)
+                    if r.returncode != 0:
+                        raise ZgpuError(-4, "building libzgpu.so failed:\n" + r.stdout[-2000:] + r.stderr[-4000:])
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return so
 
 
