@@ -77,7 +77,9 @@ typedef struct {
   uint32_t work_budget;      /* 0 = default; expansion rounds per 32-check batch
                                 before unresolved checks report ZG_ITEM_ERROR
                                 (the analogue of a request deadline)              */
-  uint32_t reserved;
+  uint16_t shard_rank;       /* object-hash sharded store: this engine keeps only    */
+  uint16_t shard_count;      /* relationships whose resource id % count == rank;
+                                0 or 1 = whole store (replica)                       */
 } zg_config;
 
 /* One interned check: 16 bytes in, 1 byte out. Object ids are dense per type. */
@@ -220,6 +222,19 @@ void zg_host_free(void *p);
  * class for subject id `res`. Returns 0 / ZG_E2BIG (*n_out = size). */
 int zg_debug_row(zg_engine *e, uint16_t rel_slot, uint32_t res, uint32_t cls, uint32_t *out,
                  uint64_t cap, uint64_t *n_out);
+
+/* ---- object-hash sharded store (one engine per GPU, shard_count > 1) --------
+ * A check starts on the owner of its resource; an edge to an object owned by another shard (or
+ * into a non-pure permission) is raised as a sub-query. The host runs the ranks pass by pass
+ * and exchanges the raised sub-queries (all-to-all) until none are left, then folds the values
+ * back level by level (spicedb-kubeapi-proxy_b200/dist.py ShardedStoreChecker). On sharded
+ * engines zg_check_bulk / zg_lookup_resources are refused: use these three calls. */
+int zg_shard_pass(zg_engine *e, const zg_check *queries, uint64_t n, int level, uint64_t *n_sub);
+/* The sub-queries pass `level` raised, in emission order (same layout; flags = hop depth). */
+int zg_shard_subqueries(zg_engine *e, int level, zg_check *out, uint64_t n);
+/* child_vals[i]: value of raised sub-query i (bit0 HAS, bit1 ERROR). out[q]: level 0: v1 code of
+ * query q; deeper levels: its value bits, to be sent back to the rank that raised it. */
+int zg_shard_fold(zg_engine *e, int level, const uint8_t *child_vals, uint64_t n_sub, uint8_t *out);
 
 /* ---- measurement --------------------------------------------------------- */
 int zg_stats_get(zg_engine *e, zg_stats *out);

@@ -33,7 +33,7 @@ class ZgpuError(RuntimeError):
 
 class _Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("subquery_capacity", C.c_uint64),
-                ("work_budget", C.c_uint32), ("reserved", C.c_uint32)]
+                ("work_budget", C.c_uint32), ("shard_rank", C.c_uint16), ("shard_count", C.c_uint16)]
 
 
 class _RelStr(C.Structure):
@@ -124,6 +124,9 @@ _SIGS = {
                                       C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "zg_lookup_resources_str": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p,
                                           C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]),
+    "zg_shard_pass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
+    "zg_shard_subqueries": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]),
+    "zg_shard_fold": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]),
     "zg_debug_row": (C.c_int, [C.c_void_p, C.c_uint16, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
                                C.POINTER(C.c_uint64)]),
     "zg_host_alloc": (C.c_void_p, [C.c_size_t]),
@@ -196,11 +199,12 @@ class Engine:
     """One zg_engine: schema + relationship store + published CSR snapshot in HBM."""
 
     def __init__(self, schema: str | None = None, device: int = -1, subquery_capacity: int = 0, work_budget: int = 0,
-                 host_only: bool = False, forward_only: bool = False):
+                 host_only: bool = False, forward_only: bool = False, shard_rank: int = 0, shard_count: int = 0):
         """host_only=True builds schema/store/snapshot without a GPU (CPU unit tests of
         the host logic); every check/lookup on such an engine raises ZgpuError."""
         self._L = lib()
-        cfg = _Config(device, (1 if host_only else 0) | (2 if forward_only else 0), subquery_capacity, work_budget, 0)
+        cfg = _Config(device, (1 if host_only else 0) | (2 if forward_only else 0), subquery_capacity, work_budget,
+                      shard_rank, shard_count)
         h = C.c_void_p()
         rc = self._L.zg_engine_create(C.byref(cfg), C.byref(h))
         if rc:
@@ -368,6 +372,24 @@ class Engine:
                 continue
             self._ck(rc)
             return [l for l in buf.value.decode().split("\n") if l]
+
+    # -- sharded store (dist.ShardedStoreChecker drives these) --------------------
+    def shard_pass(self, queries: np.ndarray, level: int) -> int:
+        q = np.ascontiguousarray(queries, dtype=CHECK_DTYPE)
+        n = C.c_uint64(0)
+        self._ck(self._L.zg_shard_pass(self._h, q.ctypes.data, q.size, level, C.byref(n)))
+        return n.value
+
+    def shard_subqueries(self, level: int, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=CHECK_DTYPE)
+        self._ck(self._L.zg_shard_subqueries(self._h, level, out.ctypes.data, n))
+        return out
+
+    def shard_fold(self, level: int, child_vals: np.ndarray, n_queries: int) -> np.ndarray:
+        cv = np.ascontiguousarray(child_vals, dtype=np.uint8)
+        out = np.empty(n_queries, dtype=np.uint8)
+        self._ck(self._L.zg_shard_fold(self._h, level, cv.ctypes.data, cv.size, out.ctypes.data))
+        return out
 
     def debug_row(self, type_name, rel, res, cls=0, reverse=False) -> np.ndarray:
         """Forward row (resource `res`, class) or, reverse=True, the reverse row of subject `res`."""

@@ -56,6 +56,8 @@ struct zg_engine {
 };
 
 static thread_local std::string g_err;
+static const char* kShardedMsg =
+    "sharded engine: use zg_shard_pass / zg_shard_subqueries / zg_shard_fold (dist.ShardedStoreChecker)";
 
 static int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -85,6 +87,14 @@ extern "C" int zg_engine_create(const zg_config* cfg, zg_engine** out) {
     return fail(ZG_ECUDA, err);
   }
   if (cfg && (cfg->flags & ZG_FLAG_FORWARD_ONLY)) e->dev.invert = false;
+  if (cfg && cfg->shard_count > 1) {
+    if (cfg->shard_rank >= cfg->shard_count) {
+      delete e;
+      return fail(ZG_EINVAL, "shard_rank must be < shard_count");
+    }
+    e->dev.shard_count = cfg->shard_count;
+    e->dev.shard_rank = cfg->shard_rank;
+  }
   *out = e;
   return ZG_OK;
 }
@@ -99,6 +109,8 @@ extern "C" int zg_load_schema(zg_engine* e, const char* dsl, size_t len) {
   e->schema = std::move(s);
   e->has_schema = true;
   e->store.reset(&e->schema);
+  e->store.shard_count = e->dev.shard_count;
+  e->store.shard_rank = e->dev.shard_rank;
   e->dev.snap.reset();
   e->dirty = true;
   return ZG_OK;
@@ -478,6 +490,7 @@ extern "C" int zg_read_relationships(zg_engine* e, const zg_filter_str* filter, 
 
 static int ensure_published(zg_engine* e) {
   if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
+  if (e->dev.shard_count > 1) return fail(ZG_EINVAL, kShardedMsg);
   if (e->dirty || !e->dev.snap) return publish_locked(e);
   return ZG_OK;
 }
@@ -487,7 +500,10 @@ static void run_group(zg_engine* e, std::vector<BatchReq*>& group) {
   std::lock_guard<std::mutex> g(e->mu);
   int rc = ZG_OK;
   std::string err;
-  if (e->host_only) {
+  if (e->dev.shard_count > 1) {
+    rc = ZG_EINVAL;
+    err = kShardedMsg;
+  } else if (e->host_only) {
     rc = ZG_ECUDA;
     err = "host-only engine: no CUDA device, and libzgpu has no CPU fallback";
   } else if (!e->dev.snap) {
@@ -546,6 +562,7 @@ extern "C" int zg_check_bulk_device(zg_engine* e, const zg_check* d_items, uint6
   if ((!d_items || !d_out) && n) return fail(ZG_EINVAL, "NULL argument");
   std::lock_guard<std::mutex> g(e->mu);
   if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
+  if (e->dev.shard_count > 1) return fail(ZG_EINVAL, kShardedMsg);
   e->dev.now = now_of(e);
   std::string err;
   int rc = e->dev.check_device(d_items, n, d_out, static_cast<cudaStream_t>(stream), true, nullptr, &err);
@@ -646,6 +663,7 @@ extern "C" int zg_lookup_resources(zg_engine* e, uint16_t res_type, uint16_t per
   if (!n_out) return fail(ZG_EINVAL, "NULL n_out");
   std::lock_guard<std::mutex> g(e->mu);
   if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
+  if (e->dev.shard_count > 1) return fail(ZG_EINVAL, kShardedMsg);
   if (!e->dev.snap) return fail(ZG_ENOSNAPSHOT, "no snapshot published (call zg_publish)");
   std::vector<uint32_t> ids;
   int rc = lookup_locked(e, res_type, perm, stype, subj, srel, &ids);
@@ -721,6 +739,36 @@ extern "C" int zg_stats_get(zg_engine* e, zg_stats* out) {
     out->snapshot_bytes = e->dev.snap->bytes;
   }
   return ZG_OK;
+}
+
+extern "C" int zg_shard_pass(zg_engine* e, const zg_check* queries, uint64_t n, int level, uint64_t* n_sub) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if ((!queries && n) || !n_sub || level < 0 || level > ZG_MAX_DEPTH + 2) return fail(ZG_EINVAL, "bad argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
+  if (!e->dev.snap) return fail(ZG_ENOSNAPSHOT, "no snapshot published (call zg_publish)");
+  e->dev.now = now_of(e);
+  std::string err;
+  int rc = e->dev.shard_pass(queries, n, level, n_sub, &err);
+  return rc ? fail(rc, err) : ZG_OK;
+}
+extern "C" int zg_shard_subqueries(zg_engine* e, int level, zg_check* out, uint64_t n) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if ((!out && n) || level < 0) return fail(ZG_EINVAL, "bad argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
+  std::string err;
+  int rc = e->dev.shard_subqueries(level, out, n, &err);
+  return rc ? fail(rc, err) : ZG_OK;
+}
+extern "C" int zg_shard_fold(zg_engine* e, int level, const uint8_t* child_vals, uint64_t n_sub, uint8_t* out) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if ((!child_vals && n_sub) || level < 0) return fail(ZG_EINVAL, "bad argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
+  std::string err;
+  int rc = e->dev.shard_fold(level, child_vals, n_sub, out, &err);
+  return rc ? fail(rc, err) : ZG_OK;
 }
 
 extern "C" int zg_debug_row(zg_engine* e, uint16_t rel_slot, uint32_t res, uint32_t cls, uint32_t* out, uint64_t cap,

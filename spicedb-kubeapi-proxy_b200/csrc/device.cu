@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "kernels.cuh"
 
@@ -235,8 +236,19 @@ std::string Device::finish_publish(std::shared_ptr<Snapshot> s, const HostSnapsh
   // occupancy for this program size (dynamic shared memory = program + warp stacks)
   size_t sm = smem_bytes(s->prog_bytes);
   if (sm > 200 * 1024) return "schema program too large for shared memory";
-  cudaFuncSetAttribute(check_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
-  cudaFuncSetAttribute(check_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+  {
+    // The attribute is per function, i.e. shared by every engine of the process (several
+    // engines / shards may publish programs of different sizes): only ever raise it.
+    static std::mutex attr_mu;
+    static size_t attr_by_device[64] = {0};
+    size_t& attr_bytes = attr_by_device[device & 63];
+    std::lock_guard<std::mutex> g(attr_mu);
+    if (sm > attr_bytes) {
+      cudaFuncSetAttribute(check_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+      cudaFuncSetAttribute(check_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+      attr_bytes = sm;
+    }
+  }
   int occ = 0, occ_c = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, check_kernel<false>, kThreads, sm);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, check_kernel<true>, kThreads, sm);
@@ -260,7 +272,7 @@ int Device::run_pass(const Snapshot& s, const zg_check* jobs, uint64_t njobs, ui
   p.exp = s.exp.p ? s.exp.as<uint32_t>() : nullptr;
   p.rrow_ptr = s.rrow_ptr.as<uint32_t>();
   p.rcol = s.rcol.as<uint32_t>();
-  p.invert = invert ? 1 : 0;
+  p.invert = (invert && shard_count <= 1) ? 1 : 0;  // a shard does not hold the subject's reverse rows
   p.prog = s.prog.as<uint8_t>();
   p.prog_bytes = s.prog_bytes;
   p.jobs = jobs;
@@ -283,6 +295,8 @@ int Device::run_pass(const Snapshot& s, const zg_check* jobs, uint64_t njobs, ui
   p.memo = memo_.as<unsigned long long>();
   p.memo_entries = memo_.p ? memo_entries_ : 0;
   p.memo_after = memo_after_;
+  p.shard_count = shard_count;
+  p.shard_rank = shard_rank;
   ZG_CUDA(cudaMemsetAsync(ctrl, 0, 16, st));  // next, subq_count
   const int per_sm = count ? blocks_per_sm_count_ : blocks_per_sm_;
   uint64_t want = (njobs + kThreads - 1) / kThreads;
@@ -391,7 +405,7 @@ int Device::check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cu
       fold_kernel<<<static_cast<unsigned>((m + blk - 1) / blk), blk, 0, st>>>(
           s->prog.as<uint8_t>(), lv == 0 ? d_items : q_[lv].as<zg_check>(), m, L, val_[lv].as<uint8_t>(),
           lv == 0 ? d_out : nullptr, lv == 0 ? nullptr : parent_[lv].as<uint32_t>(),
-          lv == 0 ? nullptr : val_[lv - 1].as<uint8_t>());
+          lv == 0 ? nullptr : val_[lv - 1].as<uint8_t>(), 0);
       ++launches;
     }
     ZG_CUDA(cudaGetLastError());
@@ -505,6 +519,122 @@ int Device::check_host_multi(const std::vector<HostReq>& reqs, std::string* err)
   }
   ++coalesced_launches;
   coalesced_requests += reqs.size();
+  return ZG_OK;
+}
+
+// ---- sharded store: one pass per call; the host exchanges the raised sub-queries -----------
+//
+// Buffers per level lv: q_[lv] = this level's queries, jobs_/val_[lv] = their leaf jobs,
+// q_[lv+1] / parent_[lv+1] = the sub-queries the pass raised (the same buffers the single-GPU
+// multi-pass loop uses; here their consumers live on other ranks).
+int Device::shard_pass(const zg_check* queries, uint64_t n, int level, uint64_t* n_sub, std::string* err) {
+  std::shared_ptr<Snapshot> s = snap;
+  if (!s) {
+    if (err) *err = "no snapshot published";
+    return ZG_ENOSNAPSHOT;
+  }
+  ZG_CUDA(cudaSetDevice(device));
+  const size_t lv = static_cast<size_t>(level);
+  if (q_.size() <= lv + 1) {
+    q_.resize(lv + 2);
+    parent_.resize(lv + 2);
+    jobs_.resize(lv + 2);
+    val_.resize(lv + 2);
+  }
+  if (shard_nq_.size() <= lv) {
+    shard_nq_.resize(lv + 1);
+    shard_nsub_.resize(lv + 1);
+  }
+  shard_nq_[lv] = n;
+  shard_nsub_[lv] = 0;
+  *n_sub = 0;
+  if (n == 0) return ZG_OK;
+  const uint32_t L = s->max_leaves;
+  if (n * L >= (1ull << 32)) {
+    if (err) *err = "pass too large (n * leaves >= 2^32)";
+    return ZG_EINVAL;
+  }
+  if (have_last_) ZG_CUDA(cudaStreamWaitEvent(stream, last_done_, 0));
+  // level > 0 queries arrive in a host buffer too; keep level 0 separate from the raised-sub-query
+  // buffer q_[1] by staging every level's queries in shard_tmp_-free storage: jobs_[lv] doubles as input
+  DevBuf& qbuf = lv == 0 ? stage_in_ : q_[lv];  // q_[lv] (lv > 0) was the producer-side buffer of level lv-1 on
+                                              // THIS rank; its content was already read back by shard_subqueries
+  if (!qbuf.ensure(std::max<size_t>(n * sizeof(zg_check), subq_cap_ * sizeof(zg_check))) ||
+      !jobs_[lv].ensure(n * L * sizeof(zg_check)) || !val_[lv].ensure(n * L + 4) ||
+      !q_[lv + 1].ensure(subq_cap_ * sizeof(zg_check)) || !parent_[lv + 1].ensure(subq_cap_ * 4)) {
+    if (err) *err = "out of device memory (shard pass buffers)";
+    return ZG_ENOMEM;
+  }
+  ZG_CUDA(cudaMemcpyAsync(qbuf.p, queries, n * sizeof(zg_check), cudaMemcpyHostToDevice, stream));
+  unsigned long long* ctrl = ctrl_.as<unsigned long long>();
+  ZG_CUDA(cudaMemsetAsync(ctrl + 2, 0, 16, stream));
+  const unsigned blk = 256;
+  prep_jobs_kernel<<<static_cast<unsigned>((n + blk - 1) / blk), blk, 0, stream>>>(
+      s->prog.as<uint8_t>(), qbuf.as<zg_check>(), n, L, jobs_[lv].as<zg_check>(), level == 0 ? 1 : 0);
+  ++launches;
+  int rc = run_pass(*s, jobs_[lv].as<zg_check>(), n * L, val_[lv].as<uint8_t>(), false, false, q_[lv + 1].as<zg_check>(),
+                    parent_[lv + 1].as<uint32_t>(), stream, false, err);
+  if (rc) return rc;
+  unsigned long long host_ctrl[4];
+  ZG_CUDA(cudaMemcpyAsync(host_ctrl, ctrl, sizeof host_ctrl, cudaMemcpyDeviceToHost, stream));
+  ZG_CUDA(cudaEventRecord(last_done_, stream));
+  have_last_ = true;
+  ZG_CUDA(cudaStreamSynchronize(stream));
+  const uint32_t flags = static_cast<uint32_t>(host_ctrl[3] & 0xFFFFFFFFu);
+  if (flags & 2u) {
+    if (err) *err = "sub-query buffer overflow: raise zg_config.subquery_capacity or shrink the batch";
+    return ZG_ENOMEM;
+  }
+  if (flags & 1u) {
+    if (err) *err = "expansion stack overflow";
+    return ZG_ENOMEM;
+  }
+  shard_nsub_[lv] = host_ctrl[1];
+  *n_sub = host_ctrl[1];
+  checks += level == 0 ? n : 0;
+  ++passes;
+  return ZG_OK;
+}
+
+int Device::shard_subqueries(int level, zg_check* out, uint64_t n, std::string* err) {
+  const size_t lv = static_cast<size_t>(level);
+  if (lv >= shard_nsub_.size() || n != shard_nsub_[lv]) {
+    if (err) *err = "shard_subqueries: level / count mismatch";
+    return ZG_EINVAL;
+  }
+  if (n == 0) return ZG_OK;
+  ZG_CUDA(cudaSetDevice(device));
+  ZG_CUDA(cudaMemcpyAsync(out, q_[lv + 1].p, n * sizeof(zg_check), cudaMemcpyDeviceToHost, stream));
+  ZG_CUDA(cudaStreamSynchronize(stream));
+  return ZG_OK;
+}
+
+int Device::shard_fold(int level, const uint8_t* child_vals, uint64_t n_sub, uint8_t* out, std::string* err) {
+  std::shared_ptr<Snapshot> s = snap;
+  const size_t lv = static_cast<size_t>(level);
+  if (!s || lv >= shard_nq_.size() || n_sub != shard_nsub_[lv]) {
+    if (err) *err = "shard_fold: level / count mismatch";
+    return ZG_EINVAL;
+  }
+  const uint64_t n = shard_nq_[lv];
+  if (n == 0) return ZG_OK;
+  ZG_CUDA(cudaSetDevice(device));
+  const unsigned blk = 256;
+  if (n_sub) {
+    if (!shard_tmp_.ensure(n_sub)) return ZG_ENOMEM;
+    ZG_CUDA(cudaMemcpyAsync(shard_tmp_.p, child_vals, n_sub, cudaMemcpyHostToDevice, stream));
+    or_children_kernel<<<static_cast<unsigned>((n_sub + blk - 1) / blk), blk, 0, stream>>>(
+        parent_[lv + 1].as<uint32_t>(), shard_tmp_.as<uint8_t>(), n_sub, val_[lv].as<uint8_t>());
+    ++launches;
+  }
+  if (!stage_out_.ensure(n)) return ZG_ENOMEM;
+  const DevBuf& qbuf = lv == 0 ? stage_in_ : q_[lv];
+  fold_kernel<<<static_cast<unsigned>((n + blk - 1) / blk), blk, 0, stream>>>(
+      s->prog.as<uint8_t>(), qbuf.as<zg_check>(), n, s->max_leaves, val_[lv].as<uint8_t>(), stage_out_.as<uint8_t>(),
+      nullptr, nullptr, level == 0 ? 0 : 1);
+  ++launches;
+  ZG_CUDA(cudaMemcpyAsync(out, stage_out_.p, n, cudaMemcpyDeviceToHost, stream));
+  ZG_CUDA(cudaStreamSynchronize(stream));
   return ZG_OK;
 }
 

@@ -65,6 +65,16 @@ class Device {
   int check_host_multi(const std::vector<HostReq>& reqs, std::string* err);
   int lookup(uint16_t res_type, const zg_check& proto, std::vector<uint32_t>* ids, std::string* err);
 
+  // ---- object-hash sharded store: one pass at a time, sub-queries routed by the host ----
+  uint32_t shard_count = 1, shard_rank = 0;
+  // Evaluates `n` host queries as pass `level` (level 0: caller items; deeper: routed
+  // sub-queries, depth in flags). *n_sub = sub-queries this pass raised.
+  int shard_pass(const zg_check* queries, uint64_t n, int level, uint64_t* n_sub, std::string* err);
+  int shard_subqueries(int level, zg_check* out, uint64_t n, std::string* err);
+  // child_vals: one byte per raised sub-query (kValT|kValE bits) in emission order. out: one byte
+  // per query of the level: v1 codes at level 0, value bits deeper.
+  int shard_fold(int level, const uint8_t* child_vals, uint64_t n_sub, uint8_t* out, std::string* err);
+
   std::shared_ptr<Snapshot> snap;
   cudaStream_t stream = nullptr;
   int device = 0;
@@ -87,6 +97,8 @@ class Device {
   DevBuf spill_, ctrl_, memo_;
   uint32_t memo_entries_ = 8192, memo_after_ = 2048;  // ctrl: [0] next, [1] subq_count, [2] alg_bytes, then flags u32
   std::vector<DevBuf> q_, parent_, jobs_, val_;  // per pass level
+  std::vector<uint64_t> shard_nq_, shard_nsub_;  // sharded mode: queries / raised sub-queries per level
+  DevBuf shard_tmp_;
   DevBuf stage_in_, stage_out_, lk_jobs_, lk_codes_, lk_ids_;
   DevBuf rb_visited_, rb_front_[2], rb_cand_;
   uint64_t rb_cap_ = 1ull << 22;  // frontier / candidate capacity before falling back to the exhaustive scan

@@ -76,6 +76,11 @@ struct KParams {
   unsigned long long* memo;
   uint32_t memo_entries;  // per warp, power of two (0 = disabled)
   uint32_t memo_after;    // iterations before the memo is switched on for a batch
+  // Object-hash sharded store: this device only holds the relationships whose
+  // RESOURCE it owns (owner = object id % shard_count); an edge to an object of another shard
+  // becomes a sub-query that the host routes to its owner between passes.
+  uint32_t shard_count;   // 0 / 1 = not sharded
+  uint32_t shard_rank;
   unsigned long long* alg_bytes;  // COUNT variant only
 };
 
@@ -510,7 +515,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
       uint32_t cunit = 0;
       if (active) {
         const DSlot s = pr.slots()[tslot];
-        if (s.kind == SK_NONPURE) {
+        const bool remote = p.shard_count > 1 && (child % p.shard_count) != p.shard_rank;
+        if (s.kind == SK_NONPURE || remote) {
           // defer: Check(child#tslot @ S) becomes a sub-query of the next pass
           const unsigned long long at = atomicAdd(p.subq_count, 1ull);
           if (at < p.subq_cap) {
@@ -593,7 +599,7 @@ __device__ __forceinline__ uint32_t kleene_and(uint32_t a, uint32_t b) {
 // Evaluates each query's boolean tree over its leaf-job values. final: write the
 // v1 code to out[q]; otherwise OR the value into the parent job of the previous pass.
 __global__ void fold_kernel(const uint8_t* prog, const zg_check* queries, unsigned long long n, uint32_t L,
-                            const uint8_t* val, uint8_t* out, const uint32_t* parent, uint8_t* parent_val) {
+                            const uint8_t* val, uint8_t* out, const uint32_t* parent, uint8_t* parent_val, int raw_out) {
   const Prog pr = make_prog(prog);
   unsigned long long q = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
   if (q >= n) return;
@@ -638,12 +644,25 @@ __global__ void fold_kernel(const uint8_t* prog, const zg_check* queries, unsign
     }
   }
   if (out) {
-    out[q] = r == 1 ? ZG_HAS_PERMISSION : (r == 2 ? ZG_ITEM_ERROR : ZG_NO_PERMISSION);
+    if (raw_out) out[q] = r == 1 ? kValT : (r == 2 ? kValE : 0);  // value of a routed sub-query
+    else out[q] = r == 1 ? ZG_HAS_PERMISSION : (r == 2 ? ZG_ITEM_ERROR : ZG_NO_PERMISSION);
   } else if (r) {
     const uint32_t pj = parent[q];
     const uint32_t bits = r == 1 ? kValT : kValE;
     atomicOr(reinterpret_cast<unsigned int*>(parent_val + (pj & ~3u)), bits << (8 * (pj & 3u)));
   }
+}
+
+// Sharded store: values of routed sub-queries come back from their owners and are OR-ed into
+// the jobs that raised them.
+__global__ void or_children_kernel(const uint32_t* parent, const uint8_t* child_val, unsigned long long n,
+                                   uint8_t* parent_val) {
+  unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t bits = child_val[i] & (kValT | kValE);
+  if (!bits) return;
+  const uint32_t pj = parent[i];
+  atomicOr(reinterpret_cast<unsigned int*>(parent_val + (pj & ~3u)), bits << (8 * (pj & 3u)));
 }
 
 // ---- LookupResources: candidate generation by reverse BFS ----------------------------

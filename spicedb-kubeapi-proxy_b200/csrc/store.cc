@@ -71,23 +71,25 @@ std::string Store::load(const zg_tuple* t, const uint32_t* ex, uint64_t n) {
       last = sig;
     }
   }
-  size_t base = tuples.size();
-  tuples.resize(base + n);
-  expires.resize(base + n);
+  tuples.reserve(tuples.size() + (shard_count > 1 ? n / shard_count + 1 : n));
+  expires.reserve(tuples.capacity());
+  uint64_t kept = 0;
   for (uint64_t i = 0; i < n; ++i) {
     zg_tuple x = t[i];
     x.flags = 0;
     if (x.srel == kWildcard) x.subj = 0;
-    tuples[base + i] = x;
-    expires[base + i] = ex ? ex[i] : 0;
     TypeObjs& rt = objs_[schema->slots[x.rel].type];
     if (x.res + 1 > rt.n_numeric) rt.n_numeric = x.res + 1;
     if (x.srel != kWildcard) {
       TypeObjs& st = objs_[x.stype];
       if (x.subj + 1 > st.n_numeric) st.n_numeric = x.subj + 1;
     }
+    if (shard_count > 1 && x.res % shard_count != shard_rank) continue;  // another shard owns it
+    tuples.push_back(x);
+    expires.push_back(ex ? ex[i] : 0);
+    ++kept;
   }
-  live_ += n;  // upper bound until duplicates are folded by ensure_index()/build()
+  live_ += kept;  // upper bound until duplicates are folded by ensure_index()/build()
   indexed_ = false;
   return "";
 }
@@ -135,6 +137,12 @@ std::string Store::apply(const zg_update* u, uint64_t n, int* code) {
     zg_tuple t = u[i].t;
     t.flags = 0;
     if (t.srel == kWildcard) t.subj = 0;
+    if (shard_count > 1) {  // keep id spaces aligned across shards, store only what this shard owns
+      TypeObjs& rt0 = objs_[schema->slots[t.rel].type];
+      if (t.res + 1 > rt0.n_numeric) rt0.n_numeric = t.res + 1;
+      if (t.srel != kWildcard && t.subj + 1 > objs_[t.stype].n_numeric) objs_[t.stype].n_numeric = t.subj + 1;
+      if (t.res % shard_count != shard_rank) continue;
+    }
     Key k = key_of(t);
     auto it = index_.find(k);
     if (u[i].op == ZG_OP_DELETE) {

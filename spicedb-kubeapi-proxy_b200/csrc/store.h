@@ -85,6 +85,9 @@ class Store {
   uint64_t size() const { return live_; }
 
   const Schema* schema = nullptr;
+  // object-hash sharding: relationships whose resource id % shard_count != shard_rank are dropped
+  // (object counts still follow every relationship seen, so ids mean the same on all shards)
+  uint32_t shard_count = 1, shard_rank = 0;
   std::vector<zg_tuple> tuples;  // flags bit0 = dead (tombstone)
   std::vector<uint32_t> expires; // parallel to tuples (always sized like tuples)
 

@@ -76,3 +76,63 @@ def test_shard_bounds_cover_exactly():
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
             assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
+
+
+def _a2a_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    import zgpu  # noqa: F401
+    from spicedb_kubeapi_proxy_b200 import dist as zdist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        t = zdist.TorchTransport()
+        # rank r sends (r + d + 1) bytes of value 10*r + d to rank d (ragged, some empty)
+        send = [np.full((rank + d) % 3 * 5, 10 * rank + d, dtype=np.uint8) for d in range(world)]
+        recv = t.alltoall(send)
+        ok = all(np.array_equal(recv[s], np.full((s + rank) % 3 * 5, 10 * s + rank, dtype=np.uint8)) for s in range(world))
+        q.put((rank, ok, t.allreduce_sum(rank + 1)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_torch_transport_ragged_alltoall_world3():
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_a2a_worker, args=(r, 3, port, q)) for r in range(3)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in procs)
+    [p.join(timeout=60) for p in procs]
+    assert [r[1] for r in res] == [True, True, True], res
+    assert [r[2] for r in res] == [6, 6, 6]
+
+
+def test_local_transport_matches_semantics():
+    import threading
+
+    sys.path.insert(0, ROOT)
+    import zgpu  # noqa: F401
+    from spicedb_kubeapi_proxy_b200.dist import LocalTransport
+
+    ts = LocalTransport.cluster(3)
+    out = [None] * 3
+
+    def run(t):
+        send = [np.full(t.rank + d, 10 * t.rank + d, dtype=np.uint8) for d in range(3)]
+        recv = t.alltoall(send)
+        out[t.rank] = (all(np.array_equal(recv[s], np.full(s + t.rank, 10 * s + t.rank, dtype=np.uint8)) for s in range(3)),
+                       t.allreduce_sum(t.rank))
+
+    th = [threading.Thread(target=run, args=(t,)) for t in ts]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert out == [(True, 3)] * 3
