@@ -147,12 +147,10 @@ class ShardedStoreChecker:
 
     def _route(self, subs):
         w = self.t.world
-        dest = (subs["res"] % w).astype(np.int64)
-        order = np.argsort(dest, kind="stable")
-        counts = np.bincount(dest, minlength=w)
-        offs = np.concatenate([[0], np.cumsum(counts)])
-        srt = subs[order]
-        return order, [srt[offs[d]:offs[d + 1]].view(np.uint8) for d in range(w)]
+        dest = subs["res"] % np.uint32(w)
+        groups = [np.flatnonzero(dest == d) for d in range(w)]  # stable partition, O(n * w), no sort
+        order = np.concatenate(groups) if groups else np.empty(0, np.int64)
+        return order, [subs[g].view(np.uint8) for g in groups]
 
     def check_bulk(self, items: np.ndarray) -> np.ndarray:
         items = np.ascontiguousarray(items, dtype=self.dtype)
