@@ -348,8 +348,8 @@ class Engine:
 
     def lookup_resources_ids(self, res_type, perm, subj_type, subj, srel=None) -> np.ndarray:
         sr = SREL_NONE if srel is None else self.slot_id(subj_type, srel)
-        cap = 1 << 12
-        while True:
+        cap = 1 << 14
+        while True:  # on ZG_E2BIG the library keeps the answer: the retry only copies it
             out = np.empty(cap, dtype=np.uint32)
             n = C.c_uint64(0)
             rc = self._L.zg_lookup_resources(self._h, self.type_id(res_type), self.slot_id(res_type, perm),

@@ -122,6 +122,16 @@ int bits_for(unsigned long long max_value) {
 
 }  // namespace
 
+std::string sort_u32(const uint32_t* d_in, uint32_t* d_out, uint64_t n, cudaStream_t st) {
+  static thread_local DevBuf tmp;  // grow-only scratch per calling thread
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, bytes, d_in, d_out, n, 0, 32, st);
+  if (!tmp.ensure(bytes + 256)) return "out of device memory (sort scratch)";
+  bytes = tmp.cap;
+  BCUDA(cub::DeviceRadixSort::SortKeys(tmp.p, bytes, d_in, d_out, n, 0, 32, st));
+  return "";
+}
+
 // Fills `s` (row_ptr, col, exp, rrow_ptr, rcol, resources) from the store's relationship list.
 // `lay` comes from Store::layout(); on return lay->cls has CF_EMPTY cleared for non-empty classes.
 std::string gpu_build_snapshot(const Store& store, const Schema& sc, HostSnapshot* lay, cudaStream_t st, Snapshot* s) {

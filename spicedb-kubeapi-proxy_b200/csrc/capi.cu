@@ -51,6 +51,19 @@ struct zg_engine {
   uint64_t revision = 0;
   bool dirty = false;  // store changed since the last publish
   bool host_only = false;
+  // ZG_E2BIG protocol: the answer of the last lookup is kept so that the caller's retry with a
+  // larger buffer does not recompute it (same arguments, same snapshot revision)
+  struct LookupKey {
+    uint64_t revision = ~0ull;
+    uint32_t subj = 0;
+    uint16_t res_type = 0, perm = 0, stype = 0, srel = 0;
+    int64_t clock = 0;
+    bool operator==(const LookupKey& o) const {
+      return revision == o.revision && subj == o.subj && res_type == o.res_type && perm == o.perm && stype == o.stype &&
+             srel == o.srel && clock == o.clock;
+    }
+  } last_lookup_key;
+  std::vector<uint32_t> last_lookup_ids;
   HostSnapshot last_built;  // kept only for zg_debug_row / host-only engines
   bool keep_built = false;
 };
@@ -647,6 +660,18 @@ static int lookup_locked(zg_engine* e, uint16_t res_type, uint16_t perm, uint16_
   proto.stype = stype;
   proto.srel = srel;
   e->dev.now = now_of(e);
+  zg_engine::LookupKey key;
+  key.revision = e->revision;
+  key.subj = subj;
+  key.res_type = res_type;
+  key.perm = perm;
+  key.stype = stype;
+  key.srel = srel;
+  key.clock = e->clock ? e->clock : -static_cast<int64_t>(e->dev.now);  // wall clock: valid within the same second
+  if (key == e->last_lookup_key) {
+    *ids = e->last_lookup_ids;
+    return ZG_OK;
+  }
   std::string err;
   int rc = e->dev.lookup(res_type, proto, ids, &err);
   if (rc) return fail(rc, err);
@@ -654,6 +679,8 @@ static int lookup_locked(zg_engine* e, uint16_t res_type, uint16_t perm, uint16_
   if (srel == perm && stype == res_type && subj < ZG_NO_OBJECT - 1 &&
       !std::binary_search(ids->begin(), ids->end(), subj))
     ids->insert(std::upper_bound(ids->begin(), ids->end(), subj), subj);
+  e->last_lookup_key = key;
+  e->last_lookup_ids = *ids;
   return ZG_OK;
 }
 

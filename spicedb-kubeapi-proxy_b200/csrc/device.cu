@@ -781,9 +781,20 @@ int Device::lookup(uint16_t res_type, const zg_check& proto, std::vector<uint32_
   ZG_CUDA(cudaStreamSynchronize(stream));
   ids->resize(cnt);
   if (cnt) {
-    ZG_CUDA(cudaMemcpyAsync(ids->data(), lk_ids_.p, cnt * 4, cudaMemcpyDeviceToHost, stream));
+    // ascending ids: radix-sort on the device when the answer is large (a host sort of 50 k ids
+    // costs milliseconds), into the job buffer that is free again by now
+    const uint32_t* src = lk_ids_.as<uint32_t>();
+    if (cnt > 2048) {
+      std::string serr = sort_u32(lk_ids_.as<uint32_t>(), lk_jobs_.as<uint32_t>(), cnt, stream);
+      if (!serr.empty()) {
+        if (err) *err = serr;
+        return ZG_ECUDA;
+      }
+      src = lk_jobs_.as<uint32_t>();
+    }
+    ZG_CUDA(cudaMemcpyAsync(ids->data(), src, cnt * 4, cudaMemcpyDeviceToHost, stream));
     ZG_CUDA(cudaStreamSynchronize(stream));
-    std::sort(ids->begin(), ids->end());
+    if (cnt <= 2048) std::sort(ids->begin(), ids->end());
   }
   return ZG_OK;
 }

@@ -116,6 +116,8 @@ class Device {
   void finish_timing();
 };
 
+// Device radix sort of n u32 keys (build.cu keeps the cub instantiations in one translation unit).
+std::string sort_u32(const uint32_t* d_in, uint32_t* d_out, uint64_t n, cudaStream_t st);
 std::string gpu_build_snapshot(const Store& store, const Schema& sc, HostSnapshot* lay, cudaStream_t st, Snapshot* s);
 
 }  // namespace zg
