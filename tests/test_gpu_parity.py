@@ -661,3 +661,47 @@ def test_sharded_store_depth_cap_across_shards(zg):
     assert list(got) == [o.check(*split_rel(q)) for q in checks]
     assert list(got[:5]) == [255, 2, 1, 2, 255]
     assert stats["levels"] > 20, "the 51-hop chain must cross shards level by level"
+
+
+def test_interleaved_writes_and_checks_stay_consistent(zg):
+    """FullyConsistent (every call site in the reference sets it: pkg/authz/check.go:42-44):
+    after each WriteRelationships / DeleteRelationships returns, checks and lookups observe it.
+    Random TOUCH / DELETE / delete-by-filter sequence on the engine and on the oracle in lockstep."""
+    from oracle.pyoracle import Oracle
+
+    schema = randgen.FIXED_SCHEMAS["docs"]
+    model = randgen.model_from_schema(schema)
+    rng = random.Random(4242)
+    pool = randgen.random_relationships(rng, model, n_obj=6, n_user=5, density=0.6)
+    checks = randgen.random_checks(rng, model, 120, n_obj=6, n_user=5)
+    e, o = zg.Engine(schema), Oracle(schema)
+    e.publish()
+    live = set()
+    for step in range(60):
+        op = rng.random()
+        if op < 0.6 or not live:
+            batch = rng.sample(pool, rng.randint(1, 6))
+            e.write_relationships([(zg._lib.OP_TOUCH, r, 0) for r in batch])
+            for r in batch:
+                o.touch(r)
+            live.update(batch)
+        elif op < 0.9:
+            batch = rng.sample(sorted(live), min(len(live), rng.randint(1, 4)))
+            e.write_relationships([(zg._lib.OP_DELETE, r, 0) for r in batch])
+            for r in batch:
+                o.delete(r)
+            live.difference_update(batch)
+        else:  # delete by filter: every relationship of one resource
+            rt, rid = split_rel(rng.choice(sorted(live)))[:2]
+            n = e.delete_relationships({"res_type": rt, "res_id": rid})
+            gone = {r for r in live if split_rel(r)[:2] == (rt, rid)}
+            assert n == len(gone)
+            for r in gone:
+                o.delete(r)
+            live -= gone
+        assert sorted(e.read_relationships()) == sorted(live) == sorted(o.read())
+        got = e.check_bulk_str(checks)
+        want = [o.check(*split_rel(q)) for q in checks]
+        assert list(got) == want, f"step {step}"
+        u = f"u{rng.randint(0, 4)}"
+        assert sorted(e.lookup_resources_str("document", "view", "user", u)) == sorted(o.lookup_resources("document", "view", "user", u))
