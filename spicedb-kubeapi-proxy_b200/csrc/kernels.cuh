@@ -35,8 +35,11 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 #ifndef ZG_MIN_BLOCKS
 #define ZG_MIN_BLOCKS 4
 #endif
+#ifndef ZG_STACK_CAP
+#define ZG_STACK_CAP 64
+#endif
 constexpr int kMinBlocks = ZG_MIN_BLOCKS;  // resident CTAs per SM the register budget is tuned for
-constexpr int kStackCap = 128;        // range items per warp in shared memory
+constexpr int kStackCap = ZG_STACK_CAP;       // range items per warp in shared memory
 constexpr int kRsetCap = 16;          // reverse-row entries kept per check (subject's direct memberships)
 constexpr size_t kWarpSmem = kStackCap * sizeof(uint4) + kRsetCap * 32 * sizeof(uint32_t);
 constexpr unsigned kFull = 0xFFFFFFFFu;
