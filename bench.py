@@ -191,9 +191,9 @@ def cpu_reference_arm(args, rank, world):
 
 
 def main():
-    # keep stdout to the single JSON line (NCCL prints its version banner there at VERSION level)
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # keep stdout to the single JSON line: NCCL writes its version banner / warnings to stdout
+    # unless told otherwise (the banner is printed at every level from VERSION up)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     args = parse_args()
     rank, local_rank, world = dist_env()
     if args.impl == "reference":

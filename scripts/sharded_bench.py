@@ -18,8 +18,7 @@ ap.add_argument("--scale", type=float, default=0.1)
 ap.add_argument("--checks", type=int, default=200_000)
 ap.add_argument("--steps", type=int, default=3)
 a = ap.parse_args()
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
