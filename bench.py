@@ -35,6 +35,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The single JSON line, on the process's original stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 METRIC = "Mchecks/sec (batched CheckPermission)"
 UNIT = "Mchecks/s"
 
@@ -178,7 +191,7 @@ def cpu_reference_arm(args, rank, world):
     dt = time.perf_counter() - t0
     val = n * args.steps / dt / 1e6
     desc = f"first {n} checks of the {w.name} batch per step, {cores} threads"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
@@ -187,13 +200,16 @@ def cpu_reference_arm(args, rank, world):
                          "note": "C oracle restating SpiceDB v1.47.1 check semantics; the reference's own engine is an "
                                  "un-vendored Go module and no Go toolchain exists on this box"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def main():
-    # keep stdout to the single JSON line: NCCL writes its version banner / warnings to stdout
-    # unless told otherwise (the banner is printed at every level from VERSION up)
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout must carry exactly ONE JSON line, but libraries print there too (NCCL's version banner
+    # under torchrun): point fd 1 at stderr for the whole run and emit the line on the saved fd
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
@@ -337,7 +353,7 @@ def main():
             "has_fraction": float((host_answers == 2).mean()),
             "publish_s": publish_s,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if dist:
         dist.destroy_process_group()
 
