@@ -561,7 +561,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
 
 // ---- general mode: queries -> leaf-unit jobs, and the boolean fold ------------------
 
-// jobs[q*L + l] for l < L. Pure / relation slots use one job; non-pure slots one per
+// jobs[l*n + q] for l < L (leaf-major: jobs of one leaf are contiguous, so a warp's 32 jobs do
+// similar work and the padding of queries with fewer leaves sits together at the end).
+// Pure / relation slots use one job; non-pure slots one per
 // leaf unit of their tree. Unused positions are padding (unit = kNone).
 __global__ void prep_jobs_kernel(const uint8_t* prog, const zg_check* queries, unsigned long long n, uint32_t L,
                                  zg_check* jobs, int raw_items) {
@@ -588,7 +590,7 @@ __global__ void prep_jobs_kernel(const uint8_t* prog, const zg_check* queries, u
     zg_check j = it;
     j.perm = l < nl ? (leaf ? leaf[l] : single) : kNone;
     j.flags = static_cast<uint16_t>(depth | kJobIsUnit);
-    jobs[q * L + l] = j;
+    jobs[static_cast<unsigned long long>(l) * n + q] = j;
   }
 }
 
@@ -613,7 +615,7 @@ __global__ void fold_kernel(const uint8_t* prog, const zg_check* queries, unsign
   if (ok) {
     const DSlot s = pr.slots()[it.perm];
     auto leafval = [&](uint32_t l) -> uint32_t {
-      const uint8_t v = val[q * L + l];
+      const uint8_t v = val[static_cast<unsigned long long>(l) * n + q];
       return (v & kValT) ? 1u : ((v & kValE) ? 2u : 0u);
     };
     if (s.kind != SK_NONPURE) {
