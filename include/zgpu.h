@@ -236,6 +236,40 @@ int zg_shard_subqueries(zg_engine *e, int level, zg_check *out, uint64_t n);
  * query q; deeper levels: its value bits, to be sent back to the rank that raised it. */
 int zg_shard_fold(zg_engine *e, int level, const uint8_t *child_vals, uint64_t n_sub, uint8_t *out);
 
+/* ---- list-response filter (host code, no GPU) -------
+ * Replaces the unmarshal / re-marshal round trip of pkg/authz/postfilter.go:17-55
+ * (filterListResponse) and the name extraction of postfilter.go:67-119: one structural pass
+ * over the body, then a splice of the kept items' bytes. */
+typedef struct zg_list_item {
+  uint64_t begin, end;  /* byte range of the item's JSON value inside the body           */
+  uint64_t name_off;    /* metadata.name: offset of the string CONTENTS (still escaped)  */
+  uint64_t ns_off;      /* metadata.namespace, same                                      */
+  uint32_t name_len;    /* 0 = absent or not a string                                    */
+  uint32_t ns_len;
+  uint32_t flags;       /* ZG_ITEM_*                                                     */
+  uint32_t reserved;
+} zg_list_item;
+#define ZG_ITEM_IS_OBJECT 1u    /* the item is a JSON object (others are never checked)  */
+#define ZG_ITEM_HAS_METADATA 2u /* ... with an object-valued "metadata"                  */
+#define ZG_ITEM_HAS_OBJECT 4u   /* table rows: the row has an "object" key (any value)   */
+#define ZG_LIST_ITEMS 0u        /* scan "items"; metadata at item level                  */
+#define ZG_LIST_TABLE_ROWS 1u   /* scan "rows"; metadata under rows[i].object (metav1.Table,
+                                   pkg/authz/responsefilterer.go:349-374)                */
+#define ZG_LIST_EMPTY_AS_NULL 1u /* zg_list_filter flag: nothing kept -> null, not []    */
+/* Scans a kube List (or Table) body. Returns the number of elements of the top-level "items" ("rows") array
+ * (0 if there is no such array: the reference then passes the body through), ZG_EINVAL on
+ * malformed JSON, ZG_E2BIG if out != NULL and cap is too small. [*items_begin, *items_end) is
+ * the byte range of the array, brackets included. */
+int64_t zg_list_scan(const char *body, size_t len, uint32_t mode, zg_list_item *out, uint64_t cap,
+                     uint64_t *items_begin, uint64_t *items_end);
+/* Writes the body with only the items whose keep[i] != 0; every other byte is preserved.
+ * With nothing kept the array becomes `[]` (the pre-filter's filterList / filterTable,
+ * responsefilterer.go:356,377) or, with ZG_LIST_EMPTY_AS_NULL, `null` (the post-filter's re-marshal of
+ * a nil slice, postfilter.go:138). Returns 0, or ZG_E2BIG with *out_len = bytes required. */
+int zg_list_filter(const char *body, size_t len, const zg_list_item *items, uint64_t n,
+                   const uint8_t *keep, uint64_t items_begin, uint64_t items_end, uint32_t flags,
+                   char *out, size_t cap, size_t *out_len);
+
 /* ---- measurement --------------------------------------------------------- */
 int zg_stats_get(zg_engine *e, zg_stats *out);
 /* Runs the batch through the instrumented kernel variant and returns the

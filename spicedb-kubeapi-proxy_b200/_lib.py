@@ -54,6 +54,18 @@ class _Stats(C.Structure):
                 ("last_kernel_ms", C.c_double), ("coalesced_launches", C.c_uint64), ("coalesced_requests", C.c_uint64)]
 
 
+class _ListItem(C.Structure):
+    _fields_ = [("begin", C.c_uint64), ("end", C.c_uint64), ("name_off", C.c_uint64), ("ns_off", C.c_uint64),
+                ("name_len", C.c_uint32), ("ns_len", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+LIST_ITEM_DTYPE = np.dtype([("begin", "<u8"), ("end", "<u8"), ("name_off", "<u8"), ("ns_off", "<u8"),
+                            ("name_len", "<u4"), ("ns_len", "<u4"), ("flags", "<u4"), ("reserved", "<u4")])
+ITEM_IS_OBJECT, ITEM_HAS_METADATA, ITEM_HAS_OBJECT = 1, 2, 4
+LIST_ITEMS, LIST_TABLE_ROWS = 0, 1
+LIST_EMPTY_AS_NULL = 1
+
+
 def library_path() -> str:
     # ZGPU_LIB selects an alternative build of the same sources (tuning experiments)
     return os.environ.get("ZGPU_LIB") or os.path.join(_HERE, "libzgpu.so")
@@ -131,6 +143,10 @@ _SIGS = {
                                C.POINTER(C.c_uint64)]),
     "zg_host_alloc": (C.c_void_p, [C.c_size_t]),
     "zg_host_free": (None, [C.c_void_p]),
+    "zg_list_scan": (C.c_int64, [C.c_char_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
+                                 C.POINTER(C.c_uint64)]),
+    "zg_list_filter": (C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64,
+                                 C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "zg_stats_get": (C.c_int, [C.c_void_p, C.POINTER(_Stats)]),
     "zg_count_alg_bytes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
 }
@@ -173,6 +189,40 @@ def split_rel(rel: str):
     st, srest = right.split(":", 1)
     sid, _, srel = srest.partition("#")
     return rt, rid, r, st, sid, srel
+
+
+def list_scan(body: bytes, mode: int = LIST_ITEMS):
+    """zg_list_scan: (items structured array, items_begin, items_end), or None when the body has no
+    top-level "items" ("rows" with LIST_TABLE_ROWS) array. Raises ZgpuError(-1) on malformed JSON."""
+    L = lib()
+    ib, ie = C.c_uint64(0), C.c_uint64(0)
+    cap = max(16, body.count(b'"metadata"') + 16)
+    while True:
+        items = np.zeros(cap, dtype=LIST_ITEM_DTYPE)
+        n = L.zg_list_scan(body, len(body), mode, items.ctypes.data, cap, C.byref(ib), C.byref(ie))
+        if n == -7:
+            cap *= 4
+            continue
+        if n < 0:
+            raise ZgpuError(int(n), "malformed list body")
+        if ie.value == 0:
+            return None
+        return items[:n], ib.value, ie.value
+
+
+def list_filter(body: bytes, items: np.ndarray, keep: np.ndarray, items_begin: int, items_end: int,
+                flags: int = 0) -> bytes:
+    """zg_list_filter: the body with only the kept items, every other byte untouched."""
+    L = lib()
+    items = np.ascontiguousarray(items, dtype=LIST_ITEM_DTYPE)
+    keep = np.ascontiguousarray(keep, dtype=np.uint8)
+    out = np.empty(len(body) + 8, dtype=np.uint8)  # the filtered body is never longer than body + 2
+    need = C.c_size_t(0)
+    rc = L.zg_list_filter(body, len(body), items.ctypes.data, len(items), keep.ctypes.data, items_begin, items_end,
+                          flags, out.ctypes.data, out.size, C.byref(need))
+    if rc != 0:
+        raise ZgpuError(rc, "zg_list_filter failed")
+    return out[:need.value].tobytes()
 
 
 class PinnedArray:

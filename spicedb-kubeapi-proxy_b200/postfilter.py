@@ -1,0 +1,256 @@
+"""filter_list_response -- host mirror of the reference's list post-filter.
+
+Reference: pkg/authz/postfilter.go:17-55 (filterListResponse) and :58-178
+(filterItemsWithBulkPermissions). Same decisions, different mechanics:
+
+  reference                                   here
+  json.Unmarshal(body) into maps              zg_list_scan: one structural pass, byte ranges only
+  metadata["name"], ["namespace"] per item    offsets recorded by the scan (escapes decoded lazily)
+  one CheckBulkPermissions for all items      the same single call (-> one GPU launch)
+  json.Marshal(filtered map)                  zg_list_filter: splice of the kept items' bytes
+
+Decisions that are mirrored exactly (each is what the Go code does, not what one might prefer):
+  * no top-level "items" array, or an empty one  -> body returned unchanged      (postfilter.go:25-35)
+  * an item that is not an object                -> never checked, always kept   (:68-71, :141-146)
+  * a template that fails to resolve for an item -> that check is skipped        (:91-95)
+  * an item with no checks at all                -> kept                         (:141-146)
+  * several post-filters                         -> ALL must be HAS_PERMISSION   (:149-170)
+  * a per-pair error                             -> the item is dropped          (:158-162)
+  * the bulk call itself failing                 -> the whole filter fails       (:127-130)
+  * nothing kept                                 -> "items": null                (:138, nil slice)
+  * name/namespace fall back to the request's; `namespaces` lists clear the namespace;
+    namespacedName = "ns/name" or "name"                       (pkg/rules/rules.go:312-339)
+
+Only the plain `{{dotted.name}}` form of the reference's relationship templates is resolved here
+(name, namespace, namespacedName, resourceId, user.name, user.uid, request.*): the expression
+language behind `{{ }}` belongs to the rules engine, which SURVEY.md 8 puts out of scope. A
+callable `(fields) -> "type:id#perm@stype:sid"` can be passed instead of a template string.
+"""
+from __future__ import annotations
+
+import json
+import re
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Sequence, Union
+
+import numpy as np
+
+from . import _lib
+from .client import (LOOKUP_PERMISSIONSHIP_HAS_PERMISSION, PERMISSIONSHIP_HAS_PERMISSION, CheckBulkPermissionsRequest,
+                     CheckBulkPermissionsRequestItem, LookupResourcesRequest, ObjectReference, SubjectReference)
+
+_TPL = re.compile(r"\{\{\s*([A-Za-z_][A-Za-z0-9_.]*)\s*\}\}")
+
+
+@dataclass
+class RequestInfo:
+    """The fields of k8s.io/apiserver request.RequestInfo the normalisation reads."""
+    verb: str = "list"
+    resource: str = ""
+    name: str = ""
+    namespace: str = ""
+    api_group: str = ""
+    api_version: str = ""
+
+
+@dataclass
+class UserInfo:
+    name: str = ""
+    uid: str = ""
+    groups: List[str] = field(default_factory=list)
+
+
+class ResolveError(ValueError):
+    pass
+
+
+PostFilter = Union[str, Callable[[Dict[str, str]], str]]
+
+
+def _fields(req: RequestInfo, user: UserInfo, has_meta: bool, name: str, namespace: str) -> Dict[str, str]:
+    # pkg/rules/rules.go:312-339 NewResolveInput
+    if not has_meta:
+        name = namespace = ""
+    name = name or req.name
+    namespace = namespace or req.namespace
+    if req.resource == "namespaces":
+        namespace = ""
+    nn = f"{namespace}/{name}" if namespace else name
+    return {"name": name, "namespace": namespace, "namespacedName": nn, "resourceId": nn, "user.name": user.name,
+            "user.uid": user.uid, "request.verb": req.verb, "request.resource": req.resource,
+            "request.name": req.name, "request.namespace": req.namespace, "request.apiGroup": req.api_group,
+            "request.apiVersion": req.api_version}
+
+
+def resolve_rel(f: PostFilter, fields: Dict[str, str]):
+    """-> (res_type, res_id, permission, subj_type, subj_id, subj_rel); ResolveError if it cannot."""
+    if callable(f):
+        rel = f(fields)
+    else:
+        def sub(m):
+            if m.group(1) not in fields:
+                raise ResolveError(f"unknown template field {m.group(1)!r}")
+            return fields[m.group(1)]
+        rel = _TPL.sub(sub, f)
+    try:
+        parts = _lib.split_rel(rel)
+    except ValueError:
+        raise ResolveError(f"not a relationship: {rel!r}") from None
+    if not all(parts[:5]):
+        raise ResolveError(f"relationship with an empty field: {rel!r}")
+    return parts
+
+
+def _text(body: bytes, off: int, ln: int) -> str:
+    raw = body[off:off + ln]
+    if b"\\" in raw:
+        return json.loads(b'"' + raw + b'"')
+    return raw.decode("utf-8", "replace")
+
+
+def filter_list_response(body: bytes, post_filters: Sequence[PostFilter], request: RequestInfo, user: UserInfo,
+                         permissions_client) -> bytes:
+    """Returns the (possibly filtered) list body. Raises ValueError on a malformed body and whatever
+    `permissions_client.CheckBulkPermissions` raises."""
+    try:
+        scanned = _lib.list_scan(body)
+    except _lib.ZgpuError:
+        raise ValueError("failed to parse list response") from None
+    if scanned is None:
+        return body
+    items, ib, ie = scanned
+    if len(items) == 0:
+        return body
+
+    bulk: List[CheckBulkPermissionsRequestItem] = []
+    owner: List[int] = []
+    for i, it in enumerate(items):
+        flags = int(it["flags"])
+        if not flags & _lib.ITEM_IS_OBJECT:
+            continue
+        fields = _fields(request, user, bool(flags & _lib.ITEM_HAS_METADATA),
+                         _text(body, int(it["name_off"]), int(it["name_len"])),
+                         _text(body, int(it["ns_off"]), int(it["ns_len"])))
+        for f in post_filters:
+            try:
+                rt, rid, perm, st, sid, srel = resolve_rel(f, fields)
+            except ResolveError:
+                continue
+            bulk.append(CheckBulkPermissionsRequestItem(ObjectReference(rt, rid), perm,
+                                                        SubjectReference(ObjectReference(st, sid), srel)))
+            owner.append(i)
+
+    keep = np.ones(len(items), dtype=np.uint8)
+    if bulk:
+        resp = permissions_client.CheckBulkPermissions(CheckBulkPermissionsRequest(bulk))
+        for k, i in enumerate(owner):
+            if k >= len(resp.pairs):
+                keep[i] = 0
+                continue
+            pair = resp.pairs[k]
+            item = pair.GetItem()
+            if pair.GetError() is not None or item is None or item.permissionship != PERMISSIONSHIP_HAS_PERMISSION:
+                keep[i] = 0
+    # the reference re-marshals even when everything is kept; the splice then reproduces the body
+    return _lib.list_filter(body, items, keep, ib, ie, _lib.LIST_EMPTY_AS_NULL)
+
+
+# ---- the pre-filter side: LookupResources -> allowed set -> list / table / object ---------------------
+# Reference: pkg/authz/lookups.go:19-36 (prefilterResult), :44-132 (runLookupResources),
+# pkg/authz/responsefilterer.go:349-415 (filterTable / filterList / filterObject).
+
+
+def split_name(resource_id: str) -> str:
+    """The usual fromObjectIDNameExpr: the part after the last '/' of "namespace/name"."""
+    return resource_id.rsplit("/", 1)[-1]
+
+
+def split_namespace(resource_id: str):
+    """The usual fromObjectIDNamespaceExpr: the part before the '/', None for cluster-scoped ids."""
+    return resource_id.rsplit("/", 1)[0] if "/" in resource_id else None
+
+
+class Unauthorized(Exception):
+    pass
+
+
+@dataclass
+class PrefilterResult:
+    """lookups.go:19-36."""
+    all_allowed: bool = False
+    allowed_results: set = field(default_factory=set)  # of (namespace, name)
+
+    def IsAllowed(self, namespace: str, name: str) -> bool:
+        return self.all_allowed or (namespace, name) in self.allowed_results
+
+
+def run_lookup_resources(permissions_client, rel, request: RequestInfo,
+                         name_from_object_id: Callable[[str], str] = split_name,
+                         namespace_from_object_id: Callable[[str], object] = split_namespace) -> PrefilterResult:
+    """lookups.go:44-132. `rel` = (res_type, "$", permission, subj_type, subj_id, subj_rel); the two
+    callables stand in for the rule's Bloblang expressions (rules engine: out of scope)."""
+    rt, rid, perm, st, sid, srel = rel
+    if rid != "$":
+        raise ValueError("preFilter called with non-$ resource ID")  # lookups.go:45-48
+    res = PrefilterResult()
+    stream = permissions_client.LookupResources(
+        LookupResourcesRequest(rt, perm, SubjectReference(ObjectReference(st, sid), srel or "")))
+    for resp in stream:
+        if resp.permissionship != LOOKUP_PERMISSIONSHIP_HAS_PERMISSION:
+            continue  # conditional results are skipped (lookups.go:86-89)
+        name = name_from_object_id(resp.resource_object_id)
+        if not name:
+            raise ValueError("unable to determine name for resource")  # lookups.go:106-109
+        ns = namespace_from_object_id(resp.resource_object_id)
+        if ns is None:
+            ns = request.namespace or ""  # the expression is re-run on the request input (lookups.go:117-127)
+        res.allowed_results.add((ns, name))
+    return res
+
+
+def _filter_by_result(body: bytes, result: PrefilterResult, mode: int, what: str) -> bytes:
+    try:
+        scanned = _lib.list_scan(body, mode)
+    except _lib.ZgpuError:
+        raise ValueError(f"failed to decode response body as a {what}") from None
+    if scanned is None:
+        return body
+    items, ib, ie = scanned
+    keep = np.zeros(len(items), dtype=np.uint8)
+    for i, it in enumerate(items):
+        flags = int(it["flags"])
+        if not flags & _lib.ITEM_IS_OBJECT:
+            raise ValueError(f"failed to decode response body as a {what}: element {i} is not an object")
+        if mode == _lib.LIST_TABLE_ROWS and not flags & _lib.ITEM_HAS_OBJECT:
+            # an empty RawExtension does not decode (responsefilterer.go:361-365)
+            raise ValueError("error decoding partial object metadata from table row")
+        keep[i] = result.IsAllowed(_text(body, int(it["ns_off"]), int(it["ns_len"])),
+                                   _text(body, int(it["name_off"]), int(it["name_len"])))
+    return _lib.list_filter(body, items, keep, ib, ie)
+
+
+def filter_list(body: bytes, result: PrefilterResult) -> bytes:
+    """responsefilterer.go:376-400: keep the items whose (namespace, name) is allowed; [] when none."""
+    return _filter_by_result(body, result, _lib.LIST_ITEMS, "list")
+
+
+def filter_table(body: bytes, result: PrefilterResult) -> bytes:
+    """responsefilterer.go:349-374: the same over metav1.Table rows (rows[i].object.metadata)."""
+    return _filter_by_result(body, result, _lib.LIST_TABLE_ROWS, "table")
+
+
+def filter_object(body: bytes, result: PrefilterResult) -> bytes:
+    """responsefilterer.go:403-415: a single object passes unchanged or the request is unauthorized."""
+    wrapped = b'{"items":[' + body + b']}'  # reuse the item scanner for the one object
+    try:
+        scanned = _lib.list_scan(wrapped)
+    except _lib.ZgpuError:
+        raise ValueError("failed to decode response body") from None
+    items = scanned[0] if scanned else ()
+    if len(items) != 1 or not int(items[0]["flags"]) & _lib.ITEM_IS_OBJECT:
+        raise ValueError("failed to decode response body")
+    it = items[0]
+    if not result.IsAllowed(_text(wrapped, int(it["ns_off"]), int(it["ns_len"])),
+                            _text(wrapped, int(it["name_off"]), int(it["name_len"]))):
+        raise Unauthorized("unauthorized")
+    return body

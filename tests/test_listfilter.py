@@ -1,0 +1,308 @@
+"""List-response filter: zg_list_scan / zg_list_filter and the host mirror of
+pkg/authz/postfilter.go. The checker for the byte-level work is Python's json module (decode both
+sides, compare values); the reference's own cases (postfilter_test.go:151-323) are transcribed with
+a mock client shaped like its mockPermissionsClient (postfilter_test.go:19-66)."""
+import json
+import random
+
+import numpy as np
+import pytest
+
+import zgpu  # noqa: F401  (registers the package under an importable name)
+from spicedb_kubeapi_proxy_b200 import _lib, client as cl, postfilter as pf
+
+
+class MockPermissionsClient:
+    """postfilter_test.go:19-66: a map from 'type:id#perm@stype:sid' to a permissionship, default NO."""
+
+    def __init__(self, responses, errors=(), fail=False, short=False):
+        self.responses, self.errors, self.fail, self.short = responses, set(errors), fail, short
+        self.calls = []
+
+    def CheckBulkPermissions(self, req):
+        if self.fail:
+            raise cl.RpcError("UNAVAILABLE", "down")
+        self.calls.append(len(req.items))
+        pairs = []
+        for it in req.items:
+            key = f"{it.resource.object_type}:{it.resource.object_id}#{it.permission}@" \
+                  f"{it.subject.object.object_type}:{it.subject.object.object_id}"
+            if key in self.errors:
+                pairs.append(cl.CheckBulkPermissionsPair(it, error="boom"))
+            else:
+                pairs.append(cl.CheckBulkPermissionsPair(it, item=cl.CheckBulkPermissionsResponseItem(
+                    self.responses.get(key, cl.PERMISSIONSHIP_NO_PERMISSION))))
+        return cl.CheckBulkPermissionsResponse(pairs[:-1] if self.short else pairs)
+
+
+HAS, NO = cl.PERMISSIONSHIP_HAS_PERMISSION, cl.PERMISSIONSHIP_NO_PERMISSION
+TPL = "pod:{{name}}#view@user:{{user.name}}"
+REQ, USER = pf.RequestInfo(verb="list"), pf.UserInfo(name="testuser")
+
+
+def pod(name, ns="default", **extra):
+    return {"metadata": {"name": name, "namespace": ns}, **extra}
+
+
+def test_reference_filter_list_response():
+    # postfilter_test.go:151-244 TestFilterListResponse
+    body = json.dumps({"apiVersion": "v1", "kind": "PodList", "items": [pod("pod1"), pod("pod2")]}).encode()
+    mock = MockPermissionsClient({"pod:pod1#view@user:testuser": HAS, "pod:pod2#view@user:testuser": NO})
+    out = json.loads(pf.filter_list_response(body, [TPL], REQ, USER, mock))
+    assert len(out["items"]) == 1 and out["items"][0]["metadata"]["name"] == "pod1"
+    assert out["apiVersion"] == "v1" and out["kind"] == "PodList"
+    assert mock.calls == [2]  # ONE bulk call for the whole list
+
+
+def test_reference_filter_items_with_bulk_permissions():
+    # postfilter_test.go:246-323 TestFilterItemsWithBulkPermissions (incl. the empty-items leg)
+    mock = MockPermissionsClient({"pod:testpod1#view@user:testuser": HAS, "pod:testpod2#view@user:testuser": NO})
+    body = json.dumps({"items": [pod("testpod1"), pod("testpod2")]}).encode()
+    out = json.loads(pf.filter_list_response(body, [TPL], REQ, USER, mock))
+    assert [i["metadata"]["name"] for i in out["items"]] == ["testpod1"]
+    empty = b'{"items": []}'
+    assert pf.filter_list_response(empty, [TPL], REQ, USER, mock) == empty
+    assert mock.calls == [2]  # no call for an empty list
+
+
+def test_mirrored_decisions():
+    mock = MockPermissionsClient({"pod:a#view@user:testuser": HAS, "pod:a#edit@user:testuser": HAS,
+                                  "pod:b#view@user:testuser": HAS, "pod:req#view@user:testuser": HAS},
+                                 errors={"pod:e#view@user:testuser"})
+    # no "items" array / items of another type: passthrough, byte for byte
+    for raw in (b'{"kind":"Status","code":403}', b'{"items":"x"}', b'{"items":{"a":1}}', b' {"items" : null} '):
+        assert pf.filter_list_response(raw, [TPL], REQ, USER, mock) is raw
+    # non-object items are kept; an item without metadata takes the request's name (rules.go:321-326)
+    body = json.dumps({"items": [3, "s", None, [pod("zz")], pod("a"), pod("nope"), {"spec": 1}]}).encode()
+    out = json.loads(pf.filter_list_response(body, [TPL], pf.RequestInfo(name="req"), USER, mock))
+    assert out["items"] == [3, "s", None, [pod("zz")], pod("a"), {"spec": 1}]
+    # all post-filters must pass; per-pair error drops the item; unresolvable template = check skipped
+    body = json.dumps({"items": [pod("a"), pod("b"), pod("e")]}).encode()
+    both = [TPL, "pod:{{name}}#edit@user:{{user.name}}"]
+    assert [i["metadata"]["name"] for i in json.loads(pf.filter_list_response(body, both, REQ, USER, mock))["items"]] == ["a"]
+    assert [i["metadata"]["name"] for i in json.loads(pf.filter_list_response(body, [TPL], REQ, USER, mock))["items"]] == ["a", "b"]
+    skipped = ["pod:{{nosuchfield}}#view@user:{{user.name}}"]
+    assert json.loads(pf.filter_list_response(body, skipped, REQ, USER, mock))["items"] == [pod("a"), pod("b"), pod("e")]
+    # nothing kept: "items": null, as a re-marshalled nil slice (postfilter.go:138)
+    none = pf.filter_list_response(json.dumps({"items": [pod("x")], "kind": "L"}).encode(), [TPL], REQ, USER, mock)
+    assert json.loads(none) == {"items": None, "kind": "L"}
+    # a short response drops the items whose pair is missing (postfilter.go:151-155)
+    short = MockPermissionsClient({"pod:a#view@user:testuser": HAS, "pod:b#view@user:testuser": HAS}, short=True)
+    body = json.dumps({"items": [pod("a"), pod("b")]}).encode()
+    assert json.loads(pf.filter_list_response(body, [TPL], REQ, USER, short))["items"] == [pod("a")]
+    # the bulk call failing fails the filter; a malformed body too
+    with pytest.raises(cl.RpcError):
+        pf.filter_list_response(body, [TPL], REQ, USER, MockPermissionsClient({}, fail=True))
+    for bad in (b'{"items":[', b'{"items":[{]}', b'{"items":[1,]}', b'{"items":[]} x', b'', b'[1]', b'{"a":"\x01"}',
+                b'{"a":tru}', b'{"a":nulll}', b'{"a":01}', b'{"a":1.}', b'{"a":-}', b'{"a":1e}', b'{"a":.5}',
+                b'{"a":"\\x"}', b'{"a":"\\u12g4"}', b'{"a":1 "b":2}', b'{"a"}', b'{a:1}', b'{"items":[1 2]}'):
+        with pytest.raises(ValueError):
+            pf.filter_list_response(bad, [TPL], REQ, USER, mock)
+
+
+def test_namespaced_name_normalisation():
+    # pkg/rules/rules.go:312-339: ns/name, request fallbacks, `namespaces` clears the namespace
+    seen = []
+
+    def probe(fields):
+        seen.append((fields["name"], fields["namespace"], fields["namespacedName"]))
+        return f"pod:{fields['namespacedName']}#view@user:u"
+    mock = MockPermissionsClient({})
+    body = json.dumps({"items": [pod("p", "ns1"), {"metadata": {"name": "q"}}, {"metadata": {"namespace": "ns2"}},
+                                 {"metadata": {"name": 5, "namespace": ["x"]}}]}).encode()
+    pf.filter_list_response(body, [probe], pf.RequestInfo(name="rn", namespace="rns"), USER, mock)
+    assert seen == [("p", "ns1", "ns1/p"), ("q", "rns", "rns/q"), ("rn", "ns2", "ns2/rn"), ("rn", "rns", "rns/rn")]
+    seen.clear()
+    pf.filter_list_response(json.dumps({"items": [pod("team-a", "team-a")]}).encode(), [probe],
+                            pf.RequestInfo(resource="namespaces"), USER, mock)
+    assert seen == [("team-a", "", "team-a")]
+
+
+def test_duplicate_and_escaped_keys_follow_encoding_json():
+    # encoding/json: the last duplicate key wins; keys are compared after unescaping
+    raw = (b'{"items":[{"metadata":{"name":"old"}}],"x":1,'
+           b'"\\u0069tems":[{"metadata":{"name":"first","name":"n\\u0061me2"},"\\u006detadata":{"n\\u0061me":"last"}},'
+           b'{"metadata":{"name":"gone"},"metadata":7}]}')
+    items, ib, ie = _lib.list_scan(raw)
+    got = [(raw[i["name_off"]:i["name_off"] + i["name_len"]], int(i["flags"])) for i in items]
+    assert got == [(b"last", 3), (b"", 1)]
+    ref = json.loads(raw)  # Python's json keeps the last duplicate too
+    assert [i["metadata"]["name"] if isinstance(i["metadata"], dict) else None for i in ref["items"]] == ["last", None]
+    assert raw[ib:ie] == raw[raw.index(b"[", raw.index(b"\\u0069tems")):-1]
+    # escaped VALUES are handed over raw and decoded by the caller
+    seen = []
+    pf.filter_list_response(b'{"items":[{"metadata":{"name":"a\\u00e9\\"b","namespace":"n\\\\s"}}]}',
+                            [lambda f: seen.append(f["namespacedName"]) or "pod:x#view@user:u"], REQ, USER,
+                            MockPermissionsClient({}))
+    assert seen == ['n\\s/aé"b']
+
+
+def _rand_value(rng, depth=0):
+    k = rng.randrange(9 if depth < 4 else 6)
+    if k == 0:
+        return rng.choice([None, True, False])
+    if k == 1:
+        return rng.choice([0, -1, 17, 2**53, 1.5, -2.25e-7, 1e300, 12345678901234567890])
+    if k in (2, 3, 4, 5):
+        alphabet = ['a', 'Z', '0', ' ', '"', '\\', '/', '{', '}', '[', ']', ',', ':', '\n', '\t', 'é', '中',
+                    '\U0001f600', 'items', 'metadata', 'name']
+        return "".join(rng.choice(alphabet) for _ in range(rng.randrange(8)))
+    if k in (6, 7):
+        return {str(_rand_value(rng, 9)) if rng.random() < 0.3 else rng.choice(["a", "name", "metadata", "items", "spec"]):
+                _rand_value(rng, depth + 1) for _ in range(rng.randrange(4))}
+    return [_rand_value(rng, depth + 1) for _ in range(rng.randrange(4))]
+
+
+def _rand_item(rng):
+    r = rng.random()
+    if r < 0.1:
+        return _rand_value(rng, 2)
+    meta = {}
+    if rng.random() < 0.9:
+        meta["name"] = rng.choice(["pod-%d" % rng.randrange(50), _rand_value(rng, 9), "né\"\\x"])
+    if rng.random() < 0.7:
+        meta["namespace"] = rng.choice(["ns-%d" % rng.randrange(5), _rand_value(rng, 9)])
+    meta["labels"] = _rand_value(rng, 2)
+    item = {"spec": _rand_value(rng, 1), "metadata": meta if rng.random() < 0.9 else _rand_value(rng, 3),
+            "status": _rand_value(rng, 1)}
+    keys = list(item)
+    rng.shuffle(keys)
+    return {k: item[k] for k in keys}
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_scan_and_filter_against_json_module(seed):
+    rng = random.Random(seed)
+    doc = {"kind": "PodList", "apiVersion": "v1", "metadata": {"resourceVersion": "42", "name": "decoy"}}
+    items = json.loads(json.dumps([_rand_item(rng) for _ in range(rng.randrange(0, 40))]))  # keys -> str
+    pos = rng.randrange(len(doc) + 1)
+    doc = dict(list(doc.items())[:pos] + [("items", items)] + list(doc.items())[pos:])
+    style = rng.randrange(3)
+    body = json.dumps(doc, ensure_ascii=rng.random() < 0.5, indent=[None, 2, None][style],
+                      separators=[None, None, (",", ":")][style]).encode()
+    got, ib, ie = _lib.list_scan(body)
+    assert len(got) == len(items) and json.loads(body[ib:ie]) == items
+    for g, it in zip(got, items):
+        assert json.loads(body[g["begin"]:g["end"]]) == it
+        is_obj = isinstance(it, dict)
+        meta = it.get("metadata") if is_obj else None
+        assert int(g["flags"]) == (1 if is_obj else 0) | (2 if isinstance(meta, dict) else 0)
+        for key, off, ln in (("name", "name_off", "name_len"), ("namespace", "ns_off", "ns_len")):
+            want = meta.get(key) if isinstance(meta, dict) and isinstance(meta.get(key), str) else ""
+            assert json.loads(b'"' + body[g[off]:g[off] + g[ln]] + b'"') == want
+    for _ in range(3):
+        keep = np.array([rng.random() < 0.5 for _ in items], dtype=np.uint8)
+        as_null = rng.random() < 0.5
+        out = json.loads(_lib.list_filter(body, got, keep, ib, ie, _lib.LIST_EMPTY_AS_NULL if as_null else 0))
+        want = dict(doc)
+        want["items"] = [it for it, k in zip(items, keep) if k] or (None if as_null else [])
+        assert out == want and list(out) == list(want)  # values AND key order preserved
+
+
+def test_filter_buffer_contract():
+    import ctypes as C
+    body = b'{"items":[{"a":1},{"b":2}],"k":1}'
+    items, ib, ie = _lib.list_scan(body)
+    L = _lib.lib()
+    need = C.c_size_t(0)
+    keep = np.array([1, 0], dtype=np.uint8)
+    rc = L.zg_list_filter(body, len(body), items.ctypes.data, 2, keep.ctypes.data, ib, ie, 0, None, 0, C.byref(need))
+    assert rc == -7 and need.value == len(b'{"items":[{"a":1}],"k":1}')
+    buf = C.create_string_buffer(need.value)
+    assert L.zg_list_filter(body, len(body), items.ctypes.data, 2, keep.ctypes.data, ib, ie, 0, buf, need.value,
+                            C.byref(need)) == 0
+    assert buf.raw == b'{"items":[{"a":1}],"k":1}'
+    # capacity too small for the scan: E2BIG, and a count-only call (out = NULL) reports the size
+    small = np.zeros(1, dtype=_lib.LIST_ITEM_DTYPE)
+    assert L.zg_list_scan(body, len(body), 0, small.ctypes.data, 1, None, None) == -7
+    assert L.zg_list_scan(body, len(body), 0, None, 0, None, None) == 2
+    assert L.zg_list_scan(body, len(body), 2, None, 0, None, None) == -1  # unknown mode
+    # deep nesting is bounded, not a stack overflow
+    deep = b'{"items":[' + b'[' * 100000 + b']' * 100000 + b']}'
+    assert L.zg_list_scan(deep, len(deep), 0, None, 0, None, None) == -1
+
+
+class MockLookupClient:
+    def __init__(self, ids, conditional=()):
+        self.ids, self.conditional = ids, set(conditional)
+
+    def LookupResources(self, req):
+        self.req = req
+        return iter([cl.LookupResourcesResponse(i, 2 if i in self.conditional else cl.LOOKUP_PERMISSIONSHIP_HAS_PERMISSION)
+                     for i in self.ids])
+
+
+def test_prefilter_lookup_to_allowed_set():
+    # lookups.go:44-132
+    mock = MockLookupClient(["ns1/a", "ns2/b", "clusterwide", "ns3/cond"], conditional={"ns3/cond"})
+    rel = ("pod", "$", "view", "user", "alice", "")
+    res = pf.run_lookup_resources(mock, rel, pf.RequestInfo(namespace="reqns"))
+    assert res.allowed_results == {("ns1", "a"), ("ns2", "b"), ("reqns", "clusterwide")}
+    assert (mock.req.resource_object_type, mock.req.permission, mock.req.subject.object.object_id) == ("pod", "view", "alice")
+    assert res.IsAllowed("ns1", "a") and not res.IsAllowed("ns1", "b") and pf.PrefilterResult(all_allowed=True).IsAllowed("x", "y")
+    with pytest.raises(ValueError):
+        pf.run_lookup_resources(mock, ("pod", "p1", "view", "user", "alice", ""), pf.RequestInfo())
+    with pytest.raises(ValueError):  # a name expression that yields nothing fails the whole pre-filter
+        pf.run_lookup_resources(MockLookupClient(["ns/"]), rel, pf.RequestInfo())
+
+
+def test_prefilter_list_table_object():
+    res = pf.PrefilterResult(allowed_results={("ns1", "a"), ("", "node1")})
+    body = json.dumps({"kind": "PodList", "items": [pod("a", "ns1"), pod("a", "ns2"), {"metadata": {"name": "node1"}},
+                                                    {"spec": {}}], "metadata": {}}).encode()
+    out = json.loads(pf.filter_list(body, res))
+    assert out == {"kind": "PodList", "items": [pod("a", "ns1"), {"metadata": {"name": "node1"}}], "metadata": {}}
+    # nothing allowed: [] (make(..., 0), responsefilterer.go:377), not the post-filter's null
+    assert json.loads(pf.filter_list(body, pf.PrefilterResult()))["items"] == []
+    assert json.loads(pf.filter_list(body, pf.PrefilterResult(all_allowed=True))) == json.loads(body)
+    with pytest.raises(ValueError):
+        pf.filter_list(b'{"items":[1]}', res)
+    # metav1.Table: rows[i].object carries the PartialObjectMetadata (responsefilterer.go:349-374)
+    row = lambda n, ns, **kw: {"cells": [n, "Running", "metadata"], "object": {"kind": "PartialObjectMetadata", **pod(n, ns)}, **kw}
+    table = {"kind": "Table", "columnDefinitions": [{"name": "Name", "type": "string"}],
+             "rows": [row("a", "ns1"), row("a", "ns2", metadata={"name": "decoy"}), row("b", "ns1"),
+                      {"cells": [], "object": None}]}
+    tb = json.dumps(table).encode()
+    out = json.loads(pf.filter_table(tb, res))
+    assert out["rows"] == [row("a", "ns1")] and out["columnDefinitions"] == table["columnDefinitions"]
+    assert json.loads(pf.filter_table(tb, pf.PrefilterResult()))["rows"] == []
+    with pytest.raises(ValueError):  # a row without "object": empty RawExtension does not decode
+        pf.filter_table(json.dumps({"rows": [{"cells": []}]}).encode(), res)
+    # a row-level "metadata" is not the object's: only rows[i].object.metadata counts
+    items, _, _ = _lib.list_scan(json.dumps({"rows": [{"metadata": {"name": "x"}, "object": {"metadata": {"name": "y"}}}]}).encode(),
+                                 _lib.LIST_TABLE_ROWS)
+    assert int(items[0]["name_len"]) == 1 and int(items[0]["flags"]) == 7
+    # single object (responsefilterer.go:403-415)
+    one = json.dumps(pod("a", "ns1", spec={"x": [1, 2]})).encode()
+    assert pf.filter_object(one, res) is one
+    with pytest.raises(pf.Unauthorized):
+        pf.filter_object(json.dumps(pod("zz", "ns1")).encode(), res)
+    with pytest.raises(ValueError):
+        pf.filter_object(b'{"a":1},{"b":2}', res)
+
+
+@pytest.mark.gpu
+def test_gpu_filter_through_engine():
+    """The whole post-filter through the real engine: cfg1-like schema, one bulk call, one launch."""
+    schema = """
+    definition user {}
+    definition namespace { relation viewer: user  permission view = viewer }
+    definition pod { relation namespace: namespace  relation viewer: user | user:*
+                     permission view = viewer + namespace->view }
+    """
+    c = cl.PermissionsClient(schema, ["namespace:team-a#viewer@user:alice", "pod:team-a/p1#namespace@namespace:team-a",
+                                      "pod:team-b/p2#namespace@namespace:team-b", "pod:team-b/p3#viewer@user:alice",
+                                      "pod:team-b/p4#viewer@user:*"])
+    body = json.dumps({"kind": "PodList", "items": [pod("p1", "team-a"), pod("p2", "team-b"), pod("p3", "team-b"),
+                                                    pod("p4", "team-b"), pod("p5", "team-b")]}).encode()
+    tpl = "pod:{{namespacedName}}#view@user:{{user.name}}"
+    before = c.engine.stats()["launches"]
+    out = json.loads(pf.filter_list_response(body, [tpl], REQ, pf.UserInfo(name="alice"), c))
+    assert [i["metadata"]["name"] for i in out["items"]] == ["p1", "p3", "p4"]
+    assert c.engine.stats()["launches"] > before
+    out = json.loads(pf.filter_list_response(body, [tpl], REQ, pf.UserInfo(name="bob"), c))
+    assert [i["metadata"]["name"] for i in out["items"]] == ["p4"]
+    # the pre-filter path over the same store: LookupResources -> allowed set -> list
+    res = pf.run_lookup_resources(c, ("pod", "$", "view", "user", "alice", ""), REQ)
+    assert res.allowed_results == {("team-a", "p1"), ("team-b", "p3"), ("team-b", "p4")}
+    assert [i["metadata"]["name"] for i in json.loads(pf.filter_list(body, res))["items"]] == ["p1", "p3", "p4"]
