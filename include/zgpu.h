@@ -17,6 +17,7 @@
  *   zg_write_relationships      WriteRelationships     pkg/authz/distributedtx/activity.go:54-76
  *   zg_delete_relationships     DeleteRelationships    (v1 API; filter semantics update.go:207-271)
  *   zg_read_relationships       ReadRelationships      pkg/authz/distributedtx/activity.go:128-171
+ *   zg_watch_read               WatchService.Watch     pkg/authz/watch.go:27-48
  *   zg_engine_create/load_schema embedded SpiceDB ctor pkg/spicedb/spicedb.go:18-57
  *
  * Return codes: 0 = OK, negative = error (message: zg_last_error).
@@ -235,6 +236,17 @@ int zg_shard_subqueries(zg_engine *e, int level, zg_check *out, uint64_t n);
 /* child_vals[i]: value of raised sub-query i (bit0 HAS, bit1 ERROR). out[q]: level 0: v1 code of
  * query q; deeper levels: its value bits, to be sent back to the rank that raised it. */
 int zg_shard_fold(zg_engine *e, int level, const uint8_t *child_vals, uint64_t n_sub, uint8_t *out);
+
+/* Watch feed (v1.WatchServiceClient.Watch, pkg/authz/watch.go:27-48): the relationship changes made
+ * visible by revisions > since_revision, oldest first, as '\n'-separated lines
+ *   "<revision> <TOUCH|CREATE|DELETE> <type:id#rel@stype:sid[#srel]>[ <expires_at>]"
+ * restricted to resources of res_type (NULL/"" = all; WatchRequest.OptionalObjectTypes). Only
+ * zg_write_relationships / zg_delete_relationships feed it (interned bulk loads do not); a DELETE
+ * of a relationship that did not exist is not a change. *through_revision = the engine's current
+ * revision: pass it as the next since_revision. ZG_EPRECOND when since_revision is older than the
+ * retained feed (2^20 changes), ZG_E2BIG with *need = bytes required incl. NUL. */
+int zg_watch_read(zg_engine *e, uint64_t since_revision, const char *res_type, char *buf, size_t cap,
+                  size_t *need, uint64_t *n_out, uint64_t *through_revision);
 
 /* ---- list-response filter (host code, no GPU) -------
  * Replaces the unmarshal / re-marshal round trip of pkg/authz/postfilter.go:17-55

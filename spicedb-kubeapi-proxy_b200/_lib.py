@@ -129,6 +129,8 @@ _SIGS = {
                                           C.POINTER(C.c_uint64)]),
     "zg_read_relationships": (C.c_int, [C.c_void_p, C.POINTER(_RelStr), C.c_char_p, C.c_size_t,
                                         C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]),
+    "zg_watch_read": (C.c_int, [C.c_void_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t),
+                                C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "zg_check_bulk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "zg_check_bulk_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "zg_check_bulk_str": (C.c_int, [C.c_void_p, C.POINTER(_RelStr), C.c_uint64, C.c_void_p]),
@@ -368,6 +370,24 @@ class Engine:
             return [l for l in buf.value.decode().split("\n") if l]
 
     # -- hot path ---------------------------------------------------------------
+    def watch_read(self, since_revision: int, res_type: str = ""):
+        """-> ([(revision, op_name, relationship text, expires_at)], through_revision)."""
+        cap = 1 << 16
+        while True:
+            buf = C.create_string_buffer(cap)
+            need, n, through = C.c_size_t(0), C.c_uint64(0), C.c_uint64(0)
+            rc = self._L.zg_watch_read(self._h, since_revision, _b(res_type), buf, cap, C.byref(need), C.byref(n),
+                                       C.byref(through))
+            if rc == -7:
+                cap = need.value
+                continue
+            self._ck(rc)
+            out = []
+            for line in buf.value.decode().splitlines():
+                parts = line.split(" ")
+                out.append((int(parts[0]), parts[1], parts[2], int(parts[3]) if len(parts) > 3 else 0))
+            return out, through.value
+
     def check_bulk(self, items: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         """CheckBulkPermissions on interned items (HOST buffers; copies inside the call)."""
         items = np.ascontiguousarray(items, dtype=CHECK_DTYPE)

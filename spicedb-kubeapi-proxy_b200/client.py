@@ -7,6 +7,7 @@ these methods on it:
     CheckBulkPermissions   pkg/authz/check.go:48, pkg/authz/postfilter.go:134
     CheckPermission        pkg/authz/watch.go:50
     LookupResources        pkg/authz/lookups.go:65  (server stream until io.EOF)
+    Watch                  pkg/authz/watch.go:29   (v1.WatchServiceClient, same connection)
     WriteRelationships     pkg/authz/distributedtx/activity.go:60
     ReadRelationships      pkg/authz/distributedtx/activity.go:107,154
     DeleteRelationships    (v1 API; the proxy deletes by read-then-write, workflow.go:354-389)
@@ -196,6 +197,18 @@ class ReadRelationshipsResponse:
     relationship: Relationship
 
 
+@dataclass
+class WatchRequest:
+    optional_object_types: List[str] = field(default_factory=list)
+    optional_start_cursor: Optional[int] = None  # revision; None = changes after the call (watch.go:29-31)
+
+
+@dataclass
+class WatchResponse:
+    updates: List[RelationshipUpdate]
+    changes_through: int  # revision; usable as the next optional_start_cursor
+
+
 class RpcError(Exception):
     """Stands in for a gRPC status error (codes follow google.rpc.Code names)."""
 
@@ -271,9 +284,59 @@ class PermissionsClient:
         except ZgpuError as e:
             raise _rpc(e) from None
 
+    def Watch(self, req: WatchRequest) -> "WatchStream":
+        """v1.WatchServiceClient.Watch (pkg/authz/watch.go:27-48). The returned stream is polled:
+        `Recv()` hands back the next WatchResponse (one per revision, as SpiceDB groups updates by
+        transaction) or None when the feed is drained -- the gRPC stream would block instead."""
+        for t in req.optional_object_types:
+            if self.engine.type_id(t) < 0:
+                raise RpcError("INVALID_ARGUMENT", f"object definition `{t}` not found")
+        start = req.optional_start_cursor
+        if start is None:
+            start = self.engine.stats()["revision"]
+        return WatchStream(self.engine, list(req.optional_object_types), start)
+
     def ReadRelationships(self, req: ReadRelationshipsRequest) -> Iterator[ReadRelationshipsResponse]:
         try:
             lines = self.engine.read_relationships(**req.relationship_filter.fields())
         except ZgpuError as e:
             raise _rpc(e) from None
         return iter([ReadRelationshipsResponse(Relationship.parse(l)) for l in lines])
+
+
+_WATCH_OP = {"TOUCH": OPERATION_TOUCH, "CREATE": OPERATION_CREATE, "DELETE": OPERATION_DELETE}
+
+
+class WatchStream:
+    def __init__(self, engine: Engine, object_types: List[str], cursor: int):
+        self.engine, self.object_types, self.cursor = engine, object_types, cursor
+        self._pending: List[WatchResponse] = []
+
+    def _fill(self):
+        try:
+            if len(self.object_types) == 1:
+                changes, through = self.engine.watch_read(self.cursor, self.object_types[0])
+            else:
+                changes, through = self.engine.watch_read(self.cursor, "")
+                if self.object_types:
+                    keep = tuple(t + ":" for t in self.object_types)
+                    changes = [c for c in changes if c[2].startswith(keep)]
+        except ZgpuError as e:
+            raise _rpc(e) from None
+        by_rev: dict = {}
+        for rev, op, rel, exp in changes:
+            by_rev.setdefault(rev, []).append(RelationshipUpdate(_WATCH_OP[op], Relationship.parse(rel, exp)))
+        self._pending = [WatchResponse(ups, rev) for rev, ups in sorted(by_rev.items())]
+        self.cursor = through
+
+    def Recv(self) -> Optional[WatchResponse]:
+        if not self._pending:
+            self._fill()
+        return self._pending.pop(0) if self._pending else None
+
+    def __iter__(self):
+        while True:
+            r = self.Recv()
+            if r is None:
+                return
+            yield r

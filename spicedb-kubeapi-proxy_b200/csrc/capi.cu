@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <deque>
 #include <mutex>
 #include <new>
 #include <string>
@@ -66,6 +67,27 @@ struct zg_engine {
   std::vector<uint32_t> last_lookup_ids;
   HostSnapshot last_built;  // kept only for zg_debug_row / host-only engines
   bool keep_built = false;
+  // Watch feed (pkg/authz/watch.go:29-31): what WriteRelationships / DeleteRelationships changed,
+  // stamped with the revision that made it visible. Bounded: the oldest entries are dropped and
+  // a reader that asks for them is told so (as SpiceDB does past its GC window).
+  struct WatchEntry {
+    uint64_t revision;
+    zg_tuple t;
+    uint32_t expires_at, op;
+  };
+  std::deque<WatchEntry> watch_log;
+  uint64_t watch_floor = 0;  // every change of a revision <= floor may be gone
+  static constexpr size_t kWatchCap = 1u << 20;
+  void log_changes(const std::vector<zg_update>& u, const std::vector<uint8_t>& changed) {
+    for (size_t i = 0; i < u.size(); ++i)
+      if (changed[i]) watch_log.push_back(WatchEntry{revision, u[i].t, u[i].expires_at, u[i].op});
+    while (watch_log.size() > kWatchCap) {
+      watch_floor = watch_log.front().revision;
+      watch_log.pop_front();
+    }
+    // a revision is dropped whole: a reader never sees part of a write
+    while (!watch_log.empty() && watch_log.front().revision <= watch_floor) watch_log.pop_front();
+  }
 };
 
 static thread_local std::string g_err;
@@ -426,9 +448,12 @@ extern "C" int zg_write_relationships(zg_engine* e, const zg_update_str* ups, ui
   int rc = check_preconditions(e, pre, n_pre);
   if (rc) return rc;
   int code = ZG_OK;
-  std::string err = e->store.apply(u.data(), n, &code);
+  std::vector<uint8_t> changed;
+  std::string err = e->store.apply(u.data(), n, &code, &changed);
   if (!err.empty()) return fail(code, err);
-  return publish_locked(e);
+  rc = publish_locked(e);
+  if (rc == ZG_OK) e->log_changes(u, changed);
+  return rc;
 }
 
 extern "C" int zg_delete_relationships(zg_engine* e, const zg_filter_str* filter, const zg_precondition_str* pre,
@@ -450,10 +475,13 @@ extern "C" int zg_delete_relationships(zg_engine* e, const zg_filter_str* filter
     u[i].op = ZG_OP_DELETE;
   }
   int code = ZG_OK;
-  err = e->store.apply(u.data(), u.size(), &code);
+  std::vector<uint8_t> changed;
+  err = e->store.apply(u.data(), u.size(), &code, &changed);
   if (!err.empty()) return fail(code, err);
   if (n_deleted) *n_deleted = idx.size();
-  return publish_locked(e);
+  rc = publish_locked(e);
+  if (rc == ZG_OK) e->log_changes(u, changed);
+  return rc;
 }
 
 static std::string tuple_text(const zg_engine* e, const zg_tuple& t) {
@@ -496,6 +524,44 @@ extern "C" int zg_read_relationships(zg_engine* e, const zg_filter_str* filter, 
     buf[w++] = '\n';
   }
   buf[w] = 0;
+  return ZG_OK;
+}
+
+extern "C" int zg_watch_read(zg_engine* e, uint64_t since_revision, const char* res_type, char* buf, size_t cap,
+                             size_t* need, uint64_t* n_out, uint64_t* through_revision) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  std::lock_guard<std::mutex> g(e->mu);
+  int want = -1;
+  if (res_type && *res_type) {
+    want = e->schema.type_id(res_type);
+    if (want < 0) return fail(ZG_EINVAL, std::string("object definition `") + res_type + "` not found");
+  }
+  if (since_revision < e->watch_floor)
+    return fail(ZG_EPRECOND, "watch: revision " + std::to_string(since_revision) + " is older than the retained feed (" +
+                                 std::to_string(e->watch_floor) + ")");
+  static const char* kOp[] = {"TOUCH", "CREATE", "DELETE"};
+  std::string out;
+  uint64_t n = 0;
+  // entries are in revision order: binary search for the first one after `since`
+  auto it = std::partition_point(e->watch_log.begin(), e->watch_log.end(),
+                                 [&](const zg_engine::WatchEntry& w) { return w.revision <= since_revision; });
+  for (; it != e->watch_log.end(); ++it) {
+    if (want >= 0 && e->schema.slots[it->t.rel].type != want) continue;
+    out += std::to_string(it->revision);
+    out += ' ';
+    out += kOp[it->op];
+    out += ' ';
+    out += tuple_text(e, it->t);
+    if (it->expires_at && it->op != ZG_OP_DELETE) out += " " + std::to_string(it->expires_at);
+    out += '\n';
+    ++n;
+  }
+  if (need) *need = out.size() + 1;
+  if (n_out) *n_out = n;
+  if (through_revision) *through_revision = e->revision;
+  if (out.size() + 1 > cap || !buf) return ZG_E2BIG;
+  std::memcpy(buf, out.data(), out.size());
+  buf[out.size()] = 0;
   return ZG_OK;
 }
 

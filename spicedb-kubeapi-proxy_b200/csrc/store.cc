@@ -112,8 +112,9 @@ void Store::ensure_index() {
   indexed_ = true;
 }
 
-std::string Store::apply(const zg_update* u, uint64_t n, int* code) {
+std::string Store::apply(const zg_update* u, uint64_t n, int* code, std::vector<uint8_t>* changed) {
   *code = ZG_EINVAL;
+  if (changed) changed->assign(n, 0);
   for (uint64_t i = 0; i < n; ++i) {
     if (u[i].op > ZG_OP_DELETE) return "update " + std::to_string(i) + ": unknown operation";
     if (u[i].op == ZG_OP_DELETE) {
@@ -150,9 +151,11 @@ std::string Store::apply(const zg_update* u, uint64_t n, int* code) {
         tuples[it->second].flags |= 1;
         index_.erase(it);
         --live_;
+        if (changed) (*changed)[i] = 1;
       }
       continue;
     }
+    if (changed) (*changed)[i] = 1;
     if (it != index_.end()) {
       expires[it->second] = u[i].expires_at;
       continue;

@@ -60,7 +60,9 @@ class Store {
   // Returns "" or an error message; `code` receives the ZG_* code.
   std::string validate(const zg_tuple& t, bool has_expiry) const;
   std::string load(const zg_tuple* t, const uint32_t* expires, uint64_t n);
-  std::string apply(const zg_update* u, uint64_t n, int* code);
+  // `changed` (optional, n entries): 1 where the update took effect (a DELETE of a relationship that
+  // does not exist changes nothing; TOUCH and CREATE always count).
+  std::string apply(const zg_update* u, uint64_t n, int* code, std::vector<uint8_t>* changed = nullptr);
 
   // Live relationships matching a filter (unset field = -1 / ZG_NO_OBJECT-1 sentinel via has_*).
   struct Filter {

@@ -254,3 +254,42 @@ def filter_object(body: bytes, result: PrefilterResult) -> bytes:
                             _text(wrapped, int(it["name_off"]), int(it["name_len"]))):
         raise Unauthorized("unauthorized")
     return body
+
+
+# ---- the watch side: relationship updates -> re-checks -> allowed/denied changes ----------------------
+# Reference: pkg/authz/watch.go:27-107 (RunWatch). One difference in mechanics, none in decisions: the
+# reference issues one CheckPermission per update; here all updates of a WatchResponse go out as ONE
+# CheckBulkPermissions (one GPU launch), and the results are reported in the same order.
+
+
+@dataclass
+class ResultChange:
+    """watch.go:20-23."""
+    allowed: bool
+    namespaced_name: tuple  # (namespace, name)
+
+
+def run_watch(watch_stream, check_client, rel, name_from_object_id: Callable[[str], str] = split_name,
+              namespace_from_object_id: Callable[[str], object] = split_namespace) -> List[ResultChange]:
+    """Drains `watch_stream` (client.WatchStream or any iterable of WatchResponse) and returns the
+    ResultChange the reference would push on tracker.foundChanged for each update, in order. `rel` is the
+    pre-filter's (res_type, "$", permission, subj_type, subj_id, subj_rel). A per-pair error or a failing
+    bulk call ends the watch (the reference returns from RunWatch on a CheckPermission error): raises."""
+    rt, _, perm, st, sid, srel = rel
+    out: List[ResultChange] = []
+    for resp in watch_stream:
+        ids = [u.relationship.resource.object_id for u in resp.updates]  # the operation is not inspected
+        if not ids:
+            continue
+        bulk = CheckBulkPermissionsRequest([CheckBulkPermissionsRequestItem(
+            ObjectReference(rt, i), perm, SubjectReference(ObjectReference(st, sid), srel or "")) for i in ids])
+        pairs = check_client.CheckBulkPermissions(bulk).pairs
+        for i, pair in zip(ids, pairs):
+            if pair.GetError() is not None:
+                raise RuntimeError(f"error on CheckPermission: {pair.GetError()}")
+            name = name_from_object_id(i)
+            if not name:
+                return out  # watch.go:92-94: the watch ends silently
+            ns = namespace_from_object_id(i)
+            out.append(ResultChange(pair.GetItem().permissionship == PERMISSIONSHIP_HAS_PERMISSION, (ns or "", name)))
+    return out

@@ -222,3 +222,72 @@ def test_workload_generators_are_deterministic_and_sized():
     assert ("document", "viewer", "user", None, True) in rels and ("folder", "parent", "folder", None, False) in rels
     o = Oracle(w4.schema)
     w4.load_into(o)  # every generated relationship is valid under the schema
+
+
+def test_watch_feed():
+    """v1.WatchServiceClient.Watch as the proxy uses it (pkg/authz/watch.go:27-48): updates for one resource
+    type, after the point the watch started, every applied change, grouped per write."""
+    C = zgpu.client
+    e = zgpu.Engine(workloads.BOOTSTRAP_SCHEMA, host_only=True)
+    cl = C.PermissionsClient(workloads.BOOTSTRAP_SCHEMA, engine=e)
+    up = lambda op, rel, exp=0: C.RelationshipUpdate(op, C.Relationship.parse(rel, exp))
+    write = lambda *u, pre=(): cl.WriteRelationships(C.WriteRelationshipsRequest(list(u), list(pre))).written_at
+    r0 = write(up(C.OPERATION_TOUCH, "namespace:old#creator@user:paul"))
+    pods = cl.Watch(C.WatchRequest(["pod"]))            # starts "now": the write above is not replayed
+    everything = cl.Watch(C.WatchRequest([], optional_start_cursor=0))
+    assert pods.Recv() is None
+    r1 = write(up(C.OPERATION_CREATE, "pod:ns1/p1#viewer@user:app"), up(C.OPERATION_TOUCH, "namespace:ns1#creator@user:paul"),
+               up(C.OPERATION_TOUCH, "pod:ns1/p2#viewer@user:app"))
+    r2 = write(up(C.OPERATION_TOUCH, "pod:ns1/p1#viewer@user:app"),          # TOUCH of an existing one is still a change
+               up(C.OPERATION_DELETE, "pod:ns1/never#viewer@user:app"),     # deleting nothing is not
+               up(C.OPERATION_DELETE, "pod:ns1/p2#viewer@user:app"))
+    assert r0 < r1 < r2
+    got = [(r.changes_through, [(u.operation, u.relationship.text()) for u in r.updates]) for r in pods]
+    assert got == [(r1, [(C.OPERATION_CREATE, "pod:ns1/p1#viewer@user:app"), (C.OPERATION_TOUCH, "pod:ns1/p2#viewer@user:app")]),
+                   (r2, [(C.OPERATION_TOUCH, "pod:ns1/p1#viewer@user:app"), (C.OPERATION_DELETE, "pod:ns1/p2#viewer@user:app")])]
+    assert pods.Recv() is None and pods.cursor == r2
+    # a failed write (precondition, CREATE of an existing relationship) leaves no trace in the feed
+    pre = C.Precondition(C.PRECONDITION_MUST_MATCH, C.RelationshipFilter("pod", "nope"))
+    with pytest.raises(C.RpcError):
+        write(up(C.OPERATION_TOUCH, "pod:ns1/p3#viewer@user:app"), pre=[pre])
+    with pytest.raises(C.RpcError):
+        write(up(C.OPERATION_TOUCH, "pod:ns1/p4#viewer@user:app"), up(C.OPERATION_CREATE, "pod:ns1/p1#viewer@user:app"))
+    assert pods.Recv() is None
+    # delete by filter reports every relationship it removed; expirations ride along
+    write(up(C.OPERATION_TOUCH, "workflow:w#idempotency_key@activity:a", 2_000_000_000))
+    assert cl.DeleteRelationships(C.DeleteRelationshipsRequest(C.RelationshipFilter("pod"))) == 1
+    r = pods.Recv()
+    assert [(u.operation, u.relationship.text()) for u in r.updates] == [(C.OPERATION_DELETE, "pod:ns1/p1#viewer@user:app")]
+    allu = [(u.operation, u.relationship.text(), u.relationship.optional_expires_at) for r in everything for u in r.updates]
+    assert allu[0] == (C.OPERATION_TOUCH, "namespace:old#creator@user:paul", 0) and len(allu) == 8
+    assert (C.OPERATION_TOUCH, "workflow:w#idempotency_key@activity:a", 2_000_000_000) in allu
+    # several types: filtered client-side; unknown type: INVALID_ARGUMENT
+    two = cl.Watch(C.WatchRequest(["pod", "workflow"], optional_start_cursor=0))
+    assert sum(len(r.updates) for r in two) == 6
+    with pytest.raises(C.RpcError, match="INVALID_ARGUMENT"):
+        cl.Watch(C.WatchRequest(["nosuchtype"]))
+    # E2BIG protocol of the C entry point
+    import ctypes as ct
+    L = zgpu._lib.lib()
+    need, n, through = ct.c_size_t(0), ct.c_uint64(0), ct.c_uint64(0)
+    assert L.zg_watch_read(e._h, 0, b"", None, 0, ct.byref(need), ct.byref(n), ct.byref(through)) == -7
+    assert n.value == 8 and through.value == e.stats()["revision"]
+    buf = ct.create_string_buffer(need.value)
+    assert L.zg_watch_read(e._h, 0, None, buf, need.value, ct.byref(need), ct.byref(n), ct.byref(through)) == 0
+    assert buf.value.decode().splitlines()[0] == f"{r0} TOUCH namespace:old#creator@user:paul"
+    assert buf.value.decode().splitlines()[-2].endswith("TOUCH workflow:w#idempotency_key@activity:a 2000000000")
+
+
+def test_watch_drives_recheck_like_run_watch():
+    """RunWatch's loop (watch.go:36-107) over the mirror: every update of the watched type names a resource to
+    re-check; the operation is not inspected."""
+    C = zgpu.client
+    e = zgpu.Engine(workloads.BOOTSTRAP_SCHEMA, host_only=True)
+    cl = C.PermissionsClient(workloads.BOOTSTRAP_SCHEMA, engine=e)
+    stream = cl.Watch(C.WatchRequest(["pod"]))
+    for i in range(5):
+        cl.WriteRelationships(C.WriteRelationshipsRequest([C.RelationshipUpdate(
+            C.OPERATION_TOUCH, C.Relationship.parse(f"pod:ns/p{i}#viewer@user:u{i}"))]))
+    rechecks = [(u.relationship.resource.object_id, u.relationship.subject.object.object_id)
+                for r in stream for u in r.updates]
+    assert rechecks == [(f"ns/p{i}", f"u{i}") for i in range(5)]

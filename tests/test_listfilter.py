@@ -281,6 +281,19 @@ def test_prefilter_list_table_object():
         pf.filter_object(b'{"a":1},{"b":2}', res)
 
 
+def test_run_watch_rechecks_every_update_in_one_bulk_call():
+    # watch.go:48-107 with the per-update CheckPermission folded into one bulk call per WatchResponse
+    up = lambda op, rel: cl.RelationshipUpdate(op, cl.Relationship.parse(rel))
+    stream = [cl.WatchResponse([up(cl.OPERATION_TOUCH, "pod:ns1/a#viewer@user:x"), up(cl.OPERATION_DELETE, "pod:ns1/b#viewer@user:y")], 7),
+              cl.WatchResponse([], 8), cl.WatchResponse([up(cl.OPERATION_CREATE, "pod:cw#viewer@user:z")], 9)]
+    mock = MockPermissionsClient({"pod:ns1/a#view@user:alice": HAS, "pod:cw#view@user:alice": HAS})
+    got = pf.run_watch(stream, mock, ("pod", "$", "view", "user", "alice", ""))
+    assert got == [pf.ResultChange(True, ("ns1", "a")), pf.ResultChange(False, ("ns1", "b")), pf.ResultChange(True, ("", "cw"))]
+    assert mock.calls == [2, 1]
+    with pytest.raises(RuntimeError):
+        pf.run_watch(stream, MockPermissionsClient({}, errors={"pod:ns1/b#view@user:alice"}), ("pod", "$", "view", "user", "alice", ""))
+
+
 @pytest.mark.gpu
 def test_gpu_filter_through_engine():
     """The whole post-filter through the real engine: cfg1-like schema, one bulk call, one launch."""
@@ -306,3 +319,10 @@ def test_gpu_filter_through_engine():
     res = pf.run_lookup_resources(c, ("pod", "$", "view", "user", "alice", ""), REQ)
     assert res.allowed_results == {("team-a", "p1"), ("team-b", "p3"), ("team-b", "p4")}
     assert [i["metadata"]["name"] for i in json.loads(pf.filter_list(body, res))["items"]] == ["p1", "p3", "p4"]
+    # the watch path: a write shows up on the feed and is re-checked against the new snapshot
+    stream = c.Watch(cl.WatchRequest(["pod"]))
+    c.WriteRelationships(cl.WriteRelationshipsRequest([
+        cl.RelationshipUpdate(cl.OPERATION_TOUCH, cl.Relationship.parse("pod:team-b/p2#viewer@user:alice")),
+        cl.RelationshipUpdate(cl.OPERATION_DELETE, cl.Relationship.parse("pod:team-b/p3#viewer@user:alice"))]))
+    assert pf.run_watch(stream, c, ("pod", "$", "view", "user", "alice", "")) == [
+        pf.ResultChange(True, ("team-b", "p2")), pf.ResultChange(False, ("team-b", "p3"))]
