@@ -200,8 +200,14 @@ int zg_check_bulk(zg_engine *e, const zg_check *items, uint64_t n, uint8_t *out)
  * asynchronous when the schema needs no sub-query pass. */
 int zg_check_bulk_device(zg_engine *e, const zg_check *d_items, uint64_t n, uint8_t *d_out,
                          void *cuda_stream);
-/* String form of CheckBulkPermissions / CheckPermission (n = 1). */
+/* String form of CheckBulkPermissions / CheckPermission (n = 1): resolves, then takes the same
+ * coalescing path as zg_check_bulk. */
 int zg_check_bulk_str(zg_engine *e, const zg_rel_str *items, uint64_t n, uint8_t *out);
+/* Only the resolution step of zg_check_bulk_str (strings -> interned checks; no GPU work, nothing is
+ * interned: never-written names get the ZG_NO_OBJECT sentinels, unknown types / permissions give an
+ * item that answers ZG_ITEM_ERROR). Lets a caller intern once and reuse the ids; they stay valid for
+ * the life of the engine. */
+int zg_resolve_checks(zg_engine *e, const zg_rel_str *items, uint64_t n, zg_check *out);
 
 /* LookupResources: ids (ascending) of every object of res_type with HAS_PERMISSION.
  * Returns 0, or ZG_E2BIG with *n_out = required capacity. */

@@ -134,6 +134,7 @@ _SIGS = {
     "zg_check_bulk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "zg_check_bulk_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "zg_check_bulk_str": (C.c_int, [C.c_void_p, C.POINTER(_RelStr), C.c_uint64, C.c_void_p]),
+    "zg_resolve_checks": (C.c_int, [C.c_void_p, C.POINTER(_RelStr), C.c_uint64, C.c_void_p]),
     "zg_lookup_resources": (C.c_int, [C.c_void_p, C.c_uint16, C.c_uint16, C.c_uint16, C.c_uint32, C.c_uint16,
                                       C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "zg_lookup_resources_str": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p,
@@ -404,16 +405,30 @@ class Engine:
         """DEVICE pointers (e.g. torch tensors' data_ptr()) on a cudaStream_t handle."""
         self._ck(self._L.zg_check_bulk_device(self._h, d_items_ptr, n, d_out_ptr, stream))
 
-    def check_bulk_str(self, rels) -> np.ndarray:
+    @staticmethod
+    def _relstr_array(rels):
         n = len(rels)
         arr = (_RelStr * max(n, 1))()
-        keep = []
+        keep = []  # the bytes objects must outlive the call
         for i, r in enumerate(rels):
             parts = [_b(x) for x in (split_rel(r) if isinstance(r, str) else r)]
             keep.append(parts)
             arr[i] = _RelStr(*parts)
+        return arr, keep
+
+    def check_bulk_str(self, rels) -> np.ndarray:
+        n = len(rels)
+        arr, _keep = self._relstr_array(rels)
         out = np.empty(n, dtype=np.uint8)
         self._ck(self._L.zg_check_bulk_str(self._h, arr, n, out.ctypes.data))
+        return out
+
+    def resolve_checks(self, rels) -> np.ndarray:
+        """Strings -> interned zg_check items (no GPU work); feed them to check_bulk."""
+        n = len(rels)
+        arr, _keep = self._relstr_array(rels)
+        out = np.zeros(n, dtype=CHECK_DTYPE)
+        self._ck(self._L.zg_resolve_checks(self._h, arr, n, out.ctypes.data))
         return out
 
     def lookup_resources_ids(self, res_type, perm, subj_type, subj, srel=None) -> np.ndarray:

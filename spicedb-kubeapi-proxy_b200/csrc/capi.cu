@@ -10,6 +10,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/zgpu.h"
@@ -671,8 +672,63 @@ extern "C" int zg_count_alg_bytes(zg_engine* e, const zg_check* items, uint64_t 
 }
 
 // Resolve a CHECK item without interning anything (query strings must not grow the store).
-static void resolve_check(const zg_engine* e, const zg_rel_str& r, zg_check* c) {
-  const Schema& sc = e->schema;
+// The items of one bulk call mostly repeat their literal fields -- a post-filter sends one template
+// per list item, so type, permission and subject are constant and only the resource id varies
+// (pkg/authz/postfilter.go:88-110; "low-hanging fruit" in pkg/rules/rules.go:1015-1017) -- so the
+// schema lookups and the subject lookup of the previous item are reused when the strings repeat.
+struct ResolveMemo {
+  struct SchemaPart {  // (res_type, relation, subj_type, subj_rel) -> slots
+    std::string res_type, relation, subj_type, subj_rel;
+    int rt = -1, st = -1, perm = -1;
+    uint16_t srel = kNone;
+    bool ok = false, used = false;
+  };
+  static constexpr int kWays = 4;  // a bulk request interleaves a handful of templates at most
+  SchemaPart parts[kWays];
+  int last = 0, next = 0;
+  std::string subj_id;  // subject of the previous item
+  int subj_st = -1;
+  uint32_t su = ZG_NO_OBJECT;
+};
+
+static inline bool same(const std::string& a, const char* b) { return std::strcmp(a.c_str(), b) == 0; }
+
+static const ResolveMemo::SchemaPart& resolve_schema_part(const Schema& sc, const zg_rel_str& r, const char* srel_s,
+                                                          ResolveMemo* m) {
+  for (int k = 0; k < ResolveMemo::kWays; ++k) {
+    const int w = (m->last + k) % ResolveMemo::kWays;
+    const ResolveMemo::SchemaPart& p = m->parts[w];
+    if (p.used && same(p.res_type, r.res_type) && same(p.relation, r.relation) && same(p.subj_type, r.subj_type) &&
+        same(p.subj_rel, srel_s)) {
+      m->last = w;
+      return p;
+    }
+  }
+  const int w = m->next;
+  m->next = (m->next + 1) % ResolveMemo::kWays;
+  ResolveMemo::SchemaPart& p = m->parts[w];
+  p.res_type = r.res_type;
+  p.relation = r.relation;
+  p.subj_type = r.subj_type;
+  p.subj_rel = srel_s;
+  p.used = true;
+  p.ok = false;
+  p.srel = kNone;
+  p.rt = sc.type_id(r.res_type);
+  p.st = sc.type_id(r.subj_type);
+  if (p.rt >= 0 && p.st >= 0) {
+    p.perm = sc.slot_id(p.rt, r.relation);
+    const int sr = *srel_s ? sc.slot_id(p.st, srel_s) : 0;
+    if (p.perm >= 0 && sr >= 0) {
+      if (*srel_s) p.srel = static_cast<uint16_t>(sr);
+      p.ok = true;
+    }
+  }
+  m->last = w;
+  return p;
+}
+
+static void resolve_check(const zg_engine* e, const zg_rel_str& r, zg_check* c, ResolveMemo* m) {
   c->res = ZG_NO_OBJECT;
   c->subj = ZG_NO_OBJECT - 1;
   c->perm = kNone;  // invalid -> ZG_ITEM_ERROR
@@ -680,37 +736,66 @@ static void resolve_check(const zg_engine* e, const zg_rel_str& r, zg_check* c) 
   c->srel = kNone;
   c->flags = 0;
   if (!r.res_type || !r.res_id || !r.relation || !r.subj_type || !r.subj_id) return;
-  int rt = sc.type_id(r.res_type), st = sc.type_id(r.subj_type);
-  if (rt < 0 || st < 0) return;
-  int perm = sc.slot_id(rt, r.relation);
-  if (perm < 0) return;
-  if (!none_rel(r.subj_rel)) {
-    int sr = sc.slot_id(st, r.subj_rel);
-    if (sr < 0) return;
-    c->srel = static_cast<uint16_t>(sr);
-  }
+  const ResolveMemo::SchemaPart& p = resolve_schema_part(e->schema, r, none_rel(r.subj_rel) ? "" : r.subj_rel, m);
+  if (!p.ok) return;
+  const int rt = p.rt, st = p.st;
+  c->srel = p.srel;
   c->stype = static_cast<uint16_t>(st);
-  c->res = e->store.find(rt, r.res_id);
-  uint32_t su = e->store.find(st, r.subj_id);
+  c->res = e->store.find(rt, r.res_id, std::strlen(r.res_id));
+  if (!(m->subj_st == st && same(m->subj_id, r.subj_id))) {
+    m->subj_id = r.subj_id;
+    m->su = e->store.find(st, r.subj_id, m->subj_id.size());
+    m->subj_st = st;
+  }
+  uint32_t su = m->su;
   // two never-written names that are the same object must still compare equal
   if (su == ZG_NO_OBJECT) su = (c->res == ZG_NO_OBJECT && rt == st && std::strcmp(r.res_id, r.subj_id) == 0)
                                    ? ZG_NO_OBJECT : ZG_NO_OBJECT - 1;
   c->subj = su;
-  c->perm = static_cast<uint16_t>(perm);
+  c->perm = static_cast<uint16_t>(p.perm);
+}
+
+static void resolve_checks_locked(const zg_engine* e, const zg_rel_str* items, uint64_t n, zg_check* out) {
+  auto run = [&](uint64_t b, uint64_t en) {
+    ResolveMemo memo;
+    for (uint64_t i = b; i < en; ++i) resolve_check(e, items[i], &out[i], &memo);
+  };
+  // Resolution only reads the schema and the interning tables (the engine lock is held), so a large
+  // batch is split over host threads; below ~16k items one thread finishes before others would start.
+  constexpr uint64_t kPerThread = 8192;
+  unsigned hw = std::thread::hardware_concurrency();
+  uint64_t nt = std::min<uint64_t>({n / kPerThread, hw ? hw : 1u, 16u});
+  if (nt < 2) return run(0, n);
+  std::vector<std::thread> th;
+  th.reserve(nt - 1);
+  const uint64_t per = (n + nt - 1) / nt;
+  for (uint64_t t = 1; t < nt; ++t) th.emplace_back(run, std::min(n, t * per), std::min(n, (t + 1) * per));
+  run(0, std::min(n, per));
+  for (auto& x : th) x.join();
+}
+
+extern "C" int zg_resolve_checks(zg_engine* e, const zg_rel_str* items, uint64_t n, zg_check* out) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if ((!items || !out) && n) return fail(ZG_EINVAL, "NULL argument");
+  std::lock_guard<std::mutex> g(e->mu);
+  resolve_checks_locked(e, items, n, out);
+  return ZG_OK;
 }
 
 extern "C" int zg_check_bulk_str(zg_engine* e, const zg_rel_str* items, uint64_t n, uint8_t* out) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if ((!items || !out) && n) return fail(ZG_EINVAL, "NULL argument");
-  std::lock_guard<std::mutex> g(e->mu);
-  int rc = ensure_published(e);
-  if (rc) return rc;
   std::vector<zg_check> c(n);
-  for (uint64_t i = 0; i < n; ++i) resolve_check(e, items[i], &c[i]);
-  e->dev.now = now_of(e);
-  std::string err;
-  rc = e->dev.check_host(c.data(), n, out, &err);
-  return rc ? fail(rc, err) : ZG_OK;
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    int rc = ensure_published(e);
+    if (rc) return rc;
+    resolve_checks_locked(e, items, n, c.data());
+  }
+  // Interned ids stay valid across later writes (interning only appends), so the launch can go
+  // through the batcher like any zg_check_bulk call: concurrent string callers -- one goroutine per
+  // rule check in the proxy, pkg/authz/check.go:77-93 -- share launches too.
+  return zg_check_bulk(e, c.data(), n, out);
 }
 
 static int lookup_locked(zg_engine* e, uint16_t res_type, uint16_t perm, uint16_t stype, uint32_t subj, uint16_t srel,

@@ -17,21 +17,74 @@ void Store::reset(const Schema* s) {
   live_ = 0;
 }
 
+static inline uint64_t hash_bytes(const char* s, size_t n) {
+  uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xD6E8FEB86659FD93ull);
+  while (n >= 8) {
+    uint64_t w;
+    std::memcpy(&w, s, 8);
+    h = (h ^ w) * 0xD6E8FEB86659FD93ull;
+    h ^= h >> 32;
+    s += 8;
+    n -= 8;
+  }
+  if (n) {
+    uint64_t w = 0;
+    std::memcpy(&w, s, n);
+    h = (h ^ w) * 0xD6E8FEB86659FD93ull;
+    h ^= h >> 32;
+  }
+  h *= 0x9E3779B97F4A7C15ull;
+  return h ^ (h >> 29);
+}
+
+uint32_t Store::TypeObjs::lookup(const char* s, size_t n) const {
+  if (table.empty()) return ZG_NO_OBJECT;
+  const size_t mask = table.size() - 1;
+  for (size_t i = hash_bytes(s, n) & mask;; i = (i + 1) & mask) {
+    const uint32_t v = table[i];
+    if (!v) return ZG_NO_OBJECT;
+    const std::string& nm = names[v - 1];
+    if (nm.size() == n && std::memcmp(nm.data(), s, n) == 0) return v - 1;
+  }
+}
+
+void Store::TypeObjs::insert(uint32_t id) {
+  if ((n_interned + 1) * 2 > table.size()) {  // grow and re-index from names[]
+    std::vector<uint32_t> old;
+    old.swap(table);
+    table.assign(old.empty() ? 64 : old.size() * 2, 0);
+    const size_t mask = table.size() - 1;
+    for (uint32_t v : old)
+      if (v) {
+        const std::string& nm = names[v - 1];
+        size_t i = hash_bytes(nm.data(), nm.size()) & mask;
+        while (table[i]) i = (i + 1) & mask;
+        table[i] = v;
+      }
+  }
+  const std::string& nm = names[id];
+  const size_t mask = table.size() - 1;
+  size_t i = hash_bytes(nm.data(), nm.size()) & mask;
+  while (table[i]) i = (i + 1) & mask;
+  table[i] = id + 1;
+  ++n_interned;
+}
+
 uint32_t Store::intern(int type, const std::string& id) {
   TypeObjs& t = objs_[type];
-  auto it = t.ids.find(id);
-  if (it != t.ids.end()) return it->second;
+  const uint32_t have = t.lookup(id.data(), id.size());
+  if (have != ZG_NO_OBJECT) return have;
   // keep string ids and bulk numeric ids in one id space
   uint32_t nid = std::max<uint32_t>(static_cast<uint32_t>(t.names.size()), t.n_numeric);
   t.names.resize(nid + 1);
   t.names[nid] = id;
-  t.ids.emplace(id, nid);
+  t.insert(nid);
   return nid;
 }
-uint32_t Store::find(int type, const std::string& id) const {
+uint32_t Store::find(int type, const std::string& id) const { return find(type, id.data(), id.size()); }
+uint32_t Store::find(int type, const char* id, size_t len) const {
   if (type < 0 || type >= static_cast<int>(objs_.size())) return ZG_NO_OBJECT;
-  auto it = objs_[type].ids.find(id);
-  return it == objs_[type].ids.end() ? ZG_NO_OBJECT : it->second;
+  return objs_[type].lookup(id, len);
 }
 const std::string* Store::name(int type, uint32_t id) const {
   if (type < 0 || type >= static_cast<int>(objs_.size())) return nullptr;

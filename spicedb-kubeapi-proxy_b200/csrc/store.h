@@ -55,6 +55,7 @@ class Store {
 
   uint32_t intern(int type, const std::string& id);
   uint32_t find(int type, const std::string& id) const;  // ZG_NO_OBJECT
+  uint32_t find(int type, const char* id, size_t len) const;  // no temporary string: the check-ingress path
   const std::string* name(int type, uint32_t id) const;
 
   // Returns "" or an error message; `code` receives the ZG_* code.
@@ -95,10 +96,16 @@ class Store {
 
  private:
   void ensure_index();
+  // Interned names of one type. names[id] is the only copy of each string; `table` is an
+  // open-addressing index over it (slot = id + 1, 0 = empty, power-of-two size, load <= 1/2) so a
+  // lookup hashes the caller's bytes in place and compares against names[id].
   struct TypeObjs {
-    std::unordered_map<std::string, uint32_t> ids;
     std::vector<std::string> names;
+    std::vector<uint32_t> table;
+    uint32_t n_interned = 0;
     uint32_t n_numeric = 0;  // max numeric id seen in bulk loads + 1
+    uint32_t lookup(const char* s, size_t n) const;
+    void insert(uint32_t id);
   };
   std::vector<TypeObjs> objs_;
   std::unordered_map<Key, uint64_t, KeyHash> index_;

@@ -291,3 +291,45 @@ def test_watch_drives_recheck_like_run_watch():
     rechecks = [(u.relationship.resource.object_id, u.relationship.subject.object.object_id)
                 for r in stream for u in r.updates]
     assert rechecks == [(f"ns/p{i}", f"u{i}") for i in range(5)]
+
+
+def test_resolve_checks_matches_item_by_item_resolution():
+    """zg_resolve_checks (the ingress half of zg_check_bulk_str): the memo over repeated literal fields must not
+    change any answer -- a shuffled batch resolves exactly like the same items one call at a time."""
+    import random
+    e = zgpu.Engine(workloads.BOOTSTRAP_SCHEMA, host_only=True)
+    cl = zgpu.client.PermissionsClient(workloads.BOOTSTRAP_SCHEMA, engine=e)
+    C = zgpu.client
+    cl.WriteRelationships(C.WriteRelationshipsRequest(
+        [C.RelationshipUpdate(C.OPERATION_TOUCH, C.Relationship.parse(f"pod:ns{i % 5}/p{i}#viewer@user:u{i % 7}")) for i in range(60)] +
+        [C.RelationshipUpdate(C.OPERATION_TOUCH, C.Relationship.parse(f"namespace:ns{i}#creator@user:u{i}")) for i in range(5)]))
+    rng = random.Random(3)
+    types = ["pod", "namespace", "user", "nosuch", "cluster"]
+    rels = ["view", "viewer", "creator", "edit", "nosuch", "cluster"]
+    items = []
+    for _ in range(3000):
+        rt, st = rng.choice(types[:3] + types), rng.choice(["user"] * 4 + types)
+        rid = rng.choice([f"ns{rng.randrange(6)}/p{rng.randrange(70)}", f"ns{rng.randrange(6)}", f"u{rng.randrange(9)}", "never"])
+        sid = rng.choice([f"u{rng.randrange(9)}", "never", rid])
+        items.append((rt, rid, rng.choice(rels), st, sid, rng.choice(["", "", "", "...", "viewer", "nosuch"])))
+    # runs of repeated templates, as a post-filter produces them
+    items += [("pod", f"ns1/p{i}", "view", "user", "u3", "") for i in range(200)]
+    batch = e.resolve_checks(items)
+    single = np.concatenate([e.resolve_checks([it]) for it in items])
+    assert batch.tobytes() == single.tobytes()
+    known = [b for b in batch if b["perm"] != 0xFFFF]
+    assert len(known) > 300 and any(b["res"] != 0xFFFFFFFF for b in known) and any(b["res"] == 0xFFFFFFFF for b in known)
+    # two never-written names that are the same object share the sentinel; different ones do not
+    same, diff = e.resolve_checks([("pod", "zz", "view", "pod", "zz", "viewer"), ("pod", "zz", "view", "pod", "yy", "viewer")])
+    assert (same["res"], same["subj"]) == (0xFFFFFFFF, 0xFFFFFFFF) and (diff["res"], diff["subj"]) == (0xFFFFFFFF, 0xFFFFFFFE)
+
+
+def test_interning_index_survives_growth_and_numeric_gaps():
+    e = zgpu.Engine(workloads.CFG2_SCHEMA, host_only=True)
+    t = next(iter(n for n in ("user", "document", "doc") if e.type_id(n) >= 0))
+    ids = [e.intern(t, f"name-{i}-" + "x" * (i % 40)) for i in range(5000)]   # several table growths, short and long keys
+    assert ids == list(range(5000))
+    assert [e.find(t, f"name-{i}-" + "x" * (i % 40)) for i in range(0, 5000, 7)] == list(range(0, 5000, 7))
+    NO = 0xFFFFFFFF
+    assert e.find(t, "name-5000-") == NO and e.find(t, "") == NO and e.find(t, "name-1") == NO
+    assert e.intern(t, "name-17-" + "x" * 17) == 17
