@@ -288,6 +288,32 @@ int zg_list_filter(const char *body, size_t len, const zg_list_item *items, uint
                    const uint8_t *keep, uint64_t items_begin, uint64_t items_end, uint32_t flags,
                    char *out, size_t cap, size_t *out_len);
 
+/* The standard post-filter template, `T:{{namespacedName}}#perm@S:subject` (or `{{name}}`), for a
+ * whole scanned list at once: no per-item strings cross the boundary. */
+typedef struct zg_list_template {
+  const char *res_type, *permission;           /* literal fields of the template                */
+  const char *subj_type, *subj_id, *subj_rel;  /* the (already resolved) subject                */
+  const char *req_name, *req_namespace;        /* request fallbacks (pkg/rules/rules.go:321-326);
+                                                  NULL = ""                                     */
+  uint32_t id_kind;                            /* ZG_ID_NAME | ZG_ID_NAMESPACED_NAME            */
+  uint32_t flags;                              /* ZG_TPL_CLEAR_NAMESPACE                        */
+} zg_list_template;
+#define ZG_ID_NAME 0u            /* resource id = {{name}}                                      */
+#define ZG_ID_NAMESPACED_NAME 1u /* resource id = "namespace/name", or "name" without namespace  */
+#define ZG_TPL_CLEAR_NAMESPACE 1u /* the request is on `namespaces` (rules.go:331-333)           */
+/* Builds one interned check per scanned item straight from the body bytes (JSON escapes decoded).
+ * checked[i] = 0 for items the reference never checks (not an object: postfilter.go:68-71) or whose
+ * resource id comes out empty (the template does not resolve: :91-95); their out[i] is a placeholder
+ * and the caller keeps them. No GPU work: feed out[] to zg_check_bulk. */
+int zg_list_resolve(zg_engine *e, const char *body, size_t len, const zg_list_item *items, uint64_t n,
+                    const zg_list_template *tpl, zg_check *out, uint8_t *checked);
+/* Scan + resolve + ONE bulk check + splice, for a post-filter made of `n_tpl` such templates (an item
+ * is kept when every template answers HAS_PERMISSION, postfilter.go:149-170). Returns 0 with the
+ * filtered body in out (or the body itself, copied, when the reference would pass it through),
+ * ZG_E2BIG with *out_len = bytes required, ZG_EINVAL on a malformed body. */
+int zg_list_postfilter(zg_engine *e, const char *body, size_t len, const zg_list_template *tpl,
+                       uint32_t n_tpl, char *out, size_t cap, size_t *out_len);
+
 /* ---- measurement --------------------------------------------------------- */
 int zg_stats_get(zg_engine *e, zg_stats *out);
 /* Runs the batch through the instrumented kernel variant and returns the

@@ -48,6 +48,15 @@ class _Precond(C.Structure):
     _fields_ = [("op", C.c_uint32), ("filter", _RelStr)]
 
 
+class _ListTemplate(C.Structure):
+    _fields_ = [(k, C.c_char_p) for k in ("res_type", "permission", "subj_type", "subj_id", "subj_rel", "req_name",
+                                          "req_namespace")] + [("id_kind", C.c_uint32), ("flags", C.c_uint32)]
+
+
+ID_NAME, ID_NAMESPACED_NAME = 0, 1
+TPL_CLEAR_NAMESPACE = 1
+
+
 class _Stats(C.Structure):
     _fields_ = [("checks", C.c_uint64), ("launches", C.c_uint64), ("passes", C.c_uint64), ("tuples", C.c_uint64),
                 ("snapshot_bytes", C.c_uint64), ("revision", C.c_uint64), ("last_alg_bytes", C.c_uint64),
@@ -150,6 +159,10 @@ _SIGS = {
                                  C.POINTER(C.c_uint64)]),
     "zg_list_filter": (C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64,
                                  C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "zg_list_resolve": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_uint64, C.POINTER(_ListTemplate),
+                                  C.c_void_p, C.c_void_p]),
+    "zg_list_postfilter": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(_ListTemplate), C.c_uint32,
+                                     C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "zg_stats_get": (C.c_int, [C.c_void_p, C.POINTER(_Stats)]),
     "zg_count_alg_bytes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
 }
@@ -422,6 +435,30 @@ class Engine:
         out = np.empty(n, dtype=np.uint8)
         self._ck(self._L.zg_check_bulk_str(self._h, arr, n, out.ctypes.data))
         return out
+
+    @staticmethod
+    def list_template(res_type, permission, subj_type, subj_id, subj_rel="", id_kind=ID_NAMESPACED_NAME, req_name="",
+                      req_namespace="", clear_namespace=False):
+        return _ListTemplate(_b(res_type), _b(permission), _b(subj_type), _b(subj_id), _b(subj_rel or ""), _b(req_name),
+                             _b(req_namespace), id_kind, TPL_CLEAR_NAMESPACE if clear_namespace else 0)
+
+    def list_resolve(self, body: bytes, items: np.ndarray, tpl: "_ListTemplate"):
+        """-> (interned checks, checked mask) for the scanned items; no GPU work."""
+        items = np.ascontiguousarray(items, dtype=LIST_ITEM_DTYPE)
+        out = np.zeros(len(items), dtype=CHECK_DTYPE)
+        checked = np.zeros(len(items), dtype=np.uint8)
+        self._ck(self._L.zg_list_resolve(self._h, body, len(body), items.ctypes.data, len(items), C.byref(tpl),
+                                         out.ctypes.data, checked.ctypes.data))
+        return out, checked
+
+    def list_postfilter(self, body: bytes, templates) -> bytes:
+        """zg_list_postfilter: the whole post-filter of a list body in one call."""
+        arr = (_ListTemplate * max(len(templates), 1))(*templates)
+        out = np.empty(len(body) + 8, dtype=np.uint8)
+        need = C.c_size_t(0)
+        self._ck(self._L.zg_list_postfilter(self._h, body, len(body), arr, len(templates), out.ctypes.data, out.size,
+                                            C.byref(need)))
+        return out[:need.value].tobytes()
 
     def resolve_checks(self, rels) -> np.ndarray:
         """Strings -> interned zg_check items (no GPU work); feed them to check_bulk."""

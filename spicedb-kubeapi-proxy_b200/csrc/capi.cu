@@ -798,6 +798,183 @@ extern "C" int zg_check_bulk_str(zg_engine* e, const zg_rel_str* items, uint64_t
   return zg_check_bulk(e, c.data(), n, out);
 }
 
+// ---- list templates: scanned items -> interned checks without per-item strings --------------
+
+static void utf8_append(uint32_t cp, std::string* out) {
+  if (cp < 0x80) {
+    out->push_back(static_cast<char>(cp));
+  } else if (cp < 0x800) {
+    out->push_back(static_cast<char>(0xC0 | (cp >> 6)));
+    out->push_back(static_cast<char>(0x80 | (cp & 0x3F)));
+  } else if (cp < 0x10000) {
+    out->push_back(static_cast<char>(0xE0 | (cp >> 12)));
+    out->push_back(static_cast<char>(0x80 | ((cp >> 6) & 0x3F)));
+    out->push_back(static_cast<char>(0x80 | (cp & 0x3F)));
+  } else {
+    out->push_back(static_cast<char>(0xF0 | (cp >> 18)));
+    out->push_back(static_cast<char>(0x80 | ((cp >> 12) & 0x3F)));
+    out->push_back(static_cast<char>(0x80 | ((cp >> 6) & 0x3F)));
+    out->push_back(static_cast<char>(0x80 | (cp & 0x3F)));
+  }
+}
+
+static int hex4(const char* s) {
+  int v = 0;
+  for (int i = 0; i < 4; ++i) {
+    const char h = s[i];
+    int d = h >= '0' && h <= '9' ? h - '0' : h >= 'a' && h <= 'f' ? h - 'a' + 10 : h >= 'A' && h <= 'F' ? h - 'A' + 10 : -1;
+    if (d < 0) return -1;
+    v = v * 16 + d;
+  }
+  return v;
+}
+
+// Appends the decoded contents of a JSON string (the range zg_list_scan recorded, already validated).
+static void json_unescape_append(const char* s, size_t n, std::string* out) {
+  if (!std::memchr(s, '\\', n)) {
+    out->append(s, n);
+    return;
+  }
+  for (size_t i = 0; i < n;) {
+    if (s[i] != '\\' || i + 1 >= n) {
+      out->push_back(s[i++]);
+      continue;
+    }
+    const char x = s[i + 1];
+    i += 2;
+    switch (x) {
+      case 'b': out->push_back('\b'); break;
+      case 'f': out->push_back('\f'); break;
+      case 'n': out->push_back('\n'); break;
+      case 'r': out->push_back('\r'); break;
+      case 't': out->push_back('\t'); break;
+      case 'u': {
+        int v = i + 4 <= n ? hex4(s + i) : -1;
+        if (v < 0) {
+          utf8_append(0xFFFD, out);
+          break;
+        }
+        i += 4;
+        uint32_t cp = static_cast<uint32_t>(v);
+        if (cp >= 0xD800 && cp < 0xDC00 && i + 6 <= n && s[i] == '\\' && s[i + 1] == 'u') {
+          const int lo = hex4(s + i + 2);
+          if (lo >= 0xDC00 && lo < 0xE000) {
+            cp = 0x10000 + ((cp - 0xD800) << 10) + (static_cast<uint32_t>(lo) - 0xDC00);
+            i += 6;
+          }
+        }
+        if (cp >= 0xD800 && cp < 0xE000) cp = 0xFFFD;  // lone surrogate, as encoding/json decodes it
+        utf8_append(cp, out);
+        break;
+      }
+      default: out->push_back(x);  // \" \\ \/
+    }
+  }
+}
+
+extern "C" int zg_list_resolve(zg_engine* e, const char* body, size_t len, const zg_list_item* items, uint64_t n,
+                               const zg_list_template* tpl, zg_check* out, uint8_t* checked) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if (!tpl || ((!body || !items || !out || !checked) && n)) return fail(ZG_EINVAL, "NULL argument");
+  if (tpl->id_kind > ZG_ID_NAMESPACED_NAME) return fail(ZG_EINVAL, "unknown id_kind");
+  std::lock_guard<std::mutex> g(e->mu);
+  // the literal fields once; the resource id per item
+  ResolveMemo memo;
+  zg_check base;
+  const zg_rel_str proto{tpl->res_type, "", tpl->permission, tpl->subj_type, tpl->subj_id, tpl->subj_rel};
+  resolve_check(e, proto, &base, &memo);
+  const ResolveMemo::SchemaPart& part = memo.parts[memo.last];
+  const bool ok = base.perm != kNone;
+  const uint32_t su = ok ? memo.su : ZG_NO_OBJECT;
+  const std::string req_name = tpl->req_name ? tpl->req_name : "", req_ns = tpl->req_namespace ? tpl->req_namespace : "";
+  std::string name, ns, id;
+  for (uint64_t i = 0; i < n; ++i) {
+    const zg_list_item& it = items[i];
+    out[i] = base;
+    checked[i] = 0;
+    if (!(it.flags & ZG_ITEM_IS_OBJECT)) continue;
+    if (it.name_off + it.name_len > len || it.ns_off + it.ns_len > len) return fail(ZG_EINVAL, "item range outside the body");
+    name.clear();
+    ns.clear();
+    if (it.flags & ZG_ITEM_HAS_METADATA) {
+      json_unescape_append(body + it.name_off, it.name_len, &name);
+      json_unescape_append(body + it.ns_off, it.ns_len, &ns);
+    }
+    // pkg/rules/rules.go:312-339
+    if (name.empty()) name = req_name;
+    if (ns.empty()) ns = req_ns;
+    if (tpl->flags & ZG_TPL_CLEAR_NAMESPACE) ns.clear();
+    if (tpl->id_kind == ZG_ID_NAMESPACED_NAME && !ns.empty()) {
+      id = ns;
+      id += '/';
+      id += name;
+    } else {
+      id = name;
+    }
+    if (id.empty()) continue;  // "T:#perm@..." is not a relationship: the check is skipped
+    checked[i] = 1;
+    if (!ok) continue;  // unknown type / permission: answers ZG_ITEM_ERROR like the string path
+    const uint32_t res = e->store.find(part.rt, id.data(), id.size());
+    out[i].res = res;
+    uint32_t s2 = su;
+    if (s2 == ZG_NO_OBJECT)
+      s2 = (res == ZG_NO_OBJECT && part.rt == part.st && tpl->subj_id && id == tpl->subj_id) ? ZG_NO_OBJECT : ZG_NO_OBJECT - 1;
+    out[i].subj = s2;
+  }
+  return ZG_OK;
+}
+
+extern "C" int zg_list_postfilter(zg_engine* e, const char* body, size_t len, const zg_list_template* tpl, uint32_t n_tpl,
+                                  char* out, size_t cap, size_t* out_len) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if (!body || !out_len || (!tpl && n_tpl)) return fail(ZG_EINVAL, "NULL argument");
+  auto passthrough = [&]() {
+    *out_len = len;
+    if (len > cap || !out) return static_cast<int>(ZG_E2BIG);
+    std::memcpy(out, body, len);
+    return static_cast<int>(ZG_OK);
+  };
+  std::vector<zg_list_item> items(1024);
+  uint64_t ib = 0, ie = 0;
+  int64_t n = zg_list_scan(body, len, ZG_LIST_ITEMS, items.data(), items.size(), &ib, &ie);
+  if (n == ZG_E2BIG) {
+    n = zg_list_scan(body, len, ZG_LIST_ITEMS, nullptr, 0, &ib, &ie);  // count, then one exact rescan
+    if (n > 0) {
+      items.resize(static_cast<size_t>(n));
+      n = zg_list_scan(body, len, ZG_LIST_ITEMS, items.data(), items.size(), &ib, &ie);
+    }
+  }
+  if (n < 0) return fail(ZG_EINVAL, "failed to parse list response");
+  if (n == 0) return passthrough();  // no items array, or an empty one (postfilter.go:25-35)
+  const uint64_t N = static_cast<uint64_t>(n);
+  std::vector<uint8_t> keep(N, 1), checked(N);
+  std::vector<zg_check> one(N), all;
+  std::vector<uint64_t> owner;
+  for (uint32_t t = 0; t < n_tpl; ++t) {
+    int rc = zg_list_resolve(e, body, len, items.data(), N, &tpl[t], one.data(), checked.data());
+    if (rc) return rc;
+    for (uint64_t i = 0; i < N; ++i)
+      if (checked[i]) {
+        all.push_back(one[i]);
+        owner.push_back(i);
+      }
+  }
+  if (!all.empty()) {
+    {
+      std::lock_guard<std::mutex> g(e->mu);
+      int rc = ensure_published(e);
+      if (rc) return rc;
+    }
+    std::vector<uint8_t> codes(all.size());
+    int rc = zg_check_bulk(e, all.data(), all.size(), codes.data());  // ONE launch for the whole list
+    if (rc) return rc;
+    for (size_t k = 0; k < codes.size(); ++k)
+      if (codes[k] != ZG_HAS_PERMISSION) keep[owner[k]] = 0;
+  }
+  int rc = zg_list_filter(body, len, items.data(), N, keep.data(), ib, ie, ZG_LIST_EMPTY_AS_NULL, out, cap, out_len);
+  return rc == ZG_EINVAL ? fail(rc, "zg_list_filter: inconsistent item ranges") : rc;
+}
+
 static int lookup_locked(zg_engine* e, uint16_t res_type, uint16_t perm, uint16_t stype, uint32_t subj, uint16_t srel,
                          std::vector<uint32_t>* ids) {
   const Schema& sc = e->schema;

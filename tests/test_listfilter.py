@@ -222,6 +222,76 @@ def test_filter_buffer_contract():
     assert L.zg_list_scan(deep, len(deep), 0, None, 0, None, None) == -1
 
 
+def test_list_resolve_matches_the_string_path():
+    """zg_list_resolve builds the checks of a template straight from the body bytes; the checker is the string
+    path (postfilter._fields -> template -> zg_resolve_checks) on the same items."""
+    from spicedb_kubeapi_proxy_b200 import workloads
+    e = zgpu.Engine(workloads.BOOTSTRAP_SCHEMA, host_only=True)
+    c = cl.PermissionsClient(workloads.BOOTSTRAP_SCHEMA, engine=e)
+    c.WriteRelationships(cl.WriteRelationshipsRequest(
+        [cl.RelationshipUpdate(cl.OPERATION_TOUCH, cl.Relationship.parse(r)) for r in
+         [f"pod:ns{i % 3}/p{i}#viewer@user:alice" for i in range(20)] + ["pod:solo#viewer@user:alice", "pod:rn#viewer@user:bob",
+                                                                        "pod:rns/rn#viewer@user:bob", "namespace:ns1#creator@user:alice"]]))
+    rng = random.Random(11)
+    items = []
+    for i in range(300):
+        r = rng.random()
+        if r < 0.08:
+            items.append(rng.choice([1, "s", None, [1], True]))
+            continue
+        meta = {}
+        if rng.random() < 0.85:
+            meta["name"] = rng.choice([f"p{rng.randrange(25)}", "solo", "", 'q"uo\\te', "é中\U0001f600", "tab\tnl\n", 7])
+        if rng.random() < 0.7:
+            meta["namespace"] = rng.choice([f"ns{rng.randrange(4)}", "", None, "n/s"])
+        items.append({"spec": {"metadata": {"name": "decoy"}}, "metadata": meta} if rng.random() < 0.9 else {"kind": "NoMeta"})
+    for ensure_ascii in (True, False):
+        body = json.dumps({"items": items}, ensure_ascii=ensure_ascii).encode()
+        scanned, ib, ie = _lib.list_scan(body)
+        for kind, tplstr in ((_lib.ID_NAMESPACED_NAME, "pod:{{namespacedName}}#view@user:alice"), (_lib.ID_NAME, "pod:{{name}}#view@user:alice")):
+            for req, clear in ((pf.RequestInfo(), False), (pf.RequestInfo(name="rn", namespace="rns"), False),
+                               (pf.RequestInfo(resource="namespaces", namespace="rns"), True)):
+                tpl = e.list_template("pod", "view", "user", "alice", "", kind, req.name, req.namespace, clear)
+                got, checked = e.list_resolve(body, scanned, tpl)
+                want_rels, want_checked = [], []
+                for it in scanned:
+                    flags = int(it["flags"])
+                    rel = None
+                    if flags & _lib.ITEM_IS_OBJECT:
+                        f = pf._fields(req, pf.UserInfo(name="alice"), bool(flags & _lib.ITEM_HAS_METADATA),
+                                       pf._text(body, int(it["name_off"]), int(it["name_len"])),
+                                       pf._text(body, int(it["ns_off"]), int(it["ns_len"])))
+                        try:
+                            rel = pf.resolve_rel(tplstr, f)
+                        except pf.ResolveError:
+                            rel = None
+                    want_checked.append(rel is not None)
+                    if rel is not None:
+                        want_rels.append(rel)
+                assert checked.astype(bool).tolist() == want_checked
+                assert got[checked.astype(bool)].tobytes() == e.resolve_checks(want_rels).tobytes()
+                assert 20 < sum(want_checked) < 300 and any(int(g["res"]) != 0xFFFFFFFF for g in got[checked.astype(bool)])
+    # unknown permission / type: checked, and the item answers ZG_ITEM_ERROR like the string path (perm = 0xFFFF)
+    got, checked = e.list_resolve(body, scanned, e.list_template("pod", "nosuch", "user", "alice"))
+    assert checked.any() and (got["perm"] == 0xFFFF).all()
+    # never-written resource and subject that are the same object share the sentinel
+    b2 = b'{"items":[{"metadata":{"name":"ghost"}}]}'
+    sc2 = _lib.list_scan(b2)[0]
+    g2, _ = e.list_resolve(b2, sc2, e.list_template("pod", "view", "pod", "ghost", "viewer", _lib.ID_NAME))
+    assert (int(g2[0]["res"]), int(g2[0]["subj"])) == (0xFFFFFFFF, 0xFFFFFFFF)
+    g3, _ = e.list_resolve(b2, sc2, e.list_template("pod", "view", "pod", "other", "viewer", _lib.ID_NAME))
+    assert (int(g3[0]["res"]), int(g3[0]["subj"])) == (0xFFFFFFFF, 0xFFFFFFFE)
+    # the fused call: passthrough cases need no GPU; anything with checks fails loudly without one
+    tpl = e.list_template("pod", "view", "user", "alice")
+    for raw in (b'{"kind":"Status"}', b'{"items":[]}', b'{"items":null}'):
+        assert e.list_postfilter(raw, [tpl]) == raw
+    assert json.loads(e.list_postfilter(b'{"items":[1,"x"]}', [tpl])) == {"items": [1, "x"]}  # nothing to check
+    with pytest.raises(_lib.ZgpuError, match="no CPU fallback"):
+        e.list_postfilter(body, [tpl])
+    with pytest.raises(_lib.ZgpuError):
+        e.list_postfilter(b'{"items":[', [tpl])
+
+
 class MockLookupClient:
     def __init__(self, ids, conditional=()):
         self.ids, self.conditional = ids, set(conditional)
@@ -315,6 +385,12 @@ def test_gpu_filter_through_engine():
     assert c.engine.stats()["launches"] > before
     out = json.loads(pf.filter_list_response(body, [tpl], REQ, pf.UserInfo(name="bob"), c))
     assert [i["metadata"]["name"] for i in out["items"]] == ["p4"]
+    # the fused C entry point gives the same bytes as the mirror, with one call and one launch
+    for who in ("alice", "bob"):
+        fused = c.engine.list_postfilter(body, [c.engine.list_template("pod", "view", "user", who)])
+        assert fused == pf.filter_list_response(body, [tpl], REQ, pf.UserInfo(name=who), c)
+    both = [c.engine.list_template("pod", "view", "user", "alice"), c.engine.list_template("pod", "viewer", "user", "alice")]
+    assert [i["metadata"]["name"] for i in json.loads(c.engine.list_postfilter(body, both))["items"]] == ["p3", "p4"]
     # the pre-filter path over the same store: LookupResources -> allowed set -> list
     res = pf.run_lookup_resources(c, ("pod", "$", "view", "user", "alice", ""), REQ)
     assert res.allowed_results == {("team-a", "p1"), ("team-b", "p3"), ("team-b", "p4")}
