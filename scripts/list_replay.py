@@ -1,0 +1,148 @@
+"""Filtered kube lists end to end at the C ABI (BASELINE config 5's post-filter shape):
+concurrent clients each hand one List body to zg_list_postfilter -- scan, resolve, ONE bulk check on the GPU,
+splice -- against a store whose objects carry real "namespace/name" ids. Reports filtered lists/s and body MB/s,
+and checks a few outputs against the Python mirror of pkg/authz/postfilter.go.
+
+    python scripts/list_replay.py [--pods 200000] [--items 10000] [--clients 32] [--rounds 4] [--dry-run]
+
+--dry-run builds the store and the bodies and runs the host-only stages (scan, resolve), no GPU call.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import zgpu  # noqa: E402
+from spicedb_kubeapi_proxy_b200 import _lib, postfilter as pf  # noqa: E402
+
+SCHEMA = """
+definition user {}
+definition group { relation member: user | group#member }
+definition namespace { relation viewer: user | group#member  permission view = viewer }
+definition pod {
+  relation namespace: namespace
+  relation viewer: user | group#member | user:*
+  relation banned: user
+  permission view = (viewer + namespace->view) - banned
+}
+"""
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--pods", type=int, default=200000)
+ap.add_argument("--namespaces", type=int, default=200)
+ap.add_argument("--users", type=int, default=2000)
+ap.add_argument("--groups", type=int, default=200)
+ap.add_argument("--items", type=int, default=10000)
+ap.add_argument("--clients", type=int, default=32)
+ap.add_argument("--rounds", type=int, default=4)
+ap.add_argument("--dry-run", action="store_true")
+a = ap.parse_args()
+rng = np.random.default_rng(7)
+
+e = zgpu.Engine(SCHEMA, host_only=a.dry_run)
+t0 = time.perf_counter()
+pod_names = [f"ns-{i % a.namespaces}/pod-{i}" for i in range(a.pods)]
+pod_id = np.array([e.intern("pod", n) for n in pod_names], dtype=np.uint32)
+ns_id = np.array([e.intern("namespace", f"ns-{i}") for i in range(a.namespaces)], dtype=np.uint32)
+user_id = np.array([e.intern("user", f"user-{i}") for i in range(a.users)], dtype=np.uint32)
+group_id = np.array([e.intern("group", f"group-{i}") for i in range(a.groups)], dtype=np.uint32)
+e.add_bulk("pod", "namespace", "namespace", pod_id, ns_id[np.arange(a.pods) % a.namespaces])
+k = a.pods // 2
+e.add_bulk("pod", "viewer", "user", pod_id[rng.integers(0, a.pods, k)], user_id[rng.integers(0, a.users, k)])
+e.add_bulk("pod", "viewer", "group", pod_id[rng.integers(0, a.pods, k // 4)], group_id[rng.integers(0, a.groups, k // 4)], srel="member")
+e.add_bulk("pod", "banned", "user", pod_id[rng.integers(0, a.pods, k // 8)], user_id[rng.integers(0, a.users, k // 8)])
+e.add_bulk("namespace", "viewer", "user", ns_id[rng.integers(0, a.namespaces, a.namespaces * 4)], user_id[rng.integers(0, a.users, a.namespaces * 4)])
+e.add_bulk("namespace", "viewer", "group", ns_id[rng.integers(0, a.namespaces, a.namespaces)], group_id[rng.integers(0, a.groups, a.namespaces)], srel="member")
+e.add_bulk("group", "member", "user", group_id[rng.integers(0, a.groups, a.users * 2)], user_id[rng.integers(0, a.users, a.users * 2)])
+e.publish()
+build_s = time.perf_counter() - t0
+
+
+def pod_json(i):
+    ns, name = pod_names[i].split("/")
+    return {"apiVersion": "v1", "kind": "Pod",
+            "metadata": {"name": name, "namespace": ns, "uid": f"{i:032x}", "resourceVersion": str(10**6 + i),
+                         "labels": {"app": f"svc-{i % 50}", "tier": "backend"},
+                         "annotations": {"checksum/config": "9f86d081884c7d659a2feaa0c55ad015a3bf4f1b2b0b822cd15d6c15b0f00a08"}},
+            "spec": {"containers": [{"name": "main", "image": "registry.example/app:1.2.3", "args": ["--port=8080"] * 4,
+                                     "env": [{"name": f"VAR_{k}", "value": "v" * 24} for k in range(12)],
+                                     "resources": {"limits": {"cpu": "500m", "memory": "512Mi"}}}] * 2,
+                     "nodeName": f"node-{i % 300}"},
+            "status": {"phase": "Running", "podIP": "10.0.0.1",
+                       "conditions": [{"type": t, "status": "True"} for t in ("Initialized", "Ready", "ContainersReady", "PodScheduled")]}}
+
+
+def make_body():
+    pick = rng.integers(0, a.pods, a.items)
+    return json.dumps({"kind": "PodList", "apiVersion": "v1", "metadata": {"resourceVersion": "1"},
+                       "items": [pod_json(int(i)) for i in pick]}, separators=(",", ":")).encode()
+
+
+n_bodies = min(a.clients, 8)  # bodies are shared between clients; the subjects differ
+bodies = [make_body() for _ in range(n_bodies)]
+users = [f"user-{int(u)}" for u in rng.integers(0, a.users, a.clients)]
+tpls = [e.list_template("pod", "view", "user", u) for u in users]
+res = {"pods": a.pods, "items_per_list": a.items, "clients": a.clients, "body_mb": round(len(bodies[0]) / 1e6, 2),
+       "tuples": int(e.num_tuples()), "store_build_s": round(build_s, 2)}
+
+# host-only stages, one thread
+t = time.perf_counter()
+items, ib, ie = _lib.list_scan(bodies[0])
+res["scan_ms"] = round((time.perf_counter() - t) * 1e3, 2)
+t = time.perf_counter()
+checks, checked = e.list_resolve(bodies[0], items, tpls[0])
+res["resolve_ms"] = round((time.perf_counter() - t) * 1e3, 2)
+assert checked.all() and (checks["res"] != 0xFFFFFFFF).all()
+if a.dry_run:
+    print(json.dumps(res))
+    sys.exit(0)
+
+# the mirror (Python loop over items, strings across the boundary) on a few lists = the checker
+client = zgpu.client.PermissionsClient(SCHEMA, engine=e)
+for i in range(min(3, a.clients)):
+    want = pf.filter_list_response(bodies[i % n_bodies], ["pod:{{namespacedName}}#view@user:{{user.name}}"],
+                                   pf.RequestInfo(), pf.UserInfo(name=users[i]), client)
+    got = e.list_postfilter(bodies[i % n_bodies], [tpls[i]])
+    assert got == want, f"client {i}: fused output differs from the mirror"
+kept = len(json.loads(got)["items"] or [])
+res["kept_of_last_checked_list"] = kept
+
+errors, out_bytes = [], [0] * a.clients
+
+
+def run_phase(fn):
+    barrier = threading.Barrier(a.clients + 1)
+
+    def body(i):
+        barrier.wait()
+        try:
+            fn(i)
+        except Exception as ex:  # noqa: BLE001
+            errors.append((i, repr(ex)))
+
+    th = [threading.Thread(target=body, args=(i,)) for i in range(a.clients)]
+    [t.start() for t in th]
+    s0 = e.stats()
+    barrier.wait()
+    t0 = time.perf_counter()
+    [t.join() for t in th]
+    return time.perf_counter() - t0, s0, e.stats()
+
+
+def lists(i):
+    for _ in range(a.rounds):
+        out_bytes[i] = len(e.list_postfilter(bodies[i % n_bodies], [tpls[i]]))
+
+
+run_phase(lists)  # warm-up
+dt, s0, s1 = run_phase(lists)
+n_lists = a.clients * a.rounds
+res.update({"filtered_lists_per_s": round(n_lists / dt, 1), "body_MB_per_s": round(n_lists * len(bodies[0]) / 1e6 / dt, 1),
+            "checks_per_s": round(n_lists * a.items / dt), "launches": int(s1["launches"] - s0["launches"]),
+            "coalesced_requests": int(s1["coalesced_requests"] - s0["coalesced_requests"]), "errors": errors[:3]})
+print(json.dumps(res))
