@@ -292,6 +292,77 @@ def test_list_resolve_matches_the_string_path():
         e.list_postfilter(b'{"items":[', [tpl])
 
 
+def test_scanner_fuzz_under_sanitizers(tmp_path):
+    """tests/fuzz/listfilter_fuzz.cc: mutated bodies through zg_list_scan / zg_list_filter under ASan + UBSan
+    (exact-size heap buffers, so any over-read is a report), with range and length invariants checked."""
+    import os
+    import shutil
+    import subprocess
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "lf_fuzz")
+    build = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                            "-o", exe, os.path.join(root, "tests", "fuzz", "listfilter_fuzz.cc"),
+                            os.path.join(root, "spicedb-kubeapi-proxy_b200", "csrc", "listfilter.cc")],
+                           capture_output=True, text=True)
+    if build.returncode != 0 and "sanitize" in build.stderr:
+        pytest.skip("sanitizer runtime not available: " + build.stderr[-200:])
+    assert build.returncode == 0, build.stderr[-2000:]
+    run = subprocess.run([exe, "400000"], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0 and run.stdout.startswith("ok "), (run.stdout[-500:], run.stderr[-2000:])
+
+
+def test_scanner_accepts_exactly_what_a_json_parser_accepts():
+    """Differential against Python's json on mutated documents: the scanner is a strict validator, so it must
+    reject what a JSON parser rejects (it sits in front of one) and accept what it accepts. Known, deliberate
+    differences are normalised: Python accepts NaN/Infinity literals and lone surrogate escapes; RFC 8259 (and
+    encoding/json) do not."""
+    import ctypes as C
+    L = _lib.lib()
+    rng = random.Random(2024)
+    seeds = [json.dumps({"kind": "L", "items": [pod("a", "n", spec={"x": [1, 2.5e-3, True, None, {"y": "]}"}]}), pod("b"), 3, "s"],
+                         "metadata": {"k": "v\u00e9\"\\"}}).encode(),
+             b' { "items" : [ { "metadata" : { "name" : "x" } } , [ ] , { } ] , "n" : -0.5E+3 } ',
+             b'{"a":[[[[]]]],"items":[{"metadata":{"name":"q","namespace":"w"},"z":{"a":{"b":[1,{"c":"d"}]}}}]}']
+    alphabet = b'{}[]",:\\ \n0123456789-+.eEtrufalsn\x00\x7f\xc3\xa9'
+    agree = rejected = 0
+    for _ in range(6000):
+        b = bytearray(rng.choice(seeds))
+        for _m in range(rng.randrange(1, 4)):
+            p = rng.randrange(len(b)) if b else 0
+            k = rng.randrange(4)
+            if k == 0 and b:
+                b[p] = rng.choice(alphabet)
+            elif k == 1 and b:
+                del b[p:p + rng.randrange(1, 3)]
+            elif k == 2:
+                b.insert(p, rng.choice(alphabet))
+            elif b:
+                del b[p:]
+        raw = bytes(b)
+        try:
+            doc = json.loads(raw.decode("utf-8"), parse_constant=lambda c: (_ for _ in ()).throw(ValueError(c)))
+            ok_py = isinstance(doc, dict)  # the scanner only takes a top-level object (a List is one)
+        except (ValueError, UnicodeDecodeError, RecursionError):
+            ok_py = None
+        if ok_py is None:
+            try:  # invalid UTF-8 is not the scanner's business (encoding/json replaces it): retry leniently
+                doc = json.loads(raw.decode("utf-8", "replace"), parse_constant=lambda c: (_ for _ in ()).throw(ValueError(c)))
+                ok_py = isinstance(doc, dict) if b"\xef\xbf\xbd" not in raw else None
+            except (ValueError, RecursionError):
+                ok_py = False
+        if ok_py is None:
+            continue
+        n = L.zg_list_scan(raw, len(raw), 0, None, 0, None, None)
+        assert (n >= 0) == ok_py, (raw, n, ok_py)
+        agree += 1
+        rejected += not ok_py
+        if ok_py and isinstance(doc.get("items"), list):
+            assert n == len(doc["items"]), raw
+    assert agree > 5000 and 500 < rejected < agree - 500
+
+
 class MockLookupClient:
     def __init__(self, ids, conditional=()):
         self.ids, self.conditional = ids, set(conditional)
