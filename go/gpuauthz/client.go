@@ -361,5 +361,55 @@ func (c *Client) resync(ctx context.Context) error {
 	return nil
 }
 
+// ListTemplate is the standard post-filter template, "T:{{namespacedName}}#perm@S:subject"
+// (or {{name}}), with its literal fields already resolved for this request.
+type ListTemplate struct {
+	ResourceType, Permission                string
+	SubjectType, SubjectID, SubjectRelation string
+	RequestName, RequestNamespace           string // fallbacks of rules.NewResolveInput (pkg/rules/rules.go:321-326)
+	NameOnly                                bool   // {{name}} instead of {{namespacedName}}
+	ClearNamespace                          bool   // the request is on `namespaces` (rules.go:331-333)
+}
+
+// FilterListResponse replaces the body of filterListResponse (pkg/authz/postfilter.go:17-55) for rules whose
+// PostFilters are all standard templates: one structural scan of the body, one bulk check on the GPU, one
+// splice of the kept items -- no map[string]interface{} round trip, no per-item strings across cgo.
+// The result is the same JSON value the reference produces (unknown fields, key order and number spelling
+// are the apiserver's, since nothing is re-serialised).
+func (c *Client) FilterListResponse(body []byte, tpls []ListTemplate) ([]byte, error) {
+	if len(body) == 0 {
+		return nil, fmt.Errorf("failed to parse list response: empty body")
+	}
+	var cs cstrs
+	defer cs.free()
+	ct := make([]C.zg_list_template, len(tpls))
+	for i, t := range tpls {
+		ct[i] = C.zg_list_template{
+			res_type: cs.add(t.ResourceType), permission: cs.add(t.Permission),
+			subj_type: cs.add(t.SubjectType), subj_id: cs.add(t.SubjectID), subj_rel: cs.add(t.SubjectRelation),
+			req_name: cs.add(t.RequestName), req_namespace: cs.add(t.RequestNamespace),
+			id_kind: C.ZG_ID_NAMESPACED_NAME,
+		}
+		if t.NameOnly {
+			ct[i].id_kind = C.ZG_ID_NAME
+		}
+		if t.ClearNamespace {
+			ct[i].flags = C.ZG_TPL_CLEAR_NAMESPACE
+		}
+	}
+	var tp *C.zg_list_template
+	if len(ct) > 0 {
+		tp = &ct[0]
+	}
+	out := make([]byte, len(body)+8) // the filtered body is never longer than body + 2
+	var outLen C.size_t
+	rc := C.zg_list_postfilter(c.engine, (*C.char)(unsafe.Pointer(&body[0])), C.size_t(len(body)), tp, C.uint32_t(len(ct)),
+		(*C.char)(unsafe.Pointer(&out[0])), C.size_t(len(out)), &outLen)
+	if rc != 0 {
+		return nil, fmt.Errorf("failed to filter items with bulk permissions: %w", lastError(rc))
+	}
+	return out[:outLen], nil
+}
+
 var _ v1.PermissionsServiceClient = (*Client)(nil)
 var _ = fmt.Sprintf
