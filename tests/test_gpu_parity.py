@@ -343,68 +343,6 @@ def test_concurrent_callers_are_coalesced_and_exact(zg):
     print("coalesced", st["coalesced_requests"], "calls into", st["coalesced_launches"], "launches")
 
 
-def test_concurrent_string_callers_share_launches_and_see_writes(zg):
-    """zg_check_bulk_str resolves under the engine lock and then takes the batcher like zg_check_bulk: concurrent
-    string callers (what the Go shim issues) get exactly their own answers while a writer keeps publishing."""
-    import threading
-
-    from oracle.pyoracle import Oracle
-    from spicedb_kubeapi_proxy_b200 import workloads
-
-    schema = workloads.BOOTSTRAP_SCHEMA
-    OP_TOUCH, OP_DELETE = zg._lib.OP_TOUCH, zg._lib.OP_DELETE
-    e, o = zg.Engine(schema), Oracle(schema)
-    rels = [f"pod:ns{i % 7}/p{i}#viewer@user:u{i % 13}" for i in range(400)] + \
-           [f"namespace:ns{i}#creator@user:u{i}" for i in range(7)]
-    for k in range(0, len(rels), 500):
-        e.write_relationships([(OP_TOUCH, r, 0) for r in rels[k:k + 500]])
-    for r in rels:
-        o.touch(r)
-    queries = [("pod", f"ns{i % 7}/p{i % 450}", "view", "user", f"u{(i * 5) % 15}", "") for i in range(3000)]
-    want = np.array([o.check(*q[:5]) for q in queries], dtype=np.uint8)
-    assert 0 < (want == 2).sum() < want.size
-    errors, stop = [], threading.Event()
-
-    def reader(tid):
-        rng = np.random.default_rng(tid)
-        try:
-            for _ in range(30):
-                lo = int(rng.integers(0, len(queries) - 1))
-                n = int(rng.integers(1, min(400, len(queries) - lo)))
-                got = e.check_bulk_str(queries[lo:lo + n])
-                if not np.array_equal(got, want[lo:lo + n]):
-                    errors.append((tid, lo, n))
-        except Exception as ex:  # noqa: BLE001
-            errors.append((tid, repr(ex)))
-
-    def writer():
-        i = 0
-        try:
-            while not stop.is_set():  # relationships no query looks at: answers must not move
-                e.write_relationships([(OP_TOUCH if i % 2 == 0 else OP_DELETE, f"workflow:w{i // 2 % 50}#idempotency_key@activity:a",
-                                        4_000_000_000 if i % 2 == 0 else 0)])
-                i += 1
-        except Exception as ex:  # noqa: BLE001
-            errors.append(("writer", repr(ex)))
-
-    before = e.stats()
-    wt = threading.Thread(target=writer)
-    wt.start()
-    threads = [threading.Thread(target=reader, args=(t,)) for t in range(16)]
-    [t.start() for t in threads]
-    [t.join() for t in threads]
-    stop.set()
-    wt.join()
-    assert not errors, errors[:3]
-    st = e.stats()
-    assert st["checks"] > before["checks"] and st["revision"] > before["revision"]
-    # a write is visible to the very next string check (FullyConsistent)
-    assert e.check_bulk_str([("pod", "ns0/new", "view", "user", "late", "")])[0] == 1
-    e.write_relationships([(OP_TOUCH, "pod:ns0/new#viewer@user:late", 0)])
-    assert e.check_bulk_str([("pod", "ns0/new", "view", "user", "late", "")])[0] == 2
-    print("coalesced", st["coalesced_requests"], "string calls into", st["coalesced_launches"], "launches")
-
-
 @pytest.mark.parametrize("name,scale", [("cfg2", 0.02), ("cfg3", 0.01), ("cfg4", 0.002)])
 def test_lookup_resources_reverse_bfs_equals_exhaustive_and_oracle(zg, name, scale, monkeypatch):
     """LookupResources = reverse-BFS candidates (a superset) verified by the check kernel.

@@ -433,43 +433,3 @@ def test_run_watch_rechecks_every_update_in_one_bulk_call():
     assert mock.calls == [2, 1]
     with pytest.raises(RuntimeError):
         pf.run_watch(stream, MockPermissionsClient({}, errors={"pod:ns1/b#view@user:alice"}), ("pod", "$", "view", "user", "alice", ""))
-
-
-@pytest.mark.gpu
-def test_gpu_filter_through_engine():
-    """The whole post-filter through the real engine: cfg1-like schema, one bulk call, one launch."""
-    schema = """
-    definition user {}
-    definition namespace { relation viewer: user  permission view = viewer }
-    definition pod { relation namespace: namespace  relation viewer: user | user:*
-                     permission view = viewer + namespace->view }
-    """
-    c = cl.PermissionsClient(schema, ["namespace:team-a#viewer@user:alice", "pod:team-a/p1#namespace@namespace:team-a",
-                                      "pod:team-b/p2#namespace@namespace:team-b", "pod:team-b/p3#viewer@user:alice",
-                                      "pod:team-b/p4#viewer@user:*"])
-    body = json.dumps({"kind": "PodList", "items": [pod("p1", "team-a"), pod("p2", "team-b"), pod("p3", "team-b"),
-                                                    pod("p4", "team-b"), pod("p5", "team-b")]}).encode()
-    tpl = "pod:{{namespacedName}}#view@user:{{user.name}}"
-    before = c.engine.stats()["launches"]
-    out = json.loads(pf.filter_list_response(body, [tpl], REQ, pf.UserInfo(name="alice"), c))
-    assert [i["metadata"]["name"] for i in out["items"]] == ["p1", "p3", "p4"]
-    assert c.engine.stats()["launches"] > before
-    out = json.loads(pf.filter_list_response(body, [tpl], REQ, pf.UserInfo(name="bob"), c))
-    assert [i["metadata"]["name"] for i in out["items"]] == ["p4"]
-    # the fused C entry point gives the same bytes as the mirror, with one call and one launch
-    for who in ("alice", "bob"):
-        fused = c.engine.list_postfilter(body, [c.engine.list_template("pod", "view", "user", who)])
-        assert fused == pf.filter_list_response(body, [tpl], REQ, pf.UserInfo(name=who), c)
-    both = [c.engine.list_template("pod", "view", "user", "alice"), c.engine.list_template("pod", "viewer", "user", "alice")]
-    assert [i["metadata"]["name"] for i in json.loads(c.engine.list_postfilter(body, both))["items"]] == ["p3", "p4"]
-    # the pre-filter path over the same store: LookupResources -> allowed set -> list
-    res = pf.run_lookup_resources(c, ("pod", "$", "view", "user", "alice", ""), REQ)
-    assert res.allowed_results == {("team-a", "p1"), ("team-b", "p3"), ("team-b", "p4")}
-    assert [i["metadata"]["name"] for i in json.loads(pf.filter_list(body, res))["items"]] == ["p1", "p3", "p4"]
-    # the watch path: a write shows up on the feed and is re-checked against the new snapshot
-    stream = c.Watch(cl.WatchRequest(["pod"]))
-    c.WriteRelationships(cl.WriteRelationshipsRequest([
-        cl.RelationshipUpdate(cl.OPERATION_TOUCH, cl.Relationship.parse("pod:team-b/p2#viewer@user:alice")),
-        cl.RelationshipUpdate(cl.OPERATION_DELETE, cl.Relationship.parse("pod:team-b/p3#viewer@user:alice"))]))
-    assert pf.run_watch(stream, c, ("pod", "$", "view", "user", "alice", "")) == [
-        pf.ResultChange(True, ("team-b", "p2")), pf.ResultChange(False, ("team-b", "p3"))]
