@@ -212,9 +212,9 @@ def list_scan(body: bytes, mode: int = LIST_ITEMS):
     top-level "items" ("rows" with LIST_TABLE_ROWS) array. Raises ZgpuError(-1) on malformed JSON."""
     L = lib()
     ib, ie = C.c_uint64(0), C.c_uint64(0)
-    cap = max(16, body.count(b'"metadata"') + 16)
+    cap = len(body) // 128 + 16  # an item is rarely shorter; untouched pages of the buffer cost nothing
     while True:
-        items = np.zeros(cap, dtype=LIST_ITEM_DTYPE)
+        items = np.empty(cap, dtype=LIST_ITEM_DTYPE)
         n = L.zg_list_scan(body, len(body), mode, items.ctypes.data, cap, C.byref(ib), C.byref(ie))
         if n == -7:
             cap *= 4

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <ctime>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -934,14 +935,20 @@ extern "C" int zg_list_postfilter(zg_engine* e, const char* body, size_t len, co
     std::memcpy(out, body, len);
     return static_cast<int>(ZG_OK);
   };
-  std::vector<zg_list_item> items(1024);
+  // one scan in the common case: an item is rarely shorter than 128 bytes (the buffer is not
+  // initialised, so its untouched pages cost nothing)
+  size_t icap = len / 128 + 16;
+  std::unique_ptr<zg_list_item[]> items(new (std::nothrow) zg_list_item[icap]);
+  if (!items) return fail(ZG_ENOMEM, "out of host memory");
   uint64_t ib = 0, ie = 0;
-  int64_t n = zg_list_scan(body, len, ZG_LIST_ITEMS, items.data(), items.size(), &ib, &ie);
+  int64_t n = zg_list_scan(body, len, ZG_LIST_ITEMS, items.get(), icap, &ib, &ie);
   if (n == ZG_E2BIG) {
     n = zg_list_scan(body, len, ZG_LIST_ITEMS, nullptr, 0, &ib, &ie);  // count, then one exact rescan
     if (n > 0) {
-      items.resize(static_cast<size_t>(n));
-      n = zg_list_scan(body, len, ZG_LIST_ITEMS, items.data(), items.size(), &ib, &ie);
+      icap = static_cast<size_t>(n);
+      items.reset(new (std::nothrow) zg_list_item[icap]);
+      if (!items) return fail(ZG_ENOMEM, "out of host memory");
+      n = zg_list_scan(body, len, ZG_LIST_ITEMS, items.get(), icap, &ib, &ie);
     }
   }
   if (n < 0) return fail(ZG_EINVAL, "failed to parse list response");
@@ -951,7 +958,7 @@ extern "C" int zg_list_postfilter(zg_engine* e, const char* body, size_t len, co
   std::vector<zg_check> one(N), all;
   std::vector<uint64_t> owner;
   for (uint32_t t = 0; t < n_tpl; ++t) {
-    int rc = zg_list_resolve(e, body, len, items.data(), N, &tpl[t], one.data(), checked.data());
+    int rc = zg_list_resolve(e, body, len, items.get(), N, &tpl[t], one.data(), checked.data());
     if (rc) return rc;
     for (uint64_t i = 0; i < N; ++i)
       if (checked[i]) {
@@ -971,7 +978,7 @@ extern "C" int zg_list_postfilter(zg_engine* e, const char* body, size_t len, co
     for (size_t k = 0; k < codes.size(); ++k)
       if (codes[k] != ZG_HAS_PERMISSION) keep[owner[k]] = 0;
   }
-  int rc = zg_list_filter(body, len, items.data(), N, keep.data(), ib, ie, ZG_LIST_EMPTY_AS_NULL, out, cap, out_len);
+  int rc = zg_list_filter(body, len, items.get(), N, keep.data(), ib, ie, ZG_LIST_EMPTY_AS_NULL, out, cap, out_len);
   return rc == ZG_EINVAL ? fail(rc, "zg_list_filter: inconsistent item ranges") : rc;
 }
 

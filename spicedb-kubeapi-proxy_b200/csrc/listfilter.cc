@@ -36,126 +36,165 @@ inline int hexv(char h) {
   return -1;
 }
 
-// Skips a string starting at the opening quote; returns [begin, end) of its raw contents.
-inline bool skip_string(Cur& c, size_t* b, size_t* e) {
-  if (c.i >= c.n || c.s[c.i] != '"') return c.ok = false;
-  size_t i = c.i + 1;
-  *b = i;
-  while (i < c.n) {
+// Pointer-style primitives (everything stays in registers): each returns the position after what
+// it consumed, or nullptr on malformed input.
+
+// p at the opening quote; returns the position after the closing quote, *close = its position.
+inline const char* str_end(const char* p, const char* end, const char** close) {
+  if (p >= end || *p != '"') return nullptr;
+  ++p;
+  while (p < end) {
 #if defined(__SSE2__)
-    // 16 bytes at a time up to the next quote, backslash or control character (most of a kube
-    // body is string contents)
-    while (i + 16 <= c.n) {
-      const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(c.s + i));
+    // 16 bytes at a time up to the next quote, backslash or control character
+    while (p + 16 <= end) {
+      const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p));
       const __m128i special = _mm_or_si128(
           _mm_or_si128(_mm_cmpeq_epi8(v, _mm_set1_epi8('"')), _mm_cmpeq_epi8(v, _mm_set1_epi8('\\'))),
           _mm_cmpeq_epi8(_mm_max_epu8(v, _mm_set1_epi8(0x1f)), _mm_set1_epi8(0x1f)));  // byte <= 0x1f
       const int m = _mm_movemask_epi8(special);
       if (m) {
-        i += __builtin_ctz(m);
+        p += __builtin_ctz(m);
         break;
       }
-      i += 16;
+      p += 16;
     }
-    if (i >= c.n) break;
+    if (p >= end) break;
 #endif
-    const char ch = c.s[i];
+    const char ch = *p;
     if (ch == '"') {
-      *e = i;
-      c.i = i + 1;
-      return true;
+      *close = p;
+      return p + 1;
     }
     if (ch == '\\') {
-      if (i + 1 >= c.n) break;
-      const char x = c.s[i + 1];
+      if (p + 1 >= end) break;
+      const char x = p[1];
       if (x == 'u') {
-        if (i + 6 > c.n || hexv(c.s[i + 2]) < 0 || hexv(c.s[i + 3]) < 0 || hexv(c.s[i + 4]) < 0 || hexv(c.s[i + 5]) < 0)
-          break;
-        i += 6;
+        if (p + 6 > end || hexv(p[2]) < 0 || hexv(p[3]) < 0 || hexv(p[4]) < 0 || hexv(p[5]) < 0) break;
+        p += 6;
         continue;
       }
       if (x != '"' && x != '\\' && x != '/' && x != 'b' && x != 'f' && x != 'n' && x != 'r' && x != 't') break;
-      i += 2;
+      p += 2;
       continue;
     }
     if (static_cast<unsigned char>(ch) < 0x20) break;  // raw control characters are not JSON
-    ++i;
+    ++p;
   }
-  return c.ok = false;
+  return nullptr;
 }
 
-bool skip_value(Cur& c, int depth);
+inline const char* skip_ws(const char* p, const char* end) {
+  if (p < end && static_cast<unsigned char>(*p) > ' ') return p;  // compact bodies: nothing to skip
+  while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p;
+  return p;
+}
 
-bool skip_container(Cur& c, char open, char close, int depth) {
-  if (depth > 512) return c.ok = false;
-  ++c.i;  // opening bracket
-  ws(c);
-  if (c.i < c.n && c.s[c.i] == close) {
-    ++c.i;
-    return true;
+// true / false / null / number: -? (0 | [1-9][0-9]*) (. [0-9]+)? ([eE] [+-]? [0-9]+)?
+inline const char* scalar_end(const char* p, const char* end) {
+  const char ch = *p;
+  if (ch == 't') return (end - p >= 4 && std::memcmp(p, "true", 4) == 0) ? p + 4 : nullptr;
+  if (ch == 'f') return (end - p >= 5 && std::memcmp(p, "false", 5) == 0) ? p + 5 : nullptr;
+  if (ch == 'n') return (end - p >= 4 && std::memcmp(p, "null", 4) == 0) ? p + 4 : nullptr;
+  if (p < end && *p == '-') ++p;
+  if (p < end && *p == '0') {
+    ++p;
+  } else {
+    const char* d = p;
+    while (p < end && *p >= '0' && *p <= '9') ++p;
+    if (p == d) return nullptr;
   }
+  if (p < end && *p == '.') {
+    const char* d = ++p;
+    while (p < end && *p >= '0' && *p <= '9') ++p;
+    if (p == d) return nullptr;
+  }
+  if (p < end && (*p == 'e' || *p == 'E')) {
+    ++p;
+    if (p < end && (*p == '+' || *p == '-')) ++p;
+    const char* d = p;
+    while (p < end && *p >= '0' && *p <= '9') ++p;
+    if (p == d) return nullptr;
+  }
+  return p;
+}
+
+constexpr int kMaxDepth = 512;  // containers nested below the value a skip starts at
+
+// Validates ONE value of any shape starting at p and returns the position after it. Iterative (an
+// explicit stack of container kinds), strict: commas, colons, literals, numbers and string escapes
+// are all checked -- this is where nearly all bytes of a list body are spent.
+const char* value_end(const char* p, const char* end, int depth0) {
+  char stack[kMaxDepth + 2];
+  int sp = 0;
   for (;;) {
-    ws(c);
-    if (open == '{') {
-      size_t b, e;
-      if (!skip_string(c, &b, &e)) return false;
-      ws(c);
-      if (c.i >= c.n || c.s[c.i] != ':') return c.ok = false;
-      ++c.i;
+    // ---- a value is expected at p
+    p = skip_ws(p, end);
+    if (p >= end) return nullptr;
+    const char ch = *p;
+    if (ch == '"') {
+      const char* q;
+      if (!(p = str_end(p, end, &q))) return nullptr;
+    } else if (ch == '{' || ch == '[') {
+      if (depth0 + sp > kMaxDepth) return nullptr;
+      stack[sp++] = ch;
+      p = skip_ws(p + 1, end);
+      if (p >= end) return nullptr;
+      if (ch == '[') {
+        if (*p != ']') continue;  // first element
+        ++p;
+        --sp;
+      } else if (*p == '}') {
+        ++p;
+        --sp;
+      } else {
+        goto key;
+      }
+    } else if (!(p = scalar_end(p, end))) {
+      return nullptr;
     }
-    if (!skip_value(c, depth + 1)) return false;
-    ws(c);
-    if (c.i >= c.n) return c.ok = false;
-    if (c.s[c.i] == ',') {
-      ++c.i;
-      continue;
+    // ---- a value just ended
+    for (;;) {
+      if (sp == 0) return p;
+      p = skip_ws(p, end);
+      if (p >= end) return nullptr;
+      const char c2 = *p++;
+      if (stack[sp - 1] == '{') {
+        if (c2 == ',') goto key_ws;
+        if (c2 != '}') return nullptr;
+      } else {
+        if (c2 == ',') break;  // next element
+        if (c2 != ']') return nullptr;
+      }
+      --sp;
     }
-    if (c.s[c.i] == close) {
-      ++c.i;
-      return true;
-    }
-    return c.ok = false;
+    continue;
+  key_ws:
+    p = skip_ws(p, end);
+  key : {
+    const char* q;
+    if (!(p = str_end(p, end, &q))) return nullptr;
+    p = skip_ws(p, end);
+    if (p >= end || *p != ':') return nullptr;
+    ++p;
+  }
   }
 }
 
-bool skip_value(Cur& c, int depth) {
-  ws(c);
-  if (c.i >= c.n) return c.ok = false;
-  const char ch = c.s[c.i];
-  if (ch == '{') return skip_container(c, '{', '}', depth);
-  if (ch == '[') return skip_container(c, '[', ']', depth);
-  if (ch == '"') {
-    size_t b, e;
-    return skip_string(c, &b, &e);
-  }
-  for (const char* lit : {"true", "false", "null"}) {
-    const size_t n = std::strlen(lit);
-    if (ch == lit[0]) {
-      if (c.i + n > c.n || std::memcmp(c.s + c.i, lit, n) != 0) return c.ok = false;
-      c.i += n;
-      return true;
-    }
-  }
-  // number: -? (0 | [1-9][0-9]*) (. [0-9]+)? ([eE] [+-]? [0-9]+)?
-  size_t i = c.i;
-  auto digits = [&]() {
-    const size_t s0 = i;
-    while (i < c.n && c.s[i] >= '0' && c.s[i] <= '9') ++i;
-    return i - s0;
-  };
-  if (i < c.n && c.s[i] == '-') ++i;
-  if (i < c.n && c.s[i] == '0') ++i;
-  else if (!digits()) return c.ok = false;
-  if (i < c.n && c.s[i] == '.') {
-    ++i;
-    if (!digits()) return c.ok = false;
-  }
-  if (i < c.n && (c.s[i] == 'e' || c.s[i] == 'E')) {
-    ++i;
-    if (i < c.n && (c.s[i] == '+' || c.s[i] == '-')) ++i;
-    if (!digits()) return c.ok = false;
-  }
-  c.i = i;
+// Cursor adapters for the outer walkers below.
+inline bool skip_string(Cur& c, size_t* b, size_t* e) {
+  const char* q;
+  const char* p = str_end(c.s + c.i, c.s + c.n, &q);
+  if (!p) return c.ok = false;
+  *b = c.i + 1;
+  *e = static_cast<size_t>(q - c.s);
+  c.i = static_cast<size_t>(p - c.s);
+  return true;
+}
+
+inline bool skip_value(Cur& c, int depth) {
+  const char* p = value_end(c.s + c.i, c.s + c.n, depth);
+  if (!p) return c.ok = false;
+  c.i = static_cast<size_t>(p - c.s);
   return true;
 }
 

@@ -286,6 +286,8 @@ def test_list_resolve_matches_the_string_path():
     for raw in (b'{"kind":"Status"}', b'{"items":[]}', b'{"items":null}'):
         assert e.list_postfilter(raw, [tpl]) == raw
     assert json.loads(e.list_postfilter(b'{"items":[1,"x"]}', [tpl])) == {"items": [1, "x"]}  # nothing to check
+    tiny = json.dumps({"items": [1] * 5000, "k": "v"}, separators=(",", ":")).encode()  # more items than the first guess
+    assert json.loads(e.list_postfilter(tiny, [tpl])) == json.loads(tiny)
     with pytest.raises(_lib.ZgpuError, match="no CPU fallback"):
         e.list_postfilter(body, [tpl])
     with pytest.raises(_lib.ZgpuError):
