@@ -894,7 +894,8 @@ extern "C" int zg_list_resolve(zg_engine* e, const char* body, size_t len, const
     out[i] = base;
     checked[i] = 0;
     if (!(it.flags & ZG_ITEM_IS_OBJECT)) continue;
-    if (it.name_off + it.name_len > len || it.ns_off + it.ns_len > len) return fail(ZG_EINVAL, "item range outside the body");
+    if (it.name_off > len || it.name_len > len - it.name_off || it.ns_off > len || it.ns_len > len - it.ns_off)
+      return fail(ZG_EINVAL, "item range outside the body");
     name.clear();
     ns.clear();
     if (it.flags & ZG_ITEM_HAS_METADATA) {

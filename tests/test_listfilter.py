@@ -281,6 +281,12 @@ def test_list_resolve_matches_the_string_path():
     assert (int(g2[0]["res"]), int(g2[0]["subj"])) == (0xFFFFFFFF, 0xFFFFFFFF)
     g3, _ = e.list_resolve(b2, sc2, e.list_template("pod", "view", "pod", "other", "viewer", _lib.ID_NAME))
     assert (int(g3[0]["res"]), int(g3[0]["subj"])) == (0xFFFFFFFF, 0xFFFFFFFE)
+    # item ranges handed back by the caller are bounds-checked (overflow-safe) before any byte is read
+    for off, ln in ((10**9, 1), (2**64 - 2, 5), (len(b2) - 1, 2)):
+        bad = sc2.copy()
+        bad["name_off"], bad["name_len"] = off, ln
+        with pytest.raises(_lib.ZgpuError, match="outside the body"):
+            e.list_resolve(b2, bad, e.list_template("pod", "view", "user", "u", "", _lib.ID_NAME))
     # the fused call: passthrough cases need no GPU; anything with checks fails loudly without one
     tpl = e.list_template("pod", "view", "user", "alice")
     for raw in (b'{"kind":"Status"}', b'{"items":[]}', b'{"items":null}'):
