@@ -354,3 +354,40 @@ def test_host_code_under_sanitizers(tmp_path):
     assert build.returncode == 0, build.stderr[-2000:]
     run = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=600)
     assert run.returncode == 0 and run.stdout.strip().endswith("ok"), (run.stdout[-800:], run.stderr[-2000:])
+
+
+def test_batcher_under_concurrent_callers_without_a_gpu():
+    """The group-commit batcher (csrc/capi.cu) runs before any CUDA call, so its queueing, leader hand-over and
+    wake-ups can be stressed here: on a host-only engine every caller must come back with the loud ZG_ECUDA
+    error -- its own, exactly once, no deadlock -- while a writer keeps taking the engine lock."""
+    import threading
+    e = zgpu.Engine(workloads.BOOTSTRAP_SCHEMA, host_only=True)
+    e.write_relationships([(zgpu._lib.OP_TOUCH, "pod:ns/p#viewer@user:u", 0)])
+    items = np.zeros(64, dtype=zgpu.CHECK_DTYPE)
+    results, stop = [], threading.Event()
+
+    def caller(tid):
+        got = 0
+        for k in range(150):
+            try:
+                e.check_bulk(items[: 1 + (tid + k) % 64])
+            except zgpu.ZgpuError as ex:
+                got += "no CPU fallback" in str(ex)
+        results.append(got)
+
+    def writer():
+        i = 0
+        while not stop.is_set():
+            e.write_relationships([(zgpu._lib.OP_TOUCH if i % 2 == 0 else zgpu._lib.OP_DELETE, "pod:ns/q#viewer@user:u", 0)])
+            i += 1
+
+    wt = threading.Thread(target=writer)
+    wt.start()
+    th = [threading.Thread(target=caller, args=(t,)) for t in range(24)]
+    [t.start() for t in th]
+    for t in th:
+        t.join(timeout=120)
+    stop.set()
+    wt.join(timeout=30)
+    assert not any(t.is_alive() for t in th) and not wt.is_alive(), "batcher deadlock"
+    assert results == [150] * 24
