@@ -314,6 +314,21 @@ int zg_list_resolve(zg_engine *e, const char *body, size_t len, const zg_list_it
 int zg_list_postfilter(zg_engine *e, const char *body, size_t len, const zg_list_template *tpl,
                        uint32_t n_tpl, char *out, size_t cap, size_t *out_len);
 
+/* The pre-filter side of the same scan (pkg/authz/lookups.go:44-132 + responsefilterer.go:349-400):
+ * keep[i] = 1 when the item's (namespace, name) is what an allowed resource id maps to under the usual
+ * id <-> name rule ("namespace/name" -> (namespace, name); "name" -> (request namespace or "", name)).
+ * `allowed` = object ids of res_type, ascending, as zg_lookup_resources returns them; self_name
+ * (NULL = none) is one more allowed id given by name. mode = ZG_LIST_ITEMS | ZG_LIST_TABLE_ROWS. An
+ * element that is not an object, or a table row without "object", is ZG_EINVAL (the reference fails to
+ * decode such a body). No GPU work. */
+int zg_list_keep_allowed(zg_engine *e, const char *body, size_t len, const zg_list_item *items, uint64_t n,
+                         uint32_t mode, const char *res_type, const char *req_namespace,
+                         const uint32_t *allowed, uint64_t n_allowed, const char *self_name, uint8_t *keep);
+/* LookupResources (tpl's literal fields; id_kind / req_name are not used) + scan + keep + splice: the
+ * whole pre-filtered List or Table response in one call. Nothing kept gives [] here. */
+int zg_list_prefilter(zg_engine *e, const char *body, size_t len, uint32_t mode, const zg_list_template *tpl,
+                      char *out, size_t cap, size_t *out_len);
+
 /* ---- measurement --------------------------------------------------------- */
 int zg_stats_get(zg_engine *e, zg_stats *out);
 /* Runs the batch through the instrumented kernel variant and returns the

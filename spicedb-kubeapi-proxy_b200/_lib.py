@@ -163,6 +163,10 @@ _SIGS = {
                                   C.c_void_p, C.c_void_p]),
     "zg_list_postfilter": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(_ListTemplate), C.c_uint32,
                                      C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "zg_list_keep_allowed": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_uint32, C.c_char_p,
+                                       C.c_char_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_void_p]),
+    "zg_list_prefilter": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint32, C.POINTER(_ListTemplate), C.c_void_p,
+                                    C.c_size_t, C.POINTER(C.c_size_t)]),
     "zg_stats_get": (C.c_int, [C.c_void_p, C.POINTER(_Stats)]),
     "zg_count_alg_bytes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
 }
@@ -458,6 +462,25 @@ class Engine:
         need = C.c_size_t(0)
         self._ck(self._L.zg_list_postfilter(self._h, body, len(body), arr, len(templates), out.ctypes.data, out.size,
                                             C.byref(need)))
+        return out[:need.value].tobytes()
+
+    def list_keep_allowed(self, body: bytes, items: np.ndarray, res_type: str, allowed_ids: np.ndarray, mode: int = LIST_ITEMS,
+                          req_namespace: str = "", self_name: str | None = None) -> np.ndarray:
+        """keep mask of the scanned items given the (ascending) object ids a LookupResources returned; no GPU work."""
+        items = np.ascontiguousarray(items, dtype=LIST_ITEM_DTYPE)
+        allowed = np.ascontiguousarray(allowed_ids, dtype=np.uint32)
+        keep = np.zeros(len(items), dtype=np.uint8)
+        self._ck(self._L.zg_list_keep_allowed(self._h, body, len(body), items.ctypes.data, len(items), mode, _b(res_type),
+                                              _b(req_namespace), allowed.ctypes.data, allowed.size, _b(self_name),
+                                              keep.ctypes.data))
+        return keep
+
+    def list_prefilter(self, body: bytes, tpl: "_ListTemplate", mode: int = LIST_ITEMS) -> bytes:
+        """zg_list_prefilter: LookupResources + scan + keep + splice in one call."""
+        out = np.empty(len(body) + 8, dtype=np.uint8)
+        need = C.c_size_t(0)
+        self._ck(self._L.zg_list_prefilter(self._h, body, len(body), mode, C.byref(tpl), out.ctypes.data, out.size,
+                                           C.byref(need)))
         return out[:need.value].tobytes()
 
     def resolve_checks(self, rels) -> np.ndarray:

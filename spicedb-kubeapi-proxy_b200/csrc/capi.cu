@@ -1084,6 +1084,118 @@ extern "C" int zg_lookup_resources_str(zg_engine* e, const char* res_type, const
   return ZG_OK;
 }
 
+// ---- pre-filter: LookupResources ids -> kept list items --------------------------------------
+
+extern "C" int zg_list_keep_allowed(zg_engine* e, const char* body, size_t len, const zg_list_item* items, uint64_t n,
+                                    uint32_t mode, const char* res_type, const char* req_namespace, const uint32_t* allowed,
+                                    uint64_t n_allowed, const char* self_name, uint8_t* keep) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if (!res_type || ((!body || !items || !keep) && n) || (!allowed && n_allowed)) return fail(ZG_EINVAL, "NULL argument");
+  if (mode > ZG_LIST_TABLE_ROWS) return fail(ZG_EINVAL, "unknown mode");
+  std::lock_guard<std::mutex> g(e->mu);
+  const int rt = e->schema.type_id(res_type);
+  if (rt < 0) return fail(ZG_EINVAL, std::string("object definition `") + res_type + "` not found");
+  const std::string req_ns = req_namespace ? req_namespace : "", self = self_name ? self_name : "";
+  auto has = [&](const std::string& id) {
+    if (!self.empty() && id == self) return true;
+    const uint32_t oid = e->store.find(rt, id.data(), id.size());
+    return oid != ZG_NO_OBJECT && std::binary_search(allowed, allowed + n_allowed, oid);
+  };
+  std::string name, ns, id;
+  for (uint64_t i = 0; i < n; ++i) {
+    const zg_list_item& it = items[i];
+    keep[i] = 0;
+    if (!(it.flags & ZG_ITEM_IS_OBJECT)) return fail(ZG_EINVAL, "failed to decode response body: element is not an object");
+    if (mode == ZG_LIST_TABLE_ROWS && !(it.flags & ZG_ITEM_HAS_OBJECT))
+      return fail(ZG_EINVAL, "error decoding partial object metadata from table row");
+    if (it.name_off > len || it.name_len > len - it.name_off || it.ns_off > len || it.ns_len > len - it.ns_off)
+      return fail(ZG_EINVAL, "item range outside the body");
+    name.clear();
+    ns.clear();
+    if (it.flags & ZG_ITEM_HAS_METADATA) {
+      json_unescape_append(body + it.name_off, it.name_len, &name);
+      json_unescape_append(body + it.ns_off, it.ns_len, &ns);
+    }
+    // an allowed id maps to (text before the last '/', text after it): a name holding a '/' maps from none
+    if (name.empty() || name.find('/') != std::string::npos) continue;
+    id = ns;
+    id += '/';
+    id += name;
+    bool k = has(id);
+    if (!k && ns == req_ns) k = has(name);  // cluster-scoped ids take the request's namespace (lookups.go:117-127)
+    keep[i] = k ? 1 : 0;
+  }
+  return ZG_OK;
+}
+
+extern "C" int zg_list_prefilter(zg_engine* e, const char* body, size_t len, uint32_t mode, const zg_list_template* tpl,
+                                 char* out, size_t cap, size_t* out_len) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if (!body || !out_len || !tpl) return fail(ZG_EINVAL, "NULL argument");
+  if (!tpl->res_type || !tpl->permission || !tpl->subj_type || !tpl->subj_id) return fail(ZG_EINVAL, "NULL template field");
+  if (mode > ZG_LIST_TABLE_ROWS) return fail(ZG_EINVAL, "unknown mode");
+  // 1. the allowed ids (one LookupResources on the GPU)
+  std::vector<uint32_t> ids;
+  std::string self;
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    int rc = ensure_published(e);
+    if (rc) return rc;
+    const Schema& sc = e->schema;
+    const int rt = sc.type_id(tpl->res_type), st = sc.type_id(tpl->subj_type);
+    if (rt < 0) return fail(ZG_EINVAL, std::string("object definition `") + tpl->res_type + "` not found");
+    if (st < 0) return fail(ZG_EINVAL, std::string("object definition `") + tpl->subj_type + "` not found");
+    const int p = sc.slot_id(rt, tpl->permission);
+    if (p < 0) return fail(ZG_EINVAL, std::string("relation/permission `") + tpl->permission + "` not found");
+    uint16_t sr = kNone;
+    if (!none_rel(tpl->subj_rel)) {
+      const int s2 = sc.slot_id(st, tpl->subj_rel);
+      if (s2 < 0) return fail(ZG_EINVAL, std::string("relation `") + tpl->subj_rel + "` not found");
+      sr = static_cast<uint16_t>(s2);
+    }
+    const uint32_t su = e->store.find(st, tpl->subj_id);
+    rc = lookup_locked(e, static_cast<uint16_t>(rt), static_cast<uint16_t>(p), static_cast<uint16_t>(st),
+                       su == ZG_NO_OBJECT ? ZG_NO_OBJECT - 1 : su, sr, &ids);
+    if (rc) return rc;
+    if (su == ZG_NO_OBJECT && sr == p && st == rt) self = tpl->subj_id;  // never-written userset subject naming itself
+    // lookups.go:106-109: an id that yields no name fails the whole pre-filter
+    for (uint32_t id : ids) {
+      const std::string* nm = e->store.name(rt, id);
+      if (nm && (nm->empty() || nm->back() == '/')) return fail(ZG_EINVAL, "unable to determine name for resource");
+    }
+  }
+  // 2. scan
+  size_t icap = len / 128 + 16;
+  std::unique_ptr<zg_list_item[]> items(new (std::nothrow) zg_list_item[icap]);
+  if (!items) return fail(ZG_ENOMEM, "out of host memory");
+  uint64_t ib = 0, ie = 0;
+  int64_t n = zg_list_scan(body, len, mode, items.get(), icap, &ib, &ie);
+  if (n == ZG_E2BIG) {
+    n = zg_list_scan(body, len, mode, nullptr, 0, &ib, &ie);
+    if (n > 0) {
+      icap = static_cast<size_t>(n);
+      items.reset(new (std::nothrow) zg_list_item[icap]);
+      if (!items) return fail(ZG_ENOMEM, "out of host memory");
+      n = zg_list_scan(body, len, mode, items.get(), icap, &ib, &ie);
+    }
+  }
+  if (n < 0) return fail(ZG_EINVAL, "failed to decode response body");
+  if (ie == 0) {  // no such array: the body passes through
+    *out_len = len;
+    if (len > cap || !out) return ZG_E2BIG;
+    std::memcpy(out, body, len);
+    return ZG_OK;
+  }
+  // 3. keep + splice
+  const uint64_t N = static_cast<uint64_t>(n);
+  std::vector<uint8_t> keep(N);
+  int rc = zg_list_keep_allowed(e, body, len, items.get(), N, mode, tpl->res_type, tpl->req_namespace, ids.data(), ids.size(),
+                                self.empty() ? nullptr : self.c_str(), keep.data());
+  if (rc) return rc;
+  rc = zg_list_filter(body, len, items.get(), N, keep.data(), ib, ie, 0, out, cap, out_len);
+  return rc == ZG_EINVAL ? fail(rc, "zg_list_filter: inconsistent item ranges") : rc;
+}
+
 extern "C" int zg_stats_get(zg_engine* e, zg_stats* out) {
   if (!e || !out) return fail(ZG_EINVAL, "NULL argument");
   std::lock_guard<std::mutex> g(e->mu);

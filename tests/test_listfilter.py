@@ -430,6 +430,57 @@ def test_prefilter_list_table_object():
         pf.filter_object(b'{"a":1},{"b":2}', res)
 
 
+def test_list_keep_allowed_matches_the_prefilter_mirror():
+    """zg_list_keep_allowed (ids from LookupResources -> keep mask, in C) against the mirror of lookups.go +
+    responsefilterer.go (PrefilterResult built from the same ids by name, filter_list / filter_table)."""
+    from spicedb_kubeapi_proxy_b200 import workloads
+    e = zgpu.Engine(workloads.BOOTSTRAP_SCHEMA, host_only=True)
+    names = [f"ns{i % 3}/p{i}" for i in range(30)] + ["cw1", "cw2", "rns/inreq", "/odd"]
+    ids = {n: e.intern("pod", n) for n in names}
+    rng = random.Random(5)
+    kept_total = seen_total = 0
+    for trial in range(30):
+        allowed_names = sorted(rng.sample(names, rng.randrange(0, len(names))))
+        allowed = np.array(sorted(ids[n] for n in allowed_names), dtype=np.uint32)
+        req_ns = rng.choice(["", "rns", "ns1"])
+        result = pf.run_lookup_resources(MockLookupClient(allowed_names), ("pod", "$", "view", "user", "u", ""),
+                                         pf.RequestInfo(namespace=req_ns))
+        objs = []
+        for _ in range(60):
+            meta = {}
+            if rng.random() < 0.9:
+                meta["name"] = rng.choice([f"p{rng.randrange(34)}", "cw1", "cw2", "inreq", "odd", "a/b", "", "never"])
+            if rng.random() < 0.8:
+                meta["namespace"] = rng.choice([f"ns{rng.randrange(4)}", "rns", "", "ns1"])
+            objs.append({"metadata": meta, "spec": {"x": 1}} if rng.random() < 0.95 else {"spec": 2})
+        for mode, body, mirror in (
+                (_lib.LIST_ITEMS, json.dumps({"kind": "PodList", "items": objs}).encode(), pf.filter_list),
+                (_lib.LIST_TABLE_ROWS, json.dumps({"kind": "Table", "rows": [{"cells": [1], "object": o} for o in objs]}).encode(),
+                 pf.filter_table)):
+            scanned, ib, ie = _lib.list_scan(body, mode)
+            keep = e.list_keep_allowed(body, scanned, "pod", allowed, mode, req_ns)
+            got = _lib.list_filter(body, scanned, keep, ib, ie)
+            assert got == mirror(body, result), (trial, mode)
+        kept_total += int(keep.sum())
+        seen_total += len(objs)
+    assert 100 < kept_total < seen_total - 100
+    # a never-written userset subject naming itself is allowed by name
+    b = json.dumps({"items": [pod("ghost", ""), pod("x", "")]}).encode()
+    sc = _lib.list_scan(b)[0]
+    assert e.list_keep_allowed(b, sc, "pod", np.zeros(0, np.uint32), self_name="ghost").tolist() == [1, 0]
+    # decode failures of the reference: non-object element, table row without "object"
+    with pytest.raises(_lib.ZgpuError, match="not an object"):
+        e.list_keep_allowed(b'{"items":[1]}', _lib.list_scan(b'{"items":[1]}')[0], "pod", allowed)
+    rows = b'{"rows":[{"cells":[]}]}'
+    with pytest.raises(_lib.ZgpuError, match="table row"):
+        e.list_keep_allowed(rows, _lib.list_scan(rows, _lib.LIST_TABLE_ROWS)[0], "pod", allowed, _lib.LIST_TABLE_ROWS)
+    with pytest.raises(_lib.ZgpuError, match="not found"):
+        e.list_keep_allowed(b, sc, "nosuch", allowed)
+    # the fused call needs the GPU for its LookupResources: loud failure here
+    with pytest.raises(_lib.ZgpuError, match="no CPU fallback"):
+        e.list_prefilter(b, e.list_template("pod", "view", "user", "u"))
+
+
 def test_run_watch_rechecks_every_update_in_one_bulk_call():
     # watch.go:48-107 with the per-update CheckPermission folded into one bulk call per WatchResponse
     up = lambda op, rel: cl.RelationshipUpdate(op, cl.Relationship.parse(rel))

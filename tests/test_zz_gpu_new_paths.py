@@ -53,6 +53,14 @@ def test_gpu_filter_through_engine():
     res = pf.run_lookup_resources(c, ("pod", "$", "view", "user", "alice", ""), REQ)
     assert res.allowed_results == {("team-a", "p1"), ("team-b", "p3"), ("team-b", "p4")}
     assert [i["metadata"]["name"] for i in json.loads(pf.filter_list(body, res))["items"]] == ["p1", "p3", "p4"]
+    # ... and the same in one C call (LookupResources on the GPU + scan + keep + splice), list and table
+    for who in ("alice", "bob", "nobody"):
+        r = pf.run_lookup_resources(c, ("pod", "$", "view", "user", who, ""), REQ)
+        t = c.engine.list_template("pod", "view", "user", who)
+        assert c.engine.list_prefilter(body, t) == pf.filter_list(body, r)
+        table = json.dumps({"kind": "Table", "rows": [{"cells": [i["metadata"]["name"]], "object": i}
+                                                       for i in json.loads(body)["items"]]}).encode()
+        assert c.engine.list_prefilter(table, t, zgpu._lib.LIST_TABLE_ROWS) == pf.filter_table(table, r)
     # the watch path: a write shows up on the feed and is re-checked against the new snapshot
     stream = c.Watch(cl.WatchRequest(["pod"]))
     c.WriteRelationships(cl.WriteRelationshipsRequest([
