@@ -145,4 +145,19 @@ n_lists = a.clients * a.rounds
 res.update({"filtered_lists_per_s": round(n_lists / dt, 1), "body_MB_per_s": round(n_lists * len(bodies[0]) / 1e6 / dt, 1),
             "checks_per_s": round(n_lists * a.items / dt), "launches": int(s1["launches"] - s0["launches"]),
             "coalesced_requests": int(s1["coalesced_requests"] - s0["coalesced_requests"]), "errors": errors[:3]})
+# the pre-filter shape: LookupResources + scan + keep + splice per list (pkg/authz/lookups.go:65)
+for i in range(min(2, a.clients)):
+    r = pf.run_lookup_resources(client, ("pod", "$", "view", "user", users[i], ""), pf.RequestInfo())
+    assert e.list_prefilter(bodies[i % n_bodies], tpls[i]) == pf.filter_list(bodies[i % n_bodies], r), f"client {i}: prefilter differs"
+
+
+def prelists(i):
+    for _ in range(a.rounds):
+        out_bytes[i] = len(e.list_prefilter(bodies[i % n_bodies], tpls[i]))
+
+
+run_phase(prelists)
+dt, s0, s1 = run_phase(prelists)
+res.update({"prefiltered_lists_per_s": round(n_lists / dt, 1), "prefilter_launches": int(s1["launches"] - s0["launches"]),
+            "errors": errors[:3]})
 print(json.dumps(res))
