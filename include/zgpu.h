@@ -208,6 +208,17 @@ int zg_check_bulk_str(zg_engine *e, const zg_rel_str *items, uint64_t n, uint8_t
  * item that answers ZG_ITEM_ERROR). Lets a caller intern once and reuse the ids; they stay valid for
  * the life of the engine. */
 int zg_resolve_checks(zg_engine *e, const zg_rel_str *items, uint64_t n, zg_check *out);
+/* Packed form for a bulk request whose items share their literal fields (one rule template evaluated per
+ * item: pkg/authz/postfilter.go:88-110): the n resource ids are the byte ranges
+ * [res_off[i], res_off[i+1]) of res_ids (n + 1 offsets, no terminators); the subjects likewise, or with
+ * subj_off == NULL ONE subject id for all items, NUL-terminated in subj_ids. Two buffers cross the
+ * boundary instead of 6 n C strings. zg_check_bulk_packed = zg_resolve_checks_packed + zg_check_bulk. */
+int zg_resolve_checks_packed(zg_engine *e, const char *res_type, const char *relation, const char *subj_type,
+                             const char *subj_rel, const char *res_ids, const uint32_t *res_off,
+                             const char *subj_ids, const uint32_t *subj_off, uint64_t n, zg_check *out);
+int zg_check_bulk_packed(zg_engine *e, const char *res_type, const char *relation, const char *subj_type,
+                         const char *subj_rel, const char *res_ids, const uint32_t *res_off,
+                         const char *subj_ids, const uint32_t *subj_off, uint64_t n, uint8_t *out);
 
 /* LookupResources: ids (ascending) of every object of res_type with HAS_PERMISSION.
  * Returns 0, or ZG_E2BIG with *n_out = required capacity. */

@@ -144,6 +144,8 @@ _SIGS = {
     "zg_check_bulk_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "zg_check_bulk_str": (C.c_int, [C.c_void_p, C.POINTER(_RelStr), C.c_uint64, C.c_void_p]),
     "zg_resolve_checks": (C.c_int, [C.c_void_p, C.POINTER(_RelStr), C.c_uint64, C.c_void_p]),
+    "zg_resolve_checks_packed": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "zg_check_bulk_packed": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "zg_lookup_resources": (C.c_int, [C.c_void_p, C.c_uint16, C.c_uint16, C.c_uint16, C.c_uint32, C.c_uint16,
                                       C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "zg_lookup_resources_str": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p,
@@ -482,6 +484,35 @@ class Engine:
         self._ck(self._L.zg_list_prefilter(self._h, body, len(body), mode, C.byref(tpl), out.ctypes.data, out.size,
                                            C.byref(need)))
         return out[:need.value].tobytes()
+
+    @staticmethod
+    def pack_ids(ids):
+        """[str] -> (blob, offsets[n+1]) as the packed entry points take them."""
+        enc = [_b(i) for i in ids]
+        off = np.zeros(len(enc) + 1, dtype=np.uint32)
+        np.cumsum([len(x) for x in enc], out=off[1:])
+        return b"".join(enc), off
+
+    def _packed_call(self, fn, res_type, relation, subj_type, subj_rel, res_ids, subjects, out):
+        blob, off = self.pack_ids(res_ids)
+        if isinstance(subjects, (str, bytes)):
+            sblob, soff = _b(subjects), None
+        else:
+            sblob, so = self.pack_ids(subjects)
+            soff = so.ctypes.data
+            sblob = sblob or b"\0"
+        self._ck(fn(self._h, _b(res_type), _b(relation), _b(subj_type), _b(subj_rel or ""), blob or b"\0", off.ctypes.data,
+                    sblob, soff, len(res_ids), out.ctypes.data))
+        return out
+
+    def resolve_checks_packed(self, res_type, relation, subj_type, res_ids, subjects, subj_rel="") -> np.ndarray:
+        """`subjects`: one id (str) for all items, or a list of n ids."""
+        return self._packed_call(self._L.zg_resolve_checks_packed, res_type, relation, subj_type, subj_rel, res_ids, subjects,
+                                 np.zeros(len(res_ids), dtype=CHECK_DTYPE))
+
+    def check_bulk_packed(self, res_type, relation, subj_type, res_ids, subjects, subj_rel="") -> np.ndarray:
+        return self._packed_call(self._L.zg_check_bulk_packed, res_type, relation, subj_type, subj_rel, res_ids, subjects,
+                                 np.empty(len(res_ids), dtype=np.uint8))
 
     def resolve_checks(self, rels) -> np.ndarray:
         """Strings -> interned zg_check items (no GPU work); feed them to check_bulk."""

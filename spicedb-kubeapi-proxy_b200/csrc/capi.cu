@@ -783,6 +783,82 @@ extern "C" int zg_resolve_checks(zg_engine* e, const zg_rel_str* items, uint64_t
   return ZG_OK;
 }
 
+static int resolve_packed_locked(zg_engine* e, const char* res_type, const char* relation, const char* subj_type,
+                                 const char* subj_rel, const char* res_ids, const uint32_t* res_off, const char* subj_ids,
+                                 const uint32_t* subj_off, uint64_t n, zg_check* out) {
+  for (uint64_t i = 0; i < n; ++i)
+    if (res_off[i] > res_off[i + 1] || (subj_off && subj_off[i] > subj_off[i + 1]))
+      return fail(ZG_EINVAL, "offsets must not decrease");
+  // the literal fields once (same rules as resolve_check)
+  ResolveMemo memo;
+  zg_check base;
+  const zg_rel_str proto{res_type, "", relation, subj_type, subj_off ? "" : subj_ids, subj_rel};
+  resolve_check(e, proto, &base, &memo);
+  const ResolveMemo::SchemaPart& part = memo.parts[memo.last];
+  const bool ok = base.perm != kNone;
+  const size_t one_len = subj_off ? 0 : std::strlen(subj_ids);
+  auto run = [&](uint64_t b, uint64_t en) {
+    for (uint64_t i = b; i < en; ++i) {
+      out[i] = base;
+      if (!ok) continue;  // unknown type / relation: answers ZG_ITEM_ERROR like the string path
+      const char* rid = res_ids + res_off[i];
+      const size_t rl = res_off[i + 1] - res_off[i];
+      const char* sid = subj_off ? subj_ids + subj_off[i] : subj_ids;
+      const size_t sl = subj_off ? subj_off[i + 1] - subj_off[i] : one_len;
+      const uint32_t res = e->store.find(part.rt, rid, rl);
+      uint32_t su = subj_off ? e->store.find(part.st, sid, sl) : memo.su;
+      if (su == ZG_NO_OBJECT)
+        su = (res == ZG_NO_OBJECT && part.rt == part.st && rl == sl && std::memcmp(rid, sid, rl) == 0) ? ZG_NO_OBJECT
+                                                                                                       : ZG_NO_OBJECT - 1;
+      out[i].res = res;
+      out[i].subj = su;
+    }
+  };
+  constexpr uint64_t kPerThread = 16384;
+  const unsigned hw = std::thread::hardware_concurrency();
+  const uint64_t nt = std::min<uint64_t>({n / kPerThread, hw ? hw : 1u, 16u});
+  if (nt < 2) {
+    run(0, n);
+    return ZG_OK;
+  }
+  std::vector<std::thread> th;
+  const uint64_t per = (n + nt - 1) / nt;
+  for (uint64_t t = 1; t < nt; ++t) th.emplace_back(run, std::min(n, t * per), std::min(n, (t + 1) * per));
+  run(0, std::min(n, per));
+  for (auto& x : th) x.join();
+  return ZG_OK;
+}
+
+#define PACKED_ARGS_OK() \
+  (res_type && relation && subj_type && (n == 0 || (res_ids && res_off && subj_ids && out)))
+
+extern "C" int zg_resolve_checks_packed(zg_engine* e, const char* res_type, const char* relation, const char* subj_type,
+                                        const char* subj_rel, const char* res_ids, const uint32_t* res_off,
+                                        const char* subj_ids, const uint32_t* subj_off, uint64_t n, zg_check* out) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if (!PACKED_ARGS_OK()) return fail(ZG_EINVAL, "NULL argument");
+  if (n == 0) return ZG_OK;
+  std::lock_guard<std::mutex> g(e->mu);
+  return resolve_packed_locked(e, res_type, relation, subj_type, subj_rel, res_ids, res_off, subj_ids, subj_off, n, out);
+}
+
+extern "C" int zg_check_bulk_packed(zg_engine* e, const char* res_type, const char* relation, const char* subj_type,
+                                    const char* subj_rel, const char* res_ids, const uint32_t* res_off, const char* subj_ids,
+                                    const uint32_t* subj_off, uint64_t n, uint8_t* out) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  if (!PACKED_ARGS_OK()) return fail(ZG_EINVAL, "NULL argument");
+  if (n == 0) return ZG_OK;
+  std::vector<zg_check> c(n);
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    int rc = ensure_published(e);
+    if (rc) return rc;
+    rc = resolve_packed_locked(e, res_type, relation, subj_type, subj_rel, res_ids, res_off, subj_ids, subj_off, n, c.data());
+    if (rc) return rc;
+  }
+  return zg_check_bulk(e, c.data(), n, out);
+}
+
 extern "C" int zg_check_bulk_str(zg_engine* e, const zg_rel_str* items, uint64_t n, uint8_t* out) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if ((!items || !out) && n) return fail(ZG_EINVAL, "NULL argument");

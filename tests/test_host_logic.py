@@ -391,3 +391,36 @@ def test_batcher_under_concurrent_callers_without_a_gpu():
     wt.join(timeout=30)
     assert not any(t.is_alive() for t in th) and not wt.is_alive(), "batcher deadlock"
     assert results == [150] * 24
+
+
+def test_packed_resolution_equals_the_string_path():
+    """zg_resolve_checks_packed (two buffers for n items) against zg_resolve_checks (6 n C strings)."""
+    import random
+    e = zgpu.Engine(workloads.BOOTSTRAP_SCHEMA, host_only=True)
+    for i in range(200):
+        e.intern("pod", f"ns{i % 5}/p{i}")
+        e.intern("user", f"u{i % 20}")
+    e.intern("pod", "")  # the empty name is a legal key of the index
+    rng = random.Random(9)
+    res = [rng.choice([f"ns{rng.randrange(6)}/p{rng.randrange(230)}", "never", "", "u3"]) for _ in range(40000)]
+    subs = [rng.choice([f"u{rng.randrange(25)}", "never", ""]) for _ in res]
+    for rt, rel, st, srel in (("pod", "view", "user", ""), ("pod", "viewer", "user", "..."), ("pod", "view", "pod", "viewer"),
+                              ("pod", "nosuch", "user", ""), ("nosuch", "view", "user", ""), ("pod", "view", "user", "nosuch")):
+        want = e.resolve_checks([(rt, r, rel, st, s, srel) for r, s in zip(res, subs)])
+        assert e.resolve_checks_packed(rt, rel, st, res, subs, srel).tobytes() == want.tobytes()
+        one = e.resolve_checks([(rt, r, rel, st, "u7", srel) for r in res])
+        assert e.resolve_checks_packed(rt, rel, st, res, "u7", srel).tobytes() == one.tobytes()
+    # same never-written object on both sides: shared sentinel, per item and with one subject
+    got = e.resolve_checks_packed("pod", "view", "pod", ["ghost", "ghost"], ["ghost", "other"], "viewer")
+    assert [(int(g["res"]), int(g["subj"])) for g in got] == [(0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF, 0xFFFFFFFE)]
+    got = e.resolve_checks_packed("pod", "view", "pod", ["ghost", "x"], "ghost", "viewer")
+    assert [(int(g["res"]), int(g["subj"])) for g in got] == [(0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF, 0xFFFFFFFE)]
+    assert e.resolve_checks_packed("pod", "view", "user", [], "u1").size == 0
+    # decreasing offsets are refused; the fused call fails loudly without a GPU
+    import ctypes as ct
+    L = zgpu._lib.lib()
+    off = np.array([0, 3, 1], dtype=np.uint32)
+    out = np.zeros(2, dtype=zgpu.CHECK_DTYPE)
+    assert L.zg_resolve_checks_packed(e._h, b"pod", b"view", b"user", b"", b"abc", off.ctypes.data, b"u", None, 2, out.ctypes.data) == -1
+    with pytest.raises(zgpu.ZgpuError, match="no CPU fallback"):
+        e.check_bulk_packed("pod", "view", "user", ["ns1/p1"], "u1")
