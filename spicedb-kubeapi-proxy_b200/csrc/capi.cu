@@ -11,6 +11,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <string_view>
 #include <thread>
 #include <vector>
 
@@ -207,11 +208,12 @@ extern "C" uint32_t zg_find_object(const zg_engine* e, int t, const char* id) {
 extern "C" int zg_object_name(const zg_engine* e, int t, uint32_t id, char* buf, size_t cap) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   std::lock_guard<std::mutex> g(const_cast<zg_engine*>(e)->mu);
-  const std::string* n = e->store.name(t, id);
-  if (!n) return fail(ZG_EINVAL, "object has no name");
-  if (n->size() + 1 > cap) return ZG_E2BIG;
-  std::memcpy(buf, n->c_str(), n->size() + 1);
-  return static_cast<int>(n->size());
+  std::string_view n;
+  if (!e->store.name(t, id, &n)) return fail(ZG_EINVAL, "object has no name");
+  if (n.size() + 1 > cap || !buf) return ZG_E2BIG;
+  std::memcpy(buf, n.data(), n.size());
+  buf[n.size()] = 0;
+  return static_cast<int>(n.size());
 }
 
 extern "C" int zg_load_tuples(zg_engine* e, const zg_tuple* t, const uint32_t* expires, uint64_t n) {
@@ -490,8 +492,8 @@ static std::string tuple_text(const zg_engine* e, const zg_tuple& t) {
   const Schema& sc = e->schema;
   const SlotInfo& rel = sc.slots[t.rel];
   auto obj = [&](int type, uint32_t id) {
-    const std::string* n = e->store.name(type, id);
-    return n ? *n : std::to_string(id);
+    std::string_view n;
+    return e->store.name(type, id, &n) ? std::string(n) : std::to_string(id);
   };
   std::string s = sc.types[rel.type].name + ":" + obj(rel.type, t.res) + "#" + rel.name + "@" + sc.types[t.stype].name + ":";
   if (t.srel == kWildcard) return s + "*";
@@ -1140,8 +1142,8 @@ extern "C" int zg_lookup_resources_str(zg_engine* e, const char* res_type, const
   if (rc) return rc;
   std::vector<std::string> names;
   for (uint32_t id : ids) {
-    const std::string* n = e->store.name(rt, id);
-    names.push_back(n ? *n : std::to_string(id));
+    std::string_view n;
+    names.push_back(e->store.name(rt, id, &n) ? std::string(n) : std::to_string(id));
   }
   // never-written userset subject that names itself
   if (su == ZG_NO_OBJECT && sr == p && st == rt) names.push_back(subj_id);
@@ -1236,8 +1238,8 @@ extern "C" int zg_list_prefilter(zg_engine* e, const char* body, size_t len, uin
     if (su == ZG_NO_OBJECT && sr == p && st == rt) self = tpl->subj_id;  // never-written userset subject naming itself
     // lookups.go:106-109: an id that yields no name fails the whole pre-filter
     for (uint32_t id : ids) {
-      const std::string* nm = e->store.name(rt, id);
-      if (nm && (nm->empty() || nm->back() == '/')) return fail(ZG_EINVAL, "unable to determine name for resource");
+      std::string_view nm;
+      if (e->store.name(rt, id, &nm) && nm.back() == '/') return fail(ZG_EINVAL, "unable to determine name for resource");
     }
   }
   // 2. scan

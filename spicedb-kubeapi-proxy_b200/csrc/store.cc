@@ -37,36 +37,40 @@ static inline uint64_t hash_bytes(const char* s, size_t n) {
   return h ^ (h >> 29);
 }
 
+static inline void rec_read(const std::vector<char>& arena, uint64_t off, uint32_t* id, uint32_t* len) {
+  std::memcpy(id, arena.data() + off, 4);
+  std::memcpy(len, arena.data() + off + 4, 4);
+}
+
 uint32_t Store::TypeObjs::lookup(const char* s, size_t n) const {
   if (table.empty()) return ZG_NO_OBJECT;
   const size_t mask = table.size() - 1;
   for (size_t i = hash_bytes(s, n) & mask;; i = (i + 1) & mask) {
-    const uint32_t v = table[i];
+    const uint64_t v = table[i];
     if (!v) return ZG_NO_OBJECT;
-    const std::string& nm = names[v - 1];
-    if (nm.size() == n && std::memcmp(nm.data(), s, n) == 0) return v - 1;
+    uint32_t id, len;
+    rec_read(arena, v - 1, &id, &len);
+    if (len == n && std::memcmp(arena.data() + (v - 1) + 8, s, n) == 0) return id;
   }
 }
 
-void Store::TypeObjs::insert(uint32_t id) {
-  if ((n_interned + 1) * 2 > table.size()) {  // grow and re-index from names[]
-    std::vector<uint32_t> old;
+void Store::TypeObjs::insert(uint64_t rec) {
+  auto place = [&](uint64_t off) {
+    uint32_t id, len;
+    rec_read(arena, off, &id, &len);
+    const size_t mask = table.size() - 1;
+    size_t i = hash_bytes(arena.data() + off + 8, len) & mask;
+    while (table[i]) i = (i + 1) & mask;
+    table[i] = off + 1;
+  };
+  if ((n_interned + 1) * 2 > table.size()) {  // grow and re-index from the records
+    std::vector<uint64_t> old;
     old.swap(table);
     table.assign(old.empty() ? 64 : old.size() * 2, 0);
-    const size_t mask = table.size() - 1;
-    for (uint32_t v : old)
-      if (v) {
-        const std::string& nm = names[v - 1];
-        size_t i = hash_bytes(nm.data(), nm.size()) & mask;
-        while (table[i]) i = (i + 1) & mask;
-        table[i] = v;
-      }
+    for (uint64_t v : old)
+      if (v) place(v - 1);
   }
-  const std::string& nm = names[id];
-  const size_t mask = table.size() - 1;
-  size_t i = hash_bytes(nm.data(), nm.size()) & mask;
-  while (table[i]) i = (i + 1) & mask;
-  table[i] = id + 1;
+  place(rec);
   ++n_interned;
 }
 
@@ -75,10 +79,16 @@ uint32_t Store::intern(int type, const std::string& id) {
   const uint32_t have = t.lookup(id.data(), id.size());
   if (have != ZG_NO_OBJECT) return have;
   // keep string ids and bulk numeric ids in one id space
-  uint32_t nid = std::max<uint32_t>(static_cast<uint32_t>(t.names.size()), t.n_numeric);
-  t.names.resize(nid + 1);
-  t.names[nid] = id;
-  t.insert(nid);
+  const uint32_t nid = std::max<uint32_t>(t.n_ids(), t.n_numeric);
+  t.rec_of.resize(nid + 1, 0);
+  const uint64_t rec = t.arena.size();
+  const uint32_t len = static_cast<uint32_t>(id.size());
+  t.arena.resize(rec + 8 + len);
+  std::memcpy(t.arena.data() + rec, &nid, 4);
+  std::memcpy(t.arena.data() + rec + 4, &len, 4);
+  std::memcpy(t.arena.data() + rec + 8, id.data(), len);
+  t.rec_of[nid] = rec + 1;
+  t.insert(rec);
   return nid;
 }
 uint32_t Store::find(int type, const std::string& id) const { return find(type, id.data(), id.size()); }
@@ -86,11 +96,15 @@ uint32_t Store::find(int type, const char* id, size_t len) const {
   if (type < 0 || type >= static_cast<int>(objs_.size())) return ZG_NO_OBJECT;
   return objs_[type].lookup(id, len);
 }
-const std::string* Store::name(int type, uint32_t id) const {
-  if (type < 0 || type >= static_cast<int>(objs_.size())) return nullptr;
+bool Store::name(int type, uint32_t id, std::string_view* out) const {
+  if (type < 0 || type >= static_cast<int>(objs_.size())) return false;
   const TypeObjs& t = objs_[type];
-  if (id >= t.names.size() || t.names[id].empty()) return nullptr;  // numeric-only object
-  return &t.names[id];
+  if (id >= t.rec_of.size() || !t.rec_of[id]) return false;  // numeric-only object
+  uint32_t rid, len;
+  rec_read(t.arena, t.rec_of[id] - 1, &rid, &len);
+  if (!len) return false;  // the empty name reads as "no name", as it always did
+  *out = std::string_view(t.arena.data() + (t.rec_of[id] - 1) + 8, len);
+  return true;
 }
 
 std::string Store::validate(const zg_tuple& t, bool has_expiry) const {
@@ -267,7 +281,7 @@ HostSnapshot Store::layout() const {
   const size_t nt = sc.types.size();
   h.n_objects.resize(nt);
   for (size_t t = 0; t < nt; ++t)
-    h.n_objects[t] = std::max<uint32_t>(static_cast<uint32_t>(objs_[t].names.size()), objs_[t].n_numeric);
+    h.n_objects[t] = std::max<uint32_t>(objs_[t].n_ids(), objs_[t].n_numeric);
 
   // row table: per resource type, objects x (all classes of all relations of the type)
   h.type_ncls.assign(nt, 0);

@@ -5,6 +5,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <string_view>
 #include <unordered_map>
 #include <vector>
 
@@ -56,7 +57,8 @@ class Store {
   uint32_t intern(int type, const std::string& id);
   uint32_t find(int type, const std::string& id) const;  // ZG_NO_OBJECT
   uint32_t find(int type, const char* id, size_t len) const;  // no temporary string: the check-ingress path
-  const std::string* name(int type, uint32_t id) const;
+  // false for a numeric-only object (bulk loads) or an id out of range
+  bool name(int type, uint32_t id, std::string_view* out) const;
 
   // Returns "" or an error message; `code` receives the ZG_* code.
   std::string validate(const zg_tuple& t, bool has_expiry) const;
@@ -96,16 +98,19 @@ class Store {
 
  private:
   void ensure_index();
-  // Interned names of one type. names[id] is the only copy of each string; `table` is an
-  // open-addressing index over it (slot = id + 1, 0 = empty, power-of-two size, load <= 1/2) so a
-  // lookup hashes the caller's bytes in place and compares against names[id].
+  // Interned names of one type. Each name lives once, in `arena`, as a record [u32 id][u32 len][bytes];
+  // `table` is an open-addressing index over the records (slot = record offset + 1, 0 = empty, power-of-two
+  // size, load <= 1/2), so a lookup hashes the caller's bytes in place and touches two cache lines on a hit:
+  // the slot and the record. `rec_of` maps an id back to its record (0 = no name) for the output paths.
   struct TypeObjs {
-    std::vector<std::string> names;
-    std::vector<uint32_t> table;
+    std::vector<char> arena;
+    std::vector<uint64_t> table;
+    std::vector<uint64_t> rec_of;
     uint32_t n_interned = 0;
     uint32_t n_numeric = 0;  // max numeric id seen in bulk loads + 1
     uint32_t lookup(const char* s, size_t n) const;
-    void insert(uint32_t id);
+    void insert(uint64_t rec);  // record offset
+    uint32_t n_ids() const { return static_cast<uint32_t>(rec_of.size()); }
   };
   std::vector<TypeObjs> objs_;
   std::unordered_map<Key, uint64_t, KeyHash> index_;
