@@ -424,3 +424,19 @@ def test_packed_resolution_equals_the_string_path():
     assert L.zg_resolve_checks_packed(e._h, b"pod", b"view", b"user", b"", b"abc", off.ctypes.data, b"u", None, 2, out.ctypes.data) == -1
     with pytest.raises(zgpu.ZgpuError, match="no CPU fallback"):
         e.check_bulk_packed("pod", "view", "user", ["ns1/p1"], "u1")
+
+
+def test_object_names_round_trip_across_numeric_gaps():
+    import ctypes as ct
+    e = zgpu.Engine(workloads.BOOTSTRAP_SCHEMA, host_only=True)
+    L, t = zgpu._lib.lib(), e.type_id("pod")
+    a = e.intern("pod", "ns/a")
+    e.add_bulk("pod", "viewer", "user", [5], [0])  # numeric ids 0..5 now exist for pods
+    b = e.intern("pod", "after-gap")
+    assert (a, b) == (0, 6)  # string ids and bulk numeric ids share one id space
+    buf = ct.create_string_buffer(64)
+    assert L.zg_object_name(e._h, t, a, buf, 64) == 4 and buf.value == b"ns/a"
+    assert L.zg_object_name(e._h, t, b, buf, 64) == 9 and buf.value == b"after-gap"
+    assert L.zg_object_name(e._h, t, 3, buf, 64) == -1 and L.zg_object_name(e._h, t, 99, buf, 64) == -1  # numeric-only / unknown
+    assert L.zg_object_name(e._h, t, a, buf, 3) == -7 and L.zg_object_name(e._h, t, a, None, 0) == -7
+    assert e.read_relationships(res_type="pod") == ["pod:5#viewer@user:0"]
