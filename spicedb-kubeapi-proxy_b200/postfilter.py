@@ -293,3 +293,72 @@ def run_watch(watch_stream, check_client, rel, name_from_object_id: Callable[[st
             ns = namespace_from_object_id(i)
             out.append(ResultChange(pair.GetItem().permissionship == PERMISSIONSHIP_HAS_PERMISSION, (ns or "", name)))
     return out
+
+
+# ---- the kube side of a filtered watch: frames held back until the tracker allows their object ----------
+# Reference: pkg/authz/responsefilterer.go:487-714 (filterWatch). A deterministic restatement of its event loop:
+# feed it what the two channels deliver (kube frames, tracker changes), collect what it would write.
+
+
+class WatchFrameFilter:
+    """State of one filtered watch response.
+
+      on_frame(raw)    one frame of the kube watch stream ({"type": ..., "object": {...}}), raw bytes kept as is
+      on_change(c)     one ResultChange from run_watch / the pre-filter (tracker.foundChanged)
+    Both return the list of raw chunks to write to the client now.
+
+    Mirrored decisions: a top-level v1 Status passes through and ends the stream (:585-592); only ADDED and
+    MODIFIED frames are ever written, DELETED / BOOKMARK / ERROR frames are dropped (:637); an allowed object's
+    frame is written at once, another one is buffered under its (namespace, name), a newer frame replacing an
+    older one (:665-674); `allowed` flushes the buffered frame, `denied` forgets both (:676-694); a Table frame is
+    keyed by its first row's object (:651-662); a frame that does not decode ends the stream (:578-582).
+    """
+
+    def __init__(self):
+        self.allowed_names: set = set()
+        self.buffered: Dict[tuple, bytes] = {}
+        self.closed = False
+
+    def on_frame(self, raw: bytes) -> List[bytes]:
+        if self.closed:
+            return []
+        try:
+            ev = json.loads(raw)
+            if not isinstance(ev, dict):
+                raise ValueError
+        except ValueError:
+            self.closed = True
+            return []
+        if ev.get("kind") == "Status" and ev.get("apiVersion") == "v1":
+            self.closed = True
+            return [raw]
+        if ev.get("type") not in ("ADDED", "MODIFIED"):
+            return []
+        obj = ev.get("object")
+        if not isinstance(obj, dict):
+            return []  # "could not get object metadata": skipped
+        if obj.get("kind") == "Table" and str(obj.get("apiVersion", "")).startswith("meta.k8s.io/"):
+            rows = obj.get("rows") or []
+            inner = rows[0].get("object") if rows and isinstance(rows[0], dict) else None
+            if isinstance(inner, dict):
+                obj = inner
+        meta = obj.get("metadata") if isinstance(obj.get("metadata"), dict) else {}
+        name = meta.get("name") if isinstance(meta.get("name"), str) else ""
+        ns = meta.get("namespace") if isinstance(meta.get("namespace"), str) else ""
+        key = (ns, name)
+        if key in self.allowed_names:
+            return [raw]
+        self.buffered[key] = raw
+        return []
+
+    def on_change(self, change: ResultChange) -> List[bytes]:
+        if self.closed:
+            return []
+        key = tuple(change.namespaced_name)
+        if change.allowed:
+            self.allowed_names.add(key)
+            raw = self.buffered.pop(key, None)
+            return [raw] if raw is not None else []
+        self.allowed_names.discard(key)
+        self.buffered.pop(key, None)
+        return []

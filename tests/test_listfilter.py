@@ -492,3 +492,32 @@ def test_run_watch_rechecks_every_update_in_one_bulk_call():
     assert mock.calls == [2, 1]
     with pytest.raises(RuntimeError):
         pf.run_watch(stream, MockPermissionsClient({}, errors={"pod:ns1/b#view@user:alice"}), ("pod", "$", "view", "user", "alice", ""))
+
+
+def test_watch_frame_filter_event_loop():
+    """responsefilterer.go:487-714 restated as a state machine: frames wait for the tracker."""
+    frame = lambda typ, name, ns="ns", **kw: json.dumps({"type": typ, "object": {"kind": "Pod", **pod(name, ns), **kw}}).encode()
+    f = pf.WatchFrameFilter()
+    a1, a2, b1 = frame("ADDED", "a"), frame("MODIFIED", "a", spec=2), frame("ADDED", "b")
+    assert f.on_frame(a1) == [] and f.on_frame(b1) == []           # nothing allowed yet: buffered
+    assert f.on_frame(a2) == []                                      # a newer frame replaces the buffered one
+    assert f.on_change(pf.ResultChange(True, ("ns", "a"))) == [a2]   # allowed: the buffered frame is flushed, once
+    assert f.on_change(pf.ResultChange(True, ("ns", "a"))) == []
+    a3 = frame("MODIFIED", "a", spec=3)
+    assert f.on_frame(a3) == [a3]                                    # allowed objects pass at once
+    assert f.on_frame(frame("DELETED", "a")) == [] and f.on_frame(frame("BOOKMARK", "a")) == []  # never written
+    assert f.on_change(pf.ResultChange(False, ("ns", "b"))) == []    # denied: the buffered frame is forgotten
+    assert f.on_change(pf.ResultChange(True, ("ns", "b"))) == []
+    assert f.on_change(pf.ResultChange(False, ("ns", "a"))) == [] and f.on_frame(a3) == []  # revoked: buffered again
+    # a Table frame is keyed by its first row's object
+    table = json.dumps({"type": "ADDED", "object": {"kind": "Table", "apiVersion": "meta.k8s.io/v1",
+                                                    "rows": [{"cells": ["t"], "object": pod("t", "ns")}]}}).encode()
+    assert f.on_frame(table) == [] and f.on_change(pf.ResultChange(True, ("ns", "t"))) == [table]
+    # cluster-scoped objects have an empty namespace
+    node = json.dumps({"type": "ADDED", "object": {"metadata": {"name": "node1"}}}).encode()
+    assert f.on_change(pf.ResultChange(True, ("", "node1"))) == [] and f.on_frame(node) == [node]
+    # a Status passes through and ends the stream; so does a frame that does not decode
+    status = b'{"kind":"Status","apiVersion":"v1","status":"Failure","code":410}'
+    assert f.on_frame(status) == [status] and f.closed and f.on_frame(a3) == [] and f.on_change(pf.ResultChange(True, ("x", "y"))) == []
+    g = pf.WatchFrameFilter()
+    assert g.on_frame(b'{"type":"ADDED","object":') == [] and g.closed
