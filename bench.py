@@ -55,13 +55,17 @@ UNIT = "Mchecks/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="zgpu", choices=["zgpu", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg2", "cfg2-zipf", "cfg3", "cfg4"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="checks in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="cfg2,cfg4",
+                    help="other BASELINE configurations reported as sub-results under `configs` ('' = none)")
+    ap.add_argument("--sustain-s", type=float, default=2.5,
+                    help="length of the back-to-back 'sustained' leg of the primary workload (0 = skip)")
     return ap.parse_args()
 
 
@@ -98,7 +102,8 @@ def measured_peak():
 
 
 def ncu_traffic(workload):
-    """dram bytes per launch of check_kernel from the committed ncu capture, if any."""
+    """dram bytes per launch of check_kernel from the committed ncu capture of the same build, if any:
+    {"dram_bytes": ..., "kernel_ms": ..., "source": "profiles/..."} (older entries: a bare number)."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
@@ -203,40 +208,34 @@ def cpu_reference_arm(args, rank, world):
     })
 
 
-def main():
-    # stdout must carry exactly ONE JSON line, but libraries print there too (NCCL's version banner
-    # under torchrun): point fd 1 at stderr for the whole run and emit the line on the saved fd
-    global _REAL_STDOUT
-    sys.stdout.flush()
-    _REAL_STDOUT = os.dup(1)
-    os.dup2(2, 1)
-    args = parse_args()
-    rank, local_rank, world = dist_env()
-    if args.impl == "reference":
-        cpu_reference_arm(args, rank, world)
-        return
+def bound_from_evidence(dram_frac, frac):
+    """Which resource bounds the kernel, from the ncu capture of the same workload: a kernel that moves
+    under a quarter of the DRAM peak is not HBM-bound whatever its algorithmic byte rate says."""
+    if dram_frac is None:
+        return "unknown (no ncu capture committed for this workload)"
+    if dram_frac >= 0.25:
+        return "hbm"
+    return "l2-latency/issue" if (frac or 0) > dram_frac * 2 else "latency/issue"
 
+
+def measure_workload(name, args, rank, local_rank, world, dist, primary, sampler=None):
+    """One workload on this rank's GPU: device-resident value, e2e through the C ABI, algorithmic bytes,
+    live parity sample against the CPU oracle (rank 0). Returns the result dict (rank 0) or None."""
     import numpy as np
     import torch
 
     import zgpu
     from spicedb_kubeapi_proxy_b200 import workloads
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU path in libzgpu)")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    w = workloads.by_name(args.workload, args.scale)
+    steps, warmup = args.steps, max(args.warmup, 3)
+    t_gen = time.perf_counter()
+    w = workloads.by_name(name, args.scale)
     eng = zgpu.Engine(w.schema, device=local_rank)
     w.load_into(eng)
     t0 = time.perf_counter()
     eng.publish()
     publish_s = time.perf_counter() - t0
+    setup_s = time.perf_counter() - t_gen
     items = w.check_items(eng, zgpu.CHECK_DTYPE)
     if world > 1:  # each rank answers its own batch (weak scaling): rank-specific permutation
         items = items[np.random.default_rng(1000 + rank).permutation(items.size)]
@@ -253,10 +252,7 @@ def main():
     # algorithmic bytes of one launch, from the instrumented kernel variant (not timed)
     alg_bytes = eng.count_alg_bytes(items)
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()  # samples clocks / throttle reasons from the warm-up to the end of the e2e leg
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         flush.zero_()
         step_device()
     torch.cuda.synchronize()
@@ -264,7 +260,7 @@ def main():
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for a, b in evs:
         flush.zero_()  # evict the store and the batch from L2; outside the event pair
         a.record(stream)
@@ -279,7 +275,38 @@ def main():
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max = float(t.item())
-    value = n * world * args.steps / (dev_ms_max / 1e3) / 1e6
+    value = n * world * steps / (dev_ms_max / 1e3) / 1e6
+
+    # ---- sustained: the same step back to back for >= args.sustain_s seconds (clocks settle under
+    # load, unlike the 20 x 1 ms timed region); L2 flush between steps, one event pair around all
+    sustained = None
+    if primary and args.sustain_s > 0:
+        per = max(dev_ms_max / steps, 0.05)
+        reps = int(min(max(args.sustain_s * 1e3 / (per + 0.08), 50), 200000))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fl = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fl[0].record(stream)
+        for _ in range(20):
+            flush.zero_()
+        fl[1].record(stream)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        flush_ms = fl[0].elapsed_time(fl[1]) / 20.0
+        a.record(stream)
+        for _ in range(reps):
+            flush.zero_()
+            step_device()
+        b.record(stream)
+        torch.cuda.synchronize()
+        tot = a.elapsed_time(b)
+        t = torch.tensor([tot], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot = float(t.item())
+        kern = max(tot - reps * flush_ms, 1e-3)
+        sustained = {"value": n * world * reps / (kern / 1e3) / 1e6, "unit": UNIT, "steps": reps, "wall_s": tot / 1e3,
+                     "note": "back-to-back steps with an L2 flush between them; flush time (measured alone) subtracted"}
 
     # ---- e2e: the public C ABI call with pinned host buffers, copies inside the timed region
     pin_in = zgpu._lib.PinnedArray(n, zgpu.CHECK_DTYPE)
@@ -287,7 +314,7 @@ def main():
     pin_in.array[:] = items
     for _ in range(2):
         eng.check_bulk_ptr(pin_in.ptr, n, pin_out.ptr)
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(steps, 50))
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
@@ -300,59 +327,134 @@ def main():
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = n * world * e2e_steps / float(t.item()) / 1e6
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (sampler is not None and rank == 0) else None
     host_answers = pin_out.array.copy()
     assert np.array_equal(host_answers, d_out.cpu().numpy()), "host and device entry points disagree"
 
-    # ---- CPU baseline: oracle on a bounded sample (rank 0, N=1), also a live parity check
+    # ---- CPU baseline: oracle on a bounded sample (rank 0), also a live parity check of the timed batch
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         from oracle.pyoracle import Oracle
 
         o = Oracle(w.schema)
         w.load_into(o)
         cores = host_cores()
-        o.check_bulk(items[:256])
+        o.check_bulk(items[:256])  # builds the index (not timed)
         tq = time.perf_counter()
         o.check_bulk(items[:2048], nthreads=cores)
         rate = 2048 / max(time.perf_counter() - tq, 1e-6)
-        ns = args.cpu_sample or int(min(n, max(4096, rate * 15.0)))
+        budget_s = 15.0 if primary else 8.0
+        ns = args.cpu_sample or int(min(n, max(50_000 if world == 1 else 8192, rate * budget_s)))
         tq = time.perf_counter()
         want = o.check_bulk(items[:ns], nthreads=cores)
         dt = time.perf_counter() - tq
         mism = int((want != host_answers[:ns]).sum())
-        # SURVEY 8(d)'s canonical figure: forward evaluation, no short circuit (small sample)
-        canon = o.check_bytes(items[:2000]) / 2000.0
         cpu = {"value": ns / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"first {ns} checks of the same batch, {cores} threads, {dt:.1f} s",
-               "parity_mismatches_vs_gpu": mism, "canonical_forward_bytes_per_check": canon}
+               "parity_mismatches_vs_gpu": mism,
+               "algorithm": "forward recursive evaluation, no caching (pkg/spicedb/spicedb.go:44-46); the GPU path is "
+                            "direction-optimised (reverse rows of the subject), so most of the ratio is algorithmic"}
+        if primary:
+            # SURVEY 8(d)'s canonical figure: forward evaluation, no short circuit (small sample)
+            cpu["canonical_forward_bytes_per_check"] = o.check_bytes(items[:2000]) / 2000.0
         if mism:
-            raise SystemExit(f"PARITY FAILURE: {mism} of {ns} answers differ from the oracle")
+            raise SystemExit(f"PARITY FAILURE ({name}): {mism} of {ns} answers differ from the oracle")
+        del o
 
+    out = None
     if rank == 0:
         peak, peak_src = measured_peak()
-        kernel_ms = dev_ms_max / args.steps
+        kernel_ms = dev_ms_max / steps
         achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
-        traffic = ncu_traffic(w.name)
+        cap = ncu_traffic(w.name) or {}
+        traffic = cap.get("dram_bytes") if isinstance(cap, dict) else cap
+        cap_ms = cap.get("kernel_ms") if isinstance(cap, dict) else None
+        # DRAM rate of the captured launch itself (its own bytes / its own duration), and the same bytes
+        # over THIS run's kernel time: they agree when the capture is of the same build
+        dram_gbs = traffic / (kernel_ms / 1e3) / 1e9 if traffic else None
+        dram_frac = dram_gbs / peak if dram_gbs else None
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "impl": "zgpu",
+            "value": value, "unit": UNIT, "ms_per_step": kernel_ms,
             "config": workload_config(w, args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n,
                     "steps": e2e_steps, "api": "zg_check_bulk (C ABI, pinned host buffers)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "zg::check_kernel<false>",
+            "roofline": {"bound": bound_from_evidence(dram_frac, achieved / peak), "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "dram_gbs": dram_gbs,
+                         "dram_frac": dram_frac, "dram_over_algorithmic": (traffic / alg_bytes) if traffic else None,
+                         "ncu_capture": cap.get("source") if isinstance(cap, dict) else None,
+                         "ncu_capture_kernel_ms": cap_ms,
+                         "peak_source": peak_src, "kernel": "zg::check_kernel<false>",
                          "alg_bytes_per_launch": int(alg_bytes), "alg_bytes_per_check": alg_bytes / n,
                          "kernel_ms": kernel_ms,
-                         "note": "algorithmic bytes counted by the instrumented kernel variant: 16 B item + 1 B answer "
-                                 "+ 4 B per row offset, probe and edge actually needed (short circuit included)"},
+                         "note": "achieved/frac: bytes the kernel's own loads need (counted by the instrumented variant: "
+                                 "16 B item + 1 B answer + 4 B per row offset, probe and edge read, short circuit "
+                                 "included) / CUDA-event time. dram_*: ncu dram__bytes_read+write of one launch of the "
+                                 "same build / the same time -- the HBM fraction north_star asks for"},
             "cpu_baseline": cpu,
-            "clocks": clocks,
             "has_fraction": float((host_answers == 2).mean()),
-            "publish_s": publish_s,
+            "publish_s": publish_s, "setup_s": setup_s,
         }
+        if sustained:
+            out["sustained"] = sustained
+        if clocks is not None:
+            out["clocks"] = clocks
+    del d_items, d_out, flush, pin_in, pin_out
+    eng.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    # stdout must carry exactly ONE JSON line, but libraries print there too (NCCL's version banner
+    # under torchrun): point fd 1 at stderr for the whole run and emit the line on the saved fd
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+    args = parse_args()
+    rank, local_rank, world = dist_env()
+    if args.impl == "reference":
+        cpu_reference_arm(args, rank, world)
+        return
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path in libzgpu)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # samples clocks / throttle reasons from the warm-up to the end of the e2e leg
+    main_res = measure_workload(args.workload, args, rank, local_rank, world, dist, True, sampler)
+
+    # the other BASELINE configurations as sub-results of the same line (configs[1] and configs[3], the
+    # latter at its full 100 M relationships: the regime the HBM-roofline target is quoted on)
+    extra = {}
+    names = [c for c in args.configs.split(",") if c and c != args.workload] if args.scale == 1.0 else []
+    for name in names:
+        r = measure_workload(name, args, rank, local_rank, world, dist, False)
+        if r is not None:
+            extra[name] = r
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "impl": "zgpu",
+        }
+        for k in ("config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks", "sustained", "has_fraction",
+                  "publish_s", "setup_s"):
+            if k in main_res:
+                out[k] = main_res[k]
+        if extra:
+            out["configs"] = extra
         emit(out)
     if dist:
         dist.destroy_process_group()

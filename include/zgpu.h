@@ -41,6 +41,7 @@ extern "C" {
 #define ZG_ENOSNAPSHOT (-6) /* nothing published yet                             */
 #define ZG_E2BIG (-7)    /* output buffer too small; required size reported      */
 #define ZG_ENOMEM (-8)
+#define ZG_EDEPTH (-9)   /* LookupResources: a candidate hit the dispatch-depth cap / work budget */
 
 /* v1.CheckPermissionResponse.Permissionship (authzed-go v1.6.0); per-item codes */
 #define ZG_NO_PERMISSION 1

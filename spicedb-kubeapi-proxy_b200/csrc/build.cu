@@ -11,7 +11,7 @@
 //      => ordered by (row, subject), equal keys in load order (TOUCH: the last one wins)
 //   3. flag the last entry of every (row, subject) run, exclusive scan, compact
 //      => col / exp;   histogram of rows + inclusive scan => row_ptr
-//   4. reverse CSR: one more stable radix sort of (class rrow_base + subject) keys; the
+//   4. reverse CSR: one more stable radix sort of (class rrow_base + subject * rstride) keys; the
 //      entries are already in ascending resource order within a class; histogram + scan
 //   5. per type: objects that own >= 1 relationship (cub::DeviceSelect over row_ptr)
 // The host builder (store.cc) produces identical arrays; ZGPU_VERIFY_BUILD=1 compares them.
@@ -100,7 +100,7 @@ __global__ void emit_kernel(const unsigned long long* rowkey, const uint32_t* id
   const BSlot bs = slots[x.rel];
   const uint32_t gc = bs.cls_begin + static_cast<uint32_t>((row - bs.row_base) % bs.stride);
   atomicAdd(cls_cnt + gc, 1u);
-  const unsigned long long rk = cls[gc].rrow_base + s;
+  const unsigned long long rk = cls[gc].rrow_base + static_cast<unsigned long long>(s) * cls[gc].rstride;
   rkey[p] = rk;
   rres[p] = x.res;
   atomicAdd(rrow_cnt + rk + 1, 1u);

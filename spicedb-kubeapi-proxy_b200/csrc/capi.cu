@@ -1344,7 +1344,8 @@ extern "C" int zg_debug_row(zg_engine* e, uint16_t rel_slot, uint32_t res, uint3
     const DCls& c = e->last_built.cls[r.cls_begin + cls];
     const uint32_t row = c.sslot == kWildcard ? 0u : res;
     if (row >= c.nsubj) return ZG_OK;
-    uint32_t b = e->last_built.rrow_ptr[c.rrow_base + row], en = e->last_built.rrow_ptr[c.rrow_base + row + 1];
+    const uint64_t ri = c.rrow_base + uint64_t(row) * c.rstride;
+    uint32_t b = e->last_built.rrow_ptr[ri], en = e->last_built.rrow_ptr[ri + 1];
     *n_out = en - b;
     if (en - b > cap) return ZG_E2BIG;
     for (uint32_t i = b; i < en; ++i) out[i - b] = e->last_built.rcol[i];

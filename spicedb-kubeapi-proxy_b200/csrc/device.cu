@@ -59,7 +59,7 @@ Device::~Device() {
   spill_.release();
   ctrl_.release();
   memo_.release();
-  for (auto* v : {&q_, &parent_, &jobs_, &val_})
+  for (auto* v : {&q_, &parent_, &val_})
     for (auto& b : *v) b.release();
   stage_in_.release();
   stage_out_.release();
@@ -218,7 +218,7 @@ std::string Device::finish_publish(std::shared_ptr<Snapshot> s, const HostSnapsh
           const DCls& c = h.cls[r.cls_begin + k];
           if (c.flags & CF_EMPTY) continue;
           if ((c.sslot != kNone && c.sslot != kWildcard) || (c.flags & CF_EXPIRY)) { flat = false; break; }
-          fc.push_back(FlatLookupClass{c.rrow_base, c.nsubj, c.stype, static_cast<uint16_t>(c.sslot == kWildcard)});
+          fc.push_back(FlatLookupClass{c.rrow_base, c.nsubj, c.stype, static_cast<uint16_t>(c.sslot == kWildcard), c.rstride, 0});
         }
       }
       if (!flat) continue;
@@ -264,8 +264,8 @@ std::string Device::finish_publish(std::shared_ptr<Snapshot> s, const HostSnapsh
   return "";
 }
 
-int Device::run_pass(const Snapshot& s, const zg_check* jobs, uint64_t njobs, uint8_t* val, bool final_codes, bool raw,
-                     zg_check* subq, uint32_t* subq_parent, cudaStream_t st, bool count, std::string* err) {
+int Device::run_pass(const Snapshot& s, const zg_check* queries, uint64_t nq, uint8_t* val, uint8_t* out, bool final_codes,
+                     bool raw, zg_check* subq, uint32_t* subq_parent, cudaStream_t st, bool count, std::string* err) {
   KParams p{};
   p.row_ptr = s.row_ptr.as<uint32_t>();
   p.col = s.col.as<uint32_t>();
@@ -275,9 +275,11 @@ int Device::run_pass(const Snapshot& s, const zg_check* jobs, uint64_t njobs, ui
   p.invert = (invert && shard_count <= 1) ? 1 : 0;  // a shard does not hold the subject's reverse rows
   p.prog = s.prog.as<uint8_t>();
   p.prog_bytes = s.prog_bytes;
-  p.jobs = jobs;
-  p.njobs = njobs;
+  p.queries = queries;
+  p.nq = nq;
+  p.L = s.max_leaves;
   p.val = val;
+  p.out = out;
   p.final_codes = final_codes;
   unsigned long long* ctrl = ctrl_.as<unsigned long long>();
   p.next = ctrl;
@@ -299,7 +301,7 @@ int Device::run_pass(const Snapshot& s, const zg_check* jobs, uint64_t njobs, ui
   p.shard_rank = shard_rank;
   ZG_CUDA(cudaMemsetAsync(ctrl, 0, 16, st));  // next, subq_count
   const int per_sm = count ? blocks_per_sm_count_ : blocks_per_sm_;
-  uint64_t want = (njobs + kThreads - 1) / kThreads;
+  uint64_t want = (nq + kThreads - 1) / kThreads;
   int grid = static_cast<int>(std::min<uint64_t>(want, static_cast<uint64_t>(sm_count_) * per_sm));
   if (grid < 1) grid = 1;
   size_t sm = smem_bytes(s.prog_bytes);
@@ -320,7 +322,7 @@ void Device::finish_timing() {
 }
 
 int Device::check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cudaStream_t st, bool raw_items,
-                         uint64_t* count_bytes, std::string* err) {
+                         uint64_t* count_bytes, std::string* err, bool top) {
   std::shared_ptr<Snapshot> s = snap;
   if (!s) {
     if (err) *err = "no snapshot published (call zg_publish after loading relationships)";
@@ -334,13 +336,17 @@ int Device::check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cu
   if (have_last_) ZG_CUDA(cudaStreamWaitEvent(st, last_done_, 0));
   const bool count = count_bytes != nullptr;
   unsigned long long* ctrl = ctrl_.as<unsigned long long>();
-  ZG_CUDA(cudaMemsetAsync(ctrl + 2, 0, 16, st));  // alg_bytes, flags
-  cudaEventRecord(ev0_, st);
+  // alg_bytes and the sticky flags (spill overflow, budget hit) are cleared once per caller-level
+  // call: the halves of a split batch accumulate into them
+  if (top) {
+    ZG_CUDA(cudaMemsetAsync(ctrl + 2, 0, 16, st));
+    cudaEventRecord(ev0_, st);
+  }
   const uint32_t L = s->max_leaves;
   int rc = ZG_OK;
   if (!s->has_nonpure) {
-    // every slot is a relation or a pure union: one job per check, answered in one launch
-    rc = run_pass(*s, d_items, n, d_out, true, raw_items, nullptr, nullptr, st, count, err);
+    // every slot is a relation or a pure union: one leaf per check, answered in one launch
+    rc = run_pass(*s, d_items, n, nullptr, d_out, true, raw_items, nullptr, nullptr, st, count, err);
     if (rc) return rc;
   } else {
     if (n * L >= (1ull << 32)) {
@@ -352,7 +358,6 @@ int Device::check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cu
       if (q_.size() <= lv) {
         q_.resize(lv + 1);
         parent_.resize(lv + 1);
-        jobs_.resize(lv + 1);
         val_.resize(lv + 1);
       }
     };
@@ -366,23 +371,26 @@ int Device::check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cu
       }
       level(lv + 1);
       nq.push_back(cur);
-      if (!jobs_[lv].ensure(cur * L * sizeof(zg_check)) || !val_[lv].ensure(cur * L + 4) ||
-          !q_[lv + 1].ensure(subq_cap_ * sizeof(zg_check)) || !parent_[lv + 1].ensure(subq_cap_ * 4)) {
+      if (cur * L >= (1ull << 32)) {
+        if (err) *err = "pass too large (queries * leaves >= 2^32)";
+        return ZG_EINVAL;
+      }
+      if (!val_[lv].ensure(cur * L + 4) || !q_[lv + 1].ensure(subq_cap_ * sizeof(zg_check)) ||
+          !parent_[lv + 1].ensure(subq_cap_ * 4)) {
         if (err) *err = "out of device memory (pass buffers)";
         return ZG_ENOMEM;
       }
-      const unsigned blk = 256;
-      prep_jobs_kernel<<<static_cast<unsigned>((cur + blk - 1) / blk), blk, 0, st>>>(
-          s->prog.as<uint8_t>(), queries, cur, L, jobs_[lv].as<zg_check>(), raw ? 1 : 0);
-      ++launches;
-      rc = run_pass(*s, jobs_[lv].as<zg_check>(), cur * L, val_[lv].as<uint8_t>(), false, false,
+      // leaves the kernel skips (short circuit of the boolean tree) must read as "false"
+      ZG_CUDA(cudaMemsetAsync(val_[lv].p, 0, cur * L + 4, st));
+      // Level 0 writes the v1 codes straight into d_out: when the pass raises no sub-query (the
+      // common case: edges into a non-pure permission are rare) they are final and nothing is folded.
+      rc = run_pass(*s, queries, cur, val_[lv].as<uint8_t>(), lv == 0 ? d_out : nullptr, true, raw,
                     q_[lv + 1].as<zg_check>(), parent_[lv + 1].as<uint32_t>(), st, count, err);
       if (rc) return rc;
       unsigned long long host_ctrl[4];
       ZG_CUDA(cudaMemcpyAsync(host_ctrl, ctrl, sizeof host_ctrl, cudaMemcpyDeviceToHost, st));
       ZG_CUDA(cudaStreamSynchronize(st));
-      const uint32_t flags = static_cast<uint32_t>(host_ctrl[3] & 0xFFFFFFFFu);
-      if (flags & 2u) {
+      if (host_ctrl[1] > subq_cap_) {
         // more sub-queries than the pass buffer holds: checks are independent, so answer the
         // batch in two halves (each raises about half as many) instead of failing the call
         if (n < 2) {
@@ -390,30 +398,34 @@ int Device::check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cu
           return ZG_ENOMEM;
         }
         const uint64_t half = n / 2;
-        int r1 = check_device(d_items, half, d_out, st, raw_items, nullptr, err);
+        int r1 = check_device(d_items, half, d_out, st, raw_items, nullptr, err, false);
         if (r1) return r1;
-        return check_device(d_items + half, n - half, d_out + half, st, raw_items, nullptr, err);
+        return check_device(d_items + half, n - half, d_out + half, st, raw_items, nullptr, err, false);
       }
       cur = host_ctrl[1];
       queries = q_[lv + 1].as<zg_check>();
       raw = false;
       if (cur) ++passes;
     }
-    for (size_t lv = nq.size(); lv-- > 0;) {
-      const unsigned blk = 256;
-      const uint64_t m = nq[lv];
-      fold_kernel<<<static_cast<unsigned>((m + blk - 1) / blk), blk, 0, st>>>(
-          s->prog.as<uint8_t>(), lv == 0 ? d_items : q_[lv].as<zg_check>(), m, L, val_[lv].as<uint8_t>(),
-          lv == 0 ? d_out : nullptr, lv == 0 ? nullptr : parent_[lv].as<uint32_t>(),
-          lv == 0 ? nullptr : val_[lv - 1].as<uint8_t>(), 0);
-      ++launches;
+    if (nq.size() > 1) {
+      for (size_t lv = nq.size(); lv-- > 0;) {
+        const unsigned blk = 256;
+        const uint64_t m = nq[lv];
+        fold_kernel<<<static_cast<unsigned>((m + blk - 1) / blk), blk, 0, st>>>(
+            s->prog.as<uint8_t>(), lv == 0 ? d_items : q_[lv].as<zg_check>(), m, L, val_[lv].as<uint8_t>(),
+            lv == 0 ? d_out : nullptr, lv == 0 ? nullptr : parent_[lv].as<uint32_t>(),
+            lv == 0 ? nullptr : val_[lv - 1].as<uint8_t>(), 0);
+        ++launches;
+      }
+      ZG_CUDA(cudaGetLastError());
     }
-    ZG_CUDA(cudaGetLastError());
   }
-  cudaEventRecord(ev1_, st);
+  if (top) {
+    cudaEventRecord(ev1_, st);
+    timing_pending_ = true;
+  }
   cudaEventRecord(last_done_, st);
   have_last_ = true;
-  timing_pending_ = true;
   checks += n;
   if (count) {
     unsigned long long host_ctrl[4];
@@ -524,7 +536,7 @@ int Device::check_host_multi(const std::vector<HostReq>& reqs, std::string* err)
 
 // ---- sharded store: one pass per call; the host exchanges the raised sub-queries -----------
 //
-// Buffers per level lv: q_[lv] = this level's queries, jobs_/val_[lv] = their leaf jobs,
+// Buffers per level lv: q_[lv] = this level's queries, val_[lv] = their leaf values,
 // q_[lv+1] / parent_[lv+1] = the sub-queries the pass raised (the same buffers the single-GPU
 // multi-pass loop uses; here their consumers live on other ranks).
 int Device::shard_pass(const zg_check* queries, uint64_t n, int level, uint64_t* n_sub, std::string* err) {
@@ -538,7 +550,6 @@ int Device::shard_pass(const zg_check* queries, uint64_t n, int level, uint64_t*
   if (q_.size() <= lv + 1) {
     q_.resize(lv + 2);
     parent_.resize(lv + 2);
-    jobs_.resize(lv + 2);
     val_.resize(lv + 2);
   }
   if (shard_nq_.size() <= lv) {
@@ -555,12 +566,10 @@ int Device::shard_pass(const zg_check* queries, uint64_t n, int level, uint64_t*
     return ZG_EINVAL;
   }
   if (have_last_) ZG_CUDA(cudaStreamWaitEvent(stream, last_done_, 0));
-  // level > 0 queries arrive in a host buffer too; keep level 0 separate from the raised-sub-query
-  // buffer q_[1] by staging every level's queries in shard_tmp_-free storage: jobs_[lv] doubles as input
+  // level > 0 queries arrive in a host buffer too; level 0 is staged apart from the raised-sub-query buffer q_[1]
   DevBuf& qbuf = lv == 0 ? stage_in_ : q_[lv];  // q_[lv] (lv > 0) was the producer-side buffer of level lv-1 on
                                               // THIS rank; its content was already read back by shard_subqueries
-  if (!qbuf.ensure(std::max<size_t>(n * sizeof(zg_check), subq_cap_ * sizeof(zg_check))) ||
-      !jobs_[lv].ensure(n * L * sizeof(zg_check)) || !val_[lv].ensure(n * L + 4) ||
+  if (!qbuf.ensure(std::max<size_t>(n * sizeof(zg_check), subq_cap_ * sizeof(zg_check))) || !val_[lv].ensure(n * L + 4) ||
       !q_[lv + 1].ensure(subq_cap_ * sizeof(zg_check)) || !parent_[lv + 1].ensure(subq_cap_ * 4)) {
     if (err) *err = "out of device memory (shard pass buffers)";
     return ZG_ENOMEM;
@@ -568,11 +577,8 @@ int Device::shard_pass(const zg_check* queries, uint64_t n, int level, uint64_t*
   ZG_CUDA(cudaMemcpyAsync(qbuf.p, queries, n * sizeof(zg_check), cudaMemcpyHostToDevice, stream));
   unsigned long long* ctrl = ctrl_.as<unsigned long long>();
   ZG_CUDA(cudaMemsetAsync(ctrl + 2, 0, 16, stream));
-  const unsigned blk = 256;
-  prep_jobs_kernel<<<static_cast<unsigned>((n + blk - 1) / blk), blk, 0, stream>>>(
-      s->prog.as<uint8_t>(), qbuf.as<zg_check>(), n, L, jobs_[lv].as<zg_check>(), level == 0 ? 1 : 0);
-  ++launches;
-  int rc = run_pass(*s, jobs_[lv].as<zg_check>(), n * L, val_[lv].as<uint8_t>(), false, false, q_[lv + 1].as<zg_check>(),
+  ZG_CUDA(cudaMemsetAsync(val_[lv].p, 0, n * L + 4, stream));
+  int rc = run_pass(*s, qbuf.as<zg_check>(), n, val_[lv].as<uint8_t>(), nullptr, false, level == 0, q_[lv + 1].as<zg_check>(),
                     parent_[lv + 1].as<uint32_t>(), stream, false, err);
   if (rc) return rc;
   unsigned long long host_ctrl[4];
@@ -581,7 +587,7 @@ int Device::shard_pass(const zg_check* queries, uint64_t n, int level, uint64_t*
   have_last_ = true;
   ZG_CUDA(cudaStreamSynchronize(stream));
   const uint32_t flags = static_cast<uint32_t>(host_ctrl[3] & 0xFFFFFFFFu);
-  if (flags & 2u) {
+  if (host_ctrl[1] > subq_cap_) {
     if (err) *err = "sub-query buffer overflow: raise zg_config.subquery_capacity or shrink the batch";
     return ZG_ENOMEM;
   }
@@ -777,8 +783,20 @@ int Device::lookup(uint16_t res_type, const zg_check& proto, std::vector<uint32_
                                                   reinterpret_cast<uint32_t*>(ctrl_.as<unsigned long long>() + 3));
   ++launches;
   unsigned long long cnt = 0;
+  uint32_t lflags = 0;
   ZG_CUDA(cudaMemcpyAsync(&cnt, d_count, 8, cudaMemcpyDeviceToHost, stream));
+  ZG_CUDA(cudaMemcpyAsync(&lflags, ctrl_.as<unsigned long long>() + 3, 4, cudaMemcpyDeviceToHost, stream));
   ZG_CUDA(cudaStreamSynchronize(stream));
+  if (lflags & 1u) {
+    if (err) *err = "expansion stack overflow (per-warp spill area exhausted)";
+    return ZG_ENOMEM;
+  }
+  if (lflags & 8u) {
+    // a candidate's check ended in an error (dispatch depth or work budget): the embedded SpiceDB fails
+    // the LookupResources call in that case; a silently shortened answer would read as "not allowed"
+    if (err) *err = "LookupResources: a candidate could not be decided (max dispatch depth / work budget exceeded)";
+    return ZG_EDEPTH;
+  }
   ids->resize(cnt);
   if (cnt) {
     // ascending ids: radix-sort on the device when the answer is large (a host sort of 50 k ids

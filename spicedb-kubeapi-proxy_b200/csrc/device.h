@@ -54,7 +54,7 @@ class Device {
   // d_items / d_out are device pointers. count_bytes != nullptr selects the
   // instrumented kernel variant. Returns ZG_* and fills err.
   int check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cudaStream_t st, bool raw_items,
-                   uint64_t* count_bytes, std::string* err);
+                   uint64_t* count_bytes, std::string* err, bool top = true);
   int check_host(const zg_check* items, uint64_t n, uint8_t* out, std::string* err);
   // Several callers' requests answered by ONE launch sequence (see Batcher in capi.cu).
   struct HostReq {
@@ -89,14 +89,16 @@ class Device {
 
  private:
   std::string finish_publish(std::shared_ptr<Snapshot> s, const HostSnapshot& lay, const Schema& sc, uint64_t revision);
-  int run_pass(const Snapshot& s, const zg_check* jobs, uint64_t njobs, uint8_t* val, bool final_codes, bool raw,
-               zg_check* subq, uint32_t* subq_parent, cudaStream_t st, bool count, std::string* err);
+  // One check_kernel launch over `nq` queries: val (may be null) receives the per-(query, leaf) value
+  // bits, out (may be null) the per-query v1 codes / value bits.
+  int run_pass(const Snapshot& s, const zg_check* queries, uint64_t nq, uint8_t* val, uint8_t* out, bool final_codes,
+               bool raw, zg_check* subq, uint32_t* subq_parent, cudaStream_t st, bool count, std::string* err);
   int sm_count_ = 0, blocks_per_sm_ = 0, blocks_per_sm_count_ = 0;
   uint32_t spill_cap_ = 4096, budget_ = 1u << 20;
   uint64_t subq_cap_ = 1ull << 22;
   DevBuf spill_, ctrl_, memo_;
   uint32_t memo_entries_ = 8192, memo_after_ = 2048;  // ctrl: [0] next, [1] subq_count, [2] alg_bytes, then flags u32
-  std::vector<DevBuf> q_, parent_, jobs_, val_;  // per pass level
+  std::vector<DevBuf> q_, parent_, val_;  // per pass level: queries, raising (query, leaf), leaf values
   std::vector<uint64_t> shard_nq_, shard_nsub_;  // sharded mode: queries / raised sub-queries per level
   DevBuf shard_tmp_;
   DevBuf stage_in_, stage_out_, lk_jobs_, lk_codes_, lk_ids_;

@@ -38,42 +38,47 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 #ifndef ZG_STACK_CAP
 #define ZG_STACK_CAP 64
 #endif
+#ifndef ZG_RSET_CAP
+#define ZG_RSET_CAP 16
+#endif
 constexpr int kMinBlocks = ZG_MIN_BLOCKS;  // resident CTAs per SM the register budget is tuned for
-constexpr int kStackCap = ZG_STACK_CAP;       // range items per warp in shared memory
-constexpr int kRsetCap = 16;          // reverse-row entries kept per check (subject's direct memberships)
-constexpr size_t kWarpSmem = kStackCap * sizeof(uint4) + kRsetCap * 32 * sizeof(uint32_t);
+constexpr int kStackCap = ZG_STACK_CAP;    // range items per warp in shared memory
+constexpr int kRsetCap = ZG_RSET_CAP;      // reverse-row entries kept per check (subject's direct memberships), <= 31
+constexpr int kStateWords = 6;             // per-lane query state parked in shared memory between leaf passes
+constexpr size_t kWarpSmem = kStackCap * sizeof(uint4) + (kRsetCap + kStateWords) * 32 * sizeof(uint32_t);
 constexpr unsigned kFull = 0xFFFFFFFFu;
-constexpr uint16_t kJobIsUnit = 0x8000;  // zg_check.flags: perm field is a unit id
-constexpr uint16_t kJobDepthMask = 0x00FF;
+constexpr uint16_t kJobDepthMask = 0x00FF;  // zg_check.flags of a raised sub-query: hop depth
 
-// job value bits
+// value bits of a (query, leaf) pair and of a sub-query
 constexpr uint8_t kValT = 1, kValE = 2;
 
 struct KParams {
   const uint32_t* row_ptr;
   const uint32_t* col;
   const uint32_t* exp;  // nullptr unless the schema uses expiration
-  const uint32_t* rrow_ptr;  // reverse CSR (subject -> resources) per edge class
+  const uint32_t* rrow_ptr;  // reverse CSR (subject -> resources), rows interleaved per subject
   const uint32_t* rcol;
   int invert;  // answer direct probes from the subject's reverse rows when they are small
   const uint8_t* prog;
   uint32_t prog_bytes;
-  const zg_check* jobs;
-  unsigned long long njobs;
-  uint8_t* val;  // per job: final codes (final_codes=1) or kValT|kValE bits
+  const zg_check* queries;
+  unsigned long long nq;
+  uint32_t L;    // leaf stride of val (Snapshot::max_leaves)
+  uint8_t* val;  // [nq * L] value bits per (query, leaf): what the fold of a multi-pass run reads (may be null)
+  uint8_t* out;  // [nq] v1 codes (final_codes) or value bits (may be null)
   int final_codes;
   unsigned long long* next;  // batch counter (zeroed before launch)
   uint4* spill;              // per-warp spill areas
   uint32_t spill_cap;        // items per warp
-  // sub-queries raised when an edge leads into a non-pure permission
+  // sub-queries raised when an edge leads into a non-pure permission (or to another shard)
   zg_check* subq;
-  uint32_t* subq_parent;
+  uint32_t* subq_parent;  // q * L + leaf of the raising (query, leaf)
   unsigned long long* subq_count;
   unsigned long long subq_cap;
   uint32_t* flags;  // bit0: spill overflow, bit1: sub-query overflow, bit2: budget hit
   uint32_t now;
   uint32_t budget;
-  int raw_items;  // jobs are caller-supplied zg_check items: flags are ignored
+  int raw_items;  // queries are caller-supplied zg_check items: flags are ignored
   // Per-warp lossy memo of (job, slot, object, depth) child visits, switched on only for
   // batches that run long (DAG-shaped data multiplies paths; see DESIGN.md "Path memo").
   unsigned long long* memo;
@@ -81,7 +86,7 @@ struct KParams {
   uint32_t memo_after;    // iterations before the memo is switched on for a batch
   // Object-hash sharded store: this device only holds the relationships whose
   // RESOURCE it owns (owner = object id % shard_count); an edge to an object of another shard
-  // becomes a sub-query that the host routes to its owner between passes.
+  // becomes a sub-query that is routed to its owner between passes.
   uint32_t shard_count;   // 0 / 1 = not sharded
   uint32_t shard_rank;
   unsigned long long* alg_bytes;  // COUNT variant only
@@ -125,7 +130,8 @@ struct WarpCtx {
   int top, spill_top;
   uint32_t spill_cap;
   unsigned found, err;  // warp-uniform, indexed by job slot
-  uint32_t my_subj, my_ss;  // this lane's own job: subject id, stype<<16 | srel
+  unsigned raised;      // job slots that raised a sub-query in this leaf pass (their value is not final)
+  uint32_t my_subj, my_ss;  // this lane's own query: subject id, stype<<16 | srel
   // Direction-optimised probes: rset[i * 32 + job] = resource id of every direct relationship
   // of the job's subject (its reverse rows), grouped by class (boundaries in my_cst), when
   // there are <= kRsetCap.
@@ -183,25 +189,35 @@ __device__ __forceinline__ void push(WarpCtx<COUNT>& c, bool want, const uint4& 
   __syncwarp();
 }
 
+// Binary search of the sorted segment arr[lo, hi) for key.
+template <bool COUNT>
+__device__ __forceinline__ bool find_in(const uint32_t* __restrict__ arr, WarpCtx<COUNT>& c, uint32_t lo, uint32_t hi,
+                                        uint32_t key, uint32_t* at = nullptr) {
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    const uint32_t v = __ldg(arr + mid);
+    if (COUNT) c.bytes += 4;
+    if (v == key) {
+      if (at) *at = mid;
+      return true;
+    }
+    if (v < key) lo = mid + 1; else hi = mid;
+  }
+  return false;
+}
+
 // Binary search of the sorted direct-subject segment col[lo, hi) for sid.
 template <bool COUNT>
 __device__ __forceinline__ bool probe(const KParams& p, WarpCtx<COUNT>& c, uint32_t lo, uint32_t hi, uint32_t sid,
                                       bool expiry) {
-  while (lo < hi) {
-    uint32_t mid = lo + ((hi - lo) >> 1);
-    uint32_t v = __ldg(p.col + mid);
+  uint32_t at = 0;
+  if (!find_in(p.col, c, lo, hi, sid, &at)) return false;
+  if (expiry) {
+    const uint32_t e = __ldg(p.exp + at);
     if (COUNT) c.bytes += 4;
-    if (v == sid) {
-      if (expiry) {
-        uint32_t e = __ldg(p.exp + mid);
-        if (COUNT) c.bytes += 4;
-        return e == 0 || e > p.now;
-      }
-      return true;
-    }
-    if (v < sid) lo = mid + 1; else hi = mid;
+    return e == 0 || e > p.now;
   }
-  return false;
+  return true;
 }
 
 // Two independent binary searches advanced in lock step (two loads in flight per lane).
@@ -226,12 +242,52 @@ __device__ __forceinline__ void probe2(const uint32_t* __restrict__ arr, WarpCtx
   }
 }
 
+// Do the sorted segments a[a0, a1) and b[b0, b1) share an element? Sizes within 4x of each other:
+// two-pointer merge (one load per step); otherwise every element of the short one is searched in
+// the long one.
+template <bool COUNT>
+__device__ __forceinline__ bool intersects(const uint32_t* __restrict__ a, uint32_t a0, uint32_t a1,
+                                           const uint32_t* __restrict__ b, uint32_t b0, uint32_t b1, WarpCtx<COUNT>& c) {
+  const uint32_t na = a1 - a0, nb = b1 - b0;
+  if (na == 0 || nb == 0) return false;
+  if (na > 4u * nb) {
+    for (uint32_t x = b0; x < b1; ++x) {
+      const uint32_t k = __ldg(b + x);
+      if (COUNT) c.bytes += 4;
+      if (find_in(a, c, a0, a1, k)) return true;
+    }
+    return false;
+  }
+  if (nb > 4u * na) {
+    for (uint32_t x = a0; x < a1; ++x) {
+      const uint32_t k = __ldg(a + x);
+      if (COUNT) c.bytes += 4;
+      if (find_in(b, c, b0, b1, k)) return true;
+    }
+    return false;
+  }
+  uint32_t va = __ldg(a + a0), vb = __ldg(b + b0);
+  if (COUNT) c.bytes += 8;
+  for (;;) {
+    if (va == vb) return true;
+    if (va < vb) {
+      if (++a0 == a1) return false;
+      va = __ldg(a + a0);
+    } else {
+      if (++b0 == b1) return false;
+      vb = __ldg(b + b0);
+    }
+    if (COUNT) c.bytes += 4;
+  }
+}
+
 // Boundaries of a job's reverse-row set per invertible class of its subject type:
-// 5 bits each (0..16), boundary i at bit 5*i; class i owns entries [b_i, b_{i+1}).
+// 5 bits each (0..31), boundary i at bit 5*i; class i owns entries [b_i, b_{i+1}).
 __device__ __forceinline__ uint32_t cst_at(unsigned long long cst, uint32_t i) {
   return static_cast<uint32_t>(cst >> (5u * i)) & 31u;
 }
 constexpr int kMaxInvClasses = 11;
+static_assert(kRsetCap <= 31, "class boundaries are 5-bit fields");
 
 // Warp-collective node visit: every lane may carry one (job slot, object, unit).
 // Evaluates the unit's steps at the object: membership-of-itself test, direct and
@@ -302,19 +358,37 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
                 const uint32_t m0 = c.rset[r * 32 + (jslot & 31)];
                 const uint32_t m1 = r + 1 < ke ? c.rset[(r + 1) * 32 + (jslot & 31)] : 0xFFFFFFFFu;
                 if (m0 < cl.nsubj) {
-                  l0 = __ldg(p.rrow_ptr + cl.rrow_base + m0);
-                  h0 = __ldg(p.rrow_ptr + cl.rrow_base + m0 + 1);
+                  const unsigned long long ri = cl.rrow_base + static_cast<unsigned long long>(m0) * cl.rstride;
+                  l0 = __ldg(p.rrow_ptr + ri);
+                  h0 = __ldg(p.rrow_ptr + ri + 1);
                   if (COUNT) c.bytes += 8;
                 }
                 if (m1 < cl.nsubj) {
-                  l1 = __ldg(p.rrow_ptr + cl.rrow_base + m1);
-                  h1 = __ldg(p.rrow_ptr + cl.rrow_base + m1 + 1);
+                  const unsigned long long ri = cl.rrow_base + static_cast<unsigned long long>(m1) * cl.rstride;
+                  l1 = __ldg(p.rrow_ptr + ri);
+                  h1 = __ldg(p.rrow_ptr + ri + 1);
                   if (COUNT) c.bytes += 8;
                 }
                 bool hit0 = false, hit1 = false;
                 probe2(p.rcol, c, l0, h0, obj, l1, h1, obj, hit0, hit1);
                 hit = hit0 || hit1;
               }
+            }
+          } else if ((st.flags & kStepTargetL2) && inverted && depth + 2 <= ZG_MAX_DEPTH) {
+            // Two levels at once (namespace -> team#member -> group#member -> user): a child t of this
+            // range matches iff some membership g of the subject (class tinv) is a subject of t in the
+            // children's single class tgc. The reverse row of g in that class lists exactly those t, in
+            // ascending order like this range: the answer is "do the two sorted segments intersect",
+            // once per membership. The children are never visited, nothing is pushed.
+            const uint32_t kb = cst_at(cst, st.tinv), ke = stype == st.tstype ? cst_at(cst, st.tinv + 1u) : kb;
+            const DCls cl = pr.cls()[st.tgc];
+            for (uint32_t r = kb; r < ke && !hit; ++r) {
+              const uint32_t g = c.rset[r * 32 + (jslot & 31)];
+              if (g >= cl.nsubj) continue;
+              const unsigned long long ri = cl.rrow_base + static_cast<unsigned long long>(g) * cl.rstride;
+              const uint32_t l = __ldg(p.rrow_ptr + ri), h = __ldg(p.rrow_ptr + ri + 1);
+              if (COUNT) c.bytes += 8;
+              hit = intersects(p.col, lo, hi, p.rcol, l, h, c);
             }
           } else {
             want = true;
@@ -328,6 +402,47 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
   c.found |= __reduce_or_sync(kFull, hit ? (1u << jslot) : 0u);
 }
 
+__device__ __forceinline__ uint32_t kleene_or(uint32_t a, uint32_t b) {  // 0 F, 1 T, 2 E
+  return (a == 1 || b == 1) ? 1u : ((a == 2 || b == 2) ? 2u : 0u);
+}
+__device__ __forceinline__ uint32_t kleene_and(uint32_t a, uint32_t b) {
+  return (a == 0 || b == 0) ? 0u : ((a == 2 || b == 2) ? 2u : 1u);
+}
+
+// Postfix boolean program of a non-pure permission over its leaf values (2 bits per leaf in
+// `vals`: 0 F, 1 T, 2 E). Kleene's E doubles as "not evaluated yet": the connectives are monotone,
+// so a result that is not E cannot change whatever the missing leaves turn out to be.
+__device__ __forceinline__ uint32_t eval_tree(const Prog& pr, const DTree& t, unsigned long long vals, bool trivial_self,
+                                              uint32_t srel) {
+  unsigned long long st = 0;  // 2-bit entries
+  int sp = 0;
+  for (int i = t.op_begin; i < t.op_end; ++i) {
+    const DTreeOp o = pr.tree_ops()[i];
+    if (o.kind == T_LEAF) {
+      st |= ((vals >> (2u * o.arg)) & 3ull) << (2 * sp);
+      ++sp;
+    } else if (o.kind == T_TRIVIAL) {
+      const unsigned long long v = (trivial_self && srel == o.arg) ? 1ull : 0ull;
+      st |= v << (2 * sp);
+      ++sp;
+    } else {
+      const uint32_t b = (st >> (2 * (sp - 1))) & 3u, a = (st >> (2 * (sp - 2))) & 3u;
+      uint32_t v;
+      if (o.kind == T_OR) v = kleene_or(a, b);
+      else if (o.kind == T_AND) v = kleene_and(a, b);
+      else v = kleene_and(a, b == 1 ? 0u : (b == 0 ? 1u : 2u));
+      sp -= 2;
+      st &= ~(0xFull << (2 * sp));
+      st |= static_cast<unsigned long long>(v) << (2 * sp);
+      ++sp;
+    }
+  }
+  return static_cast<uint32_t>(st & 3u);
+}
+
+// Per-lane query state parked in shared memory while the warp traverses (kStateWords words):
+//   0 resource object, 1 depth | leaves << 8 | is-tree << 15 | leaf_begin-or-unit << 16,
+//   2 tree id, 3 / 4 leaf values (2 bits each), 5 unused
 template <bool COUNT>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -341,45 +456,60 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
   uint8_t* wsm = smem + p.prog_bytes + warp * kWarpSmem;
   c.stack = reinterpret_cast<uint4*>(wsm);
   c.rset = reinterpret_cast<uint32_t*>(wsm + kStackCap * sizeof(uint4));
+  uint32_t* const state = c.rset + kRsetCap * 32 + lane;  // word k at state[k * 32]
   c.spill = p.spill + (static_cast<size_t>(blockIdx.x) * kWarpsPerBlock + warp) * p.spill_cap;
   c.spill_cap = p.spill_cap;
   c.bytes = 0;
-  const uint32_t n_slots = pr.hdr()->n_slots, n_types = pr.hdr()->n_types, n_units = pr.hdr()->n_units;
+  const uint32_t n_slots = pr.hdr()->n_slots, n_types = pr.hdr()->n_types;
+  unsigned long long* const memo = p.memo + (static_cast<size_t>(blockIdx.x) * kWarpsPerBlock + warp) * p.memo_entries;
 
   for (;;) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(p.next, 32ull);
     base = __shfl_sync(kFull, base, 0);
-    if (base >= p.njobs) break;
+    if (base >= p.nq) break;
     const unsigned long long q = base + lane;
-    bool valid = q < p.njobs, bad = false;
-    uint32_t obj = 0, unit = 0, depth = 0;
+    const bool valid = q < p.nq;
+    bool bad = false, expansive = false;
+    uint32_t nl = 0;
     c.my_subj = 0;
     c.my_ss = (0u << 16) | kNone;
     if (valid) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.jobs) + q);
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.queries) + q);
       if (COUNT) c.bytes += 17;
-      obj = raw.x;
       c.my_subj = raw.y;
       const uint32_t perm = raw.z & 0xFFFFu, stype = raw.z >> 16;
       const uint32_t srel = raw.w & 0xFFFFu, fl = p.raw_items ? 0u : raw.w >> 16;
       c.my_ss = (stype << 16) | srel;
-      depth = fl & kJobDepthMask;
+      uint32_t w1 = fl & kJobDepthMask, tree = 0;
       if (stype >= n_types || (srel != kNone && (srel >= n_slots || pr.slots()[srel].type != stype))) bad = true;
-      if (fl & kJobIsUnit) {
-        unit = perm;
-        if (unit == kNone) valid = false;  // padding job: value stays 0
-        else if (unit >= n_units) bad = true;
-      } else if (perm >= n_slots || pr.slots()[perm].kind == SK_NONPURE) {
-        bad = true;  // non-pure permissions reach this kernel as leaf-unit jobs
+      if (perm >= n_slots) {
+        bad = true;
       } else {
-        unit = pr.slots()[perm].unit;
+        const DSlot s = pr.slots()[perm];
+        if (s.kind == SK_NONPURE) {
+          const DTree t = pr.trees()[s.unit];
+          tree = s.unit;
+          nl = t.n_leaves;
+          expansive = (t.flags & UF_EXPANSIVE) != 0;
+          w1 |= (nl << 8) | (1u << 15) | (static_cast<uint32_t>(t.leaf_begin) << 16);
+        } else {
+          nl = 1;
+          expansive = (pr.units()[s.unit].flags & UF_EXPANSIVE) != 0;
+          w1 |= (1u << 8) | (static_cast<uint32_t>(s.unit) << 16);
+        }
       }
+      state[0] = raw.x;
+      state[32] = w1;
+      state[64] = tree;
+      state[96] = 0xAAAAAAAAu;  // every leaf: E = not evaluated yet
+      state[128] = 0xAAAAAAAAu;
     }
     // ---- direction-optimised probes: load the subject's reverse rows (its direct
-    // memberships, class by class) when the check can fan out and they are few
+    // memberships, class by class) when the check can fan out and they are few. Loaded once per
+    // query: every leaf of a non-pure permission shares them.
     {
-      bool inv = p.invert && valid && !bad && (c.my_ss & 0xFFFFu) == kNone && (pr.units()[unit].flags & UF_EXPANSIVE);
+      bool inv = p.invert && valid && !bad && (c.my_ss & 0xFFFFu) == kNone && expansive;
       uint32_t rcnt = 0;
       unsigned long long cst = 0;
       int ib = 0, ncl = 0;
@@ -398,8 +528,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
           const uint32_t gc = pr.inv_cls()[ib + i];
           const DCls cl = pr.cls()[gc];
           if (!(cl.flags & CF_EMPTY) && c.my_subj < cl.nsubj) {
-            const uint32_t b = __ldg(p.rrow_ptr + cl.rrow_base + c.my_subj);
-            const uint32_t e = __ldg(p.rrow_ptr + cl.rrow_base + c.my_subj + 1);
+            const unsigned long long ri = cl.rrow_base + static_cast<unsigned long long>(c.my_subj) * cl.rstride;
+            const uint32_t b = __ldg(p.rrow_ptr + ri);
+            const uint32_t e = __ldg(p.rrow_ptr + ri + 1);
             if (COUNT) c.bytes += 8;
             if (rcnt + (e - b) > static_cast<uint32_t>(kRsetCap)) {
               inv = false;  // too many memberships: this check probes forward
@@ -418,138 +549,172 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
       c.my_cst = cst;
       __syncwarp();
     }
-    c.found = 0;
-    c.err = __ballot_sync(kFull, valid && bad);
-    c.top = 0;
-    c.spill_top = 0;
     c.fatal = false;
-    const unsigned live_jobs = __ballot_sync(kFull, valid && !bad);
-
-    visit(p, pr, c, valid && !bad, lane, obj, unit, depth);
-
-    uint32_t iters = 0;
-    bool use_memo = false;
-    unsigned long long* memo = p.memo + (static_cast<size_t>(blockIdx.x) * kWarpsPerBlock + warp) * p.memo_entries;
-    for (;;) {
-      if (!c.fatal && c.top == 0) {
-        if (c.spill_top == 0) break;
-        refill(c);
+    bool undet = valid && !bad;
+    uint32_t res = 2;  // invalid query -> error
+    const int maxnl = __reduce_max_sync(kFull, undet ? static_cast<int>(nl) : 0);
+    for (int l = 0; l < maxnl; ++l) {
+      const bool act = undet && l < static_cast<int>(nl);
+      const unsigned live_jobs = __ballot_sync(kFull, act);
+      if (!live_jobs) continue;
+      uint32_t obj = 0, unit = 0, depth = 0;
+      if (act) {
+        obj = state[0];
+        const uint32_t w1 = state[32];
+        depth = w1 & kJobDepthMask;
+        unit = (w1 >> 15) & 1u ? pr.leaf_units()[(w1 >> 16) + l] : (w1 >> 16);
       }
-      if ((c.found & live_jobs) == live_jobs) break;  // every check already answered
-      if (++iters > p.budget || c.fatal) {
-        if (lane == 0) atomicOr(p.flags, c.fatal ? 1u : 4u);
-        c.err |= live_jobs & ~c.found;
-        break;
-      }
-      if (!use_memo && p.memo_entries && iters > p.memo_after) {
-        // this batch is expanding far more than usual: path multiplicity. Remember child
-        // visits from here on; an identical (job, slot, object, depth) visit is skipped.
-        for (uint32_t i = lane; i < p.memo_entries; i += 32) memo[i] = 0ull;
+      c.found = 0;
+      c.err = 0;
+      c.raised = 0;
+      c.top = 0;
+      c.spill_top = 0;
+
+      visit(p, pr, c, act, lane, obj, unit, depth);
+
+      uint32_t iters = 0;
+      bool use_memo = false;
+      for (;;) {
+        if (!c.fatal && c.top == 0) {
+          if (c.spill_top == 0) break;
+          refill(c);
+        }
+        if ((c.found & live_jobs) == live_jobs) break;  // every check already answered
+        if (++iters > p.budget || c.fatal) {
+          if (lane == 0) atomicOr(p.flags, c.fatal ? 1u : 4u);
+          c.err |= live_jobs & ~c.found;
+          break;
+        }
+        if (!use_memo && p.memo_entries && iters > p.memo_after) {
+          // this batch is expanding far more than usual: path multiplicity. Remember child
+          // visits from here on; an identical (job, slot, object, depth) visit is skipped.
+          for (uint32_t i = lane; i < p.memo_entries; i += 32) memo[i] = 0ull;
+          __syncwarp();
+          use_memo = true;
+        }
+        // ---- pop ranges worth <= 32 edges from the top of the stack
+        const int n = c.top < 32 ? c.top : 32;
+        uint4 it = make_uint4(0, 0, 0, 0);
+        if (static_cast<int>(lane) < n) it = c.stack[c.top - 1 - lane];
+        const bool dead = (c.found >> (it.z & 31)) & 1u;
+        const uint32_t len = (static_cast<int>(lane) < n && !dead) ? it.y - it.x : 0u;
+        uint32_t incl = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          uint32_t v = __shfl_up_sync(kFull, incl, d);
+          if (static_cast<int>(lane) >= d) incl += v;
+        }
+        const uint32_t excl = incl - len;
+        const unsigned fullm = __ballot_sync(kFull, static_cast<int>(lane) < n && incl <= 32u);
+        const int nfull = __popc(fullm);  // prefix of fully consumed items
+        uint32_t total = __shfl_sync(kFull, incl, 31);
+        if (total > 32u) total = 32u;
         __syncwarp();
-        use_memo = true;
-      }
-      // ---- pop ranges worth <= 32 edges from the top of the stack
-      const int n = c.top < 32 ? c.top : 32;
-      uint4 it = make_uint4(0, 0, 0, 0);
-      if (static_cast<int>(lane) < n) it = c.stack[c.top - 1 - lane];
-      const bool dead = (c.found >> (it.z & 31)) & 1u;
-      const uint32_t len = (static_cast<int>(lane) < n && !dead) ? it.y - it.x : 0u;
-      uint32_t incl = len;
+        if (static_cast<int>(lane) == nfull && static_cast<int>(lane) < n)  // partially consumed item stays on top
+          c.stack[c.top - 1 - lane].x = it.x + (32u - excl);
+        c.top -= nfull;
+        __syncwarp();
+        // ---- lane k takes edge k: owner item j = #items with incl <= k
+        auto owner = [&](uint32_t u) -> int {
+          int j = 0;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        uint32_t v = __shfl_up_sync(kFull, incl, d);
-        if (static_cast<int>(lane) >= d) incl += v;
-      }
-      const uint32_t excl = incl - len;
-      const unsigned fullm = __ballot_sync(kFull, static_cast<int>(lane) < n && incl <= 32u);
-      const int nfull = __popc(fullm);  // prefix of fully consumed items
-      uint32_t total = __shfl_sync(kFull, incl, 31);
-      if (total > 32u) total = 32u;
-      __syncwarp();
-      if (static_cast<int>(lane) == nfull && static_cast<int>(lane) < n)  // partially consumed item stays on top
-        c.stack[c.top - 1 - lane].x = it.x + (32u - excl);
-      c.top -= nfull;
-      __syncwarp();
-      // ---- lane k takes edge k: owner item j = #items with incl <= k
-      auto owner = [&](uint32_t u) -> int {
-        int j = 0;
-#pragma unroll
-        for (int step = 16; step >= 1; step >>= 1) {
-          const int probe_lane = j + step - 1;
-          const uint32_t v = __shfl_sync(kFull, incl, probe_lane & 31);
-          if (probe_lane < 32 && v <= u) j += step;
-        }
-        return j;
-      };
-      const int j = owner(lane);
-      const uint32_t jb = __shfl_sync(kFull, it.x, j & 31);
-      const uint32_t jmeta = __shfl_sync(kFull, it.z, j & 31);
-      const uint32_t jexcl = __shfl_sync(kFull, excl, j & 31);
-      bool active = lane < total;
-      const uint32_t jslot = jmeta & 31u, cdepth = (jmeta >> 5) & 63u, tslot = jmeta >> 16;
-      uint32_t child = 0;
-      const uint32_t sq_subj = __shfl_sync(kFull, c.my_subj, jslot);
-      const uint32_t sq_ss = __shfl_sync(kFull, c.my_ss, jslot);
-      if (active) {
-        const uint32_t e = jb + (lane - jexcl);
-        child = __ldg(p.col + e);
-        if (COUNT) c.bytes += 4;
-        if (jmeta & (1u << 11)) {
-          const uint32_t ex = __ldg(p.exp + e);
-          if (COUNT) c.bytes += 4;
-          active = ex == 0 || ex > p.now;
-        }
-      }
-      // the 51st hop is an error (pkg/spicedb/spicedb.go:33)
-      const bool too_deep = active && cdepth > ZG_MAX_DEPTH;
-      c.err |= __reduce_or_sync(kFull, too_deep ? (1u << jslot) : 0u);
-      active = active && !too_deep;
-      if (use_memo && active) {
-        // exact key (a visit at another depth has another hop budget, so depth is part of it);
-        // direct-mapped and lossy: a lost entry only costs a repeated visit
-        const unsigned long long key = (1ull << 59) | (static_cast<unsigned long long>(jslot) << 54) |
-                                       (static_cast<unsigned long long>(cdepth) << 48) |
-                                       (static_cast<unsigned long long>(tslot) << 32) | child;
-        unsigned long long hsh = key * 0x9E3779B97F4A7C15ull;
-        const uint32_t at = static_cast<uint32_t>(hsh >> 40) & (p.memo_entries - 1u);
-        if (memo[at] == key) active = false;
-        else memo[at] = key;
-      }
-      uint32_t cunit = 0;
-      if (active) {
-        const DSlot s = pr.slots()[tslot];
-        const bool remote = p.shard_count > 1 && (child % p.shard_count) != p.shard_rank;
-        if (s.kind == SK_NONPURE || remote) {
-          // defer: Check(child#tslot @ S) becomes a sub-query of the next pass
-          const unsigned long long at = atomicAdd(p.subq_count, 1ull);
-          if (at < p.subq_cap) {
-            zg_check sq;
-            sq.res = child;
-            sq.subj = sq_subj;
-            sq.perm = static_cast<uint16_t>(tslot);
-            sq.stype = static_cast<uint16_t>(sq_ss >> 16);
-            sq.srel = static_cast<uint16_t>(sq_ss & 0xFFFFu);
-            sq.flags = static_cast<uint16_t>(cdepth);
-            p.subq[at] = sq;
-            p.subq_parent[at] = static_cast<uint32_t>(base + jslot);
-          } else {
-            atomicOr(p.flags, 2u);
+          for (int step = 16; step >= 1; step >>= 1) {
+            const int probe_lane = j + step - 1;
+            const uint32_t v = __shfl_sync(kFull, incl, probe_lane & 31);
+            if (probe_lane < 32 && v <= u) j += step;
           }
-          active = false;
+          return j;
+        };
+        const int j = owner(lane);
+        const uint32_t jb = __shfl_sync(kFull, it.x, j & 31);
+        const uint32_t jmeta = __shfl_sync(kFull, it.z, j & 31);
+        const uint32_t jexcl = __shfl_sync(kFull, excl, j & 31);
+        bool active = lane < total;
+        const uint32_t jslot = jmeta & 31u, cdepth = (jmeta >> 5) & 63u, tslot = jmeta >> 16;
+        uint32_t child = 0;
+        const uint32_t sq_subj = __shfl_sync(kFull, c.my_subj, jslot);
+        const uint32_t sq_ss = __shfl_sync(kFull, c.my_ss, jslot);
+        if (active) {
+          const uint32_t e = jb + (lane - jexcl);
+          child = __ldg(p.col + e);
+          if (COUNT) c.bytes += 4;
+          if (jmeta & (1u << 11)) {
+            const uint32_t ex = __ldg(p.exp + e);
+            if (COUNT) c.bytes += 4;
+            active = ex == 0 || ex > p.now;
+          }
+        }
+        // the 51st hop is an error (pkg/spicedb/spicedb.go:33)
+        const bool too_deep = active && cdepth > ZG_MAX_DEPTH;
+        c.err |= __reduce_or_sync(kFull, too_deep ? (1u << jslot) : 0u);
+        active = active && !too_deep;
+        if (use_memo && active) {
+          // exact key (a visit at another depth has another hop budget, so depth is part of it);
+          // direct-mapped and lossy: a lost entry only costs a repeated visit
+          const unsigned long long key = (1ull << 59) | (static_cast<unsigned long long>(jslot) << 54) |
+                                         (static_cast<unsigned long long>(cdepth) << 48) |
+                                         (static_cast<unsigned long long>(tslot) << 32) | child;
+          unsigned long long hsh = key * 0x9E3779B97F4A7C15ull;
+          const uint32_t at = static_cast<uint32_t>(hsh >> 40) & (p.memo_entries - 1u);
+          if (memo[at] == key) active = false;
+          else memo[at] = key;
+        }
+        uint32_t cunit = 0;
+        bool raise = false;
+        if (active) {
+          const DSlot s = pr.slots()[tslot];
+          const bool remote = p.shard_count > 1 && (child % p.shard_count) != p.shard_rank;
+          if (s.kind == SK_NONPURE || remote) {
+            // defer: Check(child#tslot @ S) becomes a sub-query of the next pass
+            const unsigned long long at = atomicAdd(p.subq_count, 1ull);
+            if (at < p.subq_cap) {
+              zg_check sq;
+              sq.res = child;
+              sq.subj = sq_subj;
+              sq.perm = static_cast<uint16_t>(tslot);
+              sq.stype = static_cast<uint16_t>(sq_ss >> 16);
+              sq.srel = static_cast<uint16_t>(sq_ss & 0xFFFFu);
+              sq.flags = static_cast<uint16_t>(cdepth);
+              p.subq[at] = sq;
+              p.subq_parent[at] = static_cast<uint32_t>((base + jslot) * p.L + l);
+            } else {
+              atomicOr(p.flags, 2u);
+            }
+            raise = true;
+            active = false;
+          } else {
+            cunit = s.unit;
+          }
+        }
+        c.raised |= __reduce_or_sync(kFull, raise ? (1u << jslot) : 0u);
+        visit(p, pr, c, active, jslot, child, cunit, cdepth);
+      }
+
+      if (act) {
+        const bool t = (c.found >> lane) & 1u, e = (c.err >> lane) & 1u, r = (c.raised >> lane) & 1u;
+        if (p.val) p.val[q * p.L + l] = t ? kValT : (e ? kValE : 0);
+        // a leaf that raised sub-queries is not final unless it is already true
+        const uint32_t v = t ? 1u : ((e || r) ? 2u : 0u);
+        const uint32_t w1 = state[32];
+        if ((w1 >> 15) & 1u) {
+          unsigned long long vals = (static_cast<unsigned long long>(state[128]) << 32) | state[96];
+          vals = (vals & ~(3ull << (2 * l))) | (static_cast<unsigned long long>(v) << (2 * l));
+          state[96] = static_cast<uint32_t>(vals);
+          state[128] = static_cast<uint32_t>(vals >> 32);
+          const uint32_t srel = c.my_ss & 0xFFFFu;
+          res = eval_tree(pr, pr.trees()[state[64]], vals, c.my_subj == state[0], srel);
+          if (res != 2u || l + 1 == static_cast<int>(nl)) undet = false;
         } else {
-          cunit = s.unit;
+          res = v;
+          undet = false;
         }
       }
-      visit(p, pr, c, active, jslot, child, cunit, cdepth);
     }
-
-    if (q < p.njobs) {
-      const bool t = (c.found >> lane) & 1u, e = (c.err >> lane) & 1u;
-      uint8_t v;
-      if (p.final_codes) v = t ? ZG_HAS_PERMISSION : (e ? ZG_ITEM_ERROR : ZG_NO_PERMISSION);
-      else v = t ? kValT : (e ? kValE : 0);
-      p.val[q] = v;
+    if (valid && p.out) {
+      if (p.final_codes) p.out[q] = res == 1 ? ZG_HAS_PERMISSION : (res == 2 ? ZG_ITEM_ERROR : ZG_NO_PERMISSION);
+      else p.out[q] = res == 1 ? kValT : (res == 2 ? kValE : 0);
     }
+    __syncwarp();
   }
   if (COUNT) {
     unsigned long long b = c.bytes;
@@ -559,50 +724,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
   }
 }
 
-// ---- general mode: queries -> leaf-unit jobs, and the boolean fold ------------------
+// ---- multi-pass runs: the boolean fold of a level whose queries raised sub-queries -------------
 
-// jobs[l*n + q] for l < L (leaf-major: jobs of one leaf are contiguous, so a warp's 32 jobs do
-// similar work and the padding of queries with fewer leaves sits together at the end).
-// Pure / relation slots use one job; non-pure slots one per
-// leaf unit of their tree. Unused positions are padding (unit = kNone).
-__global__ void prep_jobs_kernel(const uint8_t* prog, const zg_check* queries, unsigned long long n, uint32_t L,
-                                 zg_check* jobs, int raw_items) {
-  const Prog pr = make_prog(prog);
-  unsigned long long q = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
-  if (q >= n) return;
-  const zg_check it = queries[q];
-  const uint16_t depth = raw_items ? 0 : (it.flags & kJobDepthMask);
-  uint32_t nl = 0;
-  const uint16_t* leaf = nullptr;
-  uint16_t single = kNone;
-  if (it.perm < pr.hdr()->n_slots) {
-    const DSlot s = pr.slots()[it.perm];
-    if (s.kind == SK_NONPURE) {
-      const DTree t = pr.trees()[s.unit];
-      nl = t.n_leaves;
-      leaf = pr.leaf_units() + t.leaf_begin;
-    } else {
-      nl = 1;
-      single = s.unit;
-    }
-  }
-  for (uint32_t l = 0; l < L; ++l) {
-    zg_check j = it;
-    j.perm = l < nl ? (leaf ? leaf[l] : single) : kNone;
-    j.flags = static_cast<uint16_t>(depth | kJobIsUnit);
-    jobs[static_cast<unsigned long long>(l) * n + q] = j;
-  }
-}
-
-__device__ __forceinline__ uint32_t kleene_or(uint32_t a, uint32_t b) {  // 0 F, 1 T, 2 E
-  return (a == 1 || b == 1) ? 1u : ((a == 2 || b == 2) ? 2u : 0u);
-}
-__device__ __forceinline__ uint32_t kleene_and(uint32_t a, uint32_t b) {
-  return (a == 0 || b == 0) ? 0u : ((a == 2 || b == 2) ? 2u : 1u);
-}
-
-// Evaluates each query's boolean tree over its leaf-job values. final: write the
-// v1 code to out[q]; otherwise OR the value into the parent job of the previous pass.
+// Evaluates each query's boolean tree over its leaf values val[q * L + l] (the check kernel wrote
+// them, the folds of deeper levels OR-ed the sub-query results in). out != null: write the v1 code
+// (or the raw value bits) to out[q]; otherwise OR the value into the (query, leaf) of the previous
+// level that raised this query.
 __global__ void fold_kernel(const uint8_t* prog, const zg_check* queries, unsigned long long n, uint32_t L,
                             const uint8_t* val, uint8_t* out, const uint32_t* parent, uint8_t* parent_val, int raw_out) {
   const Prog pr = make_prog(prog);
@@ -614,38 +741,17 @@ __global__ void fold_kernel(const uint8_t* prog, const zg_check* queries, unsign
                   (it.srel == kNone || (it.srel < pr.hdr()->n_slots && pr.slots()[it.srel].type == it.stype));
   if (ok) {
     const DSlot s = pr.slots()[it.perm];
-    auto leafval = [&](uint32_t l) -> uint32_t {
-      const uint8_t v = val[static_cast<unsigned long long>(l) * n + q];
-      return (v & kValT) ? 1u : ((v & kValE) ? 2u : 0u);
+    auto leafval = [&](uint32_t l) -> unsigned long long {
+      const uint8_t v = val[q * L + l];
+      return (v & kValT) ? 1ull : ((v & kValE) ? 2ull : 0ull);
     };
     if (s.kind != SK_NONPURE) {
-      r = leafval(0);
+      r = static_cast<uint32_t>(leafval(0));
     } else {
       const DTree t = pr.trees()[s.unit];
-      unsigned long long st = 0;  // 2-bit entries
-      int sp = 0;
-      for (int i = t.op_begin; i < t.op_end; ++i) {
-        const DTreeOp o = pr.tree_ops()[i];
-        if (o.kind == T_LEAF) {
-          st |= static_cast<unsigned long long>(leafval(o.arg)) << (2 * sp);
-          ++sp;
-        } else if (o.kind == T_TRIVIAL) {
-          const uint32_t v = (it.srel == o.arg && it.subj == it.res) ? 1u : 0u;
-          st |= static_cast<unsigned long long>(v) << (2 * sp);
-          ++sp;
-        } else {
-          const uint32_t b = (st >> (2 * (sp - 1))) & 3u, a = (st >> (2 * (sp - 2))) & 3u;
-          uint32_t v;
-          if (o.kind == T_OR) v = kleene_or(a, b);
-          else if (o.kind == T_AND) v = kleene_and(a, b);
-          else v = kleene_and(a, b == 1 ? 0u : (b == 0 ? 1u : 2u));
-          sp -= 2;
-          st &= ~(0xFull << (2 * sp));
-          st |= static_cast<unsigned long long>(v) << (2 * sp);
-          ++sp;
-        }
-      }
-      r = st & 3u;
+      unsigned long long vals = 0;
+      for (uint32_t l = 0; l < t.n_leaves; ++l) vals |= leafval(l) << (2 * l);
+      r = eval_tree(pr, t, vals, it.subj == it.res, it.srel);
     }
   }
   if (out) {
@@ -717,7 +823,8 @@ __global__ void __launch_bounds__(256) rbfs_expand_kernel(const RbfsParams p) {
     } else if (obj >= cl.nsubj) {
       continue;
     }
-    const uint32_t b = __ldg(p.rrow_ptr + cl.rrow_base + row), e = __ldg(p.rrow_ptr + cl.rrow_base + row + 1);
+    const unsigned long long ri = cl.rrow_base + static_cast<unsigned long long>(row) * cl.rstride;
+    const uint32_t b = __ldg(p.rrow_ptr + ri), e = __ldg(p.rrow_ptr + ri + 1);
     const unsigned long long bit_base = p.type_bit_base[cl.rtype];
     for (uint32_t i0 = b; i0 < e; i0 += 32) {
       const uint32_t i = i0 + lane;
@@ -762,6 +869,8 @@ struct FlatLookupClass {
   uint32_t nsubj;
   uint16_t stype;     // subject type the class accepts
   uint16_t wildcard;  // row 0 regardless of the subject id
+  uint32_t rstride;   // reverse row stride per subject
+  uint32_t pad;
 };
 __global__ void lookup_flat_kernel(const uint32_t* rrow_ptr, const uint32_t* rcol, const FlatLookupClass* cls, int ncls,
                                    uint32_t stype, uint32_t subj, uint32_t* out, unsigned long long cap,
@@ -772,7 +881,8 @@ __global__ void lookup_flat_kernel(const uint32_t* rrow_ptr, const uint32_t* rco
     if (cls[c].stype != stype) continue;  // relationships with another subject type cannot match
     const uint32_t row = cls[c].wildcard ? 0u : subj;
     if (row >= cls[c].nsubj) continue;
-    const uint32_t b = rrow_ptr[cls[c].rrow_base + row], e = rrow_ptr[cls[c].rrow_base + row + 1];
+    const unsigned long long ri = cls[c].rrow_base + static_cast<unsigned long long>(row) * cls[c].rstride;
+    const uint32_t b = rrow_ptr[ri], e = rrow_ptr[ri + 1];
     for (uint32_t i = b + lane; i < e; i += 32)
       if (w + (i - b) < cap) out[w + (i - b)] = rcol[i];
     w += e - b;

@@ -520,6 +520,7 @@ std::string Schema::compile() {
         post(n);
         t.op_end = static_cast<uint16_t>(d_tree_ops.size());
         t.n_leaves = n_leaves;
+        for (uint16_t l = 0; l < n_leaves; ++l) t.flags |= d_units[d_leaf_units[t.leaf_begin + l]].flags & UF_EXPANSIVE;
         if (n_leaves > kMaxLeaves)
           throw std::runtime_error("permission " + types[slots[s].type].name + "#" + slots[s].name +
                                    " has too many union groups under & / - (max " + std::to_string(kMaxLeaves) + ")");
@@ -537,10 +538,41 @@ std::string Schema::compile() {
     return ex.what();
   }
 
+  // A direct class is worth answering from the subject's reverse rows only when it is probed after a
+  // fan-out, i.e. when some unit that contains its relation is the TARGET of a userset or arrow edge.
+  // A class that is only ever probed at the root object of a check (pod#viewer@user in a flat schema,
+  // document#banned@user) costs one forward binary search there; loading its reverse row at admission
+  // would cost the same two sectors and fill the per-check set for nothing.
+  std::vector<uint8_t> unit_pushed(d_units.size(), 0);
+  {
+    auto mark_slot = [&](uint16_t ts) {
+      if (ts == kNone || ts >= d_slots.size()) return;
+      if (d_slots[ts].kind == SK_NONPURE) {
+        const DTree& t = d_trees[d_slots[ts].unit];
+        for (uint16_t l = 0; l < t.n_leaves; ++l) unit_pushed[d_leaf_units[t.leaf_begin + l]] = 1;
+      } else {
+        unit_pushed[d_slots[ts].unit] = 1;
+      }
+    };
+    for (const DUnit& u : d_units)
+      for (int oi = u.op_begin; oi < u.op_end; ++oi) {
+        const DOp& op = d_ops[oi];
+        const auto& classes = slots[rel_slots[op.rel]].classes;
+        for (size_t k = 0; k < classes.size(); ++k) {
+          if (op.kind == OP_ARROW) mark_slot(d_tgts[op.tgt_begin + k]);
+          else if (classes[k].sslot != kNone && classes[k].sslot != kWildcard) mark_slot(classes[k].sslot);
+        }
+      }
+  }
+  std::vector<uint8_t> rel_fanout(rel_slots.size(), 0);
+  for (size_t u = 0; u < d_units.size(); ++u)
+    if (unit_pushed[u])
+      for (int oi = d_units[u].op_begin; oi < d_units[u].op_end; ++oi)
+        if (d_ops[oi].kind == OP_REL) rel_fanout[d_ops[oi].rel] = 1;
   for (int rs : rel_slots)
     for (const auto& c : slots[rs].classes) {
       uint16_t fl = c.expiry ? CF_EXPIRY : 0;
-      if (c.sslot == kNone && !c.expiry) fl |= CF_INVERT;
+      if (c.sslot == kNone && !c.expiry && rel_fanout[slots[rs].rel_index]) fl |= CF_INVERT;
       d_cls.push_back(DCls{c.stype, c.sslot, fl, static_cast<uint16_t>(slots[rs].rel_index), 0, slots[rs].type, 0, 0});
     }
   d_type_inv.assign(types.size(), DTypeInv{0, 0});
@@ -641,6 +673,18 @@ std::vector<uint8_t> Schema::blob(const std::vector<DRel>& rels, const std::vect
       st.tinv = inv_pos[st.tgc];
       st.tstype = steps[tu.step_begin].stype;
     }
+  }
+  // second level: the target unit is one userset class whose children are leaf visits
+  for (auto& st : steps) {
+    if (st.kind != ST_PUSH || st.tunit == kNone || (st.flags & (kStepTargetLeaf | CF_EXPIRY))) continue;
+    const DUnit& tu = units[st.tunit];
+    if (tu.step_end - tu.step_begin != 1) continue;
+    const DStep& in = steps[tu.step_begin];
+    if (in.kind != ST_PUSH || !(in.flags & kStepTargetLeaf) || (in.flags & CF_EXPIRY)) continue;
+    st.flags |= kStepTargetL2;
+    st.tgc = in.gc;
+    st.tinv = in.tinv;
+    st.tstype = in.tstype;
   }
   h.n_steps = static_cast<uint32_t>(steps.size());
   // (rels / ops / tgts stay on the host: the kernels only read the flattened steps)

@@ -38,6 +38,9 @@ enum UnitFlags : uint16_t {
                      // only answer "is (class, obj) one of the subject's own memberships"
 };
 constexpr uint16_t kStepTargetLeaf = 0x100;  // DStep.flags: children are UF_LEAF_INV visits
+constexpr uint16_t kStepTargetL2 = 0x200;    // DStep.flags: the children's unit is ONE userset edge class whose own
+                                             // children are UF_LEAF_INV visits (resource -> team#member -> user): the
+                                             // whole two-level range is answered from the subject's reverse rows
 
 struct DSlot {   // per slot (relation or permission)
   uint16_t kind;        // SlotKind
@@ -65,10 +68,11 @@ struct DStep {
   uint16_t flags;     // ClsFlags (CF_EXPIRY, CF_INVERT) | kStepTargetLeaf
   uint16_t gc;        // global class id (key of the subject's reverse-row set)
   uint16_t tunit;     // ST_PUSH: unit of tslot (kNone when tslot is a non-pure permission)
-  uint16_t tgc;       // kStepTargetLeaf: the single class of the target unit
+  uint16_t tgc;       // kStepTargetLeaf: the single class of the target unit; kStepTargetL2: the single
+                      // (userset) class of the target unit, whose reverse rows are streamed
   uint16_t tinv;      // ST_DIRECT: index of gc among its subject type's invertible classes;
-                      // kStepTargetLeaf: the same for tgc
-  uint16_t tstype;    // kStepTargetLeaf: subject type the target class accepts
+                      // kStepTargetLeaf: the same for tgc; kStepTargetL2: for the innermost direct class
+  uint16_t tstype;    // kStepTargetLeaf / kStepTargetL2: subject type the (innermost) direct class accepts
 };
 struct DOp {
   uint16_t kind;       // OpKind
@@ -92,8 +96,11 @@ struct DCls {
   uint16_t rel;        // data relation index this class belongs to
   uint32_t nsubj;      // reverse CSR: subject objects covered (1 for a wildcard class)
   uint16_t rtype;      // type of the resources of this class
-  uint16_t pad;
-  uint64_t rrow_base;  // reverse CSR: index into rrow_ptr of (subject 0) for this class
+  uint16_t rstride;    // reverse CSR row stride per subject: the reverse rows of ALL classes of one
+                       // subject type are interleaved per subject (one or two sectors hold every
+                       // offset of a subject), like the forward tables are per object
+  uint64_t rrow_base;  // reverse CSR: rrow_ptr index of (subject 0, this class); row of subject s =
+                       // rrow_base + s * rstride
 };
 struct DTypeInv {  // per subject type: the invertible direct classes (inv_cls[begin, end))
   uint16_t begin, end;
@@ -101,6 +108,8 @@ struct DTypeInv {  // per subject type: the invertible direct classes (inv_cls[b
 struct DTree {   // postfix boolean program of a non-pure permission
   uint16_t op_begin, op_end;     // into tree_ops[]
   uint16_t leaf_begin, n_leaves; // leaf_units[leaf_begin + i] = unit id
+  uint16_t flags;                // UF_EXPANSIVE when any leaf unit is
+  uint16_t pad;
 };
 struct DTreeOp {
   uint16_t kind;  // TreeOpKind

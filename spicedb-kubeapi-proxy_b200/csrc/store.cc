@@ -303,13 +303,34 @@ HostSnapshot Store::layout() const {
     type_used[s.type] += r.ncls;
     h.rels.push_back(r);
   }
-  // reverse CSR: one row per SUBJECT object per class (one row for a wildcard class)
+  // reverse CSR: one row per (SUBJECT object, class). All classes of one subject type are
+  // interleaved per subject (row = rrow_base + subject * rstride), classes whose probes may be
+  // answered from the subject's reverse rows (CF_INVERT) first: a check's admission reads every
+  // offset of its subject from one or two sectors, and the subject's entries are contiguous in
+  // rcol. A wildcard class has a single row of its own.
   h.cls = sc.d_cls;
   h.rpool = 0;
+  for (size_t t = 0; t < nt; ++t) {
+    std::vector<size_t> order;
+    for (int pass = 0; pass < 2; ++pass)
+      for (size_t c = 0; c < h.cls.size(); ++c)
+        if (h.cls[c].stype == t && h.cls[c].sslot != kWildcard && ((h.cls[c].flags & CF_INVERT) != 0) == (pass == 0))
+          order.push_back(c);
+    for (size_t k = 0; k < order.size(); ++k) {
+      DCls& c = h.cls[order[k]];
+      c.rrow_base = h.rpool + k;
+      c.rstride = static_cast<uint16_t>(order.size());
+      c.nsubj = h.n_objects[t];
+    }
+    h.rpool += uint64_t(order.size()) * h.n_objects[t];
+  }
   for (auto& c : h.cls) {
-    c.rrow_base = h.rpool;
-    c.nsubj = c.sslot == kWildcard ? 1u : h.n_objects[c.stype];
-    h.rpool += c.nsubj;
+    if (c.sslot == kWildcard) {
+      c.rrow_base = h.rpool;
+      c.rstride = 0;
+      c.nsubj = 1;
+      h.rpool += 1;
+    }
     c.flags |= CF_EMPTY;  // cleared by the builder for every class that has a relationship
   }
   return h;
@@ -416,7 +437,7 @@ HostSnapshot Store::build() const {
           DCls& c = h.cls[r.cls_begin + k];
           c.flags &= static_cast<uint16_t>(~CF_EMPTY);
           for (uint32_t i = b; i < e; ++i) {
-            const uint64_t ridx = c.rrow_base + (c.sslot == kWildcard ? 0u : h.col[i]);
+            const uint64_t ridx = c.rrow_base + (c.sslot == kWildcard ? 0ull : uint64_t(h.col[i]) * c.rstride);
             if (pass == 0) ++h.rrow_ptr[ridx + 1];
             else h.rcol[cur[ridx]++] = res;
           }

@@ -112,8 +112,9 @@ static int verify(const Schema& sc, const Store& st, const std::map<ModelKey, ui
     for (uint32_t c = 0; c < r.ncls; ++c) {
       const DCls& dc = h.cls[r.cls_begin + c];
       for (uint32_t s = 0; s < dc.nsubj; ++s) {
-        if (dc.rrow_base + s + 1 >= h.rrow_ptr.size()) return std::printf("rrow_ptr index out of range\n"), 1;
-        const uint32_t b = h.rrow_ptr[dc.rrow_base + s], e = h.rrow_ptr[dc.rrow_base + s + 1];
+        const uint64_t rri = dc.rrow_base + uint64_t(s) * dc.rstride;
+        if (rri + 1 >= h.rrow_ptr.size()) return std::printf("rrow_ptr index out of range\n"), 1;
+        const uint32_t b = h.rrow_ptr[rri], e = h.rrow_ptr[rri + 1];
         if (b > e || e > h.rcol.size()) return std::printf("reverse row bounds\n"), 1;
         std::vector<uint32_t> got(h.rcol.begin() + b, h.rcol.begin() + e);
         if (!std::is_sorted(got.begin(), got.end())) return std::printf("reverse row not sorted\n"), 1;
