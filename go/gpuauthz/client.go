@@ -35,8 +35,10 @@ import (
 	"context"
 	"fmt"
 	"io"
+	"runtime"
 	"strings"
 	"sync"
+	"sync/atomic"
 	"unsafe"
 
 	v1 "github.com/authzed/authzed-go/proto/authzed/api/v1"
@@ -52,22 +54,28 @@ type Client struct {
 
 	engine *C.zg_engine
 	mu     sync.Mutex // serialises the write mirror; checks are thread-safe in the library
+	// broken is set when the mirror diverged from SpiceDB and could not be rebuilt: every check path
+	// then fails (pkg/authz/authz.go:93-97 turns an error into a denial) instead of answering from a
+	// store that may still hold revoked grants.
+	broken atomic.Bool
 }
+
+var errBroken = status.Error(codes.Unavailable, "gpu mirror is out of sync with SpiceDB and could not be rebuilt")
 
 // New creates the GPU engine, loads the schema and mirrors the relationships that are
 // already in SpiceDB (bootstrap file: pkg/spicedb/spicedb.go:19-24).
 func New(ctx context.Context, inner v1.PermissionsServiceClient, schema string, device int) (*Client, error) {
 	cfg := C.zg_config{device: C.int32_t(device)}
 	var eng *C.zg_engine
-	if rc := C.zg_engine_create(&cfg, &eng); rc != 0 {
-		return nil, lastError(rc) // fail closed: no CPU fallback inside the library
+	if err := call(func() C.int { return C.zg_engine_create(&cfg, &eng) }); err != nil {
+		return nil, err // fail closed: no CPU fallback inside the library
 	}
 	c := &Client{PermissionsServiceClient: inner, engine: eng}
 	cs := C.CString(schema)
 	defer C.free(unsafe.Pointer(cs))
-	if rc := C.zg_load_schema(eng, cs, C.size_t(len(schema))); rc != 0 {
+	if err := call(func() C.int { return C.zg_load_schema(eng, cs, C.size_t(len(schema))) }); err != nil {
 		c.Close()
-		return nil, lastError(rc)
+		return nil, err
 	}
 	if err := c.resync(ctx); err != nil {
 		c.Close()
@@ -83,6 +91,19 @@ func (c *Client) Close() {
 	}
 }
 
+// call runs one C entry point and, when it fails, fetches the library's message. zg_last_error is
+// thread-local; a goroutine may migrate between OS threads from one cgo call to the next, so the pair
+// (failing call, zg_last_error) runs with the goroutine pinned to its thread.
+func call(f func() C.int) error {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	if rc := f(); rc != 0 {
+		return lastError(rc)
+	}
+	return nil
+}
+
+// lastError must run on the OS thread of the failing call: only use it through call().
 func lastError(rc C.int) error {
 	code := codes.Internal
 	switch rc {
@@ -92,7 +113,7 @@ func lastError(rc C.int) error {
 		code = codes.AlreadyExists
 	case C.ZG_EPRECOND, C.ZG_ENOSCHEMA, C.ZG_ENOSNAPSHOT:
 		code = codes.FailedPrecondition
-	case C.ZG_ENOMEM:
+	case C.ZG_ENOMEM, C.ZG_EDEPTH:
 		code = codes.ResourceExhausted
 	}
 	return status.Error(code, C.GoString(C.zg_last_error()))
@@ -156,8 +177,11 @@ func (c *Client) CheckBulkPermissions(ctx context.Context, req *v1.CheckBulkPerm
 	}
 	out := (*C.uint8_t)(C.malloc(C.size_t(n)))
 	defer C.free(unsafe.Pointer(out))
-	if rc := C.zg_check_bulk_str(c.engine, arr, C.uint64_t(n), out); rc != 0 {
-		return nil, lastError(rc) // fail closed: pkg/authz/authz.go:93-97 turns any error into a denial
+	if c.broken.Load() {
+		return nil, errBroken
+	}
+	if err := call(func() C.int { return C.zg_check_bulk_str(c.engine, arr, C.uint64_t(n), out) }); err != nil {
+		return nil, err // fail closed: pkg/authz/authz.go:93-97 turns any error into a denial
 	}
 	codesOut := unsafe.Slice((*byte)(unsafe.Pointer(out)), n)
 	for i, it := range req.GetItems() {
@@ -193,6 +217,9 @@ func (c *Client) CheckPermission(ctx context.Context, req *v1.CheckPermissionReq
 // LookupResources: pkg/authz/lookups.go:65-88 reads the stream until io.EOF and keeps
 // LOOKUP_PERMISSIONSHIP_HAS_PERMISSION entries; order is irrelevant (a set).
 func (c *Client) LookupResources(ctx context.Context, req *v1.LookupResourcesRequest, _ ...grpc.CallOption) (v1.PermissionsService_LookupResourcesClient, error) {
+	if c.broken.Load() {
+		return nil, errBroken
+	}
 	var s cstrs
 	defer s.free()
 	subj := req.GetSubject()
@@ -201,17 +228,24 @@ func (c *Client) LookupResources(ctx context.Context, req *v1.LookupResourcesReq
 		buf := (*C.char)(C.malloc(capacity))
 		var need C.size_t
 		var n C.uint64_t
-		rc := C.zg_lookup_resources_str(c.engine, s.add(req.GetResourceObjectType()), s.add(req.GetPermission()),
-			s.add(subj.GetObject().GetObjectType()), s.add(subj.GetObject().GetObjectId()),
-			s.add(subj.GetOptionalRelation()), buf, capacity, &need, &n)
+		var rc C.int
+		err := call(func() C.int {
+			rc = C.zg_lookup_resources_str(c.engine, s.add(req.GetResourceObjectType()), s.add(req.GetPermission()),
+				s.add(subj.GetObject().GetObjectType()), s.add(subj.GetObject().GetObjectId()),
+				s.add(subj.GetOptionalRelation()), buf, capacity, &need, &n)
+			if rc == C.ZG_E2BIG {
+				return 0
+			}
+			return rc
+		})
 		if rc == C.ZG_E2BIG {
 			C.free(unsafe.Pointer(buf))
 			capacity = need + 16
 			continue
 		}
-		if rc != 0 {
+		if err != nil {
 			C.free(unsafe.Pointer(buf))
-			return nil, lastError(rc)
+			return nil, err
 		}
 		ids := strings.Split(strings.TrimSuffix(C.GoString(buf), "\n"), "\n")
 		C.free(unsafe.Pointer(buf))
@@ -258,8 +292,10 @@ func (c *Client) WriteRelationships(ctx context.Context, req *v1.WriteRelationsh
 		return nil, err
 	}
 	if err := c.mirror(req.GetUpdates()); err != nil {
-		// the stores diverged: rebuild the mirror from SpiceDB rather than serve stale answers
+		// the stores diverged (SpiceDB committed, the mirror rejected the batch -- DELETEs included):
+		// rebuild the mirror from SpiceDB rather than serve stale answers
 		if rerr := c.resync(ctx); rerr != nil {
+			c.broken.Store(true)
 			return nil, status.Errorf(codes.Internal, "gpu mirror failed (%v) and resync failed: %v", err, rerr)
 		}
 	}
@@ -289,10 +325,7 @@ func (c *Client) mirror(updates []*v1.RelationshipUpdate) error {
 			ups[i].op = C.ZG_OP_DELETE
 		}
 	}
-	if rc := C.zg_write_relationships(c.engine, arr, C.uint64_t(n), nil, 0); rc != 0 {
-		return lastError(rc)
-	}
-	return nil
+	return call(func() C.int { return C.zg_write_relationships(c.engine, arr, C.uint64_t(n), nil, 0) })
 }
 
 // DeleteRelationships: delegate, then apply the same filter to the mirror.
@@ -307,16 +340,24 @@ func (c *Client) DeleteRelationships(ctx context.Context, req *v1.DeleteRelation
 	defer s.free()
 	var f C.zg_filter_str
 	s.fillFilter(&f, req.GetRelationshipFilter())
-	if rc := C.zg_delete_relationships(c.engine, &f, nil, 0, nil); rc != 0 {
+	if err := call(func() C.int { return C.zg_delete_relationships(c.engine, &f, nil, 0, nil) }); err != nil {
 		if rerr := c.resync(ctx); rerr != nil {
-			return nil, status.Errorf(codes.Internal, "gpu mirror delete failed and resync failed: %v", rerr)
+			c.broken.Store(true)
+			return nil, status.Errorf(codes.Internal, "gpu mirror delete failed (%v) and resync failed: %v", err, rerr)
 		}
 	}
 	return resp, nil
 }
 
-// resync rebuilds the mirror from a full ReadRelationships per resource type.
+// resync rebuilds the mirror from a full ReadRelationships per resource type. The mirror is EMPTIED
+// first: it runs when a mirrored write failed after SpiceDB committed, and a batch that was rejected as a
+// whole may have carried DELETEs -- re-TOUCHing what SpiceDB holds now would leave those revoked grants
+// in place (fail-open). Until the rebuilt snapshot is published nothing is visible: zg_clear_relationships
+// publishes the empty store, so a check that races the rebuild is denied, not wrongly allowed.
 func (c *Client) resync(ctx context.Context) error {
+	if err := call(func() C.int { return C.zg_clear_relationships(c.engine) }); err != nil {
+		return err
+	}
 	nTypes := int(C.zg_num_types(c.engine))
 	for t := 0; t < nTypes; t++ {
 		typeName := C.GoString(C.zg_type_name(c.engine, C.int(t)))
@@ -355,9 +396,10 @@ func (c *Client) resync(ctx context.Context) error {
 			return err
 		}
 	}
-	if rc := C.zg_publish(c.engine); rc != 0 {
-		return lastError(rc)
+	if err := call(func() C.int { return C.zg_publish(c.engine) }); err != nil {
+		return err
 	}
+	c.broken.Store(false)
 	return nil
 }
 
@@ -403,10 +445,14 @@ func (c *Client) FilterListResponse(body []byte, tpls []ListTemplate) ([]byte, e
 	}
 	out := make([]byte, len(body)+8) // the filtered body is never longer than body + 2
 	var outLen C.size_t
-	rc := C.zg_list_postfilter(c.engine, (*C.char)(unsafe.Pointer(&body[0])), C.size_t(len(body)), tp, C.uint32_t(len(ct)),
-		(*C.char)(unsafe.Pointer(&out[0])), C.size_t(len(out)), &outLen)
-	if rc != 0 {
-		return nil, fmt.Errorf("failed to filter items with bulk permissions: %w", lastError(rc))
+	if c.broken.Load() {
+		return nil, errBroken
+	}
+	if err := call(func() C.int {
+		return C.zg_list_postfilter(c.engine, (*C.char)(unsafe.Pointer(&body[0])), C.size_t(len(body)), tp, C.uint32_t(len(ct)),
+			(*C.char)(unsafe.Pointer(&out[0])), C.size_t(len(out)), &outLen)
+	}); err != nil {
+		return nil, fmt.Errorf("failed to filter items with bulk permissions: %w", err)
 	}
 	return out[:outLen], nil
 }

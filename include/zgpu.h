@@ -149,8 +149,14 @@ typedef struct {
 /* ---- lifecycle --------------------------------------------------------- */
 int zg_engine_create(const zg_config *cfg, zg_engine **out);
 void zg_engine_destroy(zg_engine *e);
-/* Thread-local message of the last failing call on this thread. */
+/* Message of the last failing call ON THE CALLING THREAD (thread-local, so concurrent callers never see
+ * each other's text). A caller whose runtime migrates it between OS threads from one foreign call to the
+ * next (Go) must fetch it on the thread of the failing call: pin the goroutine around the pair
+ * (runtime.LockOSThread; go/gpuauthz/client.go `call`) or wrap call + zg_last_error_copy in one C
+ * function of the cgo preamble. zg_last_error_copy writes at most cap - 1 bytes + NUL into buf and
+ * returns the full length of the message. */
 const char *zg_last_error(void);
+size_t zg_last_error_copy(char *buf, size_t cap);
 
 /* ---- schema (SpiceDB schema DSL subset; pkg/spicedb/bootstrap.yaml) ----- */
 int zg_load_schema(zg_engine *e, const char *dsl, size_t len);
@@ -177,6 +183,10 @@ int zg_load_tuples(zg_engine *e, const zg_tuple *t, const uint32_t *expires, uin
 int zg_apply_updates(zg_engine *e, const zg_update *u, uint64_t n);
 /* Builds the CSR snapshot in HBM and makes it the one every later check sees. */
 int zg_publish(zg_engine *e);
+/* Drops every relationship (interned names and ids stay) and publishes the empty store: what a caller
+ * that mirrors another source of truth does before re-loading it (go/gpuauthz resync). The watch feed
+ * restarts at the new revision. */
+int zg_clear_relationships(zg_engine *e);
 uint64_t zg_num_tuples(const zg_engine *e);
 /* Clock used for expiration; 0 = wall clock (default). */
 void zg_set_clock(zg_engine *e, int64_t unix_seconds);

@@ -102,6 +102,15 @@ static int fail(int code, const std::string& msg) {
   return code;
 }
 extern "C" const char* zg_last_error(void) { return g_err.c_str(); }
+extern "C" size_t zg_last_error_copy(char* buf, size_t cap) {
+  const size_t n = g_err.size();
+  if (buf && cap) {
+    const size_t m = n < cap - 1 ? n : cap - 1;
+    std::memcpy(buf, g_err.data(), m);
+    buf[m] = 0;
+  }
+  return n;
+}
 
 static uint32_t now_of(const zg_engine* e) {
   return static_cast<uint32_t>(e->clock ? e->clock : static_cast<int64_t>(time(nullptr)));
@@ -268,6 +277,17 @@ extern "C" int zg_publish(zg_engine* e) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   std::lock_guard<std::mutex> g(e->mu);
   return publish_locked(e);
+}
+extern "C" int zg_clear_relationships(zg_engine* e) {
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);
+  std::lock_guard<std::mutex> g(e->mu);
+  e->store.clear_relationships();
+  e->dirty = true;
+  // the feed cannot describe "everything went away" change by change: readers restart from here
+  e->watch_log.clear();
+  int rc = publish_locked(e);
+  e->watch_floor = e->revision;
+  return rc;
 }
 extern "C" uint64_t zg_num_tuples(const zg_engine* e) {
   if (!e || !e->has_schema) return 0;
@@ -1061,8 +1081,11 @@ extern "C" int zg_list_postfilter(zg_engine* e, const char* body, size_t len, co
   return rc == ZG_EINVAL ? fail(rc, "zg_list_filter: inconsistent item ranges") : rc;
 }
 
+// *self_member (optional): the subject is a never-written userset T:x#r (subj == ZG_NO_OBJECT - 1) that is
+// nevertheless a member of T:x#perm (r is perm itself or a relation inlined into its union).
 static int lookup_locked(zg_engine* e, uint16_t res_type, uint16_t perm, uint16_t stype, uint32_t subj, uint16_t srel,
-                         std::vector<uint32_t>* ids) {
+                         std::vector<uint32_t>* ids, bool* self_member = nullptr) {
+  if (self_member) *self_member = false;
   const Schema& sc = e->schema;
   if (res_type >= sc.types.size() || perm >= sc.slots.size() || sc.slots[perm].type != res_type)
     return fail(ZG_EINVAL, "unknown resource type or permission");
@@ -1082,6 +1105,15 @@ static int lookup_locked(zg_engine* e, uint16_t res_type, uint16_t perm, uint16_
   key.stype = stype;
   key.srel = srel;
   key.clock = e->clock ? e->clock : -static_cast<int64_t>(e->dev.now);  // wall clock: valid within the same second
+  if (self_member && srel != kNone && stype == res_type && subj >= ZG_NO_OBJECT - 1) {
+    zg_check self = proto;
+    self.res = self.subj = ZG_NO_OBJECT;  // the same never-written object on both sides
+    uint8_t code = 0;
+    std::string cerr;
+    int crc = e->dev.check_host(&self, 1, &code, &cerr);
+    if (crc) return fail(crc, cerr);
+    *self_member = code == ZG_HAS_PERMISSION;
+  }
   if (key == e->last_lookup_key) {
     *ids = e->last_lookup_ids;
     return ZG_OK;
@@ -1089,10 +1121,17 @@ static int lookup_locked(zg_engine* e, uint16_t res_type, uint16_t perm, uint16_
   std::string err;
   int rc = e->dev.lookup(res_type, proto, ids, &err);
   if (rc) return fail(rc, err);
-  // a userset subject res_type:x#perm is a member of itself even without relationships
-  if (srel == perm && stype == res_type && subj < ZG_NO_OBJECT - 1 &&
-      !std::binary_search(ids->begin(), ids->end(), subj))
-    ids->insert(std::upper_bound(ids->begin(), ids->end(), subj), subj);
+  // A userset subject T:x#r is a member of T:x#P for every relation r inlined into P's union, with or
+  // without relationships, and the reverse walk only reaches x through stored edges: ask the check
+  // kernel about the one candidate res = subj (Check is the arbiter of LookupResources everywhere else).
+  if (srel != kNone && stype == res_type && subj < ZG_NO_OBJECT - 1 && !std::binary_search(ids->begin(), ids->end(), subj)) {
+    zg_check self = proto;
+    self.res = subj;
+    uint8_t code = 0;
+    rc = e->dev.check_host(&self, 1, &code, &err);
+    if (rc) return fail(rc, err);
+    if (code == ZG_HAS_PERMISSION) ids->insert(std::upper_bound(ids->begin(), ids->end(), subj), subj);
+  }
   e->last_lookup_key = key;
   e->last_lookup_ids = *ids;
   return ZG_OK;
@@ -1137,8 +1176,9 @@ extern "C" int zg_lookup_resources_str(zg_engine* e, const char* res_type, const
   }
   uint32_t su = e->store.find(st, subj_id);
   std::vector<uint32_t> ids;
+  bool self_member = false;
   rc = lookup_locked(e, static_cast<uint16_t>(rt), static_cast<uint16_t>(p), static_cast<uint16_t>(st),
-                     su == ZG_NO_OBJECT ? ZG_NO_OBJECT - 1 : su, sr, &ids);
+                     su == ZG_NO_OBJECT ? ZG_NO_OBJECT - 1 : su, sr, &ids, &self_member);
   if (rc) return rc;
   std::vector<std::string> names;
   for (uint32_t id : ids) {
@@ -1146,7 +1186,7 @@ extern "C" int zg_lookup_resources_str(zg_engine* e, const char* res_type, const
     names.push_back(e->store.name(rt, id, &n) ? std::string(n) : std::to_string(id));
   }
   // never-written userset subject that names itself
-  if (su == ZG_NO_OBJECT && sr == p && st == rt) names.push_back(subj_id);
+  if (su == ZG_NO_OBJECT && self_member) names.push_back(subj_id);
   size_t total = 1;
   for (const auto& n : names) total += n.size() + 1;
   if (need) *need = total;
@@ -1232,10 +1272,11 @@ extern "C" int zg_list_prefilter(zg_engine* e, const char* body, size_t len, uin
       sr = static_cast<uint16_t>(s2);
     }
     const uint32_t su = e->store.find(st, tpl->subj_id);
+    bool self_member = false;
     rc = lookup_locked(e, static_cast<uint16_t>(rt), static_cast<uint16_t>(p), static_cast<uint16_t>(st),
-                       su == ZG_NO_OBJECT ? ZG_NO_OBJECT - 1 : su, sr, &ids);
+                       su == ZG_NO_OBJECT ? ZG_NO_OBJECT - 1 : su, sr, &ids, &self_member);
     if (rc) return rc;
-    if (su == ZG_NO_OBJECT && sr == p && st == rt) self = tpl->subj_id;  // never-written userset subject naming itself
+    if (su == ZG_NO_OBJECT && self_member) self = tpl->subj_id;  // never-written userset subject naming itself
     // lookups.go:106-109: an id that yields no name fails the whole pre-filter
     for (uint32_t id : ids) {
       std::string_view nm;

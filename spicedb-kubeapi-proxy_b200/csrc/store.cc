@@ -17,6 +17,14 @@ void Store::reset(const Schema* s) {
   live_ = 0;
 }
 
+void Store::clear_relationships() {
+  tuples.clear();
+  expires.clear();
+  index_.clear();
+  indexed_ = true;
+  live_ = 0;
+}
+
 static inline uint64_t hash_bytes(const char* s, size_t n) {
   uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xD6E8FEB86659FD93ull);
   while (n >= 8) {

@@ -53,6 +53,8 @@ struct HostSnapshot {
 class Store {
  public:
   void reset(const Schema* s);
+  // Drops every relationship; interned object names (and therefore ids) stay.
+  void clear_relationships();
 
   uint32_t intern(int type, const std::string& id);
   uint32_t find(int type, const std::string& id) const;  // ZG_NO_OBJECT
