@@ -144,6 +144,9 @@ typedef struct {
   double last_kernel_ms;    /* device time of the last hot-path call              */
   uint64_t coalesced_launches; /* launches that answered more than one concurrent caller */
   uint64_t coalesced_requests; /* zg_check_bulk calls answered by those launches         */
+  uint64_t stack_spills;       /* warp stacks that overflowed shared memory into HBM     */
+  uint64_t memo_batches;       /* 32-check batches that switched the path memo on        */
+  uint64_t split_batches;      /* batches answered in halves (sub-query buffer overflow) */
 } zg_stats;
 
 /* ---- lifecycle --------------------------------------------------------- */

@@ -211,6 +211,6 @@ class MiniOracle:
 
     def lookup_resources(self, rt, perm, st, sid, srel="", now=0):
         cands = {rid for (t, rid, rl) in self.rows if t == rt and self._live(t, rid, rl, now)}
-        if srel not in ("", "...", None) and st == rt and srel == perm:
-            cands.add(sid)  # a userset subject rt:x#perm is a member of itself
+        if srel not in ("", "...", None) and st == rt:
+            cands.add(sid)  # a userset subject rt:x#r may be a member of rt:x#perm with no relationship at all
         return [r for r in sorted(cands) if self.check(rt, r, perm, st, sid, srel, now) == HAS]

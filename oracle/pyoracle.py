@@ -215,8 +215,9 @@ class Oracle:
         ids = self.lookup_resources_ids(res_type, perm, subj_type, 0xFFFFFFFE if u < 0 else u,
                                         subj_rel or None, now)
         names = [self.object_name(res_type, int(i)) for i in ids]
-        if u < 0 and subj_rel and subj_type == res_type and subj_rel == perm:
-            names.append(subj_id)  # never-written userset subject that names itself
+        if u < 0 and subj_rel and subj_type == res_type and \
+                self.check(res_type, subj_id, perm, subj_type, subj_id, subj_rel, now) == 2:
+            names.append(subj_id)  # never-written userset subject that is a member of its own permission
         return names
 
     def read(self, res_type="", res_id="", rel="", subj_type="", subj_id="", subj_rel="", now=0):

@@ -60,7 +60,8 @@ TPL_CLEAR_NAMESPACE = 1
 class _Stats(C.Structure):
     _fields_ = [("checks", C.c_uint64), ("launches", C.c_uint64), ("passes", C.c_uint64), ("tuples", C.c_uint64),
                 ("snapshot_bytes", C.c_uint64), ("revision", C.c_uint64), ("last_alg_bytes", C.c_uint64),
-                ("last_kernel_ms", C.c_double), ("coalesced_launches", C.c_uint64), ("coalesced_requests", C.c_uint64)]
+                ("last_kernel_ms", C.c_double), ("coalesced_launches", C.c_uint64), ("coalesced_requests", C.c_uint64),
+                ("stack_spills", C.c_uint64), ("memo_batches", C.c_uint64), ("split_batches", C.c_uint64)]
 
 
 class _ListItem(C.Structure):

@@ -1328,6 +1328,8 @@ extern "C" int zg_stats_get(zg_engine* e, zg_stats* out) {
   out->last_kernel_ms = e->dev.last_ms;
   out->coalesced_launches = e->dev.coalesced_launches;
   out->coalesced_requests = e->dev.coalesced_requests;
+  out->split_batches = e->dev.split_batches;
+  if (!e->host_only) e->dev.read_events(&out->stack_spills, &out->memo_batches);
   if (e->dev.snap) {
     out->tuples = e->dev.snap->n_tuples;
     out->snapshot_bytes = e->dev.snap->bytes;

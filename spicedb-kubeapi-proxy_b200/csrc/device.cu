@@ -72,6 +72,12 @@ Device::~Device() {
   rb_cand_.release();
   if (pin_in_) cudaFreeHost(pin_in_);
   if (pin_out_) cudaFreeHost(pin_out_);
+  if (pin_ready_) cudaFreeHost(pin_ready_);
+  if (cstream_) {
+    cudaStreamSynchronize(cstream_);
+    cudaStreamDestroy(cstream_);
+  }
+  if (ev_reset_) cudaEventDestroy(ev_reset_);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
   if (last_done_) cudaEventDestroy(last_done_);
@@ -105,10 +111,14 @@ std::string Device::init(int dev, uint64_t subq_cap, uint32_t budget) {
   cudaEventCreate(&ev0_);
   cudaEventCreate(&ev1_);
   cudaEventCreateWithFlags(&last_done_, cudaEventDisableTiming);
+  if ((e = cudaStreamCreateWithFlags(&cstream_, cudaStreamNonBlocking)) != cudaSuccess)
+    return std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+  cudaEventCreateWithFlags(&ev_reset_, cudaEventDisableTiming);
+  if (const char* v = std::getenv("ZGPU_NO_STREAM_H2D")) stream_h2d = !(*v && *v != '0');
   if (subq_cap) subq_cap_ = subq_cap;
   if (budget) budget_ = budget;
-  if (!ctrl_.ensure(64)) return "out of device memory";
-  cudaMemset(ctrl_.p, 0, 64);
+  if (!ctrl_.ensure(128)) return "out of device memory";
+  cudaMemset(ctrl_.p, 0, 128);
   return "";
 }
 
@@ -246,11 +256,14 @@ std::string Device::finish_publish(std::shared_ptr<Snapshot> s, const HostSnapsh
     if (sm > attr_bytes) {
       cudaFuncSetAttribute(check_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
       cudaFuncSetAttribute(check_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+      cudaFuncSetAttribute(check_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
       attr_bytes = sm;
     }
   }
-  int occ = 0, occ_c = 0;
+  int occ = 0, occ_c = 0, occ_s = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, check_kernel<false>, kThreads, sm);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, check_kernel<false, true>, kThreads, sm);
+  if (occ_s < occ) occ = occ_s;  // one grid size serves both
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, check_kernel<true>, kThreads, sm);
   if (occ < 1 || occ_c < 1) return "check kernel cannot be resident (occupancy 0)";
   blocks_per_sm_ = occ;
@@ -265,8 +278,10 @@ std::string Device::finish_publish(std::shared_ptr<Snapshot> s, const HostSnapsh
 }
 
 int Device::run_pass(const Snapshot& s, const zg_check* queries, uint64_t nq, uint8_t* val, uint8_t* out, bool final_codes,
-                     bool raw, zg_check* subq, uint32_t* subq_parent, cudaStream_t st, bool count, std::string* err) {
+                     bool raw, zg_check* subq, uint32_t* subq_parent, cudaStream_t st, bool count, std::string* err,
+                     const unsigned long long* ready) {
   KParams p{};
+  p.ready = ready;
   p.row_ptr = s.row_ptr.as<uint32_t>();
   p.col = s.col.as<uint32_t>();
   p.exp = s.exp.p ? s.exp.as<uint32_t>() : nullptr;
@@ -286,6 +301,7 @@ int Device::run_pass(const Snapshot& s, const zg_check* queries, uint64_t nq, ui
   p.subq_count = ctrl + 1;
   p.alg_bytes = ctrl + 2;
   p.flags = reinterpret_cast<uint32_t*>(ctrl + 3);
+  p.events = ctrl + 8;
   p.spill = spill_.as<uint4>();
   p.spill_cap = spill_cap_;
   p.subq = subq;
@@ -306,10 +322,20 @@ int Device::run_pass(const Snapshot& s, const zg_check* queries, uint64_t nq, ui
   if (grid < 1) grid = 1;
   size_t sm = smem_bytes(s.prog_bytes);
   if (count) check_kernel<true><<<grid, kThreads, sm, st>>>(p);
+  else if (ready) check_kernel<false, true><<<grid, kThreads, sm, st>>>(p);
   else check_kernel<false><<<grid, kThreads, sm, st>>>(p);
   ZG_CUDA(cudaGetLastError());
   ++launches;
   return ZG_OK;
+}
+
+void Device::read_events(uint64_t* spills, uint64_t* memo_batches) {
+  unsigned long long ev[2] = {0, 0};
+  if (ctrl_.p && cudaSetDevice(device) == cudaSuccess &&
+      cudaMemcpyAsync(ev, ctrl_.as<unsigned long long>() + 8, sizeof ev, cudaMemcpyDeviceToHost, stream) == cudaSuccess)
+    cudaStreamSynchronize(stream);
+  *spills = ev[0];
+  *memo_batches = ev[1];
 }
 
 void Device::finish_timing() {
@@ -322,7 +348,7 @@ void Device::finish_timing() {
 }
 
 int Device::check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cudaStream_t st, bool raw_items,
-                         uint64_t* count_bytes, std::string* err, bool top) {
+                         uint64_t* count_bytes, std::string* err, bool top, const unsigned long long* ready) {
   std::shared_ptr<Snapshot> s = snap;
   if (!s) {
     if (err) *err = "no snapshot published (call zg_publish after loading relationships)";
@@ -346,7 +372,7 @@ int Device::check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cu
   int rc = ZG_OK;
   if (!s->has_nonpure) {
     // every slot is a relation or a pure union: one leaf per check, answered in one launch
-    rc = run_pass(*s, d_items, n, nullptr, d_out, true, raw_items, nullptr, nullptr, st, count, err);
+    rc = run_pass(*s, d_items, n, nullptr, d_out, true, raw_items, nullptr, nullptr, st, count, err, ready);
     if (rc) return rc;
   } else {
     if (n * L >= (1ull << 32)) {
@@ -385,7 +411,7 @@ int Device::check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cu
       // Level 0 writes the v1 codes straight into d_out: when the pass raises no sub-query (the
       // common case: edges into a non-pure permission are rare) they are final and nothing is folded.
       rc = run_pass(*s, queries, cur, val_[lv].as<uint8_t>(), lv == 0 ? d_out : nullptr, true, raw,
-                    q_[lv + 1].as<zg_check>(), parent_[lv + 1].as<uint32_t>(), st, count, err);
+                    q_[lv + 1].as<zg_check>(), parent_[lv + 1].as<uint32_t>(), st, count, err, lv == 0 ? ready : nullptr);
       if (rc) return rc;
       unsigned long long host_ctrl[4];
       ZG_CUDA(cudaMemcpyAsync(host_ctrl, ctrl, sizeof host_ctrl, cudaMemcpyDeviceToHost, st));
@@ -398,6 +424,7 @@ int Device::check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cu
           return ZG_ENOMEM;
         }
         const uint64_t half = n / 2;
+        ++split_batches;
         int r1 = check_device(d_items, half, d_out, st, raw_items, nullptr, err, false);
         if (r1) return r1;
         return check_device(d_items + half, n - half, d_out + half, st, raw_items, nullptr, err, false);
@@ -438,56 +465,18 @@ int Device::check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cu
 }
 
 int Device::check_host(const zg_check* items, uint64_t n, uint8_t* out, std::string* err) {
-  if (n == 0) return ZG_OK;
-  ZG_CUDA(cudaSetDevice(device));
-  if (!stage_in_.ensure(n * sizeof(zg_check)) || !stage_out_.ensure(n)) {
-    if (err) *err = "out of device memory (staging)";
-    return ZG_ENOMEM;
-  }
-  // Pinned caller buffers (zg_host_alloc) are copied straight from/to; pageable
-  // ones go through the engine's pinned staging area.
-  cudaPointerAttributes a{};
-  const bool in_pinned = cudaPointerGetAttributes(&a, items) == cudaSuccess && a.type == cudaMemoryTypeHost;
-  const bool out_pinned = cudaPointerGetAttributes(&a, out) == cudaSuccess && a.type == cudaMemoryTypeHost;
-  cudaGetLastError();
-  const void* src = items;
-  if (!in_pinned) {
-    if (pin_in_cap_ < n * sizeof(zg_check)) {
-      if (pin_in_) cudaFreeHost(pin_in_);
-      pin_in_cap_ = 0;
-      ZG_CUDA(cudaMallocHost(&pin_in_, n * sizeof(zg_check)));
-      pin_in_cap_ = n * sizeof(zg_check);
-    }
-    std::memcpy(pin_in_, items, n * sizeof(zg_check));
-    src = pin_in_;
-  }
-  void* dst = out;
-  if (!out_pinned) {
-    if (pin_out_cap_ < n) {
-      if (pin_out_) cudaFreeHost(pin_out_);
-      pin_out_cap_ = 0;
-      ZG_CUDA(cudaMallocHost(&pin_out_, n));
-      pin_out_cap_ = n;
-    }
-    dst = pin_out_;
-  }
-  ZG_CUDA(cudaMemcpyAsync(stage_in_.p, src, n * sizeof(zg_check), cudaMemcpyHostToDevice, stream));
-  int rc = check_device(stage_in_.as<zg_check>(), n, stage_out_.as<uint8_t>(), stream, true, nullptr, err);
-  if (rc) return rc;
-  ZG_CUDA(cudaMemcpyAsync(dst, stage_out_.p, n, cudaMemcpyDeviceToHost, stream));
-  uint32_t flags = 0;
-  ZG_CUDA(cudaMemcpyAsync(&flags, ctrl_.as<unsigned long long>() + 3, 4, cudaMemcpyDeviceToHost, stream));
-  ZG_CUDA(cudaStreamSynchronize(stream));
-  if (flags & 1u) {
-    if (err) *err = "expansion stack overflow (per-warp spill area exhausted)";
-    return ZG_ENOMEM;
-  }
-  if (!out_pinned) std::memcpy(out, pin_out_, n);
-  return ZG_OK;
+  std::vector<HostReq> one{{items, n, out}};
+  return check_host_multi(one, err);
 }
 
+// One launch sequence for the requests of one or several callers (see Batcher in capi.cu).
+//
+// Host buffers -> answers, copies included. Large inputs are STREAMED: the items go up in chunks on a copy
+// stream, each chunk followed by an 8-byte copy of "items landed so far" into the word the kernel polls, and
+// the check kernel -- launched once, persistent -- starts on the first chunk while the rest is still on the
+// PCIe bus (warps wait for their batch: KParams::ready). H2D and the kernel overlap without per-chunk
+// launches, whose tails cost more than the copies ("tried and reverted").
 int Device::check_host_multi(const std::vector<HostReq>& reqs, std::string* err) {
-  if (reqs.size() == 1) return check_host(reqs[0].items, reqs[0].n, reqs[0].out, err);
   uint64_t total = 0;
   for (const auto& r : reqs) total += r.n;
   if (total == 0) return ZG_OK;
@@ -496,41 +485,113 @@ int Device::check_host_multi(const std::vector<HostReq>& reqs, std::string* err)
     if (err) *err = "out of device memory (staging)";
     return ZG_ENOMEM;
   }
-  if (pin_in_cap_ < total * sizeof(zg_check)) {
+  // Pinned caller buffers (zg_host_alloc) are copied straight from/to; pageable ones and the requests of
+  // several callers go through the engine's pinned staging area.
+  cudaPointerAttributes a{};
+  const bool single = reqs.size() == 1;
+  const bool in_pinned = single && cudaPointerGetAttributes(&a, reqs[0].items) == cudaSuccess && a.type == cudaMemoryTypeHost;
+  const bool out_pinned = single && cudaPointerGetAttributes(&a, reqs[0].out) == cudaSuccess && a.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (!in_pinned && pin_in_cap_ < total * sizeof(zg_check)) {
     if (pin_in_) cudaFreeHost(pin_in_);
     pin_in_cap_ = 0;
     ZG_CUDA(cudaMallocHost(&pin_in_, total * sizeof(zg_check)));
     pin_in_cap_ = total * sizeof(zg_check);
   }
-  if (pin_out_cap_ < total) {
+  if (!out_pinned && pin_out_cap_ < total) {
     if (pin_out_) cudaFreeHost(pin_out_);
     pin_out_cap_ = 0;
     ZG_CUDA(cudaMallocHost(&pin_out_, total));
     pin_out_cap_ = total;
   }
-  uint64_t off = 0;
-  for (const auto& r : reqs) {
-    std::memcpy(static_cast<zg_check*>(pin_in_) + off, r.items, r.n * sizeof(zg_check));
-    off += r.n;
+  unsigned long long* d_ready = ctrl_.as<unsigned long long>() + 10;
+  const bool streamed = stream_h2d && total >= kStreamMinItems;
+  const unsigned long long* ready_arg = nullptr;
+  if (!streamed) {
+    const void* src = reqs[0].items;
+    if (!in_pinned) {
+      uint64_t off = 0;
+      for (const auto& r : reqs) {
+        std::memcpy(static_cast<zg_check*>(pin_in_) + off, r.items, r.n * sizeof(zg_check));
+        off += r.n;
+      }
+      src = pin_in_;
+    }
+    ZG_CUDA(cudaMemcpyAsync(stage_in_.p, src, total * sizeof(zg_check), cudaMemcpyHostToDevice, stream));
+  } else {
+    // copy stream: after the previous call (it may still read stage_in_ / the ready word), reset the word,
+    // then chunk, count, chunk, count ... ; the compute stream only waits for the reset
+    const uint64_t n_chunks = (total + kStreamChunkItems - 1) / kStreamChunkItems;
+    if (pin_ready_cap_ < n_chunks) {
+      if (pin_ready_) cudaFreeHost(pin_ready_);
+      pin_ready_cap_ = 0;
+      ZG_CUDA(cudaMallocHost(&pin_ready_, n_chunks * 8));
+      pin_ready_cap_ = n_chunks;
+    }
+    if (have_last_) ZG_CUDA(cudaStreamWaitEvent(cstream_, last_done_, 0));
+    ZG_CUDA(cudaMemsetAsync(d_ready, 0, 8, cstream_));
+    ZG_CUDA(cudaEventRecord(ev_reset_, cstream_));
+    ZG_CUDA(cudaStreamWaitEvent(stream, ev_reset_, 0));
+    size_t ri = 0;          // request being gathered
+    uint64_t roff = 0;      // items of it already gathered
+    for (uint64_t ck = 0; ck < n_chunks; ++ck) {
+      const uint64_t b = ck * kStreamChunkItems, e = std::min(total, b + kStreamChunkItems);
+      const zg_check* src;
+      if (in_pinned) {
+        src = reqs[0].items + b;
+      } else {
+        zg_check* dst = static_cast<zg_check*>(pin_in_) + b;
+        uint64_t need = e - b, w = 0;
+        while (need) {
+          const uint64_t take = std::min(need, reqs[ri].n - roff);
+          std::memcpy(dst + w, reqs[ri].items + roff, take * sizeof(zg_check));
+          w += take;
+          roff += take;
+          need -= take;
+          if (roff == reqs[ri].n) {
+            ++ri;
+            roff = 0;
+          }
+        }
+        src = dst;
+      }
+      ZG_CUDA(cudaMemcpyAsync(stage_in_.as<zg_check>() + b, src, (e - b) * sizeof(zg_check), cudaMemcpyHostToDevice, cstream_));
+      pin_ready_[ck] = e;
+      ZG_CUDA(cudaMemcpyAsync(d_ready, pin_ready_ + ck, 8, cudaMemcpyHostToDevice, cstream_));
+    }
+    ready_arg = d_ready;
+    ++streamed_calls;
   }
-  ZG_CUDA(cudaMemcpyAsync(stage_in_.p, pin_in_, total * sizeof(zg_check), cudaMemcpyHostToDevice, stream));
-  int rc = check_device(stage_in_.as<zg_check>(), total, stage_out_.as<uint8_t>(), stream, true, nullptr, err);
-  if (rc) return rc;
-  ZG_CUDA(cudaMemcpyAsync(pin_out_, stage_out_.p, total, cudaMemcpyDeviceToHost, stream));
+  int rc = check_device(stage_in_.as<zg_check>(), total, stage_out_.as<uint8_t>(), stream, true, nullptr, err, true, ready_arg);
+  if (rc) {
+    if (streamed) cudaStreamSynchronize(cstream_);  // nothing of this call may still be in flight
+    return rc;
+  }
+  void* dst = out_pinned ? static_cast<void*>(reqs[0].out) : pin_out_;
+  ZG_CUDA(cudaMemcpyAsync(dst, stage_out_.p, total, cudaMemcpyDeviceToHost, stream));
   uint32_t flags = 0;
   ZG_CUDA(cudaMemcpyAsync(&flags, ctrl_.as<unsigned long long>() + 3, 4, cudaMemcpyDeviceToHost, stream));
   ZG_CUDA(cudaStreamSynchronize(stream));
+  if (streamed) ZG_CUDA(cudaStreamSynchronize(cstream_));
+  if (flags & 32u) {
+    if (err) *err = "host-to-device copy of the request stalled (streamed admission timed out)";
+    return ZG_ECUDA;
+  }
   if (flags & 1u) {
     if (err) *err = "expansion stack overflow (per-warp spill area exhausted)";
     return ZG_ENOMEM;
   }
-  off = 0;
-  for (const auto& r : reqs) {
-    std::memcpy(r.out, static_cast<uint8_t*>(pin_out_) + off, r.n);
-    off += r.n;
+  if (!out_pinned) {
+    uint64_t off = 0;
+    for (const auto& r : reqs) {
+      std::memcpy(r.out, static_cast<uint8_t*>(pin_out_) + off, r.n);
+      off += r.n;
+    }
   }
-  ++coalesced_launches;
-  coalesced_requests += reqs.size();
+  if (!single) {
+    ++coalesced_launches;
+    coalesced_requests += reqs.size();
+  }
   return ZG_OK;
 }
 

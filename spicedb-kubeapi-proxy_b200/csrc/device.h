@@ -54,7 +54,7 @@ class Device {
   // d_items / d_out are device pointers. count_bytes != nullptr selects the
   // instrumented kernel variant. Returns ZG_* and fills err.
   int check_device(const zg_check* d_items, uint64_t n, uint8_t* d_out, cudaStream_t st, bool raw_items,
-                   uint64_t* count_bytes, std::string* err, bool top = true);
+                   uint64_t* count_bytes, std::string* err, bool top = true, const unsigned long long* ready = nullptr);
   int check_host(const zg_check* items, uint64_t n, uint8_t* out, std::string* err);
   // Several callers' requests answered by ONE launch sequence (see Batcher in capi.cu).
   struct HostReq {
@@ -80,6 +80,11 @@ class Device {
   int device = 0;
   uint64_t launches = 0, passes = 0, checks = 0;
   uint64_t coalesced_launches = 0, coalesced_requests = 0;
+  uint64_t streamed_calls = 0;  // host calls whose items were streamed in behind the running kernel
+  bool stream_h2d = true;       // ZGPU_NO_STREAM_H2D=1: one copy, then the kernel (A/B measurement)
+  uint64_t split_batches = 0;  // batches answered in halves because their sub-queries overflowed the pass buffer
+  // cumulative device-side event counters: stack spills to HBM, batches that switched the path memo on
+  void read_events(uint64_t* spills, uint64_t* memo_batches);
   uint64_t lookups_rbfs = 0, lookups_exhaustive = 0, lookups_flat = 0;
   bool use_rbfs = true;  // ZGPU_NO_RBFS=1: LookupResources checks every resource of the type  // batcher: launches that served > 1 caller
   double last_ms = 0;
@@ -92,7 +97,8 @@ class Device {
   // One check_kernel launch over `nq` queries: val (may be null) receives the per-(query, leaf) value
   // bits, out (may be null) the per-query v1 codes / value bits.
   int run_pass(const Snapshot& s, const zg_check* queries, uint64_t nq, uint8_t* val, uint8_t* out, bool final_codes,
-               bool raw, zg_check* subq, uint32_t* subq_parent, cudaStream_t st, bool count, std::string* err);
+               bool raw, zg_check* subq, uint32_t* subq_parent, cudaStream_t st, bool count, std::string* err,
+               const unsigned long long* ready = nullptr);
   int sm_count_ = 0, blocks_per_sm_ = 0, blocks_per_sm_count_ = 0;
   uint32_t spill_cap_ = 4096, budget_ = 1u << 20;
   uint64_t subq_cap_ = 1ull << 22;
@@ -107,6 +113,13 @@ class Device {
   // Reverse-BFS candidates of type res_type for the subject in proto; *overflow -> use the exhaustive list.
   int lookup_candidates(const Snapshot& s, uint16_t res_type, const zg_check& proto, uint64_t* n_cand, bool* overflow,
                         std::string* err);
+  // streamed admission (check_host_multi): copy stream, "reset done" event, pinned per-chunk counters
+  cudaStream_t cstream_ = nullptr;
+  cudaEvent_t ev_reset_ = nullptr;
+  unsigned long long* pin_ready_ = nullptr;
+  size_t pin_ready_cap_ = 0;
+  static constexpr uint64_t kStreamChunkItems = 1ull << 17;  // 2 MB of items per chunk
+  static constexpr uint64_t kStreamMinItems = 1ull << 18;    // smaller calls: one plain copy
   void* pin_in_ = nullptr;
   void* pin_out_ = nullptr;
   size_t pin_in_cap_ = 0, pin_out_cap_ = 0;

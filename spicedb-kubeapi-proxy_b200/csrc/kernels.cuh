@@ -90,6 +90,11 @@ struct KParams {
   uint32_t shard_count;   // 0 / 1 = not sharded
   uint32_t shard_rank;
   unsigned long long* alg_bytes;  // COUNT variant only
+  unsigned long long* events;     // [0] stack spills, [1] batches that switched the path memo on (cumulative)
+  // Streamed admission: the queries are still being copied from the host while the kernel runs. *ready =
+  // number of leading queries that have landed (a 8-byte copy enqueued after each chunk on the copy stream);
+  // a warp waits until its batch is there. nullptr: everything is resident.
+  const unsigned long long* ready;
 };
 
 // View of the program blob. Only the base pointer is kept in registers; table addresses are
@@ -139,6 +144,7 @@ struct WarpCtx {
   unsigned long long my_cst;  // class boundaries of this lane's own job (see cst_at)
   unsigned inv_mask;  // jobs whose reverse rows fit
   unsigned long long bytes;
+  unsigned long long* events;
   bool fatal;
   unsigned lane;
 };
@@ -152,6 +158,7 @@ __device__ __forceinline__ void spill_half(WarpCtx<COUNT>& c) {
     return;
   }
   for (int i = c.lane; i < H; i += 32) c.spill[c.spill_top + i] = c.stack[i];
+  if (c.lane == 0) atomicAdd(c.events, 1ull);
   __syncwarp();
   int rest = c.top - H;  // <= H: read [H, top) and write [0, rest) never overlap
   uint4 t0, t1;
@@ -440,10 +447,26 @@ __device__ __forceinline__ uint32_t eval_tree(const Prog& pr, const DTree& t, un
   return static_cast<uint32_t>(st & 3u);
 }
 
+// Streamed admission: spin until `need` leading queries have landed. If the feed stopped (a failed copy) give
+// up after seconds instead of hanging the device: the flag fails the host call, whatever is answered from
+// there on is discarded.
+__device__ __noinline__ void wait_ready(const unsigned long long* ready, unsigned long long need, uint32_t* flags) {
+  const volatile unsigned long long* rd = ready;
+  uint32_t spins = 0;
+  while (*rd < need && spins < (1u << 23)) {
+    __nanosleep(256);
+    ++spins;
+  }
+  if (spins >= (1u << 23)) atomicOr(flags, 32u);
+  // CTA-scope fence: orders the item loads after the poll without the L1 invalidate a device-scope fence
+  // costs (the items are read with ld.global.cg, which does not use L1)
+  __threadfence_block();
+}
+
 // Per-lane query state parked in shared memory while the warp traverses (kStateWords words):
 //   0 resource object, 1 depth | leaves << 8 | is-tree << 15 | leaf_begin-or-unit << 16,
 //   2 tree id, 3 / 4 leaf values (2 bits each), 5 unused
-template <bool COUNT>
+template <bool COUNT, bool STREAMED = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   for (uint32_t i = threadIdx.x; i < p.prog_bytes / 16; i += blockDim.x)
@@ -460,12 +483,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
   c.spill = p.spill + (static_cast<size_t>(blockIdx.x) * kWarpsPerBlock + warp) * p.spill_cap;
   c.spill_cap = p.spill_cap;
   c.bytes = 0;
+  c.events = p.events;
   const uint32_t n_slots = pr.hdr()->n_slots, n_types = pr.hdr()->n_types;
   unsigned long long* const memo = p.memo + (static_cast<size_t>(blockIdx.x) * kWarpsPerBlock + warp) * p.memo_entries;
 
   for (;;) {
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(p.next, 32ull);
+    if (lane == 0) {
+      base = atomicAdd(p.next, 32ull);
+      // the copy engine is still feeding the queries: wait until this batch has landed
+      if (STREAMED && base < p.nq) wait_ready(p.ready, base + 32 < p.nq ? base + 32 : p.nq, p.flags);
+    }
     base = __shfl_sync(kFull, base, 0);
     if (base >= p.nq) break;
     const unsigned long long q = base + lane;
@@ -475,7 +503,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
     c.my_subj = 0;
     c.my_ss = (0u << 16) | kNone;
     if (valid) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.queries) + q);
+      // ld.global.cg when the items are streamed in: nothing about them may come from a non-coherent cache
+      const uint4 raw = STREAMED ? __ldcg(reinterpret_cast<const uint4*>(p.queries) + q)
+                                 : __ldg(reinterpret_cast<const uint4*>(p.queries) + q);
       if (COUNT) c.bytes += 17;
       c.my_subj = raw.y;
       const uint32_t perm = raw.z & 0xFFFFu, stype = raw.z >> 16;
@@ -589,6 +619,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
           // this batch is expanding far more than usual: path multiplicity. Remember child
           // visits from here on; an identical (job, slot, object, depth) visit is skipped.
           for (uint32_t i = lane; i < p.memo_entries; i += 32) memo[i] = 0ull;
+          if (lane == 0) atomicAdd(p.events + 1, 1ull);
           __syncwarp();
           use_memo = true;
         }

@@ -250,7 +250,17 @@ def cfg3(seed=3, scale=1.0, batch=1 << 20) -> Workload:
                     note=f"3-hop nesting, {n_gm + n_tm + n_nv} tuples, batch {nb}")
 
 
-def cfg4(seed=4, scale=1.0, batch=1 << 20) -> Workload:
+# cfg4 with a NON-PURE folder#view: every document -> folder arrow then leads into a permission with `-`, so
+# each check raises sub-queries pass after pass up the folder chain (tests of the multi-pass machinery on a
+# store of the same size and shape; not a BASELINE configuration).
+CFG4X_SCHEMA = CFG4_SCHEMA.replace(
+    "  relation viewer: user | group#member\n  permission view = viewer + owner + parent->view\n",
+    "  relation viewer: user | group#member\n  relation banned: user\n"
+    "  permission view = (viewer + owner + parent->view) - banned\n")
+assert CFG4X_SCHEMA != CFG4_SCHEMA
+
+
+def cfg4(seed=4, scale=1.0, batch=1 << 20, nonpure_folders=False) -> Workload:
     """Doc-style schema; `scale`=1.0 is the 100M-tuple configuration."""
     r = _rng(seed)
     N = 100_000_000 * scale
@@ -329,6 +339,14 @@ def cfg4(seed=4, scale=1.0, batch=1 << 20) -> Workload:
         pm = r.permutation(n)
         checks.append(CheckBatch("document", perm, "user", _u32(res[pm]), _u32(sub[pm])))
     lookups = [("document", "view", "user", int(u)) for u in r.integers(0, U, 4)]
+    if nonpure_folders:
+        r2 = _rng(seed + 1000)
+        nb_ = nz(0.005 * N, 4)
+        groups.append(RelGroup("folder", "banned", "user", r2.integers(0, F, nb_, dtype=np.uint32),
+                               r2.integers(0, U, nb_, dtype=np.uint32)))
+        w = Workload("cfg4x", CFG4X_SCHEMA, groups, checks, lookups)
+        w.note = f"cfg4 with a non-pure folder#view, {w.n_tuples()} tuples, batch {w.n_checks()}"
+        return w
     w = Workload("cfg4", CFG4_SCHEMA, groups, checks, lookups)
     w.note = f"doc schema with + & - -> and user:*, {w.n_tuples()} tuples, batch {w.n_checks()}"
     return w

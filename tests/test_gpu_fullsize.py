@@ -1,0 +1,121 @@
+"""Full-size parity of BASELINE configs[3] (cfg4: + & - -> and user:*, ~95 M relationships -- the HBM regime the
+roofline target is quoted on) and of the machinery that only engages at that size: warp stacks spilling to HBM,
+sub-query buffer overflow answered in halves, the path memo. Checker = the CPU oracle (a port: "parity unpinned"
+against SpiceDB for these operators), on >= 50 000 sampled checks of the very batch bench.py times,
+spanning both `view` and `restricted_view`.
+
+ZGPU_FULLSIZE_SCALE shrinks the store for quick local runs (default 1.0)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SCALE = float(os.environ.get("ZGPU_FULLSIZE_SCALE", "1.0"))
+SAMPLE = 60_000
+
+
+@pytest.fixture(scope="module")
+def zg():
+    import zgpu
+
+    return zgpu
+
+
+@pytest.fixture(scope="module")
+def big(zg):
+    """The cfg4 workload, the oracle's answers on the sample, and the sample's indices."""
+    from oracle.pyoracle import Oracle
+    from spicedb_kubeapi_proxy_b200 import workloads
+
+    w = workloads.cfg4(scale=SCALE)
+    o = Oracle(w.schema)
+    w.load_into(o)
+    items = w.check_items(o, zg.CHECK_DTYPE)
+    n = min(SAMPLE, items.size)
+    want = o.check_bulk(items[:n], nthreads=os.cpu_count() or 8)
+    del o
+    return w, items, want
+
+
+def _engine(zg, w, **kw):
+    e = zg.Engine(w.schema, **kw)
+    w.load_into(e)
+    e.publish()
+    return e
+
+
+def test_cfg4_full_size_sample_is_bit_exact(zg, big):
+    w, items, want = big
+    e = _engine(zg, w)
+    assert e.stats()["tuples"] > 90_000_000 * SCALE
+    got = e.check_bulk(items)
+    n = want.size
+    mism = np.flatnonzero(got[:n] != want)
+    assert mism.size == 0, f"{mism.size} of {n} differ, first at {mism[:5]}: {items[mism[:5]]}"
+    # both permissions are in the sample, with both answers
+    view, rview = e.slot_id("document", "view"), e.slot_id("document", "restricted_view")
+    for perm in (view, rview):
+        sel = items["perm"][:n] == perm
+        assert sel.sum() > n // 10 and 0.02 < (want[sel] == 2).mean() < 0.98
+    assert not (got == 255).any()
+    # properties that do not need the oracle, over the whole batch: restricted_view = view & org->member can only
+    # remove grants; re-asking gives the same answers; the device entry point agrees
+    as_view = items.copy()
+    as_view["perm"] = view
+    gv = e.check_bulk(as_view)
+    r = items["perm"] == rview
+    assert not ((got[r] == 2) & (gv[r] != 2)).any()
+    assert np.array_equal(e.check_bulk(items), got)
+    st = e.stats()
+    assert st["stack_spills"] > 0, "a 1 M-check batch over folder chains is expected to spill warp stacks to HBM"
+    assert st["passes"] == 0  # folder#view is a pure union: one launch answers the batch
+    e.close()
+
+
+def test_cfg4_full_size_with_the_path_memo_forced_on(zg, big, monkeypatch):
+    """Every batch remembers its child visits from the first expansion round on: skipping a repeated
+    (check, slot, object, depth) visit must not change an answer on the large store either."""
+    w, items, want = big
+    monkeypatch.setenv("ZGPU_MEMO_AFTER", "0")
+    e = _engine(zg, w)
+    monkeypatch.delenv("ZGPU_MEMO_AFTER")
+    n = want.size
+    got = e.check_bulk(items[: 4 * n])
+    assert np.array_equal(got[:n], want)
+    assert e.stats()["memo_batches"] > 0
+    e.close()
+
+
+def test_forward_only_engine_agrees_at_full_size(zg, big):
+    """No reverse-row probes at all (ZG_FLAG_FORWARD_ONLY): the plain frontier expansion, same answers."""
+    w, items, want = big
+    e = _engine(zg, w, forward_only=True)
+    n = want.size
+    assert np.array_equal(e.check_bulk(items[:n]), want)
+    e.close()
+
+
+def test_subquery_passes_and_overflow_split_on_a_large_store(zg):
+    """cfg4 with a NON-PURE folder#view (`- banned`): every document -> folder edge raises a sub-query, level after
+    level up the folder chain. With a pass buffer far smaller than one batch's sub-queries the batch is answered in
+    halves, recursively; answers equal the oracle's and those of an engine with the default buffer."""
+    from oracle.pyoracle import Oracle
+    from spicedb_kubeapi_proxy_b200 import workloads
+
+    w = workloads.cfg4(scale=min(SCALE, 0.2), nonpure_folders=True)
+    o = Oracle(w.schema)
+    w.load_into(o)
+    items = w.check_items(o, zg.CHECK_DTYPE)
+    n = min(SAMPLE, items.size)
+    want = o.check_bulk(items[:n], nthreads=os.cpu_count() or 8)
+    del o
+    big_buf = _engine(zg, w)
+    small_buf = _engine(zg, w, subquery_capacity=20_000)
+    got = big_buf.check_bulk(items)
+    assert np.array_equal(got[:n], want)
+    assert big_buf.stats()["passes"] >= 2, "the folder chain must take several sub-query passes"
+    assert np.array_equal(small_buf.check_bulk(items), got)
+    assert small_buf.stats()["split_batches"] > 0
+    big_buf.close(), small_buf.close()

@@ -705,3 +705,37 @@ def test_interleaved_writes_and_checks_stay_consistent(zg):
         assert list(got) == want, f"step {step}"
         u = f"u{rng.randint(0, 4)}"
         assert sorted(e.lookup_resources_str("document", "view", "user", u)) == sorted(o.lookup_resources("document", "view", "user", u))
+
+
+def test_known_divergence_same_object_permission_hops_vs_the_depth_cap(zg):
+    """FENCE for the one documented semantic divergence: a permission that refers to another
+    permission of the SAME object is inlined here and costs no dispatch, while SpiceDB dispatches it. In
+        reach = member + next->via ;  via = reach
+    every link of a chain costs 1 hop here and 2 dispatches there. With the 50-dispatch cap
+    (pkg/spicedb/spicedb.go:33):
+        chain of <= 25 links : HAS here, HAS in SpiceDB                       (agree)
+        26 .. 50 links       : HAS here, SpiceDB would report max depth       (MAY DIFFER: the fenced band)
+        >= 51 links          : ERROR here, error in SpiceDB                   (agree)
+    Outside that band -- and for every schema without same-object permission references, which includes all
+    BASELINE configurations -- hop counting is identical. The oracle counts like the engine (it is the checker of
+    the engine, not of this divergence)."""
+    from oracle.pyoracle import Oracle
+
+    schema = ("definition user {}\ndefinition node {\n  relation next: node\n  relation member: user\n"
+              "  permission reach = member + next->via\n  permission via = reach\n}\n")
+    e, o = zg.Engine(schema), Oracle(schema)
+    n = 60
+    for t in (e, o):
+        t.add_bulk("node", "next", "node", np.arange(n - 1, dtype=np.uint32), np.arange(1, n, dtype=np.uint32))
+        t.add_bulk("node", "member", "user", np.array([n - 1], np.uint32), np.array([7], np.uint32))
+    e.publish()
+    items = np.zeros(n, dtype=zg.CHECK_DTYPE)
+    items["res"] = np.arange(n)
+    items["subj"] = 7
+    items["perm"], items["stype"], items["srel"] = e.slot_id("node", "reach"), e.type_id("user"), 0xFFFF
+    got = e.check_bulk(items)
+    links = (n - 1) - np.arange(n)  # arrows between the checked node and the member's node
+    assert np.array_equal(got, o.check_bulk(items))
+    assert (got[links <= 50] == 2).all() and (got[links >= 51] == 255).all()
+    band = (links >= 26) & (links <= 50)
+    assert band.sum() == 25 and (got[band] == 2).all()  # the answers SpiceDB may replace by a depth error

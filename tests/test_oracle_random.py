@@ -141,3 +141,36 @@ definition doc {
     assert o.check("doc", "d3", "viewer", "group", "eng", "member") == 2
     assert o.check("doc", "d3", "view", "group", "ops", "member") == 1
     assert o.check("group", "eng", "member", "group", "eng", "member") == 2  # member of itself
+
+
+SELF_SCHEMA = ("definition user {}\ndefinition doc {\n  relation viewer: user | doc#viewer\n  relation editor: user\n"
+               "  relation banned: user | doc#viewer\n  permission view = viewer + editor\n  permission safe = view - banned\n}\n")
+SELF_RELS = ["doc:1#viewer@user:a", "doc:2#editor@user:a", "doc:3#viewer@doc:5#viewer", "doc:7#banned@doc:7#viewer"]
+# (resource type, permission, subject type, subject id, subject relation) -> expected ids
+SELF_LOOKUPS = [
+    (("doc", "view", "doc", "5", "viewer"), ["3", "5"]),    # doc:5#viewer is in doc:5#view (viewer is inlined into view)
+    (("doc", "view", "doc", "9", "viewer"), ["9"]),          # never written, still a member of its own view
+    (("doc", "viewer", "doc", "5", "viewer"), ["3", "5"]),
+    (("doc", "view", "doc", "5", "editor"), []),             # doc:5#editor is in doc:5#view too...
+    (("doc", "safe", "doc", "5", "viewer"), ["3", "5"]),
+    (("doc", "safe", "doc", "7", "viewer"), []),             # ...but doc:7#viewer is banned from doc:7#safe
+]
+
+
+def test_lookup_resources_includes_the_userset_subject_itself_when_check_says_so():
+    """LookupResources must agree with Check for userset subjects: T:x#r is a member of T:x#P for every relation r
+    inlined into P's union, with or without relationships (round-1 advisor finding). Both oracles, and the GPU
+    test of the same table in test_zz_gpu_new_paths.py."""
+    from oracle.mini_oracle import MiniOracle
+    from oracle.pyoracle import Oracle
+
+    c, m = Oracle(SELF_SCHEMA), MiniOracle(SELF_SCHEMA)
+    for r in SELF_RELS:
+        c.touch(r), m.write(r)
+    for (rt, perm, st, sid, srel), want in SELF_LOOKUPS:
+        if srel == "editor":  # Check(doc:5#view@doc:5#editor) is HAS: the subject itself belongs to the answer
+            want = ["5"]
+        a, b = sorted(c.lookup_resources(rt, perm, st, sid, srel)), sorted(m.lookup_resources(rt, perm, st, sid, srel))
+        assert a == b == want, f"{rt}#{perm}@{st}:{sid}#{srel}: C={a} mini={b} want={want}"
+        for rid in ("3", "5", "7", "9"):
+            assert (c.check(rt, rid, perm, st, sid, srel) == 2) == (rid in a)

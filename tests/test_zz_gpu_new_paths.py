@@ -130,3 +130,23 @@ def test_concurrent_string_callers_share_launches_and_see_writes(zg):
     e.write_relationships([(OP_TOUCH, "pod:ns0/new#viewer@user:late", 0)])
     assert e.check_bulk_str([("pod", "ns0/new", "view", "user", "late", "")])[0] == 2
     print("coalesced", st["coalesced_requests"], "string calls into", st["coalesced_launches"], "launches")
+
+
+@pytest.mark.gpu
+def test_lookup_resources_agrees_with_check_for_userset_subjects():
+    """LookupResources(T, P, T:x#r) contains x whenever Check(T:x#P @ T:x#r) is HAS -- for every relation r inlined
+    into P's union, not only r == P, written or never written (round-1 advisor finding): same table as the oracle
+    test (tests/test_oracle_random.py), through the client mirror."""
+    import zgpu
+    from test_oracle_random import SELF_LOOKUPS, SELF_RELS, SELF_SCHEMA
+
+    C = zgpu.client
+    cl = C.PermissionsClient(SELF_SCHEMA)
+    cl.WriteRelationships(C.WriteRelationshipsRequest(
+        [C.RelationshipUpdate(C.OPERATION_TOUCH, C.Relationship.parse(r)) for r in SELF_RELS]))
+    for (rt, perm, st, sid, srel), want in SELF_LOOKUPS:
+        if srel == "editor":
+            want = ["5"]
+        got = sorted(r.resource_object_id for r in cl.LookupResources(C.LookupResourcesRequest(
+            rt, perm, C.SubjectReference(C.ObjectReference(st, sid), srel))))
+        assert got == want, f"{rt}#{perm}@{st}:{sid}#{srel}: {got} != {want}"
