@@ -147,6 +147,10 @@ typedef struct {
   uint64_t stack_spills;       /* warp stacks that overflowed shared memory into HBM     */
   uint64_t memo_batches;       /* 32-check batches that switched the path memo on        */
   uint64_t split_batches;      /* batches answered in halves (sub-query buffer overflow) */
+  uint64_t delta_publishes;    /* publishes that merged a journal of updates into the resident snapshot */
+  uint64_t full_publishes;     /* publishes that rebuilt the snapshot from the relationship list        */
+  double last_publish_ms;      /* device time of the last publish (merge or rebuild)                    */
+  uint64_t streamed_calls;     /* host calls whose items were copied in behind the running kernel       */
 } zg_stats;
 
 /* ---- lifecycle --------------------------------------------------------- */

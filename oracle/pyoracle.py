@@ -156,6 +156,12 @@ class Oracle:
     def delete(self, rel):
         self.write(rel, OP_DELETE)
 
+    def write_ids(self, op, rel_slot, res, stype, subj, srel=SREL_NONE, expires_at=0):
+        """One interned relationship update (same fields as zg_update)."""
+        rc = self._L.zo_write(self._h, int(op), int(rel_slot), int(res), int(stype), int(subj), int(srel), int(expires_at))
+        if rc:
+            raise OracleError(self._err())
+
     def add_bulk(self, type_name, rel, subj_type, res, subj, srel=None, wildcard=False):
         res = np.ascontiguousarray(res, dtype=np.uint32)
         subj = np.ascontiguousarray(subj, dtype=np.uint32)

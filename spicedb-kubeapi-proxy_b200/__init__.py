@@ -11,7 +11,7 @@ binding, a client that mirrors v1.PermissionsServiceClient, and the synthetic
 workload generators of SURVEY.md section 8(d).
 """
 from ._lib import (  # noqa: F401
-    CHECK_DTYPE, TUPLE_DTYPE, HAS_PERMISSION, ITEM_ERROR, NO_PERMISSION, SREL_NONE, SREL_WILDCARD,
+    CHECK_DTYPE, TUPLE_DTYPE, UPDATE_DTYPE, HAS_PERMISSION, ITEM_ERROR, NO_PERMISSION, SREL_NONE, SREL_WILDCARD,
     Engine, ZgpuError, build_library, library_path,
 )
 from .client import PermissionsClient  # noqa: F401

@@ -61,7 +61,18 @@ class _Stats(C.Structure):
     _fields_ = [("checks", C.c_uint64), ("launches", C.c_uint64), ("passes", C.c_uint64), ("tuples", C.c_uint64),
                 ("snapshot_bytes", C.c_uint64), ("revision", C.c_uint64), ("last_alg_bytes", C.c_uint64),
                 ("last_kernel_ms", C.c_double), ("coalesced_launches", C.c_uint64), ("coalesced_requests", C.c_uint64),
-                ("stack_spills", C.c_uint64), ("memo_batches", C.c_uint64), ("split_batches", C.c_uint64)]
+                ("stack_spills", C.c_uint64), ("memo_batches", C.c_uint64), ("split_batches", C.c_uint64),
+                ("delta_publishes", C.c_uint64), ("full_publishes", C.c_uint64), ("last_publish_ms", C.c_double),
+                ("streamed_calls", C.c_uint64)]
+
+
+class _Update(C.Structure):
+    _fields_ = [("res", C.c_uint32), ("subj", C.c_uint32), ("rel", C.c_uint16), ("stype", C.c_uint16),
+                ("srel", C.c_uint16), ("flags", C.c_uint16), ("expires_at", C.c_uint32), ("op", C.c_uint32)]
+
+
+UPDATE_DTYPE = np.dtype([("res", "<u4"), ("subj", "<u4"), ("rel", "<u2"), ("stype", "<u2"), ("srel", "<u2"),
+                         ("flags", "<u2"), ("expires_at", "<u4"), ("op", "<u4")])
 
 
 class _ListItem(C.Structure):
@@ -343,6 +354,11 @@ class Engine:
 
     def publish(self):
         self._ck(self._L.zg_publish(self._h))
+
+    def apply_updates(self, updates: np.ndarray):
+        """zg_apply_updates: interned CREATE / TOUCH / DELETE (UPDATE_DTYPE); visible after publish()."""
+        u = np.ascontiguousarray(updates, dtype=UPDATE_DTYPE)
+        self._ck(self._L.zg_apply_updates(self._h, u.ctypes.data, u.size))
 
     def num_tuples(self):
         return self._L.zg_num_tuples(self._h)

@@ -252,8 +252,16 @@ static int publish_locked(zg_engine* e) {
     const char* hb = std::getenv("ZGPU_HOST_BUILD");
     const char* vb = std::getenv("ZGPU_VERIFY_BUILD");
     if (!(hb && *hb && *hb != '0')) {
-      std::string err = e->dev.publish_gpu(e->store, e->schema, ++e->revision, vb && *vb && *vb != '0');
+      const bool verify = vb && *vb && *vb != '0';
+      // a few updates against a resident snapshot: merge them in (build.cu gpu_apply_delta); anything the
+      // journal cannot express (bulk load, new layout, no snapshot yet) rebuilds
+      const char* nd = std::getenv("ZGPU_NO_DELTA");
+      std::string err = (nd && *nd && *nd != '0') ? std::string("full") : e->dev.publish_delta(e->store, e->schema, e->revision + 1);
+      if (err == "full") err = e->dev.publish_gpu(e->store, e->schema, e->revision + 1, verify);
+      else if (err.empty() && verify) err = e->dev.verify_against_host(e->store, e->schema);
       if (!err.empty()) return fail(ZG_ECUDA, err);
+      ++e->revision;
+      e->store.journal_clear();
       e->last_built = HostSnapshot();
       e->dirty = false;
       return ZG_OK;
@@ -1329,6 +1337,10 @@ extern "C" int zg_stats_get(zg_engine* e, zg_stats* out) {
   out->coalesced_launches = e->dev.coalesced_launches;
   out->coalesced_requests = e->dev.coalesced_requests;
   out->split_batches = e->dev.split_batches;
+  out->delta_publishes = e->dev.delta_publishes;
+  out->full_publishes = e->dev.full_publishes;
+  out->last_publish_ms = e->dev.last_build_ms;
+  out->streamed_calls = e->dev.streamed_calls;
   if (!e->host_only) e->dev.read_events(&out->stack_spills, &out->memo_batches);
   if (e->dev.snap) {
     out->tuples = e->dev.snap->n_tuples;

@@ -48,6 +48,9 @@ Snapshot::~Snapshot() {
   prog.release();
   rrow_ptr.release();
   rcol.release();
+  col_alt.release();
+  exp_alt.release();
+  rcol_alt.release();
   type_bit_base.release();
   for (auto& r : resources) r.release();
   for (auto& f : flat_cls) f.release();
@@ -163,32 +166,99 @@ std::string Device::publish_gpu(const Store& store, const Schema& sc, uint64_t r
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   if (!err.empty()) return "GPU snapshot build failed: " + err;
+  ++full_publishes;
   if (verify) {
-    // test mode: the host builder must produce byte-identical arrays
-    HostSnapshot h = store.build();
-    if (!h.err.empty()) return h.err;
-    auto same = [&](const DevBuf& d, const std::vector<uint32_t>& v, const char* what) -> std::string {
-      std::vector<uint32_t> got(v.size());
-      if (!v.empty() && cudaMemcpy(got.data(), d.p, v.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
-        return std::string("verify: cannot read ") + what;
-      for (size_t i = 0; i < v.size(); ++i)
-        if (got[i] != v[i])
-          return std::string("verify: ") + what + " differs at " + std::to_string(i) + " (gpu " + std::to_string(got[i]) +
-                 ", host " + std::to_string(v[i]) + ")";
-      return "";
-    };
-    if (h.n_tuples != s->n_tuples) return "verify: relationship count differs";
-    for (auto m : {same(s->row_ptr, h.row_ptr, "row_ptr"), same(s->col, h.col, "col"), same(s->rrow_ptr, h.rrow_ptr, "rrow_ptr"),
-                   same(s->rcol, h.rcol, "rcol"), sc.has_expiry ? same(s->exp, h.exp, "exp") : std::string()})
-      if (!m.empty()) return m;
-    for (size_t t = 0; t < h.resources.size(); ++t) {
-      if (h.resources[t].size() != s->n_resources[t]) return "verify: resource list size differs";
-      std::string m = same(s->resources[t], h.resources[t], "resources");
-      if (!m.empty()) return m;
-    }
-    for (size_t c = 0; c < h.cls.size(); ++c)
-      if (h.cls[c].flags != lay.cls[c].flags) return "verify: class emptiness differs";
+    std::string verr = verify_snapshot(*s, store, sc, &lay);
+    if (!verr.empty()) return verr;
   }
+  return finish_publish(s, lay, sc, revision);
+}
+
+// test mode (ZGPU_VERIFY_BUILD=1): the host builder must produce byte-identical arrays
+std::string Device::verify_snapshot(Snapshot& sn, const Store& store, const Schema& sc, const HostSnapshot* lay) {
+  Snapshot* s = &sn;
+  if (s->resources_stale) {
+    std::string rerr = gpu_resource_lists(s, stream);
+    if (!rerr.empty()) return rerr;
+  }
+  cudaStreamSynchronize(stream);
+  HostSnapshot h = store.build();
+  if (!h.err.empty()) return h.err;
+  auto same = [&](const DevBuf& d, const std::vector<uint32_t>& v, const char* what) -> std::string {
+    std::vector<uint32_t> got(v.size());
+    if (!v.empty() && cudaMemcpy(got.data(), d.p, v.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+      return std::string("verify: cannot read ") + what;
+    for (size_t i = 0; i < v.size(); ++i)
+      if (got[i] != v[i])
+        return std::string("verify: ") + what + " differs at " + std::to_string(i) + " (gpu " + std::to_string(got[i]) +
+               ", host " + std::to_string(v[i]) + ")";
+    return "";
+  };
+  if (h.n_tuples != s->n_tuples) return "verify: relationship count differs";
+  for (auto m : {same(s->row_ptr, h.row_ptr, "row_ptr"), same(s->col, h.col, "col"), same(s->rrow_ptr, h.rrow_ptr, "rrow_ptr"),
+                 same(s->rcol, h.rcol, "rcol"), sc.has_expiry ? same(s->exp, h.exp, "exp") : std::string()})
+    if (!m.empty()) return m;
+  for (size_t t = 0; t < h.resources.size(); ++t) {
+    if (h.resources[t].size() != s->n_resources[t]) return "verify: resource list size differs";
+    std::string m = same(s->resources[t], h.resources[t], "resources");
+    if (!m.empty()) return m;
+  }
+  for (size_t c = 0; c < h.cls.size(); ++c) {
+    const bool empty = lay ? (lay->cls[c].flags & CF_EMPTY) != 0 : s->cls_count[c] == 0;
+    if (((h.cls[c].flags & CF_EMPTY) != 0) != empty) return "verify: class emptiness differs";
+  }
+  return "";
+}
+std::string Device::verify_against_host(const Store& store, const Schema& sc) {
+  std::shared_ptr<Snapshot> s = snap;
+  if (!s) return "verify: no snapshot";
+  cudaSetDevice(device);
+  return verify_snapshot(*s, store, sc, nullptr);
+}
+
+std::string Device::publish_delta(const Store& store, const Schema& sc, uint64_t revision) {
+  constexpr size_t kMaxDelta = 1u << 16;
+  std::shared_ptr<Snapshot> s = snap;
+  if (!s || !s->delta_ok || !store.journal_ok || shard_count > 1 || store.journal.size() > kMaxDelta || !store.layout_stable())
+    return "full";
+  cudaSetDevice(device);
+  HostSnapshot lay = store.layout();  // same capacities as the resident snapshot: same bases
+  if (lay.n_objects != s->n_objects) return "full";
+  // readers on other streams (zg_check_bulk_device) are ordered through last_done_
+  if (have_last_ && cudaStreamWaitEvent(stream, last_done_, 0) != cudaSuccess) return "full";
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, stream);
+  std::vector<uint32_t> cls_delta;
+  std::string err = gpu_apply_delta(store, sc, lay, stream, s.get(), &cls_delta);
+  cudaEventRecord(e1, stream);
+  cudaEventRecord(last_done_, stream);
+  have_last_ = true;
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  last_build_ms = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (!err.empty()) {
+    snap.reset();  // the arrays may be half merged: nobody may read them; the caller rebuilds
+    return err == "relayout" || err == "corrupt" ? "full" : err;
+  }
+  bool structural = false;
+  for (size_t c = 0; c < cls_delta.size(); ++c) {
+    const uint64_t before = s->cls_count[c];
+    s->cls_count[c] = before + static_cast<int32_t>(cls_delta[c]);
+    if ((before == 0) != (s->cls_count[c] == 0)) structural = true;
+  }
+  s->resources_stale = true;
+  s->revision = revision;
+  ++delta_publishes;
+  if (!structural) return "";
+  // a class became empty or non-empty: the flattened steps of the program change
+  for (size_t c = 0; c < lay.cls.size(); ++c)
+    if (s->cls_count[c]) lay.cls[c].flags &= static_cast<uint16_t>(~CF_EMPTY);
+  lay.n_tuples = s->n_tuples;
   return finish_publish(s, lay, sc, revision);
 }
 
@@ -809,6 +879,13 @@ int Device::lookup(uint16_t res_type, const zg_check& proto, std::vector<uint32_
     // more results than the buffer: fall through to the general path
   }
   // candidates: reverse BFS from the subject (superset of the answer), else every resource of the type
+  if (s->resources_stale) {
+    std::string rerr = gpu_resource_lists(s.get(), stream);
+    if (!rerr.empty()) {
+      if (err) *err = rerr;
+      return ZG_ECUDA;
+    }
+  }
   uint64_t n = s->n_resources[res_type];
   const uint32_t* cand = s->resources[res_type].as<uint32_t>();
   if (n == 0) return ZG_OK;

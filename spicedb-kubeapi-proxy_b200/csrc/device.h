@@ -27,6 +27,14 @@ struct DevBuf {
 // Immutable once published; shared_ptr keeps it alive for in-flight readers.
 struct Snapshot {
   DevBuf row_ptr, col, exp, prog, rrow_ptr, rcol, type_bit_base;
+  // incremental publish (build.cu gpu_apply_delta): the edge arrays are re-emitted into their alternates and
+  // swapped; per-class relationship counts tell when a class becomes (non-)empty and the program changes
+  DevBuf col_alt, exp_alt, rcol_alt;
+  std::vector<uint64_t> cls_count;
+  std::vector<uint64_t> type_base;   // per type: first row_ptr index of its objects
+  std::vector<uint32_t> type_ncls;   // per type: row stride
+  bool delta_ok = false;             // built by the GPU builder: counts are known
+  bool resources_stale = false;      // resources[] predate an incremental publish: rebuilt on first use
   std::vector<uint32_t> n_objects;  // per type
   uint64_t total_bits = 0;          // visited bitmap size for the reverse BFS
   // Per slot: device array of FlatLookupClass when the slot is a flat union of direct
@@ -49,6 +57,13 @@ class Device {
   std::string publish(const HostSnapshot& h, const Schema& sc, uint64_t revision);  // host-built arrays
   // Builds the CSR on the GPU (build.cu); verify: also build on the host and compare every array.
   std::string publish_gpu(const Store& store, const Schema& sc, uint64_t revision, bool verify);
+  // Merges the store's journal into the resident snapshot. Returns "" on success, "full" when only a rebuild
+  // can publish this state (no snapshot, re-layout, bulk load, huge delta), else an error message.
+  std::string publish_delta(const Store& store, const Schema& sc, uint64_t revision);
+  uint64_t delta_publishes = 0, full_publishes = 0;
+  // ZGPU_VERIFY_BUILD=1: every array of the resident snapshot against the host builder's
+  std::string verify_against_host(const Store& store, const Schema& sc);
+  std::string verify_snapshot(Snapshot& s, const Store& store, const Schema& sc, const HostSnapshot* lay);
   double last_build_ms = 0;
 
   // d_items / d_out are device pointers. count_bytes != nullptr selects the
@@ -134,5 +149,11 @@ class Device {
 // Device radix sort of n u32 keys (build.cu keeps the cub instantiations in one translation unit).
 std::string sort_u32(const uint32_t* d_in, uint32_t* d_out, uint64_t n, cudaStream_t st);
 std::string gpu_build_snapshot(const Store& store, const Schema& sc, HostSnapshot* lay, cudaStream_t st, Snapshot* s);
+// Applies store.journal to the arrays of `s` (same layout). cls_delta: per-class change of the relationship count.
+// "relayout" / "corrupt": the caller must rebuild.
+std::string gpu_apply_delta(const Store& store, const Schema& sc, const HostSnapshot& lay, cudaStream_t st, Snapshot* s,
+                            std::vector<uint32_t>* cls_delta);
+// (Re)builds s->resources[] / n_resources[] from the forward row table.
+std::string gpu_resource_lists(Snapshot* s, cudaStream_t st);
 
 }  // namespace zg

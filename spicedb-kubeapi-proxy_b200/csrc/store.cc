@@ -12,12 +12,17 @@ void Store::reset(const Schema* s) {
   tuples.clear();
   expires.clear();
   objs_.assign(s ? s->types.size() : 0, TypeObjs{});
+  obj_cap_.assign(s ? s->types.size() : 0, 0);
+  journal.clear();
+  journal_ok = false;
   index_.clear();
   indexed_ = true;
   live_ = 0;
 }
 
 void Store::clear_relationships() {
+  journal.clear();
+  journal_ok = false;
   tuples.clear();
   expires.clear();
   index_.clear();
@@ -166,6 +171,8 @@ std::string Store::load(const zg_tuple* t, const uint32_t* ex, uint64_t n) {
   }
   live_ += kept;  // upper bound until duplicates are folded by ensure_index()/build()
   indexed_ = false;
+  journal.clear();
+  journal_ok = false;  // bulk loads may hold duplicates: only a full build folds them
   return "";
 }
 
@@ -226,15 +233,19 @@ std::string Store::apply(const zg_update* u, uint64_t n, int* code, std::vector<
         tuples[it->second].flags |= 1;
         index_.erase(it);
         --live_;
-        if (changed) (*changed)[i] = 1;
+        if (changed) (*changed)[i] = kDeleted;
+        if (journal_ok) journal.push_back(JournalEntry{t, 0, kDeleted});
       }
       continue;
     }
-    if (changed) (*changed)[i] = 1;
     if (it != index_.end()) {
+      if (changed) (*changed)[i] = kTouched;
+      if (journal_ok && expires[it->second] != u[i].expires_at) journal.push_back(JournalEntry{t, u[i].expires_at, kTouched});
       expires[it->second] = u[i].expires_at;
       continue;
     }
+    if (changed) (*changed)[i] = kInserted;
+    if (journal_ok) journal.push_back(JournalEntry{t, u[i].expires_at, kInserted});
     index_.emplace(k, tuples.size());
     tuples.push_back(t);
     expires.push_back(u[i].expires_at);
@@ -288,8 +299,15 @@ HostSnapshot Store::layout() const {
   HostSnapshot h;
   const size_t nt = sc.types.size();
   h.n_objects.resize(nt);
-  for (size_t t = 0; t < nt; ++t)
-    h.n_objects[t] = std::max<uint32_t>(objs_[t].n_ids(), objs_[t].n_numeric);
+  obj_cap_.resize(nt, 0);
+  for (size_t t = 0; t < nt; ++t) {
+    const uint32_t need = std::max<uint32_t>(objs_[t].n_ids(), objs_[t].n_numeric);
+    if (need > obj_cap_[t]) {
+      const uint64_t want = uint64_t(need) + need / 8 + 4096;
+      obj_cap_[t] = static_cast<uint32_t>(std::min<uint64_t>(want, 0xFFFFFFF0ull));
+    }
+    h.n_objects[t] = obj_cap_[t];
+  }
 
   // row table: per resource type, objects x (all classes of all relations of the type)
   h.type_ncls.assign(nt, 0);
@@ -342,6 +360,13 @@ HostSnapshot Store::layout() const {
     c.flags |= CF_EMPTY;  // cleared by the builder for every class that has a relationship
   }
   return h;
+}
+
+bool Store::layout_stable() const {
+  if (obj_cap_.size() != objs_.size()) return false;
+  for (size_t t = 0; t < objs_.size(); ++t)
+    if (std::max<uint32_t>(objs_[t].n_ids(), objs_[t].n_numeric) > obj_cap_[t]) return false;
+  return true;
 }
 
 HostSnapshot Store::build() const {

@@ -65,9 +65,26 @@ class Store {
   // Returns "" or an error message; `code` receives the ZG_* code.
   std::string validate(const zg_tuple& t, bool has_expiry) const;
   std::string load(const zg_tuple* t, const uint32_t* expires, uint64_t n);
-  // `changed` (optional, n entries): 1 where the update took effect (a DELETE of a relationship that
-  // does not exist changes nothing; TOUCH and CREATE always count).
+  // `changed` (optional, n entries): nonzero where the update took effect (a DELETE of a relationship that
+  // does not exist changes nothing; TOUCH and CREATE always count): kTouched = the relationship existed
+  // (only its expiration may differ), kInserted, kDeleted.
+  enum : uint8_t { kUnchanged = 0, kTouched = 1, kInserted = 2, kDeleted = 3 };
   std::string apply(const zg_update* u, uint64_t n, int* code, std::vector<uint8_t>* changed = nullptr);
+
+  // Journal of what apply() changed since journal_clear(): what an incremental publish merges into the
+  // device snapshot instead of rebuilding it (build.cu gpu_apply_delta). journal_ok turns false when
+  // something the journal cannot express happened (bulk load, clear, re-layout).
+  struct JournalEntry {
+    zg_tuple t;
+    uint32_t expires;
+    uint8_t kind;  // kTouched / kInserted / kDeleted
+  };
+  std::vector<JournalEntry> journal;
+  bool journal_ok = false;
+  void journal_clear() {
+    journal.clear();
+    journal_ok = true;
+  }
 
   // Live relationships matching a filter (unset field = -1 / ZG_NO_OBJECT-1 sentinel via has_*).
   struct Filter {
@@ -87,7 +104,11 @@ class Store {
 
   // Sizes and bases only (n_objects, rels, cls with rrow_base / nsubj and CF_EMPTY set on every
   // class): what both the host builder and the GPU builder (build.cu) start from.
+  // Object counts are CAPACITIES: they grow in steps (1/8 + 4096 beyond what is needed) and never shrink, so
+  // that relationships on newly created objects -- the proxy's common write -- do not move any row table.
   HostSnapshot layout() const;
+  // true when layout() would still return the capacities it returned last time
+  bool layout_stable() const;
   HostSnapshot build() const;
   uint64_t size() const { return live_; }
 
@@ -115,6 +136,7 @@ class Store {
     uint32_t n_ids() const { return static_cast<uint32_t>(rec_of.size()); }
   };
   std::vector<TypeObjs> objs_;
+  mutable std::vector<uint32_t> obj_cap_;  // per type: capacity handed out by the last layout()
   std::unordered_map<Key, uint64_t, KeyHash> index_;
   bool indexed_ = true;  // index_ covers every live tuple
   uint64_t live_ = 0;

@@ -198,8 +198,11 @@ static int fuzz_store(int schema_i, long batches) {
     } else {
       if (!e2.empty()) return std::printf("valid batch rejected: %s\n", e2.c_str()), 1;
       for (size_t i = 0; i < ups.size(); ++i) {
-        const bool want = ups[i].op != ZG_OP_DELETE || model.count(in_batch[i]);
-        if (changed[i] != (want ? 1 : 0)) return std::printf("changed[] mask wrong\n"), 1;
+        // kinds: touched (the relationship existed) / inserted / deleted / unchanged (DELETE of nothing)
+        const bool was = model.count(in_batch[i]) != 0;
+        const uint8_t want = ups[i].op == ZG_OP_DELETE ? (was ? Store::kDeleted : Store::kUnchanged)
+                                                       : (was ? Store::kTouched : Store::kInserted);
+        if (changed[i] != want) return std::printf("changed[] mask wrong\n"), 1;
       }
       model.swap(next);
       ++applied;

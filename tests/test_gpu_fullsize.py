@@ -119,3 +119,49 @@ def test_subquery_passes_and_overflow_split_on_a_large_store(zg):
     assert np.array_equal(small_buf.check_bulk(items), got)
     assert small_buf.stats()["split_batches"] > 0
     big_buf.close(), small_buf.close()
+
+
+def test_thousand_update_write_on_the_large_store_is_a_merge(zg, big):
+    """pkg/authz/distributedtx/activity.go:47-77 writes <= 1000 updates per call (spicedb.go:34); on the 95 M store
+    such a write must not cost a rebuild (0.65 s): the journal is merged into the resident CSR in one streaming
+    pass. Timed here (device ms of the publish), answers checked on a probe set that includes every touched
+    document, against the oracle with the same updates."""
+    import json
+    import time
+
+    from oracle.pyoracle import Oracle
+    from test_gpu_parity import _random_updates
+
+    w, items, want = big
+    e = _engine(zg, w)
+    rng = np.random.default_rng(11)
+    t_full = e.stats()["last_publish_ms"]
+    times = []
+    all_ups = []
+    for _ in range(5):
+        ups = _random_updates(zg, e, w, rng, 1000, new_objects=False)
+        t0 = time.perf_counter()
+        e.apply_updates(ups)
+        e.publish()
+        times.append((time.perf_counter() - t0) * 1e3)
+        all_ups.append(ups)
+    st = e.stats()
+    assert st["delta_publishes"] == 5 and st["full_publishes"] == 1, st
+    rec = {"store_tuples": int(st["tuples"]), "updates_per_write": 1000, "wall_ms": times,
+           "device_ms_last": st["last_publish_ms"], "full_rebuild_device_ms": t_full}
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/write_merge_fullsize.json", "w") as f:
+        json.dump(rec, f)
+    assert min(times) < 50.0, rec  # target: < 5 ms; the bound leaves room for a noisy box
+    # parity after the writes: the oracle replays them (one re-index), probes = touched documents x their checks
+    o = Oracle(w.schema)
+    w.load_into(o)
+    for ups in all_ups:
+        for u in ups:
+            o.write_ids(u["op"], u["rel"], u["res"], u["stype"], u["subj"], u["srel"])
+    doc_rels = {e.slot_id("document", r) for r in ("parent", "org", "owner", "editor", "viewer", "banned")}
+    touched = np.concatenate([u["res"][np.isin(u["rel"], list(doc_rels))] for u in all_ups])
+    probe = items[:20000].copy()
+    probe["res"][: touched.size] = touched[: probe.size]
+    assert np.array_equal(e.check_bulk(probe), o.check_bulk(probe, nthreads=os.cpu_count() or 8))
+    e.close()

@@ -739,3 +739,61 @@ def test_known_divergence_same_object_permission_hops_vs_the_depth_cap(zg):
     assert (got[links <= 50] == 2).all() and (got[links >= 51] == 255).all()
     band = (links >= 26) & (links <= 50)
     assert band.sum() == 25 and (got[band] == 2).all()  # the answers SpiceDB may replace by a depth error
+
+
+def _random_updates(zg, e, w, rng, n, new_objects=True):
+    """n interned updates against workload w: deletes and touches of loaded relationships, inserts between
+    existing objects, and (new_objects) inserts on objects the store has never seen."""
+    ups = np.zeros(n, dtype=zg.UPDATE_DTYPE)
+    for i in range(n):
+        g = w.groups[rng.integers(0, len(w.groups))]
+        k = rng.integers(0, g.res.size)
+        kind = rng.random()
+        ups["rel"][i] = e.slot_id(g.res_type, g.rel)
+        ups["stype"][i] = e.type_id(g.subj_type)
+        ups["srel"][i] = 0xFFFE if g.wildcard else (0xFFFF if g.srel is None else e.slot_id(g.subj_type, g.srel))
+        ups["res"][i], ups["subj"][i] = g.res[k], 0 if g.wildcard else g.subj[k]
+        if kind < 0.35:
+            ups["op"][i] = 2  # DELETE (maybe already deleted by an earlier batch: a no-op then)
+        elif kind < 0.45:
+            ups["op"][i] = 0  # TOUCH of an existing relationship
+        else:
+            ups["op"][i] = 0  # TOUCH of a new pairing
+            ups["res"][i] = g.res[rng.integers(0, g.res.size)]
+            if new_objects and kind > 0.85:
+                ups["res"][i] = int(g.res.max()) + 1 + rng.integers(0, 50)
+            if not g.wildcard:
+                ups["subj"][i] = g.subj[rng.integers(0, g.subj.size)]
+    # one update per relationship in a batch (as WriteRelationships requires)
+    key = np.stack([ups["rel"], ups["res"], ups["stype"], ups["srel"], ups["subj"]], axis=1)
+    _, first = np.unique(key, axis=0, return_index=True)
+    return ups[np.sort(first)]
+
+
+def test_incremental_publish_equals_rebuild_and_oracle(zg, monkeypatch):
+    """A write does not rebuild the snapshot: its updates are merged into the resident CSR on the device
+    (csrc/build.cu gpu_apply_delta). With ZGPU_VERIFY_BUILD=1 every array after every merge is compared with the host
+    builder's; answers are compared with the oracle, which applies the same updates."""
+    from oracle.pyoracle import Oracle
+    from spicedb_kubeapi_proxy_b200 import workloads
+
+    monkeypatch.setenv("ZGPU_VERIFY_BUILD", "1")
+    rng = np.random.default_rng(7)
+    for w in (workloads.cfg4(scale=0.002), workloads.cfg3(scale=0.01)):
+        e, o = zg.Engine(w.schema), Oracle(w.schema)
+        w.load_into(e), w.load_into(o)
+        e.publish()
+        items = w.check_items(e, zg.CHECK_DTYPE)[:8000]
+        for step in range(6):
+            ups = _random_updates(zg, e, w, rng, [3, 40, 400, 1000, 1, 1000][step])
+            e.apply_updates(ups)
+            e.publish()  # raises if a merged array differs from the rebuilt one
+            for u in ups:
+                o.write_ids(u["op"], u["rel"], u["res"], u["stype"], u["subj"], u["srel"])
+            # checks on touched objects and on the standing batch
+            probe = items.copy()
+            probe["res"][: ups.size] = ups["res"][: probe.size][: ups.size] if w.name == "cfg3" else probe["res"][: ups.size]
+            assert np.array_equal(e.check_bulk(probe), o.check_bulk(probe)), f"{w.name} step {step}"
+        st = e.stats()
+        assert st["delta_publishes"] >= 5, st  # a batch that outgrows an object capacity may rebuild
+        e.close()
