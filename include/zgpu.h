@@ -151,6 +151,8 @@ typedef struct {
   uint64_t full_publishes;     /* publishes that rebuilt the snapshot from the relationship list        */
   double last_publish_ms;      /* device time of the last publish (merge or rebuild)                    */
   uint64_t streamed_calls;     /* host calls whose items were copied in behind the running kernel       */
+  uint64_t lookup_batches;     /* launch sequences that answered more than one LookupResources           */
+  uint64_t lookups_batched;    /* LookupResources calls answered by those                                */
 } zg_stats;
 
 /* ---- lifecycle --------------------------------------------------------- */

@@ -63,7 +63,7 @@ class _Stats(C.Structure):
                 ("last_kernel_ms", C.c_double), ("coalesced_launches", C.c_uint64), ("coalesced_requests", C.c_uint64),
                 ("stack_spills", C.c_uint64), ("memo_batches", C.c_uint64), ("split_batches", C.c_uint64),
                 ("delta_publishes", C.c_uint64), ("full_publishes", C.c_uint64), ("last_publish_ms", C.c_double),
-                ("streamed_calls", C.c_uint64)]
+                ("streamed_calls", C.c_uint64), ("lookup_batches", C.c_uint64), ("lookups_batched", C.c_uint64)]
 
 
 class _Update(C.Structure):

@@ -133,6 +133,16 @@ std::string sort_u32(const uint32_t* d_in, uint32_t* d_out, uint64_t n, cudaStre
   return "";
 }
 
+std::string sort_u64(const unsigned long long* d_in, unsigned long long* d_out, uint64_t n, int end_bit, cudaStream_t st) {
+  static thread_local DevBuf tmp;
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, bytes, d_in, d_out, n, 0, end_bit, st);
+  if (!tmp.ensure(bytes + 256)) return "out of device memory (sort scratch)";
+  bytes = tmp.cap;
+  BCUDA(cub::DeviceRadixSort::SortKeys(tmp.p, bytes, d_in, d_out, n, 0, end_bit, st));
+  return "";
+}
+
 // per type: objects that are the resource of >= 1 relationship (ascending ids), from the forward row table
 std::string gpu_resource_lists(Snapshot* s, cudaStream_t st) {
   const size_t nt = s->n_objects.size();

@@ -55,8 +55,8 @@ struct zg_engine {
   uint64_t revision = 0;
   bool dirty = false;  // store changed since the last publish
   bool host_only = false;
-  // ZG_E2BIG protocol: the answer of the last lookup is kept so that the caller's retry with a
-  // larger buffer does not recompute it (same arguments, same snapshot revision)
+  // Concurrent LookupResources calls (one goroutine per list request: pkg/authz/responsefilterer.go:165) are
+  // coalesced like the checks: the leader answers up to 64 of them with one batched launch sequence.
   struct LookupKey {
     uint64_t revision = ~0ull;
     uint32_t subj = 0;
@@ -66,8 +66,26 @@ struct zg_engine {
       return revision == o.revision && subj == o.subj && res_type == o.res_type && perm == o.perm && stype == o.stype &&
              srel == o.srel && clock == o.clock;
     }
-  } last_lookup_key;
-  std::vector<uint32_t> last_lookup_ids;
+  };
+  struct LookupJob {
+    LookupKey key;       // revision / clock filled in by the leader
+    bool want_self = false;
+    std::vector<uint32_t> ids;
+    bool self_member = false;
+    int rc = ZG_OK;
+    std::string err;
+    bool done = false;
+  };
+  struct LookupBatcher {
+    std::mutex m;
+    std::condition_variable cv;
+    std::vector<LookupJob*> queue;
+    bool leader_active = false;
+  } lookups;
+  // ZG_E2BIG protocol: recent answers are kept so that a caller's retry with a larger buffer (same arguments,
+  // same snapshot revision) does not recompute them
+  std::deque<std::pair<LookupKey, std::shared_ptr<const std::vector<uint32_t>>>> lookup_cache;
+  static constexpr size_t kLookupCache = 128;
   HostSnapshot last_built;  // kept only for zg_debug_row / host-only engines
   bool keep_built = false;
   // Watch feed (pkg/authz/watch.go:29-31): what WriteRelationships / DeleteRelationships changed,
@@ -94,6 +112,7 @@ struct zg_engine {
 };
 
 static thread_local std::string g_err;
+static constexpr size_t kMaxLookupGroup = 64;  // = kMaxLookupBatch (kernels.cuh)
 static const char* kShardedMsg =
     "sharded engine: use zg_shard_pass / zg_shard_subqueries / zg_shard_fold (dist.ShardedStoreChecker)";
 
@@ -1089,9 +1108,116 @@ extern "C" int zg_list_postfilter(zg_engine* e, const char* body, size_t len, co
   return rc == ZG_EINVAL ? fail(rc, "zg_list_filter: inconsistent item ranges") : rc;
 }
 
-// *self_member (optional): the subject is a never-written userset T:x#r (subj == ZG_NO_OBJECT - 1) that is
-// nevertheless a member of T:x#perm (r is perm itself or a relation inlined into its union).
-static int lookup_locked(zg_engine* e, uint16_t res_type, uint16_t perm, uint16_t stype, uint32_t subj, uint16_t srel,
+// Answers a group of queued lookups under the engine lock: cache hits first, the rest in one batched launch
+// sequence, then the self-membership of userset subjects (Check is the arbiter of LookupResources).
+static void run_lookup_group(zg_engine* e, std::vector<zg_engine::LookupJob*>& group) {
+  std::lock_guard<std::mutex> g(e->mu);
+  auto fail_all = [&](int rc, const std::string& msg) {
+    for (auto* j : group) {
+      j->rc = rc;
+      j->err = msg;
+    }
+  };
+  if (e->host_only) return fail_all(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
+  if (e->dev.shard_count > 1) return fail_all(ZG_EINVAL, kShardedMsg);
+  if (e->dirty || !e->dev.snap) {
+    int rc = publish_locked(e);
+    if (rc) return fail_all(rc, g_err);
+  }
+  e->dev.now = now_of(e);
+  std::vector<Device::LookupReq> reqs;
+  std::vector<size_t> owner;  // job index of each request
+  std::vector<int> dup_of(group.size(), -1);
+  for (size_t i = 0; i < group.size(); ++i) {
+    zg_engine::LookupJob* j = group[i];
+    j->key.revision = e->revision;
+    j->key.clock = e->clock ? e->clock : -static_cast<int64_t>(e->dev.now);  // wall clock: valid within the same second
+    bool hit = false;
+    for (const auto& c : e->lookup_cache)
+      if (c.first == j->key) {
+        j->ids = *c.second;
+        hit = true;
+        break;
+      }
+    if (hit) continue;
+    for (size_t k = 0; k < i && dup_of[i] < 0; ++k)
+      if (group[k]->key == j->key && dup_of[k] < 0) dup_of[i] = static_cast<int>(k);
+    if (dup_of[i] >= 0) continue;
+    zg_check proto{};
+    proto.subj = j->key.subj;
+    proto.perm = j->key.perm;
+    proto.stype = j->key.stype;
+    proto.srel = j->key.srel;
+    reqs.push_back(Device::LookupReq{j->key.res_type, proto});
+    owner.push_back(i);
+  }
+  if (!reqs.empty()) {
+    std::vector<std::vector<uint32_t>> ids;
+    std::vector<int> rcs;
+    std::string err;
+    int rc = e->dev.lookup_batch(reqs, &ids, &rcs, &err);
+    if (rc) return fail_all(rc, err);
+    for (size_t r = 0; r < reqs.size(); ++r) {
+      zg_engine::LookupJob* j = group[owner[r]];
+      if (rcs[r]) {
+        j->rc = rcs[r];
+        j->err = "LookupResources: a candidate could not be decided (max dispatch depth / work budget exceeded)";
+        continue;
+      }
+      j->ids = std::move(ids[r]);
+      // A userset subject T:x#r is a member of T:x#P for every relation r inlined into P's union, with or
+      // without relationships, and the reverse walk only reaches x through stored edges: ask the check
+      // kernel about the one candidate res = subj.
+      const zg_engine::LookupKey& k = j->key;
+      if (k.srel != kNone && k.stype == k.res_type && k.subj < ZG_NO_OBJECT - 1 &&
+          !std::binary_search(j->ids.begin(), j->ids.end(), k.subj)) {
+        zg_check self = reqs[r].proto;
+        self.res = k.subj;
+        uint8_t code = 0;
+        rc = e->dev.check_host(&self, 1, &code, &err);
+        if (rc) {
+          j->rc = rc;
+          j->err = err;
+          continue;
+        }
+        if (code == ZG_HAS_PERMISSION) j->ids.insert(std::upper_bound(j->ids.begin(), j->ids.end(), k.subj), k.subj);
+      }
+      e->lookup_cache.emplace_back(k, std::make_shared<const std::vector<uint32_t>>(j->ids));
+      while (e->lookup_cache.size() > zg_engine::kLookupCache) e->lookup_cache.pop_front();
+    }
+  }
+  for (size_t i = 0; i < group.size(); ++i) {
+    zg_engine::LookupJob* j = group[i];
+    if (dup_of[i] >= 0) {
+      const zg_engine::LookupJob* src = group[dup_of[i]];
+      j->ids = src->ids;
+      j->rc = src->rc;
+      j->err = src->err;
+    }
+    // never-written userset subject T:x#r (subj is the sentinel): still a member of T:x#perm when r is perm
+    // itself or a relation inlined into its union
+    if (!j->rc && j->want_self && j->key.srel != kNone && j->key.stype == j->key.res_type && j->key.subj >= ZG_NO_OBJECT - 1) {
+      zg_check self{};
+      self.res = self.subj = ZG_NO_OBJECT;  // the same never-written object on both sides
+      self.perm = j->key.perm;
+      self.stype = j->key.stype;
+      self.srel = j->key.srel;
+      uint8_t code = 0;
+      std::string cerr;
+      int crc = e->dev.check_host(&self, 1, &code, &cerr);
+      if (crc) {
+        j->rc = crc;
+        j->err = cerr;
+      } else {
+        j->self_member = code == ZG_HAS_PERMISSION;
+      }
+    }
+  }
+}
+
+// Queue one lookup; the first caller to arrive while nobody leads answers everything queued (<= 64 per
+// launch sequence). Must be called WITHOUT e->mu held.
+static int lookup_queued(zg_engine* e, uint16_t res_type, uint16_t perm, uint16_t stype, uint32_t subj, uint16_t srel,
                          std::vector<uint32_t>* ids, bool* self_member = nullptr) {
   if (self_member) *self_member = false;
   const Schema& sc = e->schema;
@@ -1099,49 +1225,37 @@ static int lookup_locked(zg_engine* e, uint16_t res_type, uint16_t perm, uint16_
     return fail(ZG_EINVAL, "unknown resource type or permission");
   if (stype >= sc.types.size() || (srel != kNone && (srel >= sc.slots.size() || sc.slots[srel].type != stype)))
     return fail(ZG_EINVAL, "unknown subject type or relation");
-  zg_check proto{};
-  proto.subj = subj;
-  proto.perm = perm;
-  proto.stype = stype;
-  proto.srel = srel;
-  e->dev.now = now_of(e);
-  zg_engine::LookupKey key;
-  key.revision = e->revision;
-  key.subj = subj;
-  key.res_type = res_type;
-  key.perm = perm;
-  key.stype = stype;
-  key.srel = srel;
-  key.clock = e->clock ? e->clock : -static_cast<int64_t>(e->dev.now);  // wall clock: valid within the same second
-  if (self_member && srel != kNone && stype == res_type && subj >= ZG_NO_OBJECT - 1) {
-    zg_check self = proto;
-    self.res = self.subj = ZG_NO_OBJECT;  // the same never-written object on both sides
-    uint8_t code = 0;
-    std::string cerr;
-    int crc = e->dev.check_host(&self, 1, &code, &cerr);
-    if (crc) return fail(crc, cerr);
-    *self_member = code == ZG_HAS_PERMISSION;
+  zg_engine::LookupJob me;
+  me.key.subj = subj;
+  me.key.res_type = res_type;
+  me.key.perm = perm;
+  me.key.stype = stype;
+  me.key.srel = srel;
+  me.want_self = self_member != nullptr;
+  auto& b = e->lookups;
+  std::unique_lock<std::mutex> lk(b.m);
+  b.queue.push_back(&me);
+  while (!me.done) {
+    if (b.leader_active) {
+      b.cv.wait(lk);
+      continue;
+    }
+    b.leader_active = true;
+    std::vector<zg_engine::LookupJob*> group;
+    const size_t take = std::min<size_t>(b.queue.size(), kMaxLookupGroup);
+    group.assign(b.queue.begin(), b.queue.begin() + static_cast<long>(take));
+    b.queue.erase(b.queue.begin(), b.queue.begin() + static_cast<long>(take));
+    lk.unlock();
+    run_lookup_group(e, group);
+    lk.lock();
+    for (auto* j : group) j->done = true;
+    b.leader_active = false;
+    b.cv.notify_all();
   }
-  if (key == e->last_lookup_key) {
-    *ids = e->last_lookup_ids;
-    return ZG_OK;
-  }
-  std::string err;
-  int rc = e->dev.lookup(res_type, proto, ids, &err);
-  if (rc) return fail(rc, err);
-  // A userset subject T:x#r is a member of T:x#P for every relation r inlined into P's union, with or
-  // without relationships, and the reverse walk only reaches x through stored edges: ask the check
-  // kernel about the one candidate res = subj (Check is the arbiter of LookupResources everywhere else).
-  if (srel != kNone && stype == res_type && subj < ZG_NO_OBJECT - 1 && !std::binary_search(ids->begin(), ids->end(), subj)) {
-    zg_check self = proto;
-    self.res = subj;
-    uint8_t code = 0;
-    rc = e->dev.check_host(&self, 1, &code, &err);
-    if (rc) return fail(rc, err);
-    if (code == ZG_HAS_PERMISSION) ids->insert(std::upper_bound(ids->begin(), ids->end(), subj), subj);
-  }
-  e->last_lookup_key = key;
-  e->last_lookup_ids = *ids;
+  lk.unlock();
+  if (me.rc) return fail(me.rc, me.err);
+  *ids = std::move(me.ids);
+  if (self_member) *self_member = me.self_member;
   return ZG_OK;
 }
 
@@ -1149,16 +1263,41 @@ extern "C" int zg_lookup_resources(zg_engine* e, uint16_t res_type, uint16_t per
                                    uint16_t srel, uint32_t* out_ids, uint64_t cap, uint64_t* n_out) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if (!n_out) return fail(ZG_EINVAL, "NULL n_out");
-  std::lock_guard<std::mutex> g(e->mu);
-  if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
-  if (e->dev.shard_count > 1) return fail(ZG_EINVAL, kShardedMsg);
-  if (!e->dev.snap) return fail(ZG_ENOSNAPSHOT, "no snapshot published (call zg_publish)");
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
+    if (e->dev.shard_count > 1) return fail(ZG_EINVAL, kShardedMsg);
+    if (!e->dev.snap) return fail(ZG_ENOSNAPSHOT, "no snapshot published (call zg_publish)");
+  }
   std::vector<uint32_t> ids;
-  int rc = lookup_locked(e, res_type, perm, stype, subj, srel, &ids);
+  int rc = lookup_queued(e, res_type, perm, stype, subj, srel, &ids);
   if (rc) return rc;
   *n_out = ids.size();
   if (ids.size() > cap || (!out_ids && !ids.empty())) return ZG_E2BIG;
   if (!ids.empty()) std::memcpy(out_ids, ids.data(), ids.size() * 4);
+  return ZG_OK;
+}
+
+// (resource type, permission, subject) strings -> ids, under the engine lock. su == ZG_NO_OBJECT: never written.
+static int resolve_lookup_strs(zg_engine* e, const char* res_type, const char* perm, const char* subj_type, const char* subj_id,
+                               const char* subj_rel, int* rt, int* p, int* st, uint16_t* sr, uint32_t* su) {
+  std::lock_guard<std::mutex> g(e->mu);
+  int rc = ensure_published(e);
+  if (rc) return rc;
+  const Schema& sc = e->schema;
+  *rt = sc.type_id(res_type);
+  *st = sc.type_id(subj_type);
+  if (*rt < 0) return fail(ZG_EINVAL, std::string("object definition `") + res_type + "` not found");
+  if (*st < 0) return fail(ZG_EINVAL, std::string("object definition `") + subj_type + "` not found");
+  *p = sc.slot_id(*rt, perm);
+  if (*p < 0) return fail(ZG_EINVAL, std::string("relation/permission `") + perm + "` not found under definition `" + res_type + "`");
+  *sr = kNone;
+  if (!none_rel(subj_rel)) {
+    int s = sc.slot_id(*st, subj_rel);
+    if (s < 0) return fail(ZG_EINVAL, std::string("relation `") + subj_rel + "` not found under definition `" + subj_type + "`");
+    *sr = static_cast<uint16_t>(s);
+  }
+  *su = e->store.find(*st, subj_id);
   return ZG_OK;
 }
 
@@ -1167,31 +1306,23 @@ extern "C" int zg_lookup_resources_str(zg_engine* e, const char* res_type, const
                                        uint64_t* n_out) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if (!res_type || !perm || !subj_type || !subj_id) return fail(ZG_EINVAL, "NULL argument");
-  std::lock_guard<std::mutex> g(e->mu);
-  int rc = ensure_published(e);
+  int rt, p, st;
+  uint16_t sr;
+  uint32_t su;
+  int rc = resolve_lookup_strs(e, res_type, perm, subj_type, subj_id, subj_rel, &rt, &p, &st, &sr, &su);
   if (rc) return rc;
-  const Schema& sc = e->schema;
-  int rt = sc.type_id(res_type), st = sc.type_id(subj_type);
-  if (rt < 0) return fail(ZG_EINVAL, std::string("object definition `") + res_type + "` not found");
-  if (st < 0) return fail(ZG_EINVAL, std::string("object definition `") + subj_type + "` not found");
-  int p = sc.slot_id(rt, perm);
-  if (p < 0) return fail(ZG_EINVAL, std::string("relation/permission `") + perm + "` not found under definition `" + res_type + "`");
-  uint16_t sr = kNone;
-  if (!none_rel(subj_rel)) {
-    int s = sc.slot_id(st, subj_rel);
-    if (s < 0) return fail(ZG_EINVAL, std::string("relation `") + subj_rel + "` not found under definition `" + subj_type + "`");
-    sr = static_cast<uint16_t>(s);
-  }
-  uint32_t su = e->store.find(st, subj_id);
   std::vector<uint32_t> ids;
   bool self_member = false;
-  rc = lookup_locked(e, static_cast<uint16_t>(rt), static_cast<uint16_t>(p), static_cast<uint16_t>(st),
+  rc = lookup_queued(e, static_cast<uint16_t>(rt), static_cast<uint16_t>(p), static_cast<uint16_t>(st),
                      su == ZG_NO_OBJECT ? ZG_NO_OBJECT - 1 : su, sr, &ids, &self_member);
   if (rc) return rc;
   std::vector<std::string> names;
-  for (uint32_t id : ids) {
-    std::string_view n;
-    names.push_back(e->store.name(rt, id, &n) ? std::string(n) : std::to_string(id));
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    for (uint32_t id : ids) {
+      std::string_view n;
+      names.push_back(e->store.name(rt, id, &n) ? std::string(n) : std::to_string(id));
+    }
   }
   // never-written userset subject that names itself
   if (su == ZG_NO_OBJECT && self_member) names.push_back(subj_id);
@@ -1260,32 +1391,24 @@ extern "C" int zg_list_prefilter(zg_engine* e, const char* body, size_t len, uin
   if (!body || !out_len || !tpl) return fail(ZG_EINVAL, "NULL argument");
   if (!tpl->res_type || !tpl->permission || !tpl->subj_type || !tpl->subj_id) return fail(ZG_EINVAL, "NULL template field");
   if (mode > ZG_LIST_TABLE_ROWS) return fail(ZG_EINVAL, "unknown mode");
-  // 1. the allowed ids (one LookupResources on the GPU)
+  // 1. the allowed ids (one LookupResources on the GPU; concurrent list requests share launches)
   std::vector<uint32_t> ids;
   std::string self;
+  int rt = -1;
   {
-    std::lock_guard<std::mutex> g(e->mu);
-    int rc = ensure_published(e);
+    int p, st;
+    uint16_t sr;
+    uint32_t su;
+    int rc = resolve_lookup_strs(e, tpl->res_type, tpl->permission, tpl->subj_type, tpl->subj_id, tpl->subj_rel, &rt, &p, &st,
+                                 &sr, &su);
     if (rc) return rc;
-    const Schema& sc = e->schema;
-    const int rt = sc.type_id(tpl->res_type), st = sc.type_id(tpl->subj_type);
-    if (rt < 0) return fail(ZG_EINVAL, std::string("object definition `") + tpl->res_type + "` not found");
-    if (st < 0) return fail(ZG_EINVAL, std::string("object definition `") + tpl->subj_type + "` not found");
-    const int p = sc.slot_id(rt, tpl->permission);
-    if (p < 0) return fail(ZG_EINVAL, std::string("relation/permission `") + tpl->permission + "` not found");
-    uint16_t sr = kNone;
-    if (!none_rel(tpl->subj_rel)) {
-      const int s2 = sc.slot_id(st, tpl->subj_rel);
-      if (s2 < 0) return fail(ZG_EINVAL, std::string("relation `") + tpl->subj_rel + "` not found");
-      sr = static_cast<uint16_t>(s2);
-    }
-    const uint32_t su = e->store.find(st, tpl->subj_id);
     bool self_member = false;
-    rc = lookup_locked(e, static_cast<uint16_t>(rt), static_cast<uint16_t>(p), static_cast<uint16_t>(st),
+    rc = lookup_queued(e, static_cast<uint16_t>(rt), static_cast<uint16_t>(p), static_cast<uint16_t>(st),
                        su == ZG_NO_OBJECT ? ZG_NO_OBJECT - 1 : su, sr, &ids, &self_member);
     if (rc) return rc;
     if (su == ZG_NO_OBJECT && self_member) self = tpl->subj_id;  // never-written userset subject naming itself
     // lookups.go:106-109: an id that yields no name fails the whole pre-filter
+    std::lock_guard<std::mutex> g(e->mu);
     for (uint32_t id : ids) {
       std::string_view nm;
       if (e->store.name(rt, id, &nm) && nm.back() == '/') return fail(ZG_EINVAL, "unable to determine name for resource");
@@ -1341,6 +1464,8 @@ extern "C" int zg_stats_get(zg_engine* e, zg_stats* out) {
   out->full_publishes = e->dev.full_publishes;
   out->last_publish_ms = e->dev.last_build_ms;
   out->streamed_calls = e->dev.streamed_calls;
+  out->lookup_batches = e->dev.lookup_batches;
+  out->lookups_batched = e->dev.lookups_batched;
   if (!e->host_only) e->dev.read_events(&out->stack_spills, &out->memo_batches);
   if (e->dev.snap) {
     out->tuples = e->dev.snap->n_tuples;

@@ -73,9 +73,11 @@ Device::~Device() {
   rb_front_[0].release();
   rb_front_[1].release();
   rb_cand_.release();
+  for (auto* b : {&lb_params_, &lb_owner_, &lb_ctrl_, &lb_keys_[0], &lb_keys_[1]}) b->release();
   if (pin_in_) cudaFreeHost(pin_in_);
   if (pin_out_) cudaFreeHost(pin_out_);
   if (pin_ready_) cudaFreeHost(pin_ready_);
+  if (pin_lk_) cudaFreeHost(pin_lk_);
   if (cstream_) {
     cudaStreamSynchronize(cstream_);
     cudaStreamDestroy(cstream_);
@@ -94,6 +96,7 @@ static size_t smem_bytes(uint32_t prog_bytes) {
 std::string Device::init(int dev, uint64_t subq_cap, uint32_t budget) {
   if (const char* v = std::getenv("ZGPU_NO_INVERT")) invert = !(*v && *v != '0');
   if (const char* v = std::getenv("ZGPU_NO_RBFS")) use_rbfs = !(*v && *v != '0');
+  if (const char* v = std::getenv("ZGPU_LOOKUP_BATCH_CAP")) lb_cap_ = std::max<uint64_t>(1024, std::strtoull(v, nullptr, 10));
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)
@@ -594,6 +597,7 @@ int Device::check_host_multi(const std::vector<HostReq>& reqs, std::string* err)
     const uint64_t n_chunks = (total + kStreamChunkItems - 1) / kStreamChunkItems;
     if (pin_ready_cap_ < n_chunks) {
       if (pin_ready_) cudaFreeHost(pin_ready_);
+  if (pin_lk_) cudaFreeHost(pin_lk_);
       pin_ready_cap_ = 0;
       ZG_CUDA(cudaMallocHost(&pin_ready_, n_chunks * 8));
       pin_ready_cap_ = n_chunks;
@@ -952,6 +956,166 @@ int Device::lookup(uint16_t res_type, const zg_check& proto, std::vector<uint32_
     ZG_CUDA(cudaStreamSynchronize(stream));
     if (cnt <= 2048) std::sort(ids->begin(), ids->end());
   }
+  return ZG_OK;
+}
+
+
+int Device::lookup_batch(const std::vector<LookupReq>& reqs, std::vector<std::vector<uint32_t>>* ids, std::vector<int>* rcs,
+                         std::string* err) {
+  const size_t K = reqs.size();
+  ids->assign(K, {});
+  rcs->assign(K, ZG_OK);
+  std::shared_ptr<Snapshot> s = snap;
+  if (!s) {
+    if (err) *err = "no snapshot published";
+    return ZG_ENOSNAPSHOT;
+  }
+  auto one_by_one = [&]() -> int {
+    for (size_t i = 0; i < K; ++i) {
+      std::string e1;
+      (*rcs)[i] = lookup(reqs[i].res_type, reqs[i].proto, &(*ids)[i], &e1);
+      if ((*rcs)[i] && (*rcs)[i] != ZG_EDEPTH) {
+        if (err) *err = e1;
+        return (*rcs)[i];
+      }
+    }
+    return ZG_OK;
+  };
+  // the batch buffers overflowed: halves hold about half as much (down to the single path, which degrades to
+  // the exhaustive scan by itself)
+  auto halves = [&]() -> int {
+    const size_t h = K / 2;
+    std::vector<LookupReq> a(reqs.begin(), reqs.begin() + h), b(reqs.begin() + h, reqs.end());
+    std::vector<std::vector<uint32_t>> ia, ib;
+    std::vector<int> ra, rb;
+    int rc = lookup_batch(a, &ia, &ra, err);
+    if (rc) return rc;
+    rc = lookup_batch(b, &ib, &rb, err);
+    if (rc) return rc;
+    for (size_t i = 0; i < h; ++i) (*ids)[i] = std::move(ia[i]), (*rcs)[i] = ra[i];
+    for (size_t i = h; i < K; ++i) (*ids)[i] = std::move(ib[i - h]), (*rcs)[i] = rb[i - h];
+    return ZG_OK;
+  };
+  if (K == 1 || !use_rbfs) return one_by_one();
+  if (K > kMaxLookupBatch) return halves();
+  const uint64_t cap = lb_cap_;
+  for (const auto& r : reqs)
+    if (r.res_type >= s->resources.size() || r.proto.stype >= s->n_objects.size()) return one_by_one();
+  ZG_CUDA(cudaSetDevice(device));
+  if (have_last_) ZG_CUDA(cudaStreamWaitEvent(stream, last_done_, 0));
+  const unsigned long long words = (s->total_bits + 31) / 32 + 4;
+  constexpr int kLevelsPerRound = 10;
+  const size_t n_ctrl = 8 + ZG_MAX_DEPTH + 4 + kMaxLookupBatch;  // flags, cand count, key count, err mask | level counts | per lookup
+  if (!rb_visited_.ensure(words * 4 * K) || !rb_front_[0].ensure(cap * 8) || !rb_front_[1].ensure(cap * 8) ||
+      !lk_jobs_.ensure(cap * sizeof(zg_check)) || !lb_owner_.ensure(cap) || !lk_codes_.ensure(cap) ||
+      !lb_params_.ensure(K * sizeof(LookupParam)) || !lb_ctrl_.ensure(n_ctrl * 8) || !lb_keys_[0].ensure(cap * 8) ||
+      !lb_keys_[1].ensure(cap * 8) || !lk_ids_.ensure(cap * 4))
+    return one_by_one();  // not enough memory for the batch buffers: the single path scales down by itself
+  std::vector<LookupParam> lp(K);
+  std::vector<unsigned long long> seeds(K);
+  for (size_t i = 0; i < K; ++i) {
+    const zg_check& q = reqs[i].proto;
+    lp[i] = LookupParam{q.subj, reqs[i].res_type, q.perm, q.stype, q.srel};
+    seeds[i] = (static_cast<unsigned long long>(i) << 48) | (static_cast<unsigned long long>(q.stype) << 32) | q.subj;
+  }
+  unsigned long long* ctrl = lb_ctrl_.as<unsigned long long>();
+  unsigned long long* counts = ctrl + 8;
+  unsigned long long* per_lookup = counts + ZG_MAX_DEPTH + 4;
+  ZG_CUDA(cudaMemsetAsync(ctrl, 0, n_ctrl * 8, stream));
+  ZG_CUDA(cudaMemsetAsync(rb_visited_.p, 0, words * 4 * K, stream));
+  ZG_CUDA(cudaMemcpyAsync(lb_params_.p, lp.data(), K * sizeof(LookupParam), cudaMemcpyHostToDevice, stream));
+  ZG_CUDA(cudaMemcpyAsync(rb_front_[0].p, seeds.data(), K * 8, cudaMemcpyHostToDevice, stream));
+  const unsigned long long kk = K;
+  ZG_CUDA(cudaMemcpyAsync(counts, &kk, 8, cudaMemcpyHostToDevice, stream));
+  MrbfsParams p{};
+  p.rrow_ptr = s->rrow_ptr.as<uint32_t>();
+  p.rcol = s->rcol.as<uint32_t>();
+  p.prog = s->prog.as<uint8_t>();
+  p.lk = lb_params_.as<LookupParam>();
+  p.counts = counts;
+  p.cap = cap;
+  p.visited = rb_visited_.as<uint32_t>();
+  p.words = words;
+  p.type_bit_base = s->type_bit_base.as<unsigned long long>();
+  p.cand = lk_jobs_.as<zg_check>();
+  p.cand_owner = lb_owner_.as<uint8_t>();
+  p.cand_count = ctrl + 1;
+  p.cand_cap = cap;
+  p.flags = reinterpret_cast<uint32_t*>(ctrl);
+  unsigned long long host[4] = {0, 0, 0, 0};
+  int level = 0, cur = 0;
+  for (;;) {
+    // a round of levels without a host round trip: a level whose input is empty costs one empty launch
+    for (int r = 0; r < kLevelsPerRound && level <= ZG_MAX_DEPTH + 1; ++r, ++level) {
+      p.in = rb_front_[cur].as<unsigned long long>();
+      p.out = rb_front_[cur ^ 1].as<unsigned long long>();
+      p.level = level;
+      mrbfs_expand_kernel<<<sm_count_ * 8, 256, 0, stream>>>(p);
+      ++launches;
+      cur ^= 1;
+    }
+    unsigned long long last = 0;
+    ZG_CUDA(cudaMemcpyAsync(host, ctrl, sizeof host, cudaMemcpyDeviceToHost, stream));
+    ZG_CUDA(cudaMemcpyAsync(&last, counts + level, 8, cudaMemcpyDeviceToHost, stream));
+    ZG_CUDA(cudaStreamSynchronize(stream));
+    if (static_cast<uint32_t>(host[0]) & 16u) return halves();  // frontier / candidate buffers overflowed
+    if (last == 0 || level > ZG_MAX_DEPTH + 1) break;  // deeper objects cannot be within the dispatch cap anyway
+  }
+  const uint64_t n_cand = host[1];
+  lookup_batches += 1;
+  lookups_batched += K;
+  if (n_cand == 0) return ZG_OK;
+  int rc = check_device(lk_jobs_.as<zg_check>(), n_cand, lk_codes_.as<uint8_t>(), stream, true, nullptr, err);
+  if (rc) return rc;
+  const unsigned blk = 256, grid = static_cast<unsigned>((n_cand + blk - 1) / blk);
+  lookup_keys_kernel<<<grid, blk, 0, stream>>>(lk_jobs_.as<zg_check>(), lb_owner_.as<uint8_t>(), lk_codes_.as<uint8_t>(), n_cand,
+                                               lb_keys_[0].as<unsigned long long>(), ctrl + 2, per_lookup, ctrl + 3);
+  ++launches;
+  std::vector<unsigned long long> cnt(K);
+  uint32_t cflags = 0;
+  ZG_CUDA(cudaMemcpyAsync(host, ctrl, sizeof host, cudaMemcpyDeviceToHost, stream));
+  ZG_CUDA(cudaMemcpyAsync(cnt.data(), per_lookup, K * 8, cudaMemcpyDeviceToHost, stream));
+  ZG_CUDA(cudaMemcpyAsync(&cflags, ctrl_.as<unsigned long long>() + 3, 4, cudaMemcpyDeviceToHost, stream));
+  ZG_CUDA(cudaStreamSynchronize(stream));
+  if (cflags & 1u) {
+    if (err) *err = "expansion stack overflow (per-warp spill area exhausted)";
+    return ZG_ENOMEM;
+  }
+  const uint64_t n_keys = host[2];
+  const unsigned long long err_mask = host[3];
+  if (n_keys) {
+    // ascending (lookup, id): one radix sort over the 32 id bits and the few lookup bits
+    int kbits = 1;
+    while ((1u << kbits) < K) ++kbits;
+    std::string serr = sort_u64(lb_keys_[0].as<unsigned long long>(), lb_keys_[1].as<unsigned long long>(), n_keys, 32 + kbits, stream);
+    if (!serr.empty()) {
+      if (err) *err = serr;
+      return ZG_ECUDA;
+    }
+    low_words_kernel<<<static_cast<unsigned>((n_keys + blk - 1) / blk), blk, 0, stream>>>(lb_keys_[1].as<unsigned long long>(),
+                                                                                      n_keys, lk_ids_.as<uint32_t>());
+    ++launches;
+    // one copy back into pinned memory, then split per lookup
+    if (pin_lk_cap_ < n_keys * 4) {
+      if (pin_lk_) cudaFreeHost(pin_lk_);
+      pin_lk_cap_ = 0;
+      ZG_CUDA(cudaMallocHost(&pin_lk_, n_keys * 4 + (n_keys * 4) / 4));
+      pin_lk_cap_ = n_keys * 4 + (n_keys * 4) / 4;
+    }
+    ZG_CUDA(cudaMemcpyAsync(pin_lk_, lk_ids_.p, n_keys * 4, cudaMemcpyDeviceToHost, stream));
+    ZG_CUDA(cudaStreamSynchronize(stream));
+    uint64_t off = 0;
+    for (size_t i = 0; i < K; ++i) {
+      const uint32_t* src = static_cast<const uint32_t*>(pin_lk_) + off;
+      (*ids)[i].assign(src, src + cnt[i]);
+      off += cnt[i];
+    }
+  }
+  for (size_t i = 0; i < K; ++i)
+    if ((err_mask >> i) & 1ull) {
+      (*rcs)[i] = ZG_EDEPTH;
+      (*ids)[i].clear();
+    }
   return ZG_OK;
 }
 

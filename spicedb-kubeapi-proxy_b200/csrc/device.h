@@ -79,6 +79,15 @@ class Device {
   };
   int check_host_multi(const std::vector<HostReq>& reqs, std::string* err);
   int lookup(uint16_t res_type, const zg_check& proto, std::vector<uint32_t>* ids, std::string* err);
+  // K <= 64 LookupResources in one launch sequence (multi-source reverse walk, one verification launch, one
+  // sort, one copy back). rcs[i] = ZG_OK / ZG_EDEPTH per lookup; the call's own code covers the batch.
+  struct LookupReq {
+    uint16_t res_type;
+    zg_check proto;
+  };
+  int lookup_batch(const std::vector<LookupReq>& reqs, std::vector<std::vector<uint32_t>>* ids, std::vector<int>* rcs,
+                   std::string* err);
+  uint64_t lookup_batches = 0, lookups_batched = 0;
 
   // ---- object-hash sharded store: one pass at a time, sub-queries routed by the host ----
   uint32_t shard_count = 1, shard_rank = 0;
@@ -124,6 +133,10 @@ class Device {
   DevBuf shard_tmp_;
   DevBuf stage_in_, stage_out_, lk_jobs_, lk_codes_, lk_ids_;
   DevBuf rb_visited_, rb_front_[2], rb_cand_;
+  DevBuf lb_params_, lb_owner_, lb_ctrl_, lb_keys_[2];  // batched lookups
+  uint64_t lb_cap_ = 1ull << 24;  // frontier entries / candidates of one lookup batch (ZGPU_LOOKUP_BATCH_CAP)
+  void* pin_lk_ = nullptr;
+  size_t pin_lk_cap_ = 0;
   uint64_t rb_cap_ = 1ull << 22;  // frontier / candidate capacity before falling back to the exhaustive scan
   // Reverse-BFS candidates of type res_type for the subject in proto; *overflow -> use the exhaustive list.
   int lookup_candidates(const Snapshot& s, uint16_t res_type, const zg_check& proto, uint64_t* n_cand, bool* overflow,
@@ -148,6 +161,7 @@ class Device {
 
 // Device radix sort of n u32 keys (build.cu keeps the cub instantiations in one translation unit).
 std::string sort_u32(const uint32_t* d_in, uint32_t* d_out, uint64_t n, cudaStream_t st);
+std::string sort_u64(const unsigned long long* d_in, unsigned long long* d_out, uint64_t n, int end_bit, cudaStream_t st);
 std::string gpu_build_snapshot(const Store& store, const Schema& sc, HostSnapshot* lay, cudaStream_t st, Snapshot* s);
 // Applies store.journal to the arrays of `s` (same layout). cls_delta: per-class change of the relationship count.
 // "relayout" / "corrupt": the caller must rebuild.

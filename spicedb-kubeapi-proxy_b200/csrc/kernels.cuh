@@ -892,6 +892,139 @@ __global__ void __launch_bounds__(256) rbfs_expand_kernel(const RbfsParams p) {
   }
 }
 
+// ---- batched LookupResources: K reverse walks in one frontier ---------------------------------
+//
+// The proxy runs one LookupResources per list request, concurrently (pkg/authz/responsefilterer.go:165,
+// lookups.go:49-65). K of them share every launch: frontier entries carry the lookup they belong to,
+// each lookup has its own visited bitmap slice, candidates are emitted directly as check items (the
+// lookup's subject and permission filled in) with their owner beside them, and the level loop needs no
+// host round trip: every level kernel reads its input count from device memory and an empty level is a
+// no-op launch.
+struct LookupParam {   // one per lookup of the batch
+  uint32_t subj;
+  uint16_t want_type, perm, stype, srel;
+};
+constexpr int kMaxLookupBatch = 64;
+struct MrbfsParams {
+  const uint32_t* rrow_ptr;
+  const uint32_t* rcol;
+  const uint8_t* prog;
+  const LookupParam* lk;
+  const unsigned long long* in;       // lookup << 48 | type << 32 | object
+  unsigned long long* out;
+  unsigned long long* counts;         // counts[level] = entries of `in`, counts[level + 1] = entries of `out`
+  int level;
+  unsigned long long cap;             // frontier capacity
+  uint32_t* visited;                  // K slices of `words` u32
+  unsigned long long words;
+  const unsigned long long* type_bit_base;
+  zg_check* cand;                     // candidate checks
+  uint8_t* cand_owner;
+  unsigned long long* cand_count;
+  unsigned long long cand_cap;
+  uint32_t* flags;                    // bit 4: frontier / candidate overflow
+};
+
+__global__ void __launch_bounds__(256) mrbfs_expand_kernel(const MrbfsParams p) {
+  const unsigned long long n_in = p.counts[p.level];
+  if (n_in == 0 || n_in > p.cap) return;
+  const Prog pr = make_prog(p.prog);
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned long long n_warps = (static_cast<unsigned long long>(gridDim.x) * blockDim.x) >> 5;
+  for (unsigned long long w = (blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x) >> 5; w < n_in;
+       w += n_warps) {
+    const unsigned long long item = p.in[w];
+    const uint32_t k = static_cast<uint32_t>(item >> 48), type = static_cast<uint32_t>(item >> 32) & 0xFFFFu,
+                   obj = static_cast<uint32_t>(item);
+    const LookupParam lk = p.lk[k];
+    uint32_t* const vis = p.visited + k * p.words;
+    const DTypeInv tc = pr.type_rcls()[type];
+    for (int ci = tc.begin; ci < tc.end; ++ci) {
+      const DCls cl = pr.cls()[pr.rcls()[ci]];
+      if (cl.flags & CF_EMPTY) continue;
+      uint32_t row = obj;
+      if (cl.sslot == kWildcard) {
+        if (p.level != 0 || lk.srel != kNone) continue;  // type:* only matches the original, relation-less subject
+        row = 0;
+      } else if (obj >= cl.nsubj) {
+        continue;
+      }
+      const unsigned long long ri = cl.rrow_base + static_cast<unsigned long long>(row) * cl.rstride;
+      const uint32_t b = __ldg(p.rrow_ptr + ri), e = __ldg(p.rrow_ptr + ri + 1);
+      const unsigned long long bit_base = p.type_bit_base[cl.rtype];
+      for (uint32_t i0 = b; i0 < e; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        bool fresh = false;
+        uint32_t r = 0;
+        if (i < e) {
+          r = __ldg(p.rcol + i);
+          const unsigned long long bit = bit_base + r;
+          const uint32_t mask = 1u << (bit & 31);
+          fresh = !(atomicOr(vis + (bit >> 5), mask) & mask);
+        }
+        const unsigned fm = __ballot_sync(kFull, fresh);
+        if (fm) {
+          unsigned long long at = 0;
+          if (lane == 0) at = atomicAdd(p.counts + p.level + 1, static_cast<unsigned long long>(__popc(fm)));
+          at = __shfl_sync(kFull, at, 0) + __popc(fm & ((1u << lane) - 1u));
+          if (fresh) {
+            if (at < p.cap) p.out[at] = (static_cast<unsigned long long>(k) << 48) | (static_cast<unsigned long long>(cl.rtype) << 32) | r;
+            else atomicOr(p.flags, 16u);
+          }
+        }
+        const bool is_cand = fresh && cl.rtype == lk.want_type;
+        const unsigned cm = __ballot_sync(kFull, is_cand);
+        if (cm) {
+          unsigned long long at = 0;
+          if (lane == 0) at = atomicAdd(p.cand_count, static_cast<unsigned long long>(__popc(cm)));
+          at = __shfl_sync(kFull, at, 0) + __popc(cm & ((1u << lane) - 1u));
+          if (is_cand) {
+            if (at < p.cand_cap) {
+              zg_check q;
+              q.res = r;
+              q.subj = lk.subj;
+              q.perm = lk.perm;
+              q.stype = lk.stype;
+              q.srel = lk.srel;
+              q.flags = 0;
+              p.cand[at] = q;
+              p.cand_owner[at] = static_cast<uint8_t>(k);
+            } else {
+              atomicOr(p.flags, 16u);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// HAS candidates -> keys (owner << 32 | resource id), compacted; per-lookup result counts; lookups with an
+// undecidable candidate (ITEM_ERROR) are flagged in err_mask.
+__global__ void lookup_keys_kernel(const zg_check* cand, const uint8_t* owner, const uint8_t* codes, unsigned long long n,
+                                   unsigned long long* keys, unsigned long long* n_keys, unsigned long long* per_lookup,
+                                   unsigned long long* err_mask) {
+  unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+  const bool in = i < n;
+  const uint8_t code = in ? codes[i] : 0;
+  const bool has = code == ZG_HAS_PERMISSION;
+  if (in && code == ZG_ITEM_ERROR) atomicOr(err_mask, 1ull << owner[i]);
+  const unsigned m = __ballot_sync(kFull, has);
+  if (!m) return;
+  const unsigned lane = threadIdx.x & 31;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(n_keys, static_cast<unsigned long long>(__popc(m)));
+  base = __shfl_sync(kFull, base, 0);
+  if (has) {
+    keys[base + __popc(m & ((1u << lane) - 1u))] = (static_cast<unsigned long long>(owner[i]) << 32) | cand[i].res;
+    atomicAdd(per_lookup + owner[i], 1ull);
+  }
+}
+__global__ void low_words_kernel(const unsigned long long* keys, unsigned long long n, uint32_t* out) {
+  unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] = static_cast<uint32_t>(keys[i]);
+}
+
 // LookupResources when the permission is a flat union of direct relations (the reference's
 // own schema: `permission view = viewer + creator`, pkg/spicedb/bootstrap.yaml:13): the answer
 // is the union of the subject's reverse rows of those classes. One warp copies them out.

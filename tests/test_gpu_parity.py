@@ -797,3 +797,46 @@ def test_incremental_publish_equals_rebuild_and_oracle(zg, monkeypatch):
         st = e.stats()
         assert st["delta_publishes"] >= 5, st  # a batch that outgrows an object capacity may rebuild
         e.close()
+
+
+@pytest.mark.parametrize("cap", [0, 4096])
+def test_concurrent_lookups_share_launches_and_equal_the_oracle(zg, monkeypatch, cap):
+    """One LookupResources per list request, concurrently (pkg/authz/responsefilterer.go:165): queued lookups are
+    answered K at a time by one multi-source reverse walk + one verification launch. Every answer equals the
+    oracle's; with a tiny batch buffer (cap=4096) the batch overflows and is answered in halves, same answers."""
+    import threading
+
+    from oracle.pyoracle import Oracle
+    from spicedb_kubeapi_proxy_b200 import workloads
+
+    if cap:
+        monkeypatch.setenv("ZGPU_LOOKUP_BATCH_CAP", str(cap))
+    w = workloads.cfg4(scale=0.003)
+    e, o = zg.Engine(w.schema), Oracle(w.schema)
+    w.load_into(e), w.load_into(o)
+    e.publish()
+    rng = np.random.default_rng(5)
+    n_users = int(max(g.subj.max() for g in w.groups if g.subj_type == "user" and not g.wildcard)) + 1
+    users = rng.integers(0, n_users, 96)
+    perms = ["view" if i % 3 else "restricted_view" for i in range(users.size)]
+    want = [o.lookup_resources_ids("document", p, "user", int(u)) for u, p in zip(users, perms)]
+    got = [None] * users.size
+    errs = []
+
+    def run(lo, hi):
+        try:
+            for i in range(lo, hi):
+                got[i] = e.lookup_resources_ids("document", perms[i], "user", int(users[i]))
+        except Exception as ex:  # noqa: BLE001
+            errs.append(ex)
+
+    ths = [threading.Thread(target=run, args=(i, i + 3)) for i in range(0, users.size, 3)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errs, errs
+    for i in range(users.size):
+        assert np.array_equal(got[i], want[i]), f"lookup {i}: {got[i].size} ids vs {want[i].size}"
+    st = e.stats()
+    assert st["lookups_batched"] > 0 and st["lookup_batches"] < st["lookups_batched"], st
+    assert sum(x.size for x in want) > 1000
+    e.close()
