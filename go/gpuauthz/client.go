@@ -60,12 +60,19 @@ type Client struct {
 	broken atomic.Bool
 }
 
+// AllDevices: every visible GPU from `device` on (zg_config.n_devices).
+const AllDevices = uint32(C.ZG_ALL_DEVICES)
+
 var errBroken = status.Error(codes.Unavailable, "gpu mirror is out of sync with SpiceDB and could not be rebuilt")
 
 // New creates the GPU engine, loads the schema and mirrors the relationships that are
 // already in SpiceDB (bootstrap file: pkg/spicedb/spicedb.go:19-24).
-func New(ctx context.Context, inner v1.PermissionsServiceClient, schema string, device int) (*Client, error) {
-	cfg := C.zg_config{device: C.int32_t(device)}
+//
+// nDevices > 1 (or AllDevices) makes the one engine own that many GPUs of the box, each holding a replica of the
+// snapshot and answering its slice of every bulk call: the proxy keeps a single client (pkg/proxy/options.go:81-82),
+// so this is how it uses more than one GPU.
+func New(ctx context.Context, inner v1.PermissionsServiceClient, schema string, device int, nDevices uint32) (*Client, error) {
+	cfg := C.zg_config{device: C.int32_t(device), n_devices: C.uint32_t(nDevices)}
 	var eng *C.zg_engine
 	if err := call(func() C.int { return C.zg_engine_create(&cfg, &eng) }); err != nil {
 		return nil, err // fail closed: no CPU fallback inside the library

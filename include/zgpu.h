@@ -82,7 +82,13 @@ typedef struct {
   uint16_t shard_rank;       /* object-hash sharded store: this engine keeps only    */
   uint16_t shard_count;      /* relationships whose resource id % count == rank;
                                 0 or 1 = whole store (replica)                       */
+  uint32_t n_devices;        /* 0 / 1 = the one device above; k > 1 = devices device .. device + k - 1, each
+                                holding a replica of the snapshot and answering its slice of every bulk call
+                                (SURVEY.md 8e mode 1: no data-path collective); ZG_ALL_DEVICES = every
+                                visible device from `device` on                                            */
+  uint32_t reserved;
 } zg_config;
+#define ZG_ALL_DEVICES 0xFFFFFFFFu
 
 /* One interned check: 16 bytes in, 1 byte out. Object ids are dense per type. */
 typedef struct {
@@ -153,6 +159,7 @@ typedef struct {
   uint64_t streamed_calls;     /* host calls whose items were copied in behind the running kernel       */
   uint64_t lookup_batches;     /* launch sequences that answered more than one LookupResources           */
   uint64_t lookups_batched;    /* LookupResources calls answered by those                                */
+  uint64_t devices;            /* GPUs this engine owns (counters above are summed over them)            */
 } zg_stats;
 
 /* ---- lifecycle --------------------------------------------------------- */

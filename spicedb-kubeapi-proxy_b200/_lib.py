@@ -33,7 +33,8 @@ class ZgpuError(RuntimeError):
 
 class _Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("subquery_capacity", C.c_uint64),
-                ("work_budget", C.c_uint32), ("shard_rank", C.c_uint16), ("shard_count", C.c_uint16)]
+                ("work_budget", C.c_uint32), ("shard_rank", C.c_uint16), ("shard_count", C.c_uint16),
+                ("n_devices", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class _RelStr(C.Structure):
@@ -63,7 +64,8 @@ class _Stats(C.Structure):
                 ("last_kernel_ms", C.c_double), ("coalesced_launches", C.c_uint64), ("coalesced_requests", C.c_uint64),
                 ("stack_spills", C.c_uint64), ("memo_batches", C.c_uint64), ("split_batches", C.c_uint64),
                 ("delta_publishes", C.c_uint64), ("full_publishes", C.c_uint64), ("last_publish_ms", C.c_double),
-                ("streamed_calls", C.c_uint64), ("lookup_batches", C.c_uint64), ("lookups_batched", C.c_uint64)]
+                ("streamed_calls", C.c_uint64), ("lookup_batches", C.c_uint64), ("lookups_batched", C.c_uint64),
+                ("devices", C.c_uint64)]
 
 
 class _Update(C.Structure):
@@ -285,12 +287,13 @@ class Engine:
     """One zg_engine: schema + relationship store + published CSR snapshot in HBM."""
 
     def __init__(self, schema: str | None = None, device: int = -1, subquery_capacity: int = 0, work_budget: int = 0,
-                 host_only: bool = False, forward_only: bool = False, shard_rank: int = 0, shard_count: int = 0):
+                 host_only: bool = False, forward_only: bool = False, shard_rank: int = 0, shard_count: int = 0,
+                 n_devices: int = 0):
         """host_only=True builds schema/store/snapshot without a GPU (CPU unit tests of
         the host logic); every check/lookup on such an engine raises ZgpuError."""
         self._L = lib()
         cfg = _Config(device, (1 if host_only else 0) | (2 if forward_only else 0), subquery_capacity, work_budget,
-                      shard_rank, shard_count)
+                      shard_rank, shard_count, n_devices & 0xFFFFFFFF, 0)
         h = C.c_void_p()
         rc = self._L.zg_engine_create(C.byref(cfg), C.byref(h))
         if rc:

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <ctime>
 #include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <new>
@@ -44,8 +45,62 @@ struct Batcher {
   static constexpr uint64_t kMaxItemsPerLaunch = 1ull << 24;
 };
 
+// One engine may own several GPUs of the box (zg_config.n_devices): every device holds a REPLICA of the
+// snapshot (1e8 relationships = 2 GB, two orders of magnitude under one GPU's HBM) and answers its slice of
+// every batch; no data-path collective (SURVEY.md 8e mode 1). Device 0 is driven inline by the calling
+// thread, every further device by its own worker thread (CUDA's current device is per-thread state).
+struct DeviceWorker {
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  std::function<void()> task;
+  bool has = false, stop = false, busy = false;
+  void start() {
+    th = std::thread([this] {
+      std::unique_lock<std::mutex> lk(m);
+      for (;;) {
+        cv.wait(lk, [this] { return has || stop; });
+        if (stop) return;
+        std::function<void()> f = std::move(task);
+        has = false;
+        lk.unlock();
+        f();
+        lk.lock();
+        busy = false;
+        cv.notify_all();
+      }
+    });
+  }
+  void submit(std::function<void()> f) {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [this] { return !busy; });
+    task = std::move(f);
+    has = busy = true;
+    cv.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [this] { return !busy; });
+  }
+  ~DeviceWorker() {
+    if (th.joinable()) {
+      {
+        std::lock_guard<std::mutex> lk(m);
+        stop = true;
+      }
+      cv.notify_all();
+      th.join();
+    }
+  }
+};
+struct Replica {
+  Device dev;
+  DeviceWorker worker;
+};
+
 struct zg_engine {
   std::mutex mu;  // one writer or one hot-path launch sequence at a time
+  std::vector<std::unique_ptr<Replica>> replicas;  // devices 1 .. n-1 (device 0 is `dev`)
   Batcher batcher;
   Schema schema;
   bool has_schema = false;
@@ -111,6 +166,16 @@ struct zg_engine {
   }
 };
 
+// fn(device, index) on every device of the engine, concurrently; returns when all are done.
+static void on_all_devices(zg_engine* e, const std::function<void(Device&, size_t)>& fn) {
+  for (size_t i = 0; i < e->replicas.size(); ++i) {
+    Replica* r = e->replicas[i].get();
+    r->worker.submit([r, i, &fn] { fn(r->dev, i + 1); });
+  }
+  fn(e->dev, 0);
+  for (auto& r : e->replicas) r->worker.wait();
+}
+
 static thread_local std::string g_err;
 static constexpr size_t kMaxLookupGroup = 64;  // = kMaxLookupBatch (kernels.cuh)
 static const char* kShardedMsg =
@@ -161,6 +226,36 @@ extern "C" int zg_engine_create(const zg_config* cfg, zg_engine** out) {
     e->dev.shard_count = cfg->shard_count;
     e->dev.shard_rank = cfg->shard_rank;
   }
+  if (cfg && cfg->n_devices > 1) {
+    if (cfg->shard_count > 1) {
+      delete e;
+      return fail(ZG_EINVAL, "n_devices > 1 makes replicas; a sharded engine owns one device");
+    }
+    int visible = 0;
+    cudaGetDeviceCount(&visible);
+    const int first = e->dev.device;
+    const int want = cfg->n_devices == ZG_ALL_DEVICES ? visible - first : static_cast<int>(cfg->n_devices);
+    if (want < 1 || first + want > visible) {
+      delete e;
+      return fail(ZG_EINVAL, "n_devices exceeds the visible CUDA devices");
+    }
+    std::vector<std::string> errs(static_cast<size_t>(want));
+    for (int d = 1; d < want; ++d) {
+      e->replicas.emplace_back(new Replica());
+      e->replicas.back()->worker.start();
+    }
+    const zg_config c = *cfg;
+    on_all_devices(e, [&](Device& dev, size_t i) {
+      if (i == 0) return;
+      errs[i] = dev.init(first + static_cast<int>(i), c.subquery_capacity, c.work_budget);
+      if (c.flags & ZG_FLAG_FORWARD_ONLY) dev.invert = false;
+    });
+    for (const auto& m : errs)
+      if (!m.empty()) {
+        delete e;
+        return fail(ZG_ECUDA, m);
+      }
+  }
   *out = e;
   return ZG_OK;
 }
@@ -178,6 +273,7 @@ extern "C" int zg_load_schema(zg_engine* e, const char* dsl, size_t len) {
   e->store.shard_count = e->dev.shard_count;
   e->store.shard_rank = e->dev.shard_rank;
   e->dev.snap.reset();
+  for (auto& r : e->replicas) r->dev.snap.reset();
   e->dirty = true;
   return ZG_OK;
 }
@@ -275,10 +371,16 @@ static int publish_locked(zg_engine* e) {
       // a few updates against a resident snapshot: merge them in (build.cu gpu_apply_delta); anything the
       // journal cannot express (bulk load, new layout, no snapshot yet) rebuilds
       const char* nd = std::getenv("ZGPU_NO_DELTA");
-      std::string err = (nd && *nd && *nd != '0') ? std::string("full") : e->dev.publish_delta(e->store, e->schema, e->revision + 1);
-      if (err == "full") err = e->dev.publish_gpu(e->store, e->schema, e->revision + 1, verify);
-      else if (err.empty() && verify) err = e->dev.verify_against_host(e->store, e->schema);
-      if (!err.empty()) return fail(ZG_ECUDA, err);
+      const bool no_delta = nd && *nd && *nd != '0';
+      std::vector<std::string> errs(1 + e->replicas.size());
+      on_all_devices(e, [&](Device& dev, size_t i) {  // every replica merges / builds for itself, concurrently
+        std::string err = no_delta ? std::string("full") : dev.publish_delta(e->store, e->schema, e->revision + 1);
+        if (err == "full") err = dev.publish_gpu(e->store, e->schema, e->revision + 1, verify);
+        else if (err.empty() && verify) err = dev.verify_against_host(e->store, e->schema);
+        errs[i] = err;
+      });
+      for (const auto& err : errs)
+        if (!err.empty()) return fail(ZG_ECUDA, err);
       ++e->revision;
       e->store.journal_clear();
       e->last_built = HostSnapshot();
@@ -640,11 +742,49 @@ static void run_group(zg_engine* e, std::vector<BatchReq*>& group) {
     rc = ZG_ENOSNAPSHOT;
     err = "no snapshot published (call zg_publish)";
   } else {
-    e->dev.now = now_of(e);
     std::vector<Device::HostReq> reqs;
     reqs.reserve(group.size());
-    for (BatchReq* r : group) reqs.push_back({r->items, r->n, r->out});
-    rc = e->dev.check_host_multi(reqs, &err);
+    uint64_t total = 0;
+    for (BatchReq* r : group) {
+      reqs.push_back({r->items, r->n, r->out});
+      total += r->n;
+    }
+    const size_t nd = 1 + e->replicas.size();
+    if (nd == 1 || total < nd * 4096) {
+      e->dev.now = now_of(e);
+      rc = e->dev.check_host_multi(reqs, &err);
+    } else {
+      // replicas: every device answers a contiguous slice of the group's items
+      std::vector<std::vector<Device::HostReq>> part(nd);
+      const uint64_t per = (total + nd - 1) / nd;
+      size_t d = 0;
+      uint64_t room = per;
+      for (const auto& r : reqs) {
+        uint64_t off = 0;
+        while (off < r.n) {
+          const uint64_t take = std::min(room, r.n - off);
+          part[d].push_back({r.items + off, take, r.out + off});
+          off += take;
+          room -= take;
+          if (room == 0 && d + 1 < nd) {
+            ++d;
+            room = per;
+          }
+        }
+      }
+      std::vector<int> rcs(nd, ZG_OK);
+      std::vector<std::string> errs(nd);
+      const uint32_t now = now_of(e);
+      on_all_devices(e, [&](Device& dev, size_t i) {
+        dev.now = now;
+        if (!part[i].empty()) rcs[i] = dev.check_host_multi(part[i], &errs[i]);
+      });
+      for (size_t i = 0; i < nd && !rc; ++i)
+        if (rcs[i]) {
+          rc = rcs[i];
+          err = errs[i];
+        }
+    }
   }
   for (BatchReq* r : group) {
     r->rc = rc;
@@ -1155,7 +1295,40 @@ static void run_lookup_group(zg_engine* e, std::vector<zg_engine::LookupJob*>& g
     std::vector<std::vector<uint32_t>> ids;
     std::vector<int> rcs;
     std::string err;
-    int rc = e->dev.lookup_batch(reqs, &ids, &rcs, &err);
+    int rc = ZG_OK;
+    const size_t nd = 1 + e->replicas.size();
+    if (nd == 1 || reqs.size() < 2) {
+      rc = e->dev.lookup_batch(reqs, &ids, &rcs, &err);
+    } else {
+      // replicas: the lookups of the group are dealt out to the devices
+      std::vector<std::vector<Device::LookupReq>> part(nd);
+      std::vector<std::vector<size_t>> which(nd);
+      for (size_t r = 0; r < reqs.size(); ++r) {
+        part[r % nd].push_back(reqs[r]);
+        which[r % nd].push_back(r);
+      }
+      std::vector<std::vector<std::vector<uint32_t>>> pids(nd);
+      std::vector<std::vector<int>> prcs(nd);
+      std::vector<int> drc(nd, ZG_OK);
+      std::vector<std::string> derr(nd);
+      const uint32_t now = e->dev.now;
+      on_all_devices(e, [&](Device& dev, size_t i) {
+        dev.now = now;
+        if (!part[i].empty()) drc[i] = dev.lookup_batch(part[i], &pids[i], &prcs[i], &derr[i]);
+      });
+      ids.resize(reqs.size());
+      rcs.assign(reqs.size(), ZG_OK);
+      for (size_t i = 0; i < nd; ++i) {
+        if (drc[i] && !rc) {
+          rc = drc[i];
+          err = derr[i];
+        }
+        for (size_t k = 0; k < which[i].size() && !drc[i]; ++k) {
+          ids[which[i][k]] = std::move(pids[i][k]);
+          rcs[which[i][k]] = prcs[i][k];
+        }
+      }
+    }
     if (rc) return fail_all(rc, err);
     for (size_t r = 0; r < reqs.size(); ++r) {
       zg_engine::LookupJob* j = group[owner[r]];
@@ -1467,6 +1640,19 @@ extern "C" int zg_stats_get(zg_engine* e, zg_stats* out) {
   out->lookup_batches = e->dev.lookup_batches;
   out->lookups_batched = e->dev.lookups_batched;
   if (!e->host_only) e->dev.read_events(&out->stack_spills, &out->memo_batches);
+  out->devices = 1 + e->replicas.size();
+  for (auto& r : e->replicas) {
+    const Device& d = r->dev;
+    out->checks += d.checks;
+    out->launches += d.launches;
+    out->passes += d.passes;
+    out->split_batches += d.split_batches;
+    out->delta_publishes += d.delta_publishes;
+    out->full_publishes += d.full_publishes;
+    out->streamed_calls += d.streamed_calls;
+    out->lookup_batches += d.lookup_batches;
+    out->lookups_batched += d.lookups_batched;
+  }
   if (e->dev.snap) {
     out->tuples = e->dev.snap->n_tuples;
     out->snapshot_bytes = e->dev.snap->bytes;

@@ -840,3 +840,54 @@ def test_concurrent_lookups_share_launches_and_equal_the_oracle(zg, monkeypatch,
     assert st["lookups_batched"] > 0 and st["lookup_batches"] < st["lookups_batched"], st
     assert sum(x.size for x in want) > 1000
     e.close()
+
+
+def test_one_engine_owning_several_gpus_equals_a_single_gpu_engine(zg):
+    """zg_config.n_devices: ONE handle, every device holds a replica and answers its slice of each bulk call
+    (the proxy keeps a single client: pkg/proxy/options.go:81-82). Needs >= 2 GPUs (gpurun --gpus 2)."""
+    import threading
+
+    import torch
+
+    from oracle.pyoracle import Oracle
+    from spicedb_kubeapi_proxy_b200 import workloads
+
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    w = workloads.cfg4(scale=0.005)
+    multi, o = zg.Engine(w.schema, device=0, n_devices=n_dev), Oracle(w.schema)
+    w.load_into(multi), w.load_into(o)
+    multi.publish()
+    assert multi.stats()["devices"] == n_dev
+    items = w.check_items(multi, zg.CHECK_DTYPE)
+    want = o.check_bulk(items)
+    assert np.array_equal(multi.check_bulk(items), want)
+    # a write reaches every replica before it returns
+    doc, user = int(items["res"][0]), 123
+    rel = zg.UPDATE_DTYPE
+    up = np.zeros(1, dtype=rel)
+    up["res"], up["subj"], up["rel"], up["stype"], up["srel"], up["op"] = doc, user, multi.slot_id("document", "banned"), \
+        multi.type_id("user"), 0xFFFF, 0
+    multi.apply_updates(up), multi.publish()
+    o.write_ids(0, up["rel"][0], doc, up["stype"][0], user)
+    probe = np.repeat(items[:1], 20000)
+    probe["subj"] = user
+    assert np.array_equal(multi.check_bulk(probe), o.check_bulk(probe))
+    # concurrent small callers and concurrent lookups are spread over the devices
+    got = [None] * 16
+    def run(i):
+        got[i] = multi.check_bulk(items[i * 5000:(i + 1) * 5000])
+    ths = [threading.Thread(target=run, args=(i,)) for i in range(16)]
+    [t.start() for t in ths], [t.join() for t in ths]
+    for i in range(16):
+        assert np.array_equal(got[i], o.check_bulk(items[i * 5000:(i + 1) * 5000]))
+    rt, perm, st, u = w.lookups[0]
+    lk = [None] * 8
+    def look(i):
+        lk[i] = multi.lookup_resources_ids(rt, perm, st, int(u) + i)
+    ths = [threading.Thread(target=look, args=(i,)) for i in range(8)]
+    [t.start() for t in ths], [t.join() for t in ths]
+    for i in range(8):
+        assert np.array_equal(lk[i], o.lookup_resources_ids(rt, perm, st, int(u) + i))
+    multi.close()
