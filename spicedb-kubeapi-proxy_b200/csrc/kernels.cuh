@@ -21,7 +21,10 @@
 //     (check, slot, object, depth) visits so DAG-shaped data stays polynomial;
 //   * no tensor cores, no floating point: memory-latency / issue-bound integer traversal.
 #pragma once
+#ifndef ZG_EMULATE  // tests/emu/: the same source under a CPU SIMT emulator (test infrastructure, never in libzgpu.so)
 #include <cuda_runtime.h>
+#define ZG_DYNAMIC_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+#endif
 
 #include <cstdint>
 
@@ -468,7 +471,7 @@ __device__ __noinline__ void wait_ready(const unsigned long long* ready, unsigne
 //   2 tree id, 3 / 4 leaf values (2 bits each), 5 unused
 template <bool COUNT, bool STREAMED = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KParams p) {
-  extern __shared__ __align__(16) uint8_t smem[];
+  ZG_DYNAMIC_SMEM(smem);
   for (uint32_t i = threadIdx.x; i < p.prog_bytes / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(p.prog)[i];
   __syncthreads();
