@@ -61,6 +61,7 @@ struct Block {
   std::vector<Warp> warps;
   Barrier bar;
   std::vector<uint8_t> smem;
+  uint32_t static_u32[64];  // the one static __shared__ array a kernel may declare (ZG_BLOCK_SHARED_U32)
 };
 
 struct ThreadState {
@@ -128,6 +129,8 @@ void launch(K kernel, const P& params, unsigned grid, unsigned threads, size_t s
 #define gridDim (zg_emu::ts().gridDim)
 // `extern __shared__ __align__(16) uint8_t smem[];` in kernels.cuh becomes a pointer to the block's buffer
 #define ZG_DYNAMIC_SMEM(name) uint8_t* name = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(zg_emu::ts().block->smem.data()) + 15) & ~uintptr_t(15))
+
+#define ZG_BLOCK_SHARED_U32(name, n) uint32_t* name = zg_emu::ts().block->static_u32
 
 template <class T>
 static inline T __ldg(const T* p) { return *p; }

@@ -34,7 +34,7 @@ def default_opts(**kw):
 def build() -> str:
     so = os.path.join(_HERE, "libzgemu.so")
     srcs = [os.path.join(_HERE, f) for f in ("emu_main.cc", "cuda_emu.h")] + \
-           [os.path.join(_CSRC, f) for f in ("kernels.cuh", "schema.cc", "schema.h", "store.cc", "store.h")]
+           [os.path.join(_CSRC, f) for f in ("kernels.cuh", "delta.cuh", "schema.cc", "schema.h", "store.cc", "store.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I", _HERE,
                         os.path.join(_HERE, "emu_main.cc"), os.path.join(_CSRC, "schema.cc"), os.path.join(_CSRC, "store.cc"),
@@ -58,8 +58,15 @@ def lib():
         L.emu_check.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(Opts), C.c_int]
         L.emu_lookup_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(Opts), C.c_uint64,
                                        C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.emu_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_size_t]
+        L.emu_journal_start.argtypes = [C.c_void_p]
+        L.emu_merge_and_verify.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         _LIB = L
     return _LIB
+
+
+UPDATE_DTYPE = np.dtype([("res", "<u4"), ("subj", "<u4"), ("rel", "<u2"), ("stype", "<u2"), ("srel", "<u2"),
+                         ("flags", "<u2"), ("expires_at", "<u4"), ("op", "<u4")])
 
 
 class EmuEngine:
@@ -106,6 +113,24 @@ class EmuEngine:
     def publish(self):
         if self._L.emu_publish(self._h):
             raise RuntimeError("emu_publish failed")
+        self._L.emu_journal_start(self._h)
+
+    def apply_updates(self, ups):
+        u = np.ascontiguousarray(ups, dtype=UPDATE_DTYPE)
+        err = C.create_string_buffer(512)
+        if self._L.emu_apply(self._h, u.ctypes.data, u.size, err, 512):
+            raise RuntimeError(err.value.decode())
+
+    def merge_and_verify(self) -> int:
+        """Incremental publish under the emulator, then every array against a fresh host build. 0 = identical,
+        1 = needs a rebuild (layout changed); raises on a mismatch."""
+        err = C.create_string_buffer(512)
+        rc = self._L.emu_merge_and_verify(self._h, err, 512)
+        if rc < 0:
+            raise RuntimeError(f"merge rc={rc}: {err.value.decode()}")
+        if rc == 1:
+            self.publish()
+        return rc
 
     def check_bulk(self, items, opts=None, count=False):
         items = np.ascontiguousarray(items, dtype=CHECK_DTYPE)

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <string>
 
+#include "../../spicedb-kubeapi-proxy_b200/csrc/delta.cuh"
 #include "../../spicedb-kubeapi-proxy_b200/csrc/kernels.cuh"
 #include "../../spicedb-kubeapi-proxy_b200/csrc/store.h"
 
@@ -287,3 +288,160 @@ extern "C" int emu_lookup_batch(void* h, const uint16_t* res_types, const zg_che
   }
   return 0;
 }
+
+// ---- incremental publish: build.cu gpu_apply_delta / merge_direction over host memory -----------------------------
+
+namespace {
+
+struct MergeArgs {
+  const uint32_t *old_a, *old_b;
+  uint32_t *new_a, *new_b;
+  uint32_t n_old;
+  const uint32_t *ins_pos, *del_pos;
+  uint32_t n_ins, n_del;
+};
+struct RowsArgs {
+  uint32_t* row_ptr;
+  unsigned long long first, pool;
+  const unsigned long long *ins_key, *del_key;
+  uint32_t n_ins, n_del;
+};
+
+// returns the number of delta entries that contradict the old arrays
+uint32_t merge_direction_emu(const HostDelta& h, bool with_exp, std::vector<uint32_t>& row_ptr, uint64_t pool,
+                             std::vector<uint32_t>& edges, std::vector<uint32_t>& exp) {
+  const uint32_t ni = static_cast<uint32_t>(h.ins_key.size()), nd = static_cast<uint32_t>(h.del_key.size()),
+                 nt = with_exp ? static_cast<uint32_t>(h.tch_key.size()) : 0u;
+  const uint64_t n_old = edges.size(), n_new = n_old + ni - nd;
+  std::vector<uint32_t> ins_pos(ni + 1), del_pos(nd + 1), tch_pos(nt + 1);
+  uint32_t bad = 0;
+  static const uint32_t zero = 0;
+  DeltaDev d{h.ins_key.data(), h.ins_val.data(), with_exp ? h.ins_exp.data() : nullptr, ins_pos.data(), ni,
+             h.del_key.data(), h.del_val.data(), del_pos.data(), nd,
+             h.tch_key.data(), h.tch_val.data(), h.tch_exp.data(), tch_pos.data(), nt};
+  const size_t keys = size_t(ni) + nd + nt;
+  struct LocArgs {
+    const uint32_t *row_ptr, *col;
+    DeltaDev d;
+    uint32_t* bad;
+  } la{row_ptr.data(), edges.empty() ? &zero : edges.data(), d, &bad};
+  if (keys) zg_emu::launch(+[](const LocArgs& a) { delta_locate_kernel(a.row_ptr, a.col, a.d, a.bad); }, la,
+                           static_cast<unsigned>((keys + 255) / 256), 256, 0);
+  if (ni || nd) {
+    std::vector<uint32_t> ne(std::max<uint64_t>(n_new, 1), 0xDEADBEEFu), nx(with_exp ? std::max<uint64_t>(n_new, 1) : 0);
+    MergeArgs ma{edges.data(), with_exp ? exp.data() : nullptr, ne.data(), with_exp ? nx.data() : nullptr,
+                 static_cast<uint32_t>(n_old), ins_pos.data(), del_pos.data(), ni, nd};
+    if (n_old)
+      zg_emu::launch(+[](const MergeArgs& a) { delta_merge_kernel(a.old_a, a.new_a, a.old_b, a.new_b, a.n_old, a.ins_pos, a.n_ins, a.del_pos, a.n_del); },
+                     ma, static_cast<unsigned>((n_old + kMergeTile - 1) / kMergeTile), 256, 0);
+    struct InsArgs {
+      uint32_t *new_a, *new_b;
+      const uint32_t *ins_pos, *ins_val, *ins_exp;
+      uint32_t n_ins;
+      const uint32_t* del_pos;
+      uint32_t n_del;
+    } ia{ne.data(), with_exp ? nx.data() : nullptr, ins_pos.data(), h.ins_val.data(), with_exp ? h.ins_exp.data() : nullptr, ni,
+         del_pos.data(), nd};
+    if (ni) zg_emu::launch(+[](const InsArgs& a) { delta_insert_kernel(a.new_a, a.new_b, a.ins_pos, a.ins_val, a.ins_exp, a.n_ins, a.del_pos, a.n_del); },
+                           ia, (ni + 255) / 256, 256, 0);
+    struct TchArgs {
+      uint32_t* new_exp;
+      const uint32_t *tch_pos, *tch_exp;
+      uint32_t n_tch;
+      const uint32_t* ins_pos;
+      uint32_t n_ins;
+      const uint32_t* del_pos;
+      uint32_t n_del;
+    } ta{nx.data(), tch_pos.data(), h.tch_exp.data(), nt, ins_pos.data(), ni, del_pos.data(), nd};
+    if (nt) zg_emu::launch(+[](const TchArgs& a) { delta_touch_kernel(a.new_exp, a.tch_pos, a.tch_exp, a.n_tch, a.ins_pos, a.n_ins, a.del_pos, a.n_del); },
+                           ta, (nt + 255) / 256, 256, 0);
+    unsigned long long first = pool;
+    if (ni) first = std::min<unsigned long long>(first, h.ins_key.front());
+    if (nd) first = std::min<unsigned long long>(first, h.del_key.front());
+    ++first;
+    RowsArgs ra{row_ptr.data(), first, pool, h.ins_key.data(), h.del_key.data(), ni, nd};
+    if (first <= pool)
+      zg_emu::launch(+[](const RowsArgs& a) { delta_rows_kernel(a.row_ptr, a.first, a.pool, a.ins_key, a.n_ins, a.del_key, a.n_del); }, ra,
+                     static_cast<unsigned>((pool + 1 - first + kMergeTile - 1) / kMergeTile), 256, 0);
+    ne.resize(n_new);
+    edges.swap(ne);
+    if (with_exp) {
+      nx.resize(n_new);
+      exp.swap(nx);
+    }
+  } else if (nt) {
+    struct TchArgs {
+      uint32_t* new_exp;
+      const uint32_t *tch_pos, *tch_exp;
+      uint32_t n_tch;
+    } ta{exp.data(), tch_pos.data(), h.tch_exp.data(), nt};
+    zg_emu::launch(+[](const TchArgs& a) { delta_touch_kernel(a.new_exp, a.tch_pos, a.tch_exp, a.n_tch, nullptr, 0, nullptr, 0); }, ta,
+                   (nt + 255) / 256, 256, 0);
+  }
+  return bad;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Transactional interned updates against the emulator's store (journal on once a snapshot is published).
+int emu_apply(void* h, const zg_update* u, uint64_t n, char* err, size_t cap) {
+  Emu* e = static_cast<Emu*>(h);
+  int code = 0;
+  std::string m = e->st.apply(u, n, &code);
+  if (!m.empty()) {
+    std::snprintf(err, cap, "%s", m.c_str());
+    return code ? code : -1;
+  }
+  return 0;
+}
+void emu_journal_start(void* h) { static_cast<Emu*>(h)->st.journal_clear(); }
+
+// Merges the journal into the emulator's resident arrays, then compares every array with a fresh host build.
+// 0 = identical; 1 = the layout changed (the product rebuilds); negative = mismatch / inconsistency.
+int emu_merge_and_verify(void* h, char* err, size_t cap) {
+  Emu* e = static_cast<Emu*>(h);
+  if (!e->published) return -1;
+  if (!e->st.journal_ok || !e->st.layout_stable()) return 1;
+  HostSnapshot lay = e->st.layout();
+  if (lay.n_objects != e->h.n_objects) return 1;
+  HostDelta f, r;
+  std::vector<uint32_t> cls_delta;
+  std::string perr = prepare_delta(e->st, e->sc, lay, &f, &r, &cls_delta);
+  if (perr == "relayout") return 1;
+  if (!perr.empty()) {
+    std::snprintf(err, cap, "%s", perr.c_str());
+    return -2;
+  }
+  const bool with_exp = e->sc.has_expiry;
+  std::vector<uint32_t> none;
+  uint32_t bad = merge_direction_emu(f, with_exp, e->h.row_ptr, lay.pool, e->h.col, e->h.exp);
+  bad += merge_direction_emu(r, false, e->h.rrow_ptr, lay.rpool, e->h.rcol, none);
+  if (bad) {
+    std::snprintf(err, cap, "%u delta entries contradict the resident arrays", bad);
+    return -3;
+  }
+  e->st.journal_clear();
+  HostSnapshot want = e->st.build();
+  auto same = [&](const std::vector<uint32_t>& a, const std::vector<uint32_t>& b, const char* what) {
+    if (a == b) return true;
+    size_t i = 0;
+    while (i < a.size() && i < b.size() && a[i] == b[i]) ++i;
+    std::snprintf(err, cap, "%s differs at %zu (sizes %zu / %zu)", what, i, a.size(), b.size());
+    return false;
+  };
+  if (!same(e->h.row_ptr, want.row_ptr, "row_ptr") || !same(e->h.col, want.col, "col") ||
+      !same(e->h.rrow_ptr, want.rrow_ptr, "rrow_ptr") || !same(e->h.rcol, want.rcol, "rcol") ||
+      (with_exp && !same(e->h.exp, want.exp, "exp")))
+    return -4;
+  // class emptiness (drives the program's steps) from the per-class deltas
+  for (size_t c = 0; c < want.cls.size(); ++c) {
+    e->h.cls[c].flags = want.cls[c].flags;
+  }
+  e->h.n_tuples = want.n_tuples;
+  e->blob = e->sc.blob(e->h.rels, e->h.cls);
+  return 0;
+}
+
+}  // extern "C"

@@ -231,3 +231,86 @@ def test_warp_stack_spills_to_its_overflow_area_under_the_emulator(emu):
     e.check_bulk(items, emu.default_opts(invert=0, spill_cap=32))
     assert e.stat("flags") & 1  # overflow of the overflow area is reported, not ignored
     assert 0.05 < (want == 2).mean() < 0.95
+
+
+def _random_updates(E, e, w, rng, n, new_objects=True):
+    """n interned updates against workload w: deletes and touches of loaded relationships, inserts between existing
+    objects, and (new_objects) inserts on objects the store has never seen. One update per relationship."""
+    ups = np.zeros(n, dtype=E.UPDATE_DTYPE)
+    for i in range(n):
+        g = w.groups[rng.integers(0, len(w.groups))]
+        k = rng.integers(0, g.res.size)
+        kind = rng.random()
+        ups["rel"][i] = e.slot_id(g.res_type, g.rel)
+        ups["stype"][i] = e.type_id(g.subj_type)
+        ups["srel"][i] = 0xFFFE if g.wildcard else (0xFFFF if g.srel is None else e.slot_id(g.subj_type, g.srel))
+        ups["res"][i], ups["subj"][i] = g.res[k], 0 if g.wildcard else g.subj[k]
+        if kind < 0.35:
+            ups["op"][i] = 2
+        elif kind >= 0.45:
+            ups["res"][i] = g.res[rng.integers(0, g.res.size)]
+            if new_objects and kind > 0.85:
+                ups["res"][i] = int(g.res.max()) + 1 + rng.integers(0, 50)
+            if not g.wildcard:
+                ups["subj"][i] = g.subj[rng.integers(0, g.subj.size)]
+    key = np.stack([ups["rel"], ups["res"], ups["stype"], ups["srel"], ups["subj"]], axis=1)
+    _, first = np.unique(key, axis=0, return_index=True)
+    return ups[np.sort(first)]
+
+
+@pytest.mark.parametrize("wl,scale", [("cfg4", 0.001), ("cfg3", 0.004)])
+def test_incremental_publish_kernels_equal_a_rebuild_under_the_emulator(emu, wl, scale):
+    """csrc/delta.cuh: locate the delta in the old arrays, re-emit the edge arrays in one pass (constant-shift tiles),
+    add the running insert/delete counts to the row tables in place -- forward and reverse. After every merge every
+    array equals a fresh host build of the store, and the checks equal the oracle's (which applies the same updates)."""
+    import zgpu  # noqa: F401
+    from oracle.pyoracle import Oracle
+    from spicedb_kubeapi_proxy_b200 import workloads
+
+    w = workloads.by_name(wl, scale)
+    e, o = emu.EmuEngine(w.schema), Oracle(w.schema)
+    w.load_into(e), w.load_into(o)
+    e.publish()
+    rng = np.random.default_rng(21)
+    items = w.check_items(o, emu.CHECK_DTYPE)[:1500]
+    merged = 0
+    for step, n in enumerate([1, 3, 40, 400, 1000, 7]):
+        ups = _random_updates(emu, e, w, rng, n, new_objects=step % 2 == 1)
+        e.apply_updates(ups)
+        merged += e.merge_and_verify() == 0
+        for u in ups:
+            o.write_ids(u["op"], u["rel"], u["res"], u["stype"], u["subj"], u["srel"])
+        assert np.array_equal(e.check_bulk(items), o.check_bulk(items)), f"{wl} step {step}"
+    assert merged >= 4
+
+
+def test_incremental_publish_with_expirations_and_empty_classes_under_the_emulator(emu):
+    """TOUCH of an existing relationship only changes its expiration (patched in place); a class that receives its
+    first relationship, or loses its last one, changes the program's steps."""
+    from oracle.pyoracle import Oracle
+    from spicedb_kubeapi_proxy_b200 import workloads
+
+    schema = workloads.BOOTSTRAP_SCHEMA
+    e, o = emu.EmuEngine(schema), Oracle(schema)
+    e.publish()  # empty store
+    U = emu.UPDATE_DTYPE
+
+    def up(op, rt, rel, res, st, subj, exp=0):
+        u = np.zeros(1, dtype=U)
+        u["op"], u["rel"], u["res"], u["stype"], u["subj"], u["srel"], u["expires_at"] = op, e.slot_id(rt, rel), res, e.type_id(st), subj, 0xFFFF, exp
+        return u
+
+    script = [up(0, "namespace", "viewer", 3, "user", 1), up(0, "workflow", "idempotency_key", 2, "activity", 5, 1000),
+              up(0, "workflow", "idempotency_key", 2, "activity", 5, 2000),  # expiration only
+              up(0, "namespace", "creator", 3, "user", 2), up(2, "namespace", "viewer", 3, "user", 1),
+              up(2, "namespace", "creator", 3, "user", 2), up(0, "namespace", "viewer", 4000, "user", 7)]
+    items = np.zeros(4, dtype=emu.CHECK_DTYPE)
+    items["res"], items["subj"] = [3, 3, 4000, 3], [1, 2, 7, 9]
+    items["perm"], items["stype"], items["srel"] = e.slot_id("namespace", "view"), e.type_id("user"), 0xFFFF
+    for i, u in enumerate(script):
+        e.apply_updates(u)
+        e.merge_and_verify()
+        o.write_ids(int(u["op"][0]), int(u["rel"][0]), int(u["res"][0]), int(u["stype"][0]), int(u["subj"][0]), 0xFFFF, int(u["expires_at"][0]))
+        for now in (500, 1500):
+            opts = emu.default_opts(now=now)
+            assert np.array_equal(e.check_bulk(items, opts), o.check_bulk(items, now=now)), f"step {i} now {now}"
