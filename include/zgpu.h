@@ -281,6 +281,24 @@ int zg_shard_subqueries(zg_engine *e, int level, zg_check *out, uint64_t n);
  * query q; deeper levels: its value bits, to be sent back to the rank that raised it. */
 int zg_shard_fold(zg_engine *e, int level, const uint8_t *child_vals, uint64_t n_sub, uint8_t *out);
 
+/* The same protocol with every buffer resident on the device (dist.DeviceShardedChecker): checks and raised
+ * sub-queries are bucketised by owner in a kernel, exchanged device to device (NCCL all-to-all over NVLink, or
+ * peer copies), and the values coming back are folded without a host copy. All pointers are DEVICE pointers of
+ * the engine's GPU; every call returns after its work completed (the exchange runs on the caller's stream).
+ *   zg_shard_route_dev   items (d_items, or the sub-queries raised by pass `level` when d_items is NULL) ->
+ *                        d_routed in destination-major order + d_src[i] = source index of d_routed[i];
+ *                        counts[d] (HOST array of n_dest) = items for destination d = res % n_dest
+ *   zg_shard_pass_dev    zg_shard_pass with the level's queries already on the device
+ *   zg_shard_fold_dev    d_child_vals in ROUTED order + the d_src of that routing -> d_out[q] per query of the
+ *                        level (v1 codes when final_codes, else value bits for the rank that raised it)
+ *   zg_shard_unroute_dev d_out[d_src[i]] = d_val[i]: answers restored to the caller's order */
+int zg_shard_route_dev(zg_engine *e, const zg_check *d_items, uint64_t n, int level, uint32_t n_dest,
+                       zg_check *d_routed, uint32_t *d_src, uint64_t *counts);
+int zg_shard_pass_dev(zg_engine *e, const zg_check *d_queries, uint64_t n, int level, uint64_t *n_sub);
+int zg_shard_fold_dev(zg_engine *e, int level, const uint8_t *d_child_vals, const uint32_t *d_src,
+                      uint64_t n_sub, uint8_t *d_out, int final_codes);
+int zg_shard_unroute_dev(zg_engine *e, const uint32_t *d_src, const uint8_t *d_val, uint64_t n, uint8_t *d_out);
+
 /* Watch feed (v1.WatchServiceClient.Watch, pkg/authz/watch.go:27-48): the relationship changes made
  * visible by revisions > since_revision, oldest first, as '\n'-separated lines
  *   "<revision> <TOUCH|CREATE|DELETE> <type:id#rel@stype:sid[#srel]>[ <expires_at>]"

@@ -169,6 +169,11 @@ _SIGS = {
     "zg_shard_pass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
     "zg_shard_subqueries": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]),
     "zg_shard_fold": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "zg_shard_route_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
+    "zg_shard_pass_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
+    "zg_shard_fold_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]),
+    "zg_shard_unroute_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "zg_debug_row": (C.c_int, [C.c_void_p, C.c_uint16, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
                                C.POINTER(C.c_uint64)]),
     "zg_host_alloc": (C.c_void_p, [C.c_size_t]),
@@ -588,6 +593,24 @@ class Engine:
         out = np.empty(n_queries, dtype=np.uint8)
         self._ck(self._L.zg_shard_fold(self._h, level, cv.ctypes.data, cv.size, out.ctypes.data))
         return out
+
+    # device-resident variants: every pointer is a device address on this engine's GPU (ints, e.g. tensor.data_ptr())
+    def shard_route_dev(self, d_items: int, n: int, level: int, n_dest: int, d_routed: int, d_src: int) -> list:
+        counts = (C.c_uint64 * n_dest)()
+        self._ck(self._L.zg_shard_route_dev(self._h, d_items or None, n, level, n_dest, d_routed or None, d_src or None, counts))
+        return [int(c) for c in counts]
+
+    def shard_pass_dev(self, d_queries: int, n: int, level: int) -> int:
+        ns = C.c_uint64(0)
+        self._ck(self._L.zg_shard_pass_dev(self._h, d_queries or None, n, level, C.byref(ns)))
+        return ns.value
+
+    def shard_fold_dev(self, level: int, d_child_vals: int, d_src: int, n_sub: int, d_out: int, final_codes: bool):
+        self._ck(self._L.zg_shard_fold_dev(self._h, level, d_child_vals or None, d_src or None, n_sub, d_out or None,
+                                           1 if final_codes else 0))
+
+    def shard_unroute_dev(self, d_src: int, d_val: int, n: int, d_out: int):
+        self._ck(self._L.zg_shard_unroute_dev(self._h, d_src or None, d_val or None, n, d_out or None))
 
     def debug_row(self, type_name, rel, res, cls=0, reverse=False) -> np.ndarray:
         """Forward row (resource `res`, class) or, reverse=True, the reverse row of subject `res`."""

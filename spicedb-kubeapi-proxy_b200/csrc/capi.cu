@@ -1690,6 +1690,45 @@ extern "C" int zg_shard_fold(zg_engine* e, int level, const uint8_t* child_vals,
   return rc ? fail(rc, err) : ZG_OK;
 }
 
+// ---- sharded store, device-resident protocol (no host staging between passes) ----
+#define SHARD_PROLOGUE()                                                                                              \
+  NEED_SCHEMA(e, ZG_ENOSCHEMA);                                                                                       \
+  std::lock_guard<std::mutex> g(e->mu);                                                                               \
+  if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");      \
+  if (!e->dev.snap) return fail(ZG_ENOSNAPSHOT, "no snapshot published (call zg_publish)");
+
+extern "C" int zg_shard_route_dev(zg_engine* e, const zg_check* d_items, uint64_t n, int level, uint32_t n_dest,
+                                  zg_check* d_routed, uint32_t* d_src, uint64_t* counts) {
+  if (!counts || ((!d_routed || !d_src) && n)) return fail(ZG_EINVAL, "NULL argument");
+  SHARD_PROLOGUE();
+  std::string err;
+  int rc = e->dev.route_by_owner(d_items, n, level, n_dest, d_routed, d_src, counts, &err);
+  return rc ? fail(rc, err) : ZG_OK;
+}
+extern "C" int zg_shard_pass_dev(zg_engine* e, const zg_check* d_queries, uint64_t n, int level, uint64_t* n_sub) {
+  if ((!d_queries && n) || !n_sub || level < 0 || level > ZG_MAX_DEPTH + 2) return fail(ZG_EINVAL, "bad argument");
+  SHARD_PROLOGUE();
+  e->dev.now = now_of(e);
+  std::string err;
+  int rc = e->dev.shard_pass_dev(d_queries, n, level, n_sub, &err);
+  return rc ? fail(rc, err) : ZG_OK;
+}
+extern "C" int zg_shard_fold_dev(zg_engine* e, int level, const uint8_t* d_child_vals, const uint32_t* d_src, uint64_t n_sub,
+                                 uint8_t* d_out, int final_codes) {
+  if (((!d_child_vals || !d_src) && n_sub) || level < 0) return fail(ZG_EINVAL, "bad argument");
+  SHARD_PROLOGUE();
+  std::string err;
+  int rc = e->dev.shard_fold_dev(level, d_child_vals, d_src, n_sub, d_out, final_codes != 0, &err);
+  return rc ? fail(rc, err) : ZG_OK;
+}
+extern "C" int zg_shard_unroute_dev(zg_engine* e, const uint32_t* d_src, const uint8_t* d_val, uint64_t n, uint8_t* d_out) {
+  if ((!d_src || !d_val || !d_out) && n) return fail(ZG_EINVAL, "NULL argument");
+  SHARD_PROLOGUE();
+  std::string err;
+  int rc = e->dev.unroute(d_src, d_val, n, d_out, &err);
+  return rc ? fail(rc, err) : ZG_OK;
+}
+
 extern "C" int zg_debug_row(zg_engine* e, uint16_t rel_slot, uint32_t res, uint32_t cls, uint32_t* out, uint64_t cap,
                             uint64_t* n_out) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);

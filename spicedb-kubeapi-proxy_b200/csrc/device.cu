@@ -66,6 +66,8 @@ Device::~Device() {
     for (auto& b : *v) b.release();
   stage_in_.release();
   stage_out_.release();
+  shard_tmp_.release();
+  route_ctrl_.release();
   lk_jobs_.release();
   lk_codes_.release();
   lk_ids_.release();
@@ -775,6 +777,155 @@ int Device::shard_fold(int level, const uint8_t* child_vals, uint64_t n_sub, uin
       nullptr, nullptr, level == 0 ? 0 : 1);
   ++launches;
   ZG_CUDA(cudaMemcpyAsync(out, stage_out_.p, n, cudaMemcpyDeviceToHost, stream));
+  ZG_CUDA(cudaStreamSynchronize(stream));
+  return ZG_OK;
+}
+
+int Device::route_by_owner(const zg_check* d_items, uint64_t n, int level, uint32_t n_dest, zg_check* d_routed, uint32_t* d_src,
+                           uint64_t* counts, std::string* err) {
+  if (n_dest == 0 || n_dest > kMaxRouteDest) {
+    if (err) *err = "route_by_owner: destination count out of range";
+    return ZG_EINVAL;
+  }
+  for (uint32_t d = 0; d < n_dest; ++d) counts[d] = 0;
+  ZG_CUDA(cudaSetDevice(device));
+  if (!d_items) {
+    const size_t lv = static_cast<size_t>(level);
+    if (lv >= shard_nsub_.size() || n != shard_nsub_[lv]) {
+      if (err) *err = "route_by_owner: level / count mismatch";
+      return ZG_EINVAL;
+    }
+    d_items = q_[lv + 1].as<zg_check>();
+  }
+  if (n == 0) return ZG_OK;
+  if (!route_ctrl_.ensure(2 * kMaxRouteDest * 8)) return ZG_ENOMEM;
+  unsigned long long* d_counts = route_ctrl_.as<unsigned long long>();
+  unsigned long long* d_cursor = d_counts + kMaxRouteDest;
+  if (have_last_) ZG_CUDA(cudaStreamWaitEvent(stream, last_done_, 0));
+  ZG_CUDA(cudaMemsetAsync(d_counts, 0, kMaxRouteDest * 8, stream));
+  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n + 255) / 256, static_cast<uint64_t>(sm_count_) * 8));
+  route_count_kernel<<<grid, 256, 0, stream>>>(d_items, n, n_dest, d_counts);
+  unsigned long long h[kMaxRouteDest];
+  ZG_CUDA(cudaMemcpyAsync(h, d_counts, n_dest * 8, cudaMemcpyDeviceToHost, stream));
+  ZG_CUDA(cudaStreamSynchronize(stream));
+  unsigned long long off[kMaxRouteDest], acc = 0;
+  for (uint32_t d = 0; d < n_dest; ++d) {
+    counts[d] = h[d];
+    off[d] = acc;
+    acc += h[d];
+  }
+  ZG_CUDA(cudaMemcpyAsync(d_cursor, off, n_dest * 8, cudaMemcpyHostToDevice, stream));
+  route_scatter_kernel<<<grid, 256, 0, stream>>>(d_items, n, n_dest, d_cursor, d_routed, d_src);
+  launches += 2;
+  ZG_CUDA(cudaGetLastError());
+  ZG_CUDA(cudaEventRecord(last_done_, stream));
+  have_last_ = true;
+  ZG_CUDA(cudaStreamSynchronize(stream));
+  return ZG_OK;
+}
+
+int Device::shard_pass_dev(const zg_check* d_queries, uint64_t n, int level, uint64_t* n_sub, std::string* err) {
+  std::shared_ptr<Snapshot> s = snap;
+  if (!s) {
+    if (err) *err = "no snapshot published";
+    return ZG_ENOSNAPSHOT;
+  }
+  ZG_CUDA(cudaSetDevice(device));
+  const size_t lv = static_cast<size_t>(level);
+  if (q_.size() <= lv + 1) {
+    q_.resize(lv + 2);
+    parent_.resize(lv + 2);
+    val_.resize(lv + 2);
+  }
+  if (shard_nq_.size() <= lv) {
+    shard_nq_.resize(lv + 1);
+    shard_nsub_.resize(lv + 1);
+  }
+  shard_nq_[lv] = n;
+  shard_nsub_[lv] = 0;
+  *n_sub = 0;
+  if (n == 0) return ZG_OK;
+  const uint32_t L = s->max_leaves;
+  if (n * L >= (1ull << 32)) {
+    if (err) *err = "pass too large (n * leaves >= 2^32)";
+    return ZG_EINVAL;
+  }
+  if (have_last_) ZG_CUDA(cudaStreamWaitEvent(stream, last_done_, 0));
+  // the level's queries are kept (the fold re-reads them): own copy, device to device
+  DevBuf& qbuf = lv == 0 ? stage_in_ : q_[lv];
+  if (!qbuf.ensure(std::max<size_t>(n * sizeof(zg_check), lv == 0 ? 0 : subq_cap_ * sizeof(zg_check))) ||
+      !val_[lv].ensure(n * L + 4) || !q_[lv + 1].ensure(subq_cap_ * sizeof(zg_check)) || !parent_[lv + 1].ensure(subq_cap_ * 4)) {
+    if (err) *err = "out of device memory (shard pass buffers)";
+    return ZG_ENOMEM;
+  }
+  ZG_CUDA(cudaMemcpyAsync(qbuf.p, d_queries, n * sizeof(zg_check), cudaMemcpyDeviceToDevice, stream));
+  unsigned long long* ctrl = ctrl_.as<unsigned long long>();
+  ZG_CUDA(cudaMemsetAsync(ctrl + 2, 0, 16, stream));
+  ZG_CUDA(cudaMemsetAsync(val_[lv].p, 0, n * L + 4, stream));
+  // level 0 items come from callers (flags ignored); deeper levels are raised sub-queries (flags = hop depth)
+  int rc = run_pass(*s, qbuf.as<zg_check>(), n, val_[lv].as<uint8_t>(), nullptr, false, level == 0, q_[lv + 1].as<zg_check>(),
+                    parent_[lv + 1].as<uint32_t>(), stream, false, err);
+  if (rc) return rc;
+  unsigned long long host_ctrl[4];
+  ZG_CUDA(cudaMemcpyAsync(host_ctrl, ctrl, sizeof host_ctrl, cudaMemcpyDeviceToHost, stream));
+  ZG_CUDA(cudaEventRecord(last_done_, stream));
+  have_last_ = true;
+  ZG_CUDA(cudaStreamSynchronize(stream));
+  const uint32_t flags = static_cast<uint32_t>(host_ctrl[3] & 0xFFFFFFFFu);
+  if (host_ctrl[1] > subq_cap_) {
+    if (err) *err = "sub-query buffer overflow: raise zg_config.subquery_capacity or shrink the batch";
+    return ZG_ENOMEM;
+  }
+  if (flags & 1u) {
+    if (err) *err = "expansion stack overflow";
+    return ZG_ENOMEM;
+  }
+  shard_nsub_[lv] = host_ctrl[1];
+  *n_sub = host_ctrl[1];
+  checks += level == 0 ? n : 0;
+  ++passes;
+  return ZG_OK;
+}
+
+int Device::shard_fold_dev(int level, const uint8_t* d_child_vals, const uint32_t* d_src, uint64_t n_sub, uint8_t* d_out,
+                           bool final_codes, std::string* err) {
+  std::shared_ptr<Snapshot> s = snap;
+  const size_t lv = static_cast<size_t>(level);
+  if (!s || lv >= shard_nq_.size() || n_sub != shard_nsub_[lv]) {
+    if (err) *err = "shard_fold_dev: level / count mismatch";
+    return ZG_EINVAL;
+  }
+  const uint64_t n = shard_nq_[lv];
+  if (n == 0) return ZG_OK;
+  ZG_CUDA(cudaSetDevice(device));
+  if (have_last_) ZG_CUDA(cudaStreamWaitEvent(stream, last_done_, 0));
+  const unsigned blk = 256;
+  if (n_sub) {
+    or_children_src_kernel<<<static_cast<unsigned>((n_sub + blk - 1) / blk), blk, 0, stream>>>(
+        parent_[lv + 1].as<uint32_t>(), d_src, d_child_vals, n_sub, val_[lv].as<uint8_t>());
+    ++launches;
+  }
+  const DevBuf& qbuf = lv == 0 ? stage_in_ : q_[lv];
+  fold_kernel<<<static_cast<unsigned>((n + blk - 1) / blk), blk, 0, stream>>>(
+      s->prog.as<uint8_t>(), qbuf.as<zg_check>(), n, s->max_leaves, val_[lv].as<uint8_t>(), d_out, nullptr, nullptr,
+      final_codes ? 0 : 1);
+  ++launches;
+  ZG_CUDA(cudaGetLastError());
+  ZG_CUDA(cudaEventRecord(last_done_, stream));
+  have_last_ = true;
+  ZG_CUDA(cudaStreamSynchronize(stream));
+  return ZG_OK;
+}
+
+int Device::unroute(const uint32_t* d_src, const uint8_t* d_val, uint64_t n, uint8_t* d_out, std::string* err) {
+  if (n == 0) return ZG_OK;
+  ZG_CUDA(cudaSetDevice(device));
+  if (have_last_) ZG_CUDA(cudaStreamWaitEvent(stream, last_done_, 0));
+  unroute_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(d_src, d_val, n, d_out);
+  ++launches;
+  ZG_CUDA(cudaGetLastError());
+  ZG_CUDA(cudaEventRecord(last_done_, stream));
+  have_last_ = true;
   ZG_CUDA(cudaStreamSynchronize(stream));
   return ZG_OK;
 }

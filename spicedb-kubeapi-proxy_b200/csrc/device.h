@@ -98,6 +98,18 @@ class Device {
   // child_vals: one byte per raised sub-query (kValT|kValE bits) in emission order. out: one byte
   // per query of the level: v1 codes at level 0, value bits deeper.
   int shard_fold(int level, const uint8_t* child_vals, uint64_t n_sub, uint8_t* out, std::string* err);
+  // ---- the same protocol with everything resident on the device (dist.DeviceShardedChecker) ----
+  // Bucketises n check items by owner = res % n_dest into d_routed (destination-major) with their source
+  // indices in d_src; counts[d] (host) = items for destination d. d_items == nullptr: the sub-queries raised by
+  // pass `level` (shard_pass / shard_pass_dev).
+  int route_by_owner(const zg_check* d_items, uint64_t n, int level, uint32_t n_dest, zg_check* d_routed, uint32_t* d_src,
+                     uint64_t* counts, std::string* err);
+  int shard_pass_dev(const zg_check* d_queries, uint64_t n, int level, uint64_t* n_sub, std::string* err);
+  // d_child_vals: one byte per raised sub-query in ROUTED order, d_src = the source indices route_by_owner wrote.
+  // d_out: one byte per query of the level (v1 codes when final_codes, else value bits).
+  int shard_fold_dev(int level, const uint8_t* d_child_vals, const uint32_t* d_src, uint64_t n_sub, uint8_t* d_out,
+                     bool final_codes, std::string* err);
+  int unroute(const uint32_t* d_src, const uint8_t* d_val, uint64_t n, uint8_t* d_out, std::string* err);
 
   std::shared_ptr<Snapshot> snap;
   cudaStream_t stream = nullptr;
@@ -130,7 +142,7 @@ class Device {
   uint32_t memo_entries_ = 8192, memo_after_ = 2048;  // ctrl: [0] next, [1] subq_count, [2] alg_bytes, then flags u32
   std::vector<DevBuf> q_, parent_, val_;  // per pass level: queries, raising (query, leaf), leaf values
   std::vector<uint64_t> shard_nq_, shard_nsub_;  // sharded mode: queries / raised sub-queries per level
-  DevBuf shard_tmp_;
+  DevBuf shard_tmp_, route_ctrl_;
   DevBuf stage_in_, stage_out_, lk_jobs_, lk_codes_, lk_ids_;
   DevBuf rb_visited_, rb_front_[2], rb_cand_;
   DevBuf lb_params_, lb_owner_, lb_ctrl_, lb_keys_[2];  // batched lookups

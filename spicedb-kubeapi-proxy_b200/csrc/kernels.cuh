@@ -810,6 +810,51 @@ __global__ void or_children_kernel(const uint32_t* parent, const uint8_t* child_
   atomicOr(reinterpret_cast<unsigned int*>(parent_val + (pj & ~3u)), bits << (8 * (pj & 3u)));
 }
 
+// ---- sharded store: device-side routing of checks / raised sub-queries to their owners ---------------
+//
+// owner(item) = item.res % n_dest. Two passes of a counting sort: per-destination counts (shared-memory
+// histogram, one atomic per block and destination), then a scatter that writes every item behind its
+// destination's cursor together with its source index, so that the values coming back in ROUTED order can be
+// folded into the (query, leaf) that raised them without un-permuting anything.
+constexpr int kMaxRouteDest = 64;
+__global__ void __launch_bounds__(256) route_count_kernel(const zg_check* items, unsigned long long n, uint32_t n_dest,
+                                                          unsigned long long* counts) {
+  __shared__ unsigned int hist[kMaxRouteDest];
+  for (uint32_t i = threadIdx.x; i < n_dest; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+  for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < n; i += stride)
+    atomicAdd(&hist[items[i].res % n_dest], 1u);
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n_dest; i += blockDim.x)
+    if (hist[i]) atomicAdd(counts + i, static_cast<unsigned long long>(hist[i]));
+}
+__global__ void __launch_bounds__(256) route_scatter_kernel(const zg_check* items, unsigned long long n, uint32_t n_dest,
+                                                            unsigned long long* cursor, zg_check* routed, uint32_t* src) {
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+  for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    const zg_check it = items[i];
+    const unsigned long long at = atomicAdd(cursor + (it.res % n_dest), 1ull);
+    routed[at] = it;
+    src[at] = static_cast<uint32_t>(i);
+  }
+}
+// values of routed sub-queries (routed order) OR-ed into the (query, leaf) that raised sub-query src[i]
+__global__ void or_children_src_kernel(const uint32_t* parent, const uint32_t* src, const uint8_t* child_val, unsigned long long n,
+                                       uint8_t* parent_val) {
+  unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t bits = child_val[i] & (kValT | kValE);
+  if (!bits) return;
+  const uint32_t pj = parent[src[i]];
+  atomicOr(reinterpret_cast<unsigned int*>(parent_val + (pj & ~3u)), bits << (8 * (pj & 3u)));
+}
+// out[src[i]] = val[i]: answers that came back in routed order, restored to the caller's order
+__global__ void unroute_kernel(const uint32_t* src, const uint8_t* val, unsigned long long n, uint8_t* out) {
+  unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+  if (i < n) out[src[i]] = val[i];
+}
+
 // ---- LookupResources: candidate generation by reverse BFS ----------------------------
 //
 // Every true result r of LookupResources(T, P, S) has a forward path r -> o1 -> ... -> ok

@@ -198,3 +198,148 @@ class ShardedStoreChecker:
             k = g.size // 5
             out[g[: 4 * k].view(np.uint32)] = g[4 * k:]
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# The same protocol with every buffer resident on the device (north-star's mode).
+#
+# Per level: ONE kernel pass over the level's queries (zg_shard_pass_dev), a counting-sort kernel that bucketises
+# the raised sub-queries by owner (zg_shard_route_dev), an N-int count exchange and one all-to-all of the 16-byte
+# sub-queries, device buffer to device buffer (NCCL over NVLink). Values (1 byte per sub-query) travel back with
+# the reverse all-to-all and are OR-ed into the (query, leaf) that raised them by a kernel that reads them in
+# routed order (zg_shard_fold_dev). Nothing is staged through the host; the host sees N counts per level.
+
+
+class TorchDeviceTransport:
+    """Ragged all-to-all of CUDA tensors over torch.distributed (backend nccl)."""
+
+    def __init__(self, group=None, device=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+
+    def exchange_counts(self, counts):
+        t = torch.tensor(counts, dtype=torch.int64, device=self.device)
+        r = torch.empty_like(t)
+        dist.all_to_all_single(r, t, group=self.group)
+        return [int(x) for x in r.cpu()]
+
+    def alltoall(self, send: torch.Tensor, send_counts, recv_counts, width: int) -> torch.Tensor:
+        """send: uint8 tensor of sum(send_counts) * width bytes, destination-major."""
+        out = torch.empty(sum(recv_counts) * width, dtype=torch.uint8, device=self.device)
+        dist.all_to_all_single(out, send, output_split_sizes=[c * width for c in recv_counts],
+                               input_split_sizes=[c * width for c in send_counts], group=self.group)
+        torch.cuda.current_stream().synchronize()  # the engine's calls run on its own stream
+        return out
+
+    def allreduce_sum(self, x: int) -> int:
+        t = torch.tensor([int(x)], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return int(t.item())
+
+
+class LocalDeviceTransport:
+    """`world` virtual ranks in ONE process on ONE GPU (threads): tensors change hands by reference. Tests the
+    device-resident protocol without NCCL. Build with LocalDeviceTransport.cluster(world)."""
+
+    def __init__(self, rank, world, shared):
+        self.rank, self.world, self._s = rank, world, shared
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    @staticmethod
+    def cluster(world):
+        import threading
+
+        shared = {"box": [None] * world, "bar": threading.Barrier(world), "sum": [0] * world}
+        return [LocalDeviceTransport(r, world, shared) for r in range(world)]
+
+    def exchange_counts(self, counts):
+        s = self._s
+        s["box"][self.rank] = list(counts)
+        s["bar"].wait()
+        out = [s["box"][src][self.rank] for src in range(self.world)]
+        s["bar"].wait()
+        return out
+
+    def alltoall(self, send, send_counts, recv_counts, width):
+        s = self._s
+        offs = np.concatenate([[0], np.cumsum(send_counts)]) * width
+        torch.cuda.current_stream().synchronize()
+        s["box"][self.rank] = [send[int(offs[d]):int(offs[d + 1])] for d in range(self.world)]
+        s["bar"].wait()
+        parts = [s["box"][src][self.rank] for src in range(self.world)]
+        out = torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device=self.device)
+        torch.cuda.current_stream().synchronize()
+        s["bar"].wait()
+        return out
+
+    def allreduce_sum(self, x):
+        s = self._s
+        s["sum"][self.rank] = int(x)
+        s["bar"].wait()
+        tot = sum(s["sum"])
+        s["bar"].wait()
+        return tot
+
+
+class DeviceShardedChecker:
+    """CheckBulkPermissions over an object-hash sharded store, device resident. Every rank brings ITS OWN batch
+    (a CUDA uint8 tensor of n x 16 bytes) and gets the answers of that batch (CUDA uint8 tensor of n codes):
+    checks are routed to the owner of their resource, evaluated level by level across the shards, and the
+    answers routed back."""
+
+    ITEM = 16
+
+    def __init__(self, engine, transport):
+        self.e, self.t = engine, transport
+        self.stats = {"levels": 0, "subqueries_sent": 0, "bytes_sent": 0, "exchanges": 0}
+
+    def _route(self, d_items: int, n: int, level: int):
+        """-> (routed uint8 tensor, src int32 tensor, send_counts, recv_counts)"""
+        dev, w = self.t.device, self.t.world
+        routed = torch.empty(max(n, 1) * self.ITEM, dtype=torch.uint8, device=dev)
+        src = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        counts = self.e.shard_route_dev(d_items, n, level, w, routed.data_ptr(), src.data_ptr())
+        return routed[: n * self.ITEM], src[:n], counts, self.t.exchange_counts(counts)
+
+    def check_bulk(self, d_items: torch.Tensor, n: int) -> torch.Tensor:
+        dev, t = self.t.device, self.t
+        # level "-1": this rank's own batch goes to the owners of its resources
+        routed, src0, sc, rc = self._route(d_items.data_ptr(), n, -1)
+        queries = t.alltoall(routed, sc, rc, self.ITEM)
+        self.stats["exchanges"] += 1
+        levels = [{"src": src0, "send": sc, "recv": rc}]  # routing that produced level lv's queries
+        lv = 0
+        while True:
+            nq = queries.numel() // self.ITEM
+            nsub = self.e.shard_pass_dev(queries.data_ptr() if nq else 0, nq, lv)
+            routed, src, sc, rc = self._route(0, nsub, lv)
+            nxt = t.alltoall(routed, sc, rc, self.ITEM)
+            self.stats["exchanges"] += 1
+            self.stats["subqueries_sent"] += int(nsub)
+            self.stats["bytes_sent"] += int(nsub) * self.ITEM
+            levels.append({"src": src, "send": sc, "recv": rc, "nq": nq, "nsub": int(nsub)})
+            queries = nxt
+            lv += 1
+            if t.allreduce_sum(queries.numel()) == 0:
+                break
+            if lv > 60:
+                raise RuntimeError("sharded check did not converge within the dispatch depth")
+        self.stats["levels"] = max(self.stats["levels"], lv)
+        # values flow back: level lv's outputs answer the sub-queries level lv-1 raised
+        out_next = torch.empty(0, dtype=torch.uint8, device=dev)  # outputs of the (empty) deepest level
+        for k in range(lv - 1, -1, -1):
+            L = levels[k + 1]
+            # out_next holds one byte per query that ARRIVED at level k+1, source-major: send them home
+            back = t.alltoall(out_next, L["recv"], L["send"], 1)
+            self.stats["bytes_sent"] += int(back.numel())
+            out = torch.empty(max(L["nq"], 1), dtype=torch.uint8, device=dev)
+            self.e.shard_fold_dev(k, back.data_ptr() if L["nsub"] else 0, L["src"].data_ptr() if L["nsub"] else 0, L["nsub"],
+                                  out.data_ptr(), final_codes=(k == 0))
+            out_next = out[: L["nq"]]
+        # level 0's outputs answer the checks that were routed here: back to their callers, in the callers' order
+        home = t.alltoall(out_next, levels[0]["recv"], levels[0]["send"], 1)
+        answers = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+        self.e.shard_unroute_dev(levels[0]["src"].data_ptr() if n else 0, home.data_ptr() if n else 0, n, answers.data_ptr())
+        return answers[:n]

@@ -891,3 +891,108 @@ def test_one_engine_owning_several_gpus_equals_a_single_gpu_engine(zg):
     for i in range(8):
         assert np.array_equal(lk[i], o.lookup_resources_ids(rt, perm, st, int(u) + i))
     multi.close()
+
+
+def _run_sharded_device(zg, schema, load, items, world=3):
+    """The device-resident protocol (dist.DeviceShardedChecker) on `world` virtual shards of this one GPU: every
+    rank brings a slice of the batch as a CUDA tensor and gets that slice's answers back."""
+    import threading
+
+    import torch
+
+    from spicedb_kubeapi_proxy_b200 import dist as zdist
+
+    ts = zdist.LocalDeviceTransport.cluster(world)
+    engines = [zg.Engine(schema, shard_rank=r, shard_count=world) for r in range(world)]
+    for e in engines:
+        load(e)
+        e.publish()
+    bounds = [zdist.shard_bounds(items.size, r, world) for r in range(world)]
+    out, errs, checkers = [None] * world, [], [None] * world
+
+    def run(r):
+        try:
+            lo, hi = bounds[r]
+            mine = np.ascontiguousarray(items[lo:hi])
+            d = torch.from_numpy(mine.view(np.uint8).copy()).cuda()
+            ck = zdist.DeviceShardedChecker(engines[r], ts[r])
+            checkers[r] = ck
+            out[r] = ck.check_bulk(d, hi - lo).cpu().numpy()
+        except Exception as ex:  # noqa: BLE001
+            errs.append(repr(ex))
+            ts[r]._s["bar"].abort()
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs
+    return np.concatenate(out), checkers[0].stats
+
+
+@pytest.mark.parametrize("name,scale", [("cfg3", 0.005), ("cfg4", 0.001)])
+def test_device_resident_sharded_store_equals_oracle_on_workloads(zg, name, scale):
+    from oracle.pyoracle import Oracle
+    from spicedb_kubeapi_proxy_b200 import workloads
+
+    w = workloads.by_name(name, scale)
+    o = Oracle(w.schema)
+    w.load_into(o)
+    items = w.check_items(o, zg.CHECK_DTYPE)[:6000]
+    got, stats = _run_sharded_device(zg, w.schema, w.load_into, items)
+    assert np.array_equal(got, o.check_bulk(items))
+    assert stats["subqueries_sent"] > 0 and stats["levels"] >= 2
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_device_resident_sharded_store_random_schemas(zg, seed):
+    from oracle.pyoracle import Oracle
+
+    rng = random.Random(900 + seed)
+    if seed < 3:
+        schema = randgen.FIXED_SCHEMAS[sorted(randgen.FIXED_SCHEMAS)[seed]]
+        model = randgen.model_from_schema(schema)
+    else:
+        schema, model = randgen.random_schema(rng)
+    rels = randgen.random_relationships(rng, model, n_obj=7, n_user=6, density=0.3)
+    checks = randgen.random_checks(rng, model, 500, n_obj=7, n_user=6)
+    o = Oracle(schema)
+    for r in rels:
+        o.touch(r)
+
+    def load(e):
+        ups = [(zg._lib.OP_TOUCH, r, 0) for r in rels]
+        for i in range(0, len(ups), 1000):
+            e.write_relationships(ups[i:i + 1000])
+
+    probe = zg.Engine(schema, host_only=True)
+    load(probe)
+    items = _items_from_strings(probe, zg, checks)
+    got, _ = _run_sharded_device(zg, schema, load, items)
+    want = np.array([o.check(*split_rel(q)) for q in checks], dtype=np.uint8)
+    bad = [(q, int(g), int(x)) for q, g, x in zip(checks, got, want) if g != x]
+    assert not bad, bad[:5]
+
+
+def test_device_resident_sharded_store_depth_cap_across_shards(zg):
+    from oracle.pyoracle import Oracle
+    from test_oracle_random import CHAIN
+
+    rels = [f"group:g{i}#member@group:g{i+1}#member" for i in range(51)] + ["group:g51#member@user:deep"]
+    rels += ["group:a#member@group:b#member", "group:b#member@group:a#member", "group:b#member@user:x"]
+    rels += [f"folder:f{i}#parent@folder:f{i+1}" for i in range(51)] + ["folder:f0#viewer@user:v"]
+    checks = ["group:g0#member@user:deep", "group:g1#member@user:deep", "group:g2#member@user:nobody",
+              "group:a#member@user:x", "group:a#member@user:y", "folder:f0#view@user:v", "folder:f0#view@user:w",
+              "folder:f0#not_view@user:v", "folder:f0#not_view@user:w", "folder:f40#view@user:v"]
+    o = Oracle(CHAIN)
+    for r in rels:
+        o.touch(r)
+
+    def load(e):
+        e.write_relationships([(zg._lib.OP_TOUCH, r, 0) for r in rels])
+
+    probe = zg.Engine(CHAIN, host_only=True)
+    load(probe)
+    items = _items_from_strings(probe, zg, checks)
+    got, stats = _run_sharded_device(zg, CHAIN, load, items)
+    assert list(got) == [o.check(*split_rel(q)) for q in checks]
+    assert stats["levels"] > 20
