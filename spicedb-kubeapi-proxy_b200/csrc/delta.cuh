@@ -3,7 +3,9 @@
 #pragma once
 #ifndef ZG_EMULATE
 #include <cuda_runtime.h>
+#ifndef ZG_BLOCK_SHARED_U32
 #define ZG_BLOCK_SHARED_U32(name, n) __shared__ uint32_t name[n]
+#endif
 #endif
 
 #include <algorithm>

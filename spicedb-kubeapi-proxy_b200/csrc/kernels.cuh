@@ -24,6 +24,9 @@
 #ifndef ZG_EMULATE  // tests/emu/: the same source under a CPU SIMT emulator (test infrastructure, never in libzgpu.so)
 #include <cuda_runtime.h>
 #define ZG_DYNAMIC_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+#ifndef ZG_BLOCK_SHARED_U32
+#define ZG_BLOCK_SHARED_U32(name, n) __shared__ uint32_t name[n]
+#endif
 #endif
 
 #include <cstdint>
@@ -819,7 +822,7 @@ __global__ void or_children_kernel(const uint32_t* parent, const uint8_t* child_
 constexpr int kMaxRouteDest = 64;
 __global__ void __launch_bounds__(256) route_count_kernel(const zg_check* items, unsigned long long n, uint32_t n_dest,
                                                           unsigned long long* counts) {
-  __shared__ unsigned int hist[kMaxRouteDest];
+  ZG_BLOCK_SHARED_U32(hist, kMaxRouteDest);
   for (uint32_t i = threadIdx.x; i < n_dest; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;

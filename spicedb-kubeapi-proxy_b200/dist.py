@@ -243,16 +243,21 @@ class LocalDeviceTransport:
     """`world` virtual ranks in ONE process on ONE GPU (threads): tensors change hands by reference. Tests the
     device-resident protocol without NCCL. Build with LocalDeviceTransport.cluster(world)."""
 
-    def __init__(self, rank, world, shared):
+    def __init__(self, rank, world, shared, device=None):
         self.rank, self.world, self._s = rank, world, shared
-        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def _sync(self):
+        if self.device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
 
     @staticmethod
-    def cluster(world):
+    def cluster(world, device=None):
+        """device=torch.device("cpu"): host tensors (the kernel emulator of tests/emu drives the same protocol)."""
         import threading
 
         shared = {"box": [None] * world, "bar": threading.Barrier(world), "sum": [0] * world}
-        return [LocalDeviceTransport(r, world, shared) for r in range(world)]
+        return [LocalDeviceTransport(r, world, shared, device) for r in range(world)]
 
     def exchange_counts(self, counts):
         s = self._s
@@ -265,12 +270,12 @@ class LocalDeviceTransport:
     def alltoall(self, send, send_counts, recv_counts, width):
         s = self._s
         offs = np.concatenate([[0], np.cumsum(send_counts)]) * width
-        torch.cuda.current_stream().synchronize()
+        self._sync()
         s["box"][self.rank] = [send[int(offs[d]):int(offs[d + 1])] for d in range(self.world)]
         s["bar"].wait()
         parts = [s["box"][src][self.rank] for src in range(self.world)]
         out = torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device=self.device)
-        torch.cuda.current_stream().synchronize()
+        self._sync()
         s["bar"].wait()
         return out
 

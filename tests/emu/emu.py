@@ -58,6 +58,11 @@ def lib():
         L.emu_check.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(Opts), C.c_int]
         L.emu_lookup_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(Opts), C.c_uint64,
                                        C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.emu_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.emu_shard_route.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emu_shard_pass.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Opts), C.POINTER(C.c_uint64)]
+        L.emu_shard_fold.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
+        L.emu_unroute.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.emu_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_size_t]
         L.emu_journal_start.argtypes = [C.c_void_p]
         L.emu_merge_and_verify.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
@@ -72,13 +77,38 @@ UPDATE_DTYPE = np.dtype([("res", "<u4"), ("subj", "<u4"), ("rel", "<u2"), ("styp
 class EmuEngine:
     """Same surface as zgpu.Engine / oracle.pyoracle.Oracle where the workload generators need it."""
 
-    def __init__(self, schema: str):
+    def __init__(self, schema: str, shard_rank: int = 0, shard_count: int = 1):
         self._L = lib()
         err = C.create_string_buffer(512)
         self._h = self._L.emu_create(schema.encode(), err, 512)
         if not self._h:
             raise RuntimeError(err.value.decode())
         self._names = {}  # (type, name) -> id, for string-driven tests
+        self.shard_opts = default_opts()
+        if shard_count > 1:
+            self._L.emu_set_shard(self._h, shard_rank, shard_count)
+
+    # the four device-resident shard calls of zgpu.Engine, over host memory (pointers = CPU tensor data_ptr())
+    def shard_route_dev(self, d_items, n, level, n_dest, d_routed, d_src):
+        counts = (C.c_uint64 * n_dest)()
+        if self._L.emu_shard_route(self._h, d_items or None, n, level, n_dest, d_routed or None, d_src or None, counts):
+            raise RuntimeError("emu_shard_route failed")
+        return [int(c) for c in counts]
+
+    def shard_pass_dev(self, d_queries, n, level):
+        ns = C.c_uint64(0)
+        rc = self._L.emu_shard_pass(self._h, d_queries or None, n, level, C.byref(self.shard_opts), C.byref(ns))
+        if rc:
+            raise RuntimeError(f"emu_shard_pass rc={rc}")
+        return ns.value
+
+    def shard_fold_dev(self, level, d_child_vals, d_src, n_sub, d_out, final_codes):
+        if self._L.emu_shard_fold(self._h, level, d_child_vals or None, d_src or None, n_sub, d_out or None, 1 if final_codes else 0):
+            raise RuntimeError("emu_shard_fold failed")
+
+    def shard_unroute_dev(self, d_src, d_val, n, d_out):
+        if self._L.emu_unroute(self._h, d_src or None, d_val or None, n, d_out or None):
+            raise RuntimeError("emu_unroute failed")
 
     def close(self):
         if getattr(self, "_h", None):

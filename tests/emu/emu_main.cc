@@ -28,7 +28,16 @@ struct EmuOpts {
   uint32_t streamed;     // run the STREAMED variant with everything already "landed"
 };
 
+struct ShardLevel {
+  std::vector<zg_check> q, raised;
+  std::vector<uint32_t> parent;
+  std::vector<uint8_t> val;
+  uint64_t nq = 0, nsub = 0;
+};
+
 struct Emu {
+  uint32_t shard_count = 1, shard_rank = 0;
+  std::vector<ShardLevel> levels;
   Schema sc;
   Store st;
   HostSnapshot h;
@@ -135,8 +144,9 @@ int run_pass(Emu* e, const EmuOpts& o, const zg_check* queries, uint64_t nq, uin
   p.memo = memo.data();
   p.memo_entries = o.memo_entries;
   p.memo_after = o.memo_after;
-  p.shard_count = 0;
-  p.shard_rank = 0;
+  p.shard_count = e->shard_count;
+  p.shard_rank = e->shard_rank;
+  if (e->shard_count > 1) p.invert = 0;  // a shard does not hold the subject's reverse rows
   const size_t sm = p.prog_bytes + size_t(kWarpsPerBlock) * kWarpSmem;
   if (count) zg_emu::launch(check_kernel<true, false>, p, grid, kThreads, sm);
   else if (o.streamed) zg_emu::launch(check_kernel<false, true>, p, grid, kThreads, sm);
@@ -441,6 +451,119 @@ int emu_merge_and_verify(void* h, char* err, size_t cap) {
   }
   e->h.n_tuples = want.n_tuples;
   e->blob = e->sc.blob(e->h.rels, e->h.cls);
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- object-hash sharded store: device.cu route_by_owner / shard_pass_dev / shard_fold_dev / unroute over host memory
+
+extern "C" {
+
+void emu_set_shard(void* h, uint32_t rank, uint32_t count) {
+  Emu* e = static_cast<Emu*>(h);
+  e->shard_rank = rank;
+  e->shard_count = count;
+  e->st.shard_rank = rank;
+  e->st.shard_count = count;
+}
+
+int emu_shard_route(void* h, const zg_check* items, uint64_t n, int level, uint32_t n_dest, zg_check* routed, uint32_t* src,
+                    uint64_t* counts) {
+  Emu* e = static_cast<Emu*>(h);
+  for (uint32_t d = 0; d < n_dest; ++d) counts[d] = 0;
+  if (!items) {
+    if (level < 0 || static_cast<size_t>(level) >= e->levels.size() || n != e->levels[level].nsub) return -1;
+    items = e->levels[level].raised.data();
+  }
+  if (n == 0) return 0;
+  std::vector<unsigned long long> cnt(kMaxRouteDest, 0), cursor(kMaxRouteDest, 0);
+  struct CntArgs {
+    const zg_check* items;
+    unsigned long long n;
+    uint32_t n_dest;
+    unsigned long long* counts;
+  } ca{items, n, n_dest, cnt.data()};
+  zg_emu::launch(+[](const CntArgs& a) { route_count_kernel(a.items, a.n, a.n_dest, a.counts); }, ca, 2, 256, 0);
+  unsigned long long acc = 0;
+  for (uint32_t d = 0; d < n_dest; ++d) {
+    counts[d] = cnt[d];
+    cursor[d] = acc;
+    acc += cnt[d];
+  }
+  struct ScArgs {
+    const zg_check* items;
+    unsigned long long n;
+    uint32_t n_dest;
+    unsigned long long* cursor;
+    zg_check* routed;
+    uint32_t* src;
+  } sa{items, n, n_dest, cursor.data(), routed, src};
+  zg_emu::launch(+[](const ScArgs& a) { route_scatter_kernel(a.items, a.n, a.n_dest, a.cursor, a.routed, a.src); }, sa, 2, 256, 0);
+  return 0;
+}
+
+int emu_shard_pass(void* h, const zg_check* queries, uint64_t n, int level, const EmuOpts* o, uint64_t* n_sub) {
+  Emu* e = static_cast<Emu*>(h);
+  if (!e->published) return -1;
+  if (e->levels.size() <= static_cast<size_t>(level)) e->levels.resize(level + 1);
+  ShardLevel& L = e->levels[level];
+  L.nq = n;
+  L.nsub = 0;
+  *n_sub = 0;
+  if (n == 0) return 0;
+  L.q.assign(queries, queries + n);
+  L.val.assign(n * e->sc.max_leaves + 4, 0);
+  L.raised.assign(o->subq_cap, zg_check{});
+  L.parent.assign(o->subq_cap, 0);
+  uint64_t ns = 0;
+  // final_codes does not matter here: out is null, the fold writes the level's outputs
+  run_pass(e, *o, L.q.data(), n, L.val.data(), nullptr, level == 0, L.raised.data(), L.parent.data(), &ns, false);
+  if (ns > o->subq_cap) return -3;
+  L.nsub = ns;
+  *n_sub = ns;
+  return 0;
+}
+
+int emu_shard_fold(void* h, int level, const uint8_t* child_vals, const uint32_t* src, uint64_t n_sub, uint8_t* out, int final_codes) {
+  Emu* e = static_cast<Emu*>(h);
+  if (level < 0 || static_cast<size_t>(level) >= e->levels.size() || n_sub != e->levels[level].nsub) return -1;
+  ShardLevel& L = e->levels[level];
+  if (L.nq == 0) return 0;
+  if (n_sub) {
+    struct OrArgs {
+      const uint32_t *parent, *src;
+      const uint8_t* child;
+      unsigned long long n;
+      uint8_t* val;
+    } oa{L.parent.data(), src, child_vals, n_sub, L.val.data()};
+    zg_emu::launch(+[](const OrArgs& a) { or_children_src_kernel(a.parent, a.src, a.child, a.n, a.val); }, oa,
+                   static_cast<unsigned>((n_sub + 255) / 256), 256, 0);
+  }
+  struct FoldArgs {
+    const uint8_t* prog;
+    const zg_check* q;
+    unsigned long long n;
+    uint32_t L;
+    const uint8_t* val;
+    uint8_t* out;
+    int raw;
+  } fa{e->blob.data(), L.q.data(), L.nq, e->sc.max_leaves, L.val.data(), out, final_codes ? 0 : 1};
+  zg_emu::launch(+[](const FoldArgs& a) { fold_kernel(a.prog, a.q, a.n, a.L, a.val, a.out, nullptr, nullptr, a.raw); }, fa,
+                 static_cast<unsigned>((L.nq + 255) / 256), 256, 0);
+  return 0;
+}
+
+int emu_unroute(void* h, const uint32_t* src, const uint8_t* val, uint64_t n, uint8_t* out) {
+  (void)h;
+  if (n == 0) return 0;
+  struct UArgs {
+    const uint32_t* src;
+    const uint8_t* val;
+    unsigned long long n;
+    uint8_t* out;
+  } ua{src, val, n, out};
+  zg_emu::launch(+[](const UArgs& a) { unroute_kernel(a.src, a.val, a.n, a.out); }, ua, static_cast<unsigned>((n + 255) / 256), 256, 0);
   return 0;
 }
 

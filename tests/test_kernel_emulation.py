@@ -314,3 +314,84 @@ def test_incremental_publish_with_expirations_and_empty_classes_under_the_emulat
         for now in (500, 1500):
             opts = emu.default_opts(now=now)
             assert np.array_equal(e.check_bulk(items, opts), o.check_bulk(items, now=now)), f"step {i} now {now}"
+
+
+def _run_sharded_emulated(emu, schema, load, items, world=3):
+    """dist.DeviceShardedChecker -- the product's own protocol driver -- over `world` emulated shards: CPU tensors
+    change hands by reference, the kernels (raise of remote edges, routing, fold in routed order) run emulated."""
+    import threading
+
+    import torch
+
+    import zgpu  # noqa: F401
+    from spicedb_kubeapi_proxy_b200 import dist as zdist
+
+    cpu = torch.device("cpu")
+    ts = zdist.LocalDeviceTransport.cluster(world, device=cpu)
+    engines = [emu.EmuEngine(schema, shard_rank=r, shard_count=world) for r in range(world)]
+    for e in engines:
+        load(e)
+        e.publish()
+    bounds = [zdist.shard_bounds(items.size, r, world) for r in range(world)]
+    out, errs, cks = [None] * world, [], [None] * world
+
+    def run(r):
+        try:
+            lo, hi = bounds[r]
+            d = torch.from_numpy(np.ascontiguousarray(items[lo:hi]).view(np.uint8).copy())
+            cks[r] = zdist.DeviceShardedChecker(engines[r], ts[r])
+            out[r] = cks[r].check_bulk(d, hi - lo).numpy().copy()
+        except Exception as ex:  # noqa: BLE001
+            import traceback
+
+            errs.append(traceback.format_exc())
+            ts[r]._s["bar"].abort()
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs[0]
+    return np.concatenate(out), cks[0].stats
+
+
+@pytest.mark.parametrize("wl,scale,n", [("cfg4", 0.001, 1500), ("cfg3", 0.002, 600)])
+def test_device_resident_sharded_protocol_under_the_emulator(emu, wl, scale, n):
+    import zgpu  # noqa: F401
+    from oracle.pyoracle import Oracle
+    from spicedb_kubeapi_proxy_b200 import workloads
+
+    w = workloads.by_name(wl, scale)
+    o = Oracle(w.schema)
+    w.load_into(o)
+    items = w.check_items(o, emu.CHECK_DTYPE)[:n]
+    got, stats = _run_sharded_emulated(emu, w.schema, w.load_into, items)
+    assert np.array_equal(got, o.check_bulk(items))
+    assert stats["subqueries_sent"] > 0 and stats["levels"] >= 2
+
+
+def test_sharded_protocol_with_boolean_operators_and_depth_cap_under_the_emulator(emu):
+    from oracle.pyoracle import Oracle
+    from test_oracle_random import CHAIN
+
+    rels = [f"group:g{i}#member@group:g{i+1}#member" for i in range(51)] + ["group:g51#member@user:deep"]
+    rels += ["group:a#member@group:b#member", "group:b#member@group:a#member", "group:b#member@user:x"]
+    rels += [f"folder:f{i}#parent@folder:f{i+1}" for i in range(51)] + ["folder:f0#viewer@user:v"]
+    checks = ["group:g0#member@user:deep", "group:g1#member@user:deep", "group:g2#member@user:nobody",
+              "group:a#member@user:x", "group:a#member@user:y", "folder:f0#view@user:v", "folder:f0#view@user:w",
+              "folder:f0#not_view@user:v", "folder:f0#not_view@user:w", "folder:f40#view@user:v"]
+    o = Oracle(CHAIN)
+    for r in rels:
+        o.touch(r)
+    probe = emu.EmuEngine(CHAIN)
+    probe.write_rels(rels, split_rel)
+    names = dict(probe._names)
+
+    def load(e):
+        e._names = dict(names)  # the same interning on every shard
+        e.write_rels(rels, split_rel)
+
+    items = probe.items_from_strings(checks, split_rel)
+    got, stats = _run_sharded_emulated(emu, CHAIN, load, items)
+    assert list(got) == [o.check(*split_rel(q)) for q in checks]
+    assert list(got[:5]) == [255, 2, 1, 2, 255]
+    assert stats["levels"] > 20
