@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--configs", default="cfg2,cfg4",
                     help="other BASELINE configurations reported as sub-results under `configs` ('' = none)")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the object-hash sharded cfg4 leg")
     ap.add_argument("--sustain-s", type=float, default=2.5,
                     help="length of the back-to-back 'sustained' leg of the primary workload (0 = skip)")
     return ap.parse_args()
@@ -405,6 +406,84 @@ def measure_workload(name, args, rank, local_rank, world, dist, primary, sampler
     return out
 
 
+def measure_sharded(args, rank, local_rank, world, dist):
+    """cfg4 at full size on an object-hash sharded store: each rank brings 1/N of the 1 M-check batch; the answers
+    must equal a replica's bit for bit (checked on rank 0 against an engine holding the whole store)."""
+    import numpy as np
+    import torch
+
+    import zgpu
+    from spicedb_kubeapi_proxy_b200 import dist as zdist
+    from spicedb_kubeapi_proxy_b200 import workloads
+
+    w = workloads.by_name("cfg4", args.scale)
+    eng = zgpu.Engine(w.schema, device=local_rank, shard_rank=rank, shard_count=world, subquery_capacity=1 << 24)
+    w.load_into(eng)  # keeps only the relationships this rank owns
+    eng.publish()
+    items = w.check_items(eng, zgpu.CHECK_DTYPE)
+    lo, hi = zdist.shard_bounds(items.size, rank, world)
+    mine = np.ascontiguousarray(items[lo:hi])
+    d_items = torch.from_numpy(mine.view(np.uint8).copy()).cuda()
+    ck = zdist.DeviceShardedChecker(eng, zdist.TorchDeviceTransport())
+    chunk = 1 << 16  # checks per rank per round: bounds the sub-queries a pass may raise
+    steps = max(2, min(args.steps, 5))
+
+    def one_step():
+        outs = []
+        for b in range(0, hi - lo, chunk):
+            e = min(hi - lo, b + chunk)
+            outs.append(ck.check_bulk(d_items[b * 16:e * 16], e - b))
+        return torch.cat(outs)
+
+    ans = one_step()  # warm-up
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ans = one_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    mism = None
+    gathered = [torch.empty(zdist.shard_bounds(items.size, r, world)[1] - zdist.shard_bounds(items.size, r, world)[0],
+                            dtype=torch.uint8, device="cuda") for r in range(world)]
+    # ragged all-gather of the answers (sizes differ by at most one): pad to the widest
+    width = max(g.numel() for g in gathered)
+    pad = torch.zeros(width, dtype=torch.uint8, device="cuda")
+    pad[: ans.numel()] = ans
+    blocks = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(blocks, pad)
+    n_tuples_owned = torch.tensor([eng.stats()["tuples"]], dtype=torch.int64, device="cuda")
+    dist.all_reduce(n_tuples_owned, op=dist.ReduceOp.SUM)
+    st = dict(ck.stats)
+    eng.close()
+    out = None
+    if rank == 0:
+        full = np.concatenate([blocks[r][: gathered[r].numel()].cpu().numpy() for r in range(world)])
+        rep = zgpu.Engine(w.schema, device=local_rank)
+        w.load_into(rep)
+        rep.publish()
+        want = rep.check_bulk(items)
+        mism = int((full != want).sum())
+        rep.close()
+        rounds = steps * ((hi - lo + chunk - 1) // chunk)
+        out = {"value": items.size * steps / dt / 1e6, "unit": UNIT, "ms_per_step": dt / steps * 1e3, "steps": steps,
+               "mismatches_vs_replica": mism, "tuples_over_all_shards": int(n_tuples_owned.item()),
+               "levels": st["levels"], "subqueries_per_check": st["subqueries_sent"] / max((hi - lo) * (steps + 1), 1),
+               "exchanges_per_round": st["exchanges"] / max(rounds + (hi - lo + chunk - 1) // chunk, 1),
+               "bytes_sent_per_rank_per_step": st["bytes_sent"] / (steps + 1),
+               "limiting": "per-level round trip (kernel pass + count exchange + NCCL all-to-all): latency-bound, "
+                           "bytes are far below NVLink",
+               "config": {"workload": f"cfg4 object-hash sharded x{world}: {w.note}", "chunk_checks_per_rank": chunk,
+                          "global_batch": items.size}}
+        if mism:
+            out["error"] = f"{mism} answers differ from the replica"
+    dist.barrier()
+    return out
+
+
 def main():
     # stdout must carry exactly ONE JSON line, but libraries print there too (NCCL's version banner
     # under torchrun): point fd 1 at stderr for the whole run and emit the line on the saved fd
@@ -442,6 +521,18 @@ def main():
         r = measure_workload(name, args, rank, local_rank, world, dist, False)
         if r is not None:
             extra[name] = r
+
+    # N > 1: north-star's other multi-GPU mode on the configuration it names for it (cfg4, "object-id sharded
+    # across 8 GPUs"): every rank owns the relationships whose resource id % N is its rank, checks and raised
+    # sub-queries are routed device to device (dist.DeviceShardedChecker: NCCL all-to-all of device buffers per
+    # level). A second field of the line, never the headline; a failure is reported, not fatal.
+    if world > 1 and args.scale == 1.0 and not args.no_sharded:
+        try:
+            r = measure_sharded(args, rank, local_rank, world, dist)
+        except Exception as ex:  # noqa: BLE001
+            r = {"error": repr(ex)[:400]} if rank == 0 else None
+        if r is not None:
+            extra["cfg4_sharded"] = r
 
     if rank == 0:
         out = {

@@ -4,7 +4,12 @@ LookupResources (the pre-filter shape, pkg/authz/lookups.go:65) against the cfg4
 The true end-to-end path (Go HTTP handlers) cannot run here (no Go toolchain); this drives the
 same library entry points from threads (ctypes releases the GIL inside the calls).
 
-    python scripts/cfg5_replay.py [--scale 0.1] [--clients 256] [--items 10000] [--rounds 4]
+    python scripts/cfg5_replay.py [--scale 1.0] [--clients 1000] [--items 10000] [--rounds 2] [--devices 8]
+
+--devices N: ONE engine handle owning N GPUs (zg_config.n_devices: a replica per device, every bulk call and every
+batch of lookups split across them) -- BASELINE config 5 names 8 GPUs behind the proxy's single client.
+A third phase runs both shapes at once (the proxy's pre-filter goroutine runs concurrently with the list request,
+pkg/authz/responsefilterer.go:165-183).
 """
 import argparse, json, os, sys, threading, time
 import numpy as np
@@ -13,14 +18,15 @@ import zgpu
 from spicedb_kubeapi_proxy_b200 import workloads
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--scale", type=float, default=0.1)
-ap.add_argument("--clients", type=int, default=256)
+ap.add_argument("--scale", type=float, default=1.0)
+ap.add_argument("--clients", type=int, default=1000)
 ap.add_argument("--items", type=int, default=10000)
-ap.add_argument("--rounds", type=int, default=4)
+ap.add_argument("--rounds", type=int, default=2)
+ap.add_argument("--devices", type=int, default=1)
 a = ap.parse_args()
 
 w = workloads.cfg4(scale=a.scale)
-e = zgpu.Engine(w.schema)
+e = zgpu.Engine(w.schema, device=0, n_devices=a.devices)
 w.load_into(e)
 e.publish()
 base = w.check_items(e, zgpu.CHECK_DTYPE)
@@ -71,8 +77,17 @@ def lookup_phase(i):  # pre-filter shape
     found[i] = int(e.lookup_resources_ids("document", "view", "user", int(users[i])).size)
 
 
+def mixed_phase(i):  # a list request: its pre-filter lookup and its post-filter bulk check
+    found[i] = int(e.lookup_resources_ids("document", "view", "user", int(users[i])).size)
+    out = np.empty(a.items, dtype=np.uint8)
+    e.check_bulk(lists[i], out)
+
+
 dt_c, c0, c1 = run_phase(check_phase)
+users = rng.integers(0, n_users, a.clients)  # fresh subjects: nothing comes from the answer cache
 dt_l, l0, l1 = run_phase(lookup_phase)
+users = rng.integers(0, n_users, a.clients)
+dt_m, m0, m1 = run_phase(mixed_phase)
 lists_done = a.clients * a.rounds
 print(json.dumps({
     "workload": f"cfg5 replay at the C ABI on {w.note}", "clients": a.clients, "items_per_list": a.items, "rounds": a.rounds,
@@ -82,7 +97,13 @@ print(json.dumps({
                    "coalesced": {"requests": c1["coalesced_requests"] - c0["coalesced_requests"],
                                  "launches": c1["coalesced_launches"] - c0["coalesced_launches"]}},
     "prefilter": {"lookups_per_s": a.clients / dt_l, "wall_s": dt_l, "results_per_lookup_mean": float(np.mean(found)),
-                  "results_per_s_M": float(np.sum(found)) / dt_l / 1e6, "kernel_launches": l1["launches"] - l0["launches"]},
+                  "results_per_s_M": float(np.sum(found)) / dt_l / 1e6, "kernel_launches": l1["launches"] - l0["launches"],
+                  "batches": l1["lookup_batches"] - l0["lookup_batches"],
+                  "lookups_in_batches": l1["lookups_batched"] - l0["lookups_batched"]},
+    "mixed": {"filtered_lists_per_s": a.clients / dt_m, "wall_s": dt_m,
+              "what": "per client: one LookupResources + one 10k-item bulk check, all clients at once"},
+    "devices": int(m1["devices"]), "store_tuples": int(m1["tuples"]),
     "note": "post-filter: one 10k-item zg_check_bulk per list, concurrent callers coalesced by the library's batcher; "
-            "pre-filter: one zg_lookup_resources per client (reverse BFS + verification; lookups are serialised). "
-            "Python threads drive the ABI (GIL released inside calls); the Go HTTP path cannot run here."}))
+            "pre-filter: one zg_lookup_resources per client, concurrent calls answered up to 64 per launch sequence "
+            "(multi-source reverse walk + one verification launch). Python threads drive the ABI (GIL released "
+            "inside calls); the Go HTTP path cannot run here."}))

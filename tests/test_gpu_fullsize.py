@@ -163,5 +163,8 @@ def test_thousand_update_write_on_the_large_store_is_a_merge(zg, big):
     touched = np.concatenate([u["res"][np.isin(u["rel"], list(doc_rels))] for u in all_ups])
     probe = items[:20000].copy()
     probe["res"][: touched.size] = touched[: probe.size]
-    assert np.array_equal(e.check_bulk(probe), o.check_bulk(probe, nthreads=os.cpu_count() or 8))
+    got, exp = e.check_bulk(probe), o.check_bulk(probe, nthreads=os.cpu_count() or 8)
+    bad = np.flatnonzero(got != exp)
+    assert bad.size == 0, f"{bad.size} of {probe.size} differ; first {bad[:8]} (touched probes: < {touched.size}): " \
+                          f"{probe[bad[:8]]} gpu {got[bad[:8]]} oracle {exp[bad[:8]]}"
     e.close()
