@@ -9,7 +9,9 @@
 #include <deque>
 #include <functional>
 #include <memory>
+#include <atomic>
 #include <mutex>
+#include <shared_mutex>
 #include <new>
 #include <string>
 #include <string_view>
@@ -99,7 +101,14 @@ struct Replica {
 };
 
 struct zg_engine {
-  std::mutex mu;  // one writer or one hot-path launch sequence at a time
+  // Two locks, always taken in this order:
+  //   mu     the device: one launch sequence (a coalesced group of checks, a batch of lookups) or one publish at
+  //          a time. Held for milliseconds by whoever leads a group.
+  //   names  the schema and the store (interning tables, relationship set): shared by everything that resolves
+  //          or renders names, exclusive for writers. Never held across GPU work except by a publish, so that
+  //          callers can resolve their strings and QUEUE behind a running group instead of waiting for it.
+  std::mutex mu;
+  mutable std::shared_mutex names;
   std::vector<std::unique_ptr<Replica>> replicas;  // devices 1 .. n-1 (device 0 is `dev`)
   Batcher batcher;
   Schema schema;
@@ -108,7 +117,7 @@ struct zg_engine {
   Device dev;
   int64_t clock = 0;
   uint64_t revision = 0;
-  bool dirty = false;  // store changed since the last publish
+  std::atomic<bool> dirty{false};  // store changed since the last publish
   bool host_only = false;
   // Concurrent LookupResources calls (one goroutine per list request: pkg/authz/responsefilterer.go:165) are
   // coalesced like the checks: the leader answers up to 64 of them with one batched launch sequence.
@@ -175,6 +184,10 @@ static void on_all_devices(zg_engine* e, const std::function<void(Device&, size_
   fn(e->dev, 0);
   for (auto& r : e->replicas) r->worker.wait();
 }
+
+#define LOCK_DEVICE(e) std::lock_guard<std::mutex> g((e)->mu)
+#define LOCK_NAMES_SHARED(e) std::shared_lock<std::shared_mutex> ng((e)->names)
+#define LOCK_NAMES_UNIQUE(e) std::unique_lock<std::shared_mutex> ng((e)->names)
 
 static thread_local std::string g_err;
 static constexpr size_t kMaxLookupGroup = 64;  // = kMaxLookupBatch (kernels.cuh)
@@ -263,7 +276,8 @@ extern "C" void zg_engine_destroy(zg_engine* e) { delete e; }
 
 extern "C" int zg_load_schema(zg_engine* e, const char* dsl, size_t len) {
   if (!e || !dsl) return fail(ZG_EINVAL, "NULL argument");
-  std::lock_guard<std::mutex> g(e->mu);
+  LOCK_DEVICE(e);
+  LOCK_NAMES_UNIQUE(e);
   Schema s;
   std::string err = s.parse(std::string(dsl, len));
   if (!err.empty()) return fail(ZG_EINVAL, err);
@@ -320,18 +334,18 @@ extern "C" const char* zg_type_name(const zg_engine* e, int t) {
 extern "C" uint32_t zg_intern_object(zg_engine* e, int t, const char* id) {
   NEED_SCHEMA(e, ZG_NO_OBJECT);
   if (!id || !*id || t < 0 || t >= static_cast<int>(e->schema.types.size())) return ZG_NO_OBJECT;
-  std::lock_guard<std::mutex> g(e->mu);
+  LOCK_NAMES_UNIQUE(e);
   return e->store.intern(t, id);
 }
 extern "C" uint32_t zg_find_object(const zg_engine* e, int t, const char* id) {
   NEED_SCHEMA(e, ZG_NO_OBJECT);
   if (!id) return ZG_NO_OBJECT;
-  std::lock_guard<std::mutex> g(const_cast<zg_engine*>(e)->mu);
+  LOCK_NAMES_SHARED(e);
   return e->store.find(t, id);
 }
 extern "C" int zg_object_name(const zg_engine* e, int t, uint32_t id, char* buf, size_t cap) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
-  std::lock_guard<std::mutex> g(const_cast<zg_engine*>(e)->mu);
+  LOCK_NAMES_SHARED(e);
   std::string_view n;
   if (!e->store.name(t, id, &n)) return fail(ZG_EINVAL, "object has no name");
   if (n.size() + 1 > cap || !buf) return ZG_E2BIG;
@@ -343,7 +357,8 @@ extern "C" int zg_object_name(const zg_engine* e, int t, uint32_t id, char* buf,
 extern "C" int zg_load_tuples(zg_engine* e, const zg_tuple* t, const uint32_t* expires, uint64_t n) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if (!t && n) return fail(ZG_EINVAL, "NULL tuples");
-  std::lock_guard<std::mutex> g(e->mu);
+  LOCK_DEVICE(e);
+  LOCK_NAMES_UNIQUE(e);
   std::string err = e->store.load(t, expires, n);
   if (!err.empty()) return fail(ZG_EINVAL, err);
   e->dirty = true;
@@ -352,7 +367,8 @@ extern "C" int zg_load_tuples(zg_engine* e, const zg_tuple* t, const uint32_t* e
 extern "C" int zg_apply_updates(zg_engine* e, const zg_update* u, uint64_t n) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if (!u && n) return fail(ZG_EINVAL, "NULL updates");
-  std::lock_guard<std::mutex> g(e->mu);
+  LOCK_DEVICE(e);
+  LOCK_NAMES_UNIQUE(e);
   int code = ZG_OK;
   std::string err = e->store.apply(u, n, &code);
   if (!err.empty()) return fail(code, err);
@@ -360,7 +376,9 @@ extern "C" int zg_apply_updates(zg_engine* e, const zg_update* u, uint64_t n) {
   return ZG_OK;
 }
 
+// Caller holds e->mu AND e->names exclusively.
 static int publish_locked(zg_engine* e) {
+  (void)e->store.layout();  // settles the object capacities once: the replicas' publishes below only read the store
   if (!e->host_only) {
     // default: build the CSR on the GPU (csrc/build.cu). ZGPU_HOST_BUILD=1 builds on the host
     // and uploads; ZGPU_VERIFY_BUILD=1 does both and compares every array (tests).
@@ -404,12 +422,14 @@ static int publish_locked(zg_engine* e) {
 }
 extern "C" int zg_publish(zg_engine* e) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
-  std::lock_guard<std::mutex> g(e->mu);
+  LOCK_DEVICE(e);
+  LOCK_NAMES_UNIQUE(e);
   return publish_locked(e);
 }
 extern "C" int zg_clear_relationships(zg_engine* e) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
-  std::lock_guard<std::mutex> g(e->mu);
+  LOCK_DEVICE(e);
+  LOCK_NAMES_UNIQUE(e);
   e->store.clear_relationships();
   e->dirty = true;
   // the feed cannot describe "everything went away" change by change: readers restart from here
@@ -420,7 +440,7 @@ extern "C" int zg_clear_relationships(zg_engine* e) {
 }
 extern "C" uint64_t zg_num_tuples(const zg_engine* e) {
   if (!e || !e->has_schema) return 0;
-  std::lock_guard<std::mutex> g(const_cast<zg_engine*>(e)->mu);
+  LOCK_NAMES_UNIQUE(e);  // match() folds the duplicates of bulk loads into the index
   std::vector<uint64_t> idx;
   Store::Filter f;
   e->store.match(f, 0, &idx);  // also folds duplicates of bulk loads
@@ -577,7 +597,8 @@ extern "C" int zg_write_relationships(zg_engine* e, const zg_update_str* ups, ui
     return fail(ZG_EINVAL, "update count of " + std::to_string(n) + " is greater than maximum allowed of 1000");
   if (n_pre > 1000)  // pkg/spicedb/spicedb.go:35
     return fail(ZG_EINVAL, "precondition count is greater than maximum allowed of 1000");
-  std::lock_guard<std::mutex> g(e->mu);
+  LOCK_DEVICE(e);
+  LOCK_NAMES_UNIQUE(e);
   std::vector<zg_update> u(n);
   for (uint64_t i = 0; i < n; ++i) {
     if (ups[i].op == ZG_OP_DELETE) {
@@ -613,7 +634,8 @@ extern "C" int zg_delete_relationships(zg_engine* e, const zg_filter_str* filter
                                        uint64_t n_pre, uint64_t* n_deleted) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if (!filter || (!pre && n_pre)) return fail(ZG_EINVAL, "NULL argument");
-  std::lock_guard<std::mutex> g(e->mu);
+  LOCK_DEVICE(e);
+  LOCK_NAMES_UNIQUE(e);
   std::string err;
   Store::Filter f = resolve_filter(e, *filter, &err);
   if (!err.empty()) return fail(ZG_EINVAL, err);
@@ -655,7 +677,7 @@ extern "C" int zg_read_relationships(zg_engine* e, const zg_filter_str* filter, 
                                      uint64_t* n_out) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if (!filter) return fail(ZG_EINVAL, "NULL filter");
-  std::lock_guard<std::mutex> g(e->mu);
+  LOCK_NAMES_UNIQUE(e);  // match() may (re)build the relationship index
   std::string err;
   Store::Filter f = resolve_filter(e, *filter, &err);
   if (!err.empty()) return fail(ZG_EINVAL, err);
@@ -683,7 +705,8 @@ extern "C" int zg_read_relationships(zg_engine* e, const zg_filter_str* filter, 
 extern "C" int zg_watch_read(zg_engine* e, uint64_t since_revision, const char* res_type, char* buf, size_t cap,
                              size_t* need, uint64_t* n_out, uint64_t* through_revision) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
-  std::lock_guard<std::mutex> g(e->mu);
+  LOCK_DEVICE(e);  // the change log is appended under the device lock
+  LOCK_NAMES_SHARED(e);
   int want = -1;
   if (res_type && *res_type) {
     want = e->schema.type_id(res_type);
@@ -720,10 +743,15 @@ extern "C" int zg_watch_read(zg_engine* e, uint64_t since_revision, const char* 
 
 // ---- hot path ------------------------------------------------------------------------
 
-static int ensure_published(zg_engine* e) {
+// Makes pending writes visible before a string entry point resolves against them. Takes both locks only when
+// there is something to publish; call it with NO lock held.
+static int publish_if_needed(zg_engine* e) {
   if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
   if (e->dev.shard_count > 1) return fail(ZG_EINVAL, kShardedMsg);
-  if (e->dirty || !e->dev.snap) return publish_locked(e);
+  if (!e->dirty.load() && e->dev.snap) return ZG_OK;
+  LOCK_DEVICE(e);
+  LOCK_NAMES_UNIQUE(e);
+  if (e->dirty.load() || !e->dev.snap) return publish_locked(e);
   return ZG_OK;
 }
 
@@ -967,7 +995,7 @@ static void resolve_checks_locked(const zg_engine* e, const zg_rel_str* items, u
 extern "C" int zg_resolve_checks(zg_engine* e, const zg_rel_str* items, uint64_t n, zg_check* out) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if ((!items || !out) && n) return fail(ZG_EINVAL, "NULL argument");
-  std::lock_guard<std::mutex> g(e->mu);
+  LOCK_NAMES_SHARED(e);
   resolve_checks_locked(e, items, n, out);
   return ZG_OK;
 }
@@ -1027,7 +1055,7 @@ extern "C" int zg_resolve_checks_packed(zg_engine* e, const char* res_type, cons
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if (!PACKED_ARGS_OK()) return fail(ZG_EINVAL, "NULL argument");
   if (n == 0) return ZG_OK;
-  std::lock_guard<std::mutex> g(e->mu);
+  LOCK_NAMES_SHARED(e);
   return resolve_packed_locked(e, res_type, relation, subj_type, subj_rel, res_ids, res_off, subj_ids, subj_off, n, out);
 }
 
@@ -1039,9 +1067,9 @@ extern "C" int zg_check_bulk_packed(zg_engine* e, const char* res_type, const ch
   if (n == 0) return ZG_OK;
   std::vector<zg_check> c(n);
   {
-    std::lock_guard<std::mutex> g(e->mu);
-    int rc = ensure_published(e);
+    int rc = publish_if_needed(e);
     if (rc) return rc;
+    LOCK_NAMES_SHARED(e);
     rc = resolve_packed_locked(e, res_type, relation, subj_type, subj_rel, res_ids, res_off, subj_ids, subj_off, n, c.data());
     if (rc) return rc;
   }
@@ -1053,9 +1081,9 @@ extern "C" int zg_check_bulk_str(zg_engine* e, const zg_rel_str* items, uint64_t
   if ((!items || !out) && n) return fail(ZG_EINVAL, "NULL argument");
   std::vector<zg_check> c(n);
   {
-    std::lock_guard<std::mutex> g(e->mu);
-    int rc = ensure_published(e);
+    int rc = publish_if_needed(e);
     if (rc) return rc;
+    LOCK_NAMES_SHARED(e);
     resolve_checks_locked(e, items, n, c.data());
   }
   // Interned ids stay valid across later writes (interning only appends), so the launch can go
@@ -1143,7 +1171,7 @@ extern "C" int zg_list_resolve(zg_engine* e, const char* body, size_t len, const
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if (!tpl || ((!body || !items || !out || !checked) && n)) return fail(ZG_EINVAL, "NULL argument");
   if (tpl->id_kind > ZG_ID_NAMESPACED_NAME) return fail(ZG_EINVAL, "unknown id_kind");
-  std::lock_guard<std::mutex> g(e->mu);
+  LOCK_NAMES_SHARED(e);
   // the literal fields once; the resource id per item
   ResolveMemo memo;
   zg_check base;
@@ -1234,8 +1262,7 @@ extern "C" int zg_list_postfilter(zg_engine* e, const char* body, size_t len, co
   }
   if (!all.empty()) {
     {
-      std::lock_guard<std::mutex> g(e->mu);
-      int rc = ensure_published(e);
+      int rc = publish_if_needed(e);
       if (rc) return rc;
     }
     std::vector<uint8_t> codes(all.size());
@@ -1260,7 +1287,8 @@ static void run_lookup_group(zg_engine* e, std::vector<zg_engine::LookupJob*>& g
   };
   if (e->host_only) return fail_all(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
   if (e->dev.shard_count > 1) return fail_all(ZG_EINVAL, kShardedMsg);
-  if (e->dirty || !e->dev.snap) {
+  if (e->dirty.load() || !e->dev.snap) {
+    LOCK_NAMES_UNIQUE(e);
     int rc = publish_locked(e);
     if (rc) return fail_all(rc, g_err);
   }
@@ -1436,12 +1464,7 @@ extern "C" int zg_lookup_resources(zg_engine* e, uint16_t res_type, uint16_t per
                                    uint16_t srel, uint32_t* out_ids, uint64_t cap, uint64_t* n_out) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if (!n_out) return fail(ZG_EINVAL, "NULL n_out");
-  {
-    std::lock_guard<std::mutex> g(e->mu);
-    if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
-    if (e->dev.shard_count > 1) return fail(ZG_EINVAL, kShardedMsg);
-    if (!e->dev.snap) return fail(ZG_ENOSNAPSHOT, "no snapshot published (call zg_publish)");
-  }
+  // no lock here: the call QUEUES behind a running group (the group's leader validates the engine state)
   std::vector<uint32_t> ids;
   int rc = lookup_queued(e, res_type, perm, stype, subj, srel, &ids);
   if (rc) return rc;
@@ -1454,9 +1477,9 @@ extern "C" int zg_lookup_resources(zg_engine* e, uint16_t res_type, uint16_t per
 // (resource type, permission, subject) strings -> ids, under the engine lock. su == ZG_NO_OBJECT: never written.
 static int resolve_lookup_strs(zg_engine* e, const char* res_type, const char* perm, const char* subj_type, const char* subj_id,
                                const char* subj_rel, int* rt, int* p, int* st, uint16_t* sr, uint32_t* su) {
-  std::lock_guard<std::mutex> g(e->mu);
-  int rc = ensure_published(e);
+  int rc = publish_if_needed(e);
   if (rc) return rc;
+  LOCK_NAMES_SHARED(e);
   const Schema& sc = e->schema;
   *rt = sc.type_id(res_type);
   *st = sc.type_id(subj_type);
@@ -1491,7 +1514,7 @@ extern "C" int zg_lookup_resources_str(zg_engine* e, const char* res_type, const
   if (rc) return rc;
   std::vector<std::string> names;
   {
-    std::lock_guard<std::mutex> g(e->mu);
+    LOCK_NAMES_SHARED(e);
     for (uint32_t id : ids) {
       std::string_view n;
       names.push_back(e->store.name(rt, id, &n) ? std::string(n) : std::to_string(id));
@@ -1522,7 +1545,7 @@ extern "C" int zg_list_keep_allowed(zg_engine* e, const char* body, size_t len, 
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if (!res_type || ((!body || !items || !keep) && n) || (!allowed && n_allowed)) return fail(ZG_EINVAL, "NULL argument");
   if (mode > ZG_LIST_TABLE_ROWS) return fail(ZG_EINVAL, "unknown mode");
-  std::lock_guard<std::mutex> g(e->mu);
+  LOCK_NAMES_SHARED(e);
   const int rt = e->schema.type_id(res_type);
   if (rt < 0) return fail(ZG_EINVAL, std::string("object definition `") + res_type + "` not found");
   const std::string req_ns = req_namespace ? req_namespace : "", self = self_name ? self_name : "";
@@ -1581,7 +1604,7 @@ extern "C" int zg_list_prefilter(zg_engine* e, const char* body, size_t len, uin
     if (rc) return rc;
     if (su == ZG_NO_OBJECT && self_member) self = tpl->subj_id;  // never-written userset subject naming itself
     // lookups.go:106-109: an id that yields no name fails the whole pre-filter
-    std::lock_guard<std::mutex> g(e->mu);
+    LOCK_NAMES_SHARED(e);
     for (uint32_t id : ids) {
       std::string_view nm;
       if (e->store.name(rt, id, &nm) && nm.back() == '/') return fail(ZG_EINVAL, "unable to determine name for resource");
@@ -1733,7 +1756,8 @@ extern "C" int zg_debug_row(zg_engine* e, uint16_t rel_slot, uint32_t res, uint3
                             uint64_t* n_out) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if (!n_out) return fail(ZG_EINVAL, "NULL n_out");
-  std::lock_guard<std::mutex> g(e->mu);
+  LOCK_DEVICE(e);
+  LOCK_NAMES_UNIQUE(e);
   e->keep_built = true;
   if (e->last_built.rels.empty() && !e->schema.rel_slots.empty()) {
     e->last_built = e->store.build();
