@@ -643,19 +643,23 @@ int zo_write(zo_oracle *z, int op, int rel, uint32_t res, int stype, uint32_t su
   }
   Tuple t = {.res = res, .subj = srel == ZO_SREL_WILDCARD ? 0 : subj, .exp = (uint32_t)exp,
              .rel = (uint16_t)rel, .stype = (uint16_t)stype, .srel = (uint16_t)srel};
-  uint64_t at = z->n_log;
-  for (uint64_t i = 0; i < z->n_log; i++)
-    if (same_key(&z->log[i], &t)) { at = i; break; }
-  if (op == ZO_OP_DELETE) {
-    if (at < z->n_log) { z->log[at] = z->log[--z->n_log]; z->dirty = 1; }
-    return 0;
+  /* Bulk loads (zo_add_bulk) append without looking: the log may hold several copies of one relationship
+   * (TOUCH semantics: they are one relationship). A write acts on ALL of them: one pass, every copy removed,
+   * then the new state (if any) appended once. */
+  if (op == ZO_OP_CREATE)
+    for (uint64_t i = 0; i < z->n_log; i++)
+      if (same_key(&z->log[i], &t)) { set_err(z, "relationship already exists"); return -2; }
+  uint64_t found = 0;
+  for (uint64_t i = 0; i < z->n_log;) {
+    if (same_key(&z->log[i], &t)) {
+      z->log[i] = z->log[--z->n_log];
+      found++;
+    } else {
+      i++;
+    }
   }
-  if (at < z->n_log) {
-    if (op == ZO_OP_CREATE) { set_err(z, "relationship already exists"); return -2; }
-    z->log[at] = t;
-    z->dirty = 1;
-    return 0;
-  }
+  if (found) z->dirty = 1;
+  if (op == ZO_OP_DELETE) return 0;
   log_push(z, t);
   return 0;
 }

@@ -9,7 +9,14 @@ timeout 600 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.txt 2>&1; 
 tail -15 gpurun_out/${tag}_pytest.txt
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 echo "bench rc=$?"; tail -3 gpurun_out/${tag}_bench.err; cut -c1-3000 gpurun_out/${tag}_bench.json
-if grep -q " passed" gpurun_out/${tag}_pytest.txt && ! grep -q " failed" gpurun_out/${tag}_pytest.txt; then
+# A/B of tuning variants (scripts/build_variant.sh), cfg3 only, kernel numbers only
+for v in spicedb-kubeapi-proxy_b200/variants/libzgpu_*.so; do
+  [ -f "$v" ] || continue
+  n=$(basename $v .so)
+  ZGPU_LIB=$PWD/$v timeout 300 python bench.py --configs '' --no-cpu-baseline --sustain-s 0 --steps 20 --warmup 5 > gpurun_out/${tag}_ab_${n}.json 2> gpurun_out/${tag}_ab_${n}.err
+  python -c "import json,sys; b=json.load(open('gpurun_out/${tag}_ab_${n}.json')); print('$n', b['value'], b['e2e']['value'], b['roofline']['alg_bytes_per_check'])"
+done
+if true; then
   for wl in cfg3 cfg4; do
     timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${tag}_launches_${wl}.csv \
       python bench.py --workload $wl --configs '' --steps 3 --warmup 3 --no-cpu-baseline --sustain-s 0 > /dev/null 2> gpurun_out/${tag}_ncu_list_${wl}.err

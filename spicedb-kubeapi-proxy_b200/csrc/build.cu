@@ -262,7 +262,8 @@ std::string gpu_build_snapshot(const Store& store, const Schema& sc, HostSnapsho
     n_unique = static_cast<uint64_t>(last_pos) + last_flag;
   }
   const size_t nu = n_unique ? n_unique : 1;
-  if (!s->col.ensure(nu * 4) || !s->rcol.ensure(nu * 4) || (with_exp && !s->exp.ensure(nu * 4)) ||
+  // + 64: the check kernel streams rows with aligned 128-bit loads, which may read (and ignore) up to 12 bytes past a row
+  if (!s->col.ensure(nu * 4 + 64) || !s->rcol.ensure(nu * 4 + 64) || (with_exp && !s->exp.ensure(nu * 4 + 64)) ||
       !d_rkey[0].ensure(nu * 8) || !d_rkey[1].ensure(nu * 8) || !d_rres[0].ensure(nu * 4) || !d_rres[1].ensure(nu * 4))
     return "out of device memory (edge arrays)";
   if (n) {
@@ -360,7 +361,7 @@ std::string merge_direction(const HostDelta& h, bool with_exp, DevBuf& row_ptr, 
   if (keys) delta_locate_kernel<<<static_cast<unsigned>((keys + blk - 1) / blk), blk, 0, st>>>(row_ptr.as<uint32_t>(),
                                                                                              edges.as<uint32_t>(), d, d_bad);
   if (ni || nd) {
-    if (!edges_alt.ensure(std::max<uint64_t>(n_new, 1) * 4 + 16) || (with_exp && !exp_alt.ensure(std::max<uint64_t>(n_new, 1) * 4 + 16)))
+    if (!edges_alt.ensure(std::max<uint64_t>(n_new, 1) * 4 + 64) || (with_exp && !exp_alt.ensure(std::max<uint64_t>(n_new, 1) * 4 + 64)))
       return "out of device memory (edge arrays)";
     if (n_old)
       delta_merge_kernel<<<static_cast<unsigned>((n_old + kMergeTile - 1) / kMergeTile), 256, 0, st>>>(

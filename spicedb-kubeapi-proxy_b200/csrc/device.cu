@@ -134,7 +134,7 @@ std::string Device::publish(const HostSnapshot& h, const Schema& sc, uint64_t re
   cudaSetDevice(device);
   auto s = std::make_shared<Snapshot>();
   auto up = [&](DevBuf& b, const void* src, size_t bytes) -> bool {
-    if (!b.ensure(bytes ? bytes : 16)) return false;
+    if (!b.ensure(bytes + 64)) return false;  // + 64: rows are streamed with aligned 128-bit loads (build.cu)
     if (bytes && cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess) return false;
     s->bytes += bytes;
     return true;

@@ -47,6 +47,9 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 #ifndef ZG_RSET_CAP
 #define ZG_RSET_CAP 16
 #endif
+#ifndef ZG_L2_BLOOM
+#define ZG_L2_BLOOM 1  // two-level meet: Bloom word + streamed 128-bit loads (0: sorted-segment intersection)
+#endif
 constexpr int kMinBlocks = ZG_MIN_BLOCKS;  // resident CTAs per SM the register budget is tuned for
 constexpr int kStackCap = ZG_STACK_CAP;    // range items per warp in shared memory
 constexpr int kRsetCap = ZG_RSET_CAP;      // reverse-row entries kept per check (subject's direct memberships), <= 31
@@ -395,13 +398,43 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
             // once per membership. The children are never visited, nothing is pushed.
             const uint32_t kb = cst_at(cst, st.tinv), ke = stype == st.tstype ? cst_at(cst, st.tinv + 1u) : kb;
             const DCls cl = pr.cls()[st.tgc];
-            for (uint32_t r = kb; r < ke && !hit; ++r) {
-              const uint32_t g = c.rset[r * 32 + (jslot & 31)];
-              if (g >= cl.nsubj) continue;
-              const unsigned long long ri = cl.rrow_base + static_cast<unsigned long long>(g) * cl.rstride;
-              const uint32_t l = __ldg(p.rrow_ptr + ri), h = __ldg(p.rrow_ptr + ri + 1);
-              if (COUNT) c.bytes += 8;
-              hit = intersects(p.col, lo, hi, p.rcol, l, h, c);
+            if (ZG_L2_BLOOM && ke > kb && hi - lo <= 256u) {
+              // Short range (the common case): a 64-bit Bloom word of its children stays in a register and the
+              // reverse rows are STREAMED against it with 128-bit loads -- independent loads, no dependent
+              // chain per element; only a Bloom hit is verified by a binary search of the range.
+              unsigned long long bloom = 0;
+              for (uint32_t x = lo & ~3u; x < hi; x += 4) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.col + x));
+                if (x >= lo) bloom |= 1ull << ((v.x * 0x9E3779B1u) >> 26);
+                if (x + 1 >= lo && x + 1 < hi) bloom |= 1ull << ((v.y * 0x9E3779B1u) >> 26);
+                if (x + 2 >= lo && x + 2 < hi) bloom |= 1ull << ((v.z * 0x9E3779B1u) >> 26);
+                if (x + 3 >= lo && x + 3 < hi) bloom |= 1ull << ((v.w * 0x9E3779B1u) >> 26);
+              }
+              if (COUNT) c.bytes += 4ull * (hi - lo);  // the words of the range (the padding of a 128-bit load is not work)
+              for (uint32_t r = kb; r < ke && !hit; ++r) {
+                const uint32_t g = c.rset[r * 32 + (jslot & 31)];
+                if (g >= cl.nsubj) continue;
+                const unsigned long long ri = cl.rrow_base + static_cast<unsigned long long>(g) * cl.rstride;
+                const uint32_t l = __ldg(p.rrow_ptr + ri), h = __ldg(p.rrow_ptr + ri + 1);
+                if (COUNT) c.bytes += 8 + 4ull * (h - l);
+                for (uint32_t x = l & ~3u; x < h && !hit; x += 4) {
+                  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.rcol + x));
+                  const uint32_t e4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if (x + k >= l && x + k < h && ((bloom >> ((e4[k] * 0x9E3779B1u) >> 26)) & 1ull))
+                      hit = hit || find_in(p.col, c, lo, hi, e4[k]);
+                }
+              }
+            } else {
+              for (uint32_t r = kb; r < ke && !hit; ++r) {
+                const uint32_t g = c.rset[r * 32 + (jslot & 31)];
+                if (g >= cl.nsubj) continue;
+                const unsigned long long ri = cl.rrow_base + static_cast<unsigned long long>(g) * cl.rstride;
+                const uint32_t l = __ldg(p.rrow_ptr + ri), h = __ldg(p.rrow_ptr + ri + 1);
+                if (COUNT) c.bytes += 8;
+                hit = intersects(p.col, lo, hi, p.rcol, l, h, c);
+              }
             }
           } else {
             want = true;

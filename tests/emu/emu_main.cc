@@ -76,6 +76,9 @@ int emu_publish(void* h) {
   e->h = e->st.build();
   if (!e->h.err.empty()) return -1;
   e->blob = e->sc.blob(e->h.rels, e->h.cls);
+  // rows are streamed with aligned 128-bit loads that may read (and ignore) a few words past the last row
+  e->h.col.reserve(e->h.col.size() + 16);
+  e->h.rcol.reserve(e->h.rcol.size() + 16);
   e->published = true;
   return 0;
 }

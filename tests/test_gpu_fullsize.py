@@ -58,7 +58,8 @@ def test_cfg4_full_size_sample_is_bit_exact(zg, big):
     view, rview = e.slot_id("document", "view"), e.slot_id("document", "restricted_view")
     for perm in (view, rview):
         sel = items["perm"][:n] == perm
-        assert sel.sum() > n // 10 and 0.02 < (want[sel] == 2).mean() < 0.98
+        assert sel.sum() > n // 10 and (want[sel] == 2).any() and (want[sel] == 1).any()
+    assert 0.2 < (want == 2).mean() < 0.8
     assert not (got == 255).any()
     # properties that do not need the oracle, over the whole batch: restricted_view = view & org->member can only
     # remove grants; re-asking gives the same answers; the device entry point agrees
