@@ -337,11 +337,16 @@ extern "C" int64_t zg_list_scan(const char* body, size_t len, uint32_t mode, zg_
   Cur c{body, len, 0, true};
   ws(c);
   int64_t n = 0;
-  bool found = false;
+  bool found = false, seen_key = false;
   uint64_t ib = 0, ie = 0;
   const bool ok = walk_object(c, [&](size_t kb, size_t ke) -> bool {
     if (!key_is(c, kb, ke, array_key)) return false;
-    n = 0;  // a later duplicate "items" key replaces an earlier one
+    // A second top-level "items" ("rows") key: the reference re-marshals a map, so only the LAST array would
+    // survive, filtered; a byte splice would ship the earlier array unfiltered to a first-key-wins consumer.
+    // Kube never emits this: refuse the body instead of guessing (fail closed).
+    if (seen_key) return c.ok = false;
+    seen_key = true;
+    n = 0;
     found = c.i < c.n && c.s[c.i] == '[';
     if (!found) return false;  // not an array: the reference passes the body through
     ib = c.i;

@@ -120,9 +120,14 @@ def test_namespaced_name_normalisation():
 
 def test_duplicate_and_escaped_keys_follow_encoding_json():
     # encoding/json: the last duplicate key wins; keys are compared after unescaping
-    raw = (b'{"items":[{"metadata":{"name":"old"}}],"x":1,'
+    raw = (b'{"x":1,'
            b'"\\u0069tems":[{"metadata":{"name":"first","name":"n\\u0061me2"},"\\u006detadata":{"n\\u0061me":"last"}},'
            b'{"metadata":{"name":"gone"},"metadata":7}]}')
+    # a second top-level "items" key is refused: a splice would ship the earlier array unfiltered, while the
+    # reference (re-marshalling a map) keeps only the last one -- kube never emits this, so fail closed
+    dup = b'{"items":[{"metadata":{"name":"old"}}],' + raw[1:]
+    with pytest.raises(_lib.ZgpuError):
+        _lib.list_scan(dup)
     items, ib, ie = _lib.list_scan(raw)
     got = [(raw[i["name_off"]:i["name_off"] + i["name_len"]], int(i["flags"])) for i in items]
     assert got == [(b"last", 3), (b"", 1)]
