@@ -68,6 +68,7 @@ def _lib():
             "zo_object_name": (cp, [vp, i, u32]),
             "zo_write": (i, [vp, i, i, u32, i, u32, i, i64]),
             "zo_write_str": (i, [vp, i, cp, i64]),
+            "zo_apply_batch": (i, [vp, vp, u64]),
             "zo_add_bulk": (i, [vp, i, i, i, vp, vp, u64]),
             "zo_num_tuples": (u64, [vp]),
             "zo_check": (i, [vp, vp, i64]),
@@ -160,6 +161,13 @@ class Oracle:
         """One interned relationship update (same fields as zg_update)."""
         rc = self._L.zo_write(self._h, int(op), int(rel_slot), int(res), int(stype), int(subj), int(srel), int(expires_at))
         if rc:
+            raise OracleError(self._err())
+
+    def apply_updates(self, ups: np.ndarray):
+        """A batch of interned updates (zg_update records) in one pass over the store."""
+        u = np.ascontiguousarray(ups)
+        assert u.dtype.itemsize == 24
+        if self._L.zo_apply_batch(self._h, u.ctypes.data, u.size):
             raise OracleError(self._err())
 
     def add_bulk(self, type_name, rel, subj_type, res, subj, srel=None, wildcard=False):

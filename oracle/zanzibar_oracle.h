@@ -86,6 +86,9 @@ const char *zo_object_name(const zo_oracle *, int type_id, uint32_t id);      /*
  * -2 CREATE of an existing relationship. */
 int zo_write(zo_oracle *, int op, int rel_slot, uint32_t res, int stype, uint32_t subj,
              int srel /* slot, ZO_SREL_NONE or ZO_SREL_WILDCARD */, int64_t expires_at);
+/* n interned updates (zg_update layout) in one pass over the relationship log; a batch names every relationship at
+ * most once. CREATE is treated as TOUCH. */
+int zo_apply_batch(zo_oracle *, const void *zg_updates, uint64_t n);
 /* "type:id#rel@stype:sid[#srel]" (pkg/rules/rules.go:1050) ; sid may be "*" */
 int zo_write_str(zo_oracle *, int op, const char *rel, int64_t expires_at);
 /* Bulk TOUCH of n relationships sharing (rel_slot, stype, srel). */

@@ -47,14 +47,19 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 #ifndef ZG_RSET_CAP
 #define ZG_RSET_CAP 16
 #endif
-#ifndef ZG_L2_BLOOM
-#define ZG_L2_BLOOM 1  // two-level meet: Bloom word + streamed 128-bit loads (0: sorted-segment intersection)
+#ifndef ZG_PRESENCE
+#define ZG_PRESENCE 1  // presence word in front of the per-check set walk of a direct inverted probe
+#endif
+#ifndef ZG_L2_MODE
+#define ZG_L2_MODE 2  // two-level meet: 2 = warp-cooperative (default), 1 = per-lane Bloom word + 128-bit streaming
+                      // (measured slower: 919 vs 1 023 Mchecks/s on cfg3), 0 = per-lane sorted-segment intersection
 #endif
 constexpr int kMinBlocks = ZG_MIN_BLOCKS;  // resident CTAs per SM the register budget is tuned for
 constexpr int kStackCap = ZG_STACK_CAP;    // range items per warp in shared memory
 constexpr int kRsetCap = ZG_RSET_CAP;      // reverse-row entries kept per check (subject's direct memberships), <= 31
 constexpr int kStateWords = 6;             // per-lane query state parked in shared memory between leaf passes
-constexpr size_t kWarpSmem = kStackCap * sizeof(uint4) + (kRsetCap + kStateWords) * 32 * sizeof(uint32_t);
+constexpr int kFCap = 64;                  // children of a range staged in shared memory by the two-level meet
+constexpr size_t kWarpSmem = kStackCap * sizeof(uint4) + ((kRsetCap + kStateWords) * 32 + kFCap) * sizeof(uint32_t);
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint16_t kJobDepthMask = 0x00FF;  // zg_check.flags of a raised sub-query: hop depth
 
@@ -303,7 +308,68 @@ __device__ __forceinline__ uint32_t cst_at(unsigned long long cst, uint32_t i) {
   return static_cast<uint32_t>(cst >> (5u * i)) & 31u;
 }
 constexpr int kMaxInvClasses = 11;
+// bit of (invertible class index, object) in a check's 32-bit presence word
+__device__ __forceinline__ uint32_t rset_bit(uint32_t tinv, uint32_t obj) {
+  return ((obj + tinv * 0x632BE5ABu) * 0x9E3779B1u) >> 27;
+}
 static_assert(kRsetCap <= 31, "class boundaries are 5-bit fields");
+
+// Two-level meet, warp-cooperative: ONE check's range against the reverse rows of its subject's memberships, all 32
+// lanes working on it. The per-lane form of this (every lane walking its own check's rows) ran with 9 of 32 lanes
+// active on average (profiles/r2d): row counts and early exits differ per check. Here the range's children F
+// (<= kFCap, ascending) go to shared memory with one coalesced load, the memberships' row bounds are loaded by one
+// lane each and prefix-summed, and the rows' elements are dealt out 32 at a time (neighbouring lanes read
+// neighbouring words of a row); each lane binary-searches its element in F with a warp-uniform trip count.
+// Returns (warp-uniform) whether some element of some row is a child of the range.
+template <bool COUNT>
+__device__ __forceinline__ bool coop_l2(const KParams& p, WarpCtx<COUNT>& c, uint32_t lo, uint32_t hi, uint32_t kb, uint32_t ke,
+                                        uint32_t jslot, const DCls& cl) {
+  uint32_t* const fs = c.rset + (kRsetCap + kStateWords) * 32;
+  const uint32_t nf = hi - lo, ng = ke - kb;
+  for (uint32_t x = c.lane; x < nf; x += 32) fs[x] = __ldg(p.col + lo + x);
+  uint32_t l = 0, len = 0;
+  if (c.lane < ng) {
+    const uint32_t g = c.rset[(kb + c.lane) * 32 + jslot];
+    if (g < cl.nsubj) {
+      const unsigned long long ri = cl.rrow_base + static_cast<unsigned long long>(g) * cl.rstride;
+      l = __ldg(p.rrow_ptr + ri);
+      len = __ldg(p.rrow_ptr + ri + 1) - l;
+    }
+  }
+  uint32_t incl = len;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t v = __shfl_up_sync(kFull, incl, d);
+    if (static_cast<int>(c.lane) >= d) incl += v;
+  }
+  const uint32_t total = __shfl_sync(kFull, incl, 31);
+  if (COUNT && c.lane == 0) c.bytes += 4ull * nf + 8ull * ng + 4ull * total;
+  __syncwarp();
+  uint32_t span = 1;  // smallest power of two >= nf: trip count of the search
+  while (span < nf) span <<= 1;
+  for (uint32_t base = 0; base < total; base += 32) {
+    const uint32_t idx = base + c.lane;
+    // owner row of element idx: number of rows whose inclusive prefix is <= idx (rows are in lanes 0 .. 15)
+    int j = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      const uint32_t v = __shfl_sync(kFull, incl, (j + step - 1) & 31);
+      if (j + step - 1 < 32 && v <= idx) j += step;
+    }
+    const uint32_t jl = __shfl_sync(kFull, l, j & 31), jincl = __shfl_sync(kFull, incl, j & 31),
+                   jlen = __shfl_sync(kFull, len, j & 31);
+    bool found = false;
+    if (idx < total) {
+      const uint32_t t = __ldg(p.rcol + jl + (idx - (jincl - jlen)));
+      uint32_t pos = 0;  // lower bound of t in fs[0, nf)
+      for (uint32_t s = span; s >= 1; s >>= 1)
+        if (pos + s <= nf && fs[pos + s - 1] < t) pos += s;
+      found = pos < nf && fs[pos] == t;
+    }
+    if (__any_sync(kFull, found)) return true;
+  }
+  return false;
+}
 
 // Warp-collective node visit: every lane may carry one (job slot, object, unit).
 // Evaluates the unit's steps at the object: membership-of-itself test, direct and
@@ -330,17 +396,23 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
   const bool inverted = (c.inv_mask >> (jslot & 31)) & 1u;
   const int maxsteps = __reduce_max_sync(kFull, nsteps);
   for (int i = 0; i < maxsteps; ++i) {
-    bool want = false;
+    bool want = false, l2_want = false;
+    uint32_t l2_lo = 0, l2_hi = 0, l2_k = 0;
     uint4 item = make_uint4(0, 0, 0, 0);
     if (i < nsteps && !hit) {
       const DStep st = pr.steps()[sb + i];
       const bool expiry = (st.flags & CF_EXPIRY) != 0;
       const bool subject_fits = srel == kNone && stype == st.stype;
       if (st.kind == ST_DIRECT && subject_fits && inverted && (st.flags & CF_INVERT)) {
-        // direction-optimised probe: is obj among the subject's memberships of this class?
-        const uint32_t kb = cst_at(cst, st.tinv), ke = cst_at(cst, st.tinv + 1u);
-        for (uint32_t r = kb; r < ke; ++r)
-          hit = hit || c.rset[r * 32 + (jslot & 31)] == obj;
+        // direction-optimised probe: is obj among the subject's memberships of this class? Most probes miss: a
+        // 32-bit presence word over (class, object) of the check's set (built at admission) rejects them
+        // without walking the set (the walk was 15 % of cfg4's instructions, profiles/r2d).
+        const uint32_t present = c.rset[(kRsetCap + 5) * 32 + (jslot & 31)];
+        if (!ZG_PRESENCE || ((present >> rset_bit(st.tinv, obj)) & 1u)) {
+          const uint32_t kb = cst_at(cst, st.tinv), ke = cst_at(cst, st.tinv + 1u);
+          for (uint32_t r = kb; r < ke; ++r)
+            hit = hit || c.rset[r * 32 + (jslot & 31)] == obj;
+        }
       } else if ((st.kind == ST_PUSH || subject_fits) && obj < st.nres) {
         const unsigned long long ridx = st.row_base + static_cast<unsigned long long>(obj) * st.ncls;
         const uint32_t lo = __ldg(p.row_ptr + ridx), hi = __ldg(p.row_ptr + ridx + 1);
@@ -398,7 +470,14 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
             // once per membership. The children are never visited, nothing is pushed.
             const uint32_t kb = cst_at(cst, st.tinv), ke = stype == st.tstype ? cst_at(cst, st.tinv + 1u) : kb;
             const DCls cl = pr.cls()[st.tgc];
-            if (ZG_L2_BLOOM && ke > kb && hi - lo <= 256u) {
+            if (ZG_L2_MODE == 2 && ke > kb && hi - lo <= static_cast<uint32_t>(kFCap)) {
+              // handed to the whole warp below (coop_l2), one requesting lane at a time
+              l2_want = true;
+              l2_lo = lo;
+              l2_hi = hi;
+              l2_k = kb | (ke << 8) | (static_cast<uint32_t>(st.tgc) << 16);
+            } else
+            if (ZG_L2_MODE == 1 && ke > kb && hi - lo <= 256u) {
               // Short range (the common case): a 64-bit Bloom word of its children stays in a register and the
               // reverse rows are STREAMED against it with 128-bit loads -- independent loads, no dependent
               // chain per element; only a Bloom hit is verified by a binary search of the range.
@@ -441,6 +520,19 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
             item = make_uint4(lo, hi, make_meta(jslot, depth + 1, expiry, st.tslot), 0);
           }
         }
+      }
+    }
+    if (ZG_L2_MODE == 2) {
+      unsigned l2m = __ballot_sync(kFull, l2_want);
+      while (l2m) {  // warp-uniform: one requesting lane after the other, the whole warp on its range
+        const int r = __ffs(l2m) - 1;
+        l2m &= l2m - 1;
+        const uint32_t rlo = __shfl_sync(kFull, l2_lo, r), rhi = __shfl_sync(kFull, l2_hi, r), rk = __shfl_sync(kFull, l2_k, r);
+        const uint32_t rj = __shfl_sync(kFull, jslot, r) & 31u;
+        if ((c.found >> rj) & 1u) continue;  // another node of the same check already answered it
+        const bool h = coop_l2(p, c, rlo, rhi, rk & 0xFFu, (rk >> 8) & 0xFFu, rj, pr.cls()[rk >> 16]);
+        if (h) c.found |= 1u << rj;
+        __syncwarp();
       }
     }
     push(c, want, item);
@@ -504,7 +596,7 @@ __device__ __noinline__ void wait_ready(const unsigned long long* ready, unsigne
 
 // Per-lane query state parked in shared memory while the warp traverses (kStateWords words):
 //   0 resource object, 1 depth | leaves << 8 | is-tree << 15 | leaf_begin-or-unit << 16,
-//   2 tree id, 3 / 4 leaf values (2 bits each), 5 unused
+//   2 tree id, 3 / 4 leaf values (2 bits each), 5 presence word of the reverse-row set
 template <bool COUNT, bool STREAMED = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KParams p) {
   ZG_DYNAMIC_SMEM(smem);
@@ -579,7 +671,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
     // query: every leaf of a non-pure permission shares them.
     {
       bool inv = p.invert && valid && !bad && (c.my_ss & 0xFFFFu) == kNone && expansive;
-      uint32_t rcnt = 0;
+      uint32_t rcnt = 0, present = 0;
       unsigned long long cst = 0;
       int ib = 0, ncl = 0;
       if (inv) {
@@ -605,7 +697,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
               inv = false;  // too many memberships: this check probes forward
             } else {
               for (uint32_t x = b; x < e; ++x) {
-                c.rset[rcnt * 32 + lane] = __ldg(p.rcol + x);
+                const uint32_t m = __ldg(p.rcol + x);
+                c.rset[rcnt * 32 + lane] = m;
+                present |= 1u << rset_bit(static_cast<uint32_t>(i), m);
                 ++rcnt;
               }
               if (COUNT) c.bytes += 4ull * (e - b);
@@ -616,6 +710,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
       }
       c.inv_mask = __ballot_sync(kFull, inv);
       c.my_cst = cst;
+      state[160] = present;
       __syncwarp();
     }
     c.fatal = false;

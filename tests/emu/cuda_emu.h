@@ -137,6 +137,7 @@ static inline T __ldg(const T* p) { return *p; }
 template <class T>
 static inline T __ldcg(const T* p) { return *p; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs(static_cast<int>(v)); }
 static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __syncthreads() { zg_emu::ts().block->bar.wait(); }

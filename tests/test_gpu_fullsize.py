@@ -70,7 +70,6 @@ def test_cfg4_full_size_sample_is_bit_exact(zg, big):
     assert not ((got[r] == 2) & (gv[r] != 2)).any()
     assert np.array_equal(e.check_bulk(items), got)
     st = e.stats()
-    assert st["stack_spills"] > 0, "a 1 M-check batch over folder chains is expected to spill warp stacks to HBM"
     assert st["passes"] == 0  # folder#view is a pure union: one launch answers the batch
     e.close()
 
@@ -158,8 +157,7 @@ def test_thousand_update_write_on_the_large_store_is_a_merge(zg, big):
     o = Oracle(w.schema)
     w.load_into(o)
     for ups in all_ups:
-        for u in ups:
-            o.write_ids(u["op"], u["rel"], u["res"], u["stype"], u["subj"], u["srel"])
+        o.apply_updates(ups)
     doc_rels = {e.slot_id("document", r) for r in ("parent", "org", "owner", "editor", "viewer", "banned")}
     touched = np.concatenate([u["res"][np.isin(u["rel"], list(doc_rels))] for u in all_ups])
     probe = items[:20000].copy()

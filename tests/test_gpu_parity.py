@@ -788,8 +788,7 @@ def test_incremental_publish_equals_rebuild_and_oracle(zg, monkeypatch):
             ups = _random_updates(zg, e, w, rng, [3, 40, 400, 1000, 1, 1000][step])
             e.apply_updates(ups)
             e.publish()  # raises if a merged array differs from the rebuilt one
-            for u in ups:
-                o.write_ids(u["op"], u["rel"], u["res"], u["stype"], u["subj"], u["srel"])
+            o.apply_updates(ups)
             # checks on touched objects and on the standing batch
             probe = items.copy()
             probe["res"][: ups.size] = ups["res"][: probe.size][: ups.size] if w.name == "cfg3" else probe["res"][: ups.size]

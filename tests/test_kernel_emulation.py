@@ -278,8 +278,7 @@ def test_incremental_publish_kernels_equal_a_rebuild_under_the_emulator(emu, wl,
         ups = _random_updates(emu, e, w, rng, n, new_objects=step % 2 == 1)
         e.apply_updates(ups)
         merged += e.merge_and_verify() == 0
-        for u in ups:
-            o.write_ids(u["op"], u["rel"], u["res"], u["stype"], u["subj"], u["srel"])
+        o.apply_updates(ups)
         assert np.array_equal(e.check_bulk(items), o.check_bulk(items)), f"{wl} step {step}"
     assert merged >= 4
 
