@@ -394,6 +394,7 @@ def measure_workload(name, args, rank, local_rank, world, dist, primary, sampler
                                  "same build / the same time -- the HBM fraction north_star asks for"},
             "cpu_baseline": cpu,
             "has_fraction": float((host_answers == 2).mean()),
+            "build": zgpu._lib.lib().zg_build_info().decode(),
             "publish_s": publish_s, "setup_s": setup_s,
         }
         if sustained:
@@ -541,7 +542,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "impl": "zgpu",
         }
         for k in ("config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks", "sustained", "has_fraction",
-                  "publish_s", "setup_s"):
+                  "publish_s", "setup_s", "build"):
             if k in main_res:
                 out[k] = main_res[k]
         if extra:

@@ -386,6 +386,8 @@ int zg_list_prefilter(zg_engine *e, const char *body, size_t len, uint32_t mode,
                       char *out, size_t cap, size_t *out_len);
 
 /* ---- measurement --------------------------------------------------------- */
+/* Build time and tuning macros of this library (goes into every bench line). */
+const char *zg_build_info(void);
 int zg_stats_get(zg_engine *e, zg_stats *out);
 /* Runs the batch through the instrumented kernel variant and returns the
  * ALGORITHMIC bytes it needed (DESIGN.md "Algorithmic bytes"); not for timing. */

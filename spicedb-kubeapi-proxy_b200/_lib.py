@@ -130,6 +130,7 @@ _SIGS = {
     "zg_engine_create": (C.c_int, [C.POINTER(_Config), C.POINTER(C.c_void_p)]),
     "zg_engine_destroy": (None, [C.c_void_p]),
     "zg_last_error": (C.c_char_p, []),
+    "zg_build_info": (C.c_char_p, []),
     "zg_last_error_copy": (C.c_size_t, [C.c_char_p, C.c_size_t]),
     "zg_clear_relationships": (C.c_int, [C.c_void_p]),
     "zg_load_schema": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),

@@ -1790,6 +1790,8 @@ extern "C" int zg_debug_row(zg_engine* e, uint16_t rel_slot, uint32_t res, uint3
   return ZG_OK;
 }
 
+extern "C" const char* zg_build_info(void) { return zg::build_info(); }
+
 extern "C" void* zg_host_alloc(size_t bytes) {
   void* p = nullptr;
   if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {

@@ -171,6 +171,9 @@ class Device {
   void finish_timing();
 };
 
+// Build time and tuning macros of the kernels in this library.
+const char* build_info();
+
 // Device radix sort of n u32 keys (build.cu keeps the cub instantiations in one translation unit).
 std::string sort_u32(const uint32_t* d_in, uint32_t* d_out, uint64_t n, cudaStream_t st);
 std::string sort_u64(const unsigned long long* d_in, unsigned long long* d_out, uint64_t n, int end_bit, cudaStream_t st);

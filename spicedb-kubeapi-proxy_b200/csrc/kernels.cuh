@@ -317,54 +317,42 @@ static_assert(kRsetCap <= 31, "class boundaries are 5-bit fields");
 // Two-level meet, warp-cooperative: ONE check's range against the reverse rows of its subject's memberships, all 32
 // lanes working on it. The per-lane form of this (every lane walking its own check's rows) ran with 9 of 32 lanes
 // active on average (profiles/r2d): row counts and early exits differ per check. Here the range's children F
-// (<= kFCap, ascending) go to shared memory with one coalesced load, the memberships' row bounds are loaded by one
-// lane each and prefix-summed, and the rows' elements are dealt out 32 at a time (neighbouring lanes read
-// neighbouring words of a row); each lane binary-searches its element in F with a warp-uniform trip count.
-// Returns (warp-uniform) whether some element of some row is a child of the range.
+// (<= kFCap, ascending) go to shared memory with one coalesced load, every membership row gets a fixed group of lanes
+// (neighbouring lanes read neighbouring words of the row), and each lane binary-searches its element in F with a
+// warp-uniform trip count. Returns (warp-uniform) whether some element of some row is a child of the range.
 template <bool COUNT>
 __device__ __forceinline__ bool coop_l2(const KParams& p, WarpCtx<COUNT>& c, uint32_t lo, uint32_t hi, uint32_t kb, uint32_t ke,
                                         uint32_t jslot, const DCls& cl) {
   uint32_t* const fs = c.rset + (kRsetCap + kStateWords) * 32;
-  const uint32_t nf = hi - lo, ng = ke - kb;
-  for (uint32_t x = c.lane; x < nf; x += 32) fs[x] = __ldg(p.col + lo + x);
-  uint32_t l = 0, len = 0;
-  if (c.lane < ng) {
-    const uint32_t g = c.rset[(kb + c.lane) * 32 + jslot];
+  const uint32_t nf = hi - lo, ng = ke - kb;  // nf <= kFCap (64), 1 <= ng <= kRsetCap (16)
+  if (c.lane < nf) fs[c.lane] = __ldg(p.col + lo + c.lane);
+  if (c.lane + 32 < nf) fs[c.lane + 32] = __ldg(p.col + lo + c.lane + 32);
+  // W lanes per membership row (32 / next power of two of ng): lane = row * W + k walks elements k, k + W, ... of
+  // its row. No prefix sums, no owner search: the lanes of a row read the same two offsets (one broadcast load).
+  const uint32_t sh = ng <= 2 ? 4u : (ng <= 4 ? 3u : (ng <= 8 ? 2u : 1u));  // log2(W)
+  const uint32_t w = 1u << sh, row = c.lane >> sh, k = c.lane & (w - 1u);
+  uint32_t x = 0, h = 0;
+  if (row < ng) {
+    const uint32_t g = c.rset[(kb + row) * 32 + jslot];
     if (g < cl.nsubj) {
       const unsigned long long ri = cl.rrow_base + static_cast<unsigned long long>(g) * cl.rstride;
-      l = __ldg(p.rrow_ptr + ri);
-      len = __ldg(p.rrow_ptr + ri + 1) - l;
+      x = __ldg(p.rrow_ptr + ri) + k;
+      h = __ldg(p.rrow_ptr + ri + 1);
+      if (COUNT && k == 0) c.bytes += 8ull + 4ull * (h - (x - k));
     }
   }
-  uint32_t incl = len;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t v = __shfl_up_sync(kFull, incl, d);
-    if (static_cast<int>(c.lane) >= d) incl += v;
-  }
-  const uint32_t total = __shfl_sync(kFull, incl, 31);
-  if (COUNT && c.lane == 0) c.bytes += 4ull * nf + 8ull * ng + 4ull * total;
+  if (COUNT && c.lane == 0) c.bytes += 4ull * nf;
   __syncwarp();
-  uint32_t span = 1;  // smallest power of two >= nf: trip count of the search
-  while (span < nf) span <<= 1;
-  for (uint32_t base = 0; base < total; base += 32) {
-    const uint32_t idx = base + c.lane;
-    // owner row of element idx: number of rows whose inclusive prefix is <= idx (rows are in lanes 0 .. 15)
-    int j = 0;
-#pragma unroll
-    for (int step = 16; step >= 1; step >>= 1) {
-      const uint32_t v = __shfl_sync(kFull, incl, (j + step - 1) & 31);
-      if (j + step - 1 < 32 && v <= idx) j += step;
-    }
-    const uint32_t jl = __shfl_sync(kFull, l, j & 31), jincl = __shfl_sync(kFull, incl, j & 31),
-                   jlen = __shfl_sync(kFull, len, j & 31);
+  const uint32_t span = nf > 1 ? 1u << (32 - __clz(nf - 1)) : 1u;  // smallest power of two >= nf
+  while (__any_sync(kFull, x < h)) {
     bool found = false;
-    if (idx < total) {
-      const uint32_t t = __ldg(p.rcol + jl + (idx - (jincl - jlen)));
-      uint32_t pos = 0;  // lower bound of t in fs[0, nf)
+    if (x < h) {
+      const uint32_t t = __ldg(p.rcol + x);
+      uint32_t pos = 0;  // lower bound of t in fs[0, nf): warp-uniform trip count
       for (uint32_t s = span; s >= 1; s >>= 1)
         if (pos + s <= nf && fs[pos + s - 1] < t) pos += s;
       found = pos < nf && fs[pos] == t;
+      x += w;
     }
     if (__any_sync(kFull, found)) return true;
   }
@@ -383,52 +371,69 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
   const unsigned long long cst = __shfl_sync(kFull, c.my_cst, jslot & 31);
   const uint32_t stype = ss >> 16, srel = ss & 0xFFFFu;
   bool hit = false;
-  int nsteps = 0, sb = 0;
+  int sb = 0, nprobe = 0, npush = 0;
   if (active) {
     const DUnit u = pr.units()[unit];
     if (srel != kNone && sid == obj)
       for (int m = u.mem_begin; m < u.mem_end; ++m) hit = hit || pr.members()[m] == srel;
     if (!hit) {
       sb = u.step_begin;
-      nsteps = u.step_end - u.step_begin;
+      nprobe = u.push_begin - u.step_begin;
+      npush = u.step_end - u.push_begin;
     }
   }
   const bool inverted = (c.inv_mask >> (jslot & 31)) & 1u;
-  const int maxsteps = __reduce_max_sync(kFull, nsteps);
+  // ---- probes (DIRECT / WILD classes): every lane on its own, no warp collective involved. The steps of a unit
+  // are ordered probes first (schema.cc); in round 1 every step, probe or not, went through the collective push.
+  for (int i = 0; i < nprobe && !hit; ++i) {
+    const DStep st = pr.steps()[sb + i];
+    const bool expiry = (st.flags & CF_EXPIRY) != 0;
+    const bool subject_fits = srel == kNone && stype == st.stype;
+    if (!subject_fits) continue;
+    if (st.kind == ST_DIRECT && inverted && (st.flags & CF_INVERT)) {
+      // direction-optimised probe: is obj among the subject's memberships of this class? Most probes miss: a
+      // 32-bit presence word over (class, object) of the check's set (built at admission) rejects them
+      // without walking the set (the walk was 15 % of cfg4's instructions, profiles/r2d).
+      const uint32_t present = c.rset[(kRsetCap + 5) * 32 + (jslot & 31)];
+      if (!ZG_PRESENCE || ((present >> rset_bit(st.tinv, obj)) & 1u)) {
+        const uint32_t kb = cst_at(cst, st.tinv), ke = cst_at(cst, st.tinv + 1u);
+        for (uint32_t r = kb; r < ke; ++r)
+          hit = hit || c.rset[r * 32 + (jslot & 31)] == obj;
+      }
+    } else if (obj < st.nres) {
+      const unsigned long long ridx = st.row_base + static_cast<unsigned long long>(obj) * st.ncls;
+      const uint32_t lo = __ldg(p.row_ptr + ridx), hi = __ldg(p.row_ptr + ridx + 1);
+      if (COUNT) c.bytes += 8;
+      if (hi > lo) {
+        if (st.kind == ST_DIRECT) {
+          hit = probe(p, c, lo, hi, sid, expiry);
+        } else if (expiry) {  // ST_WILD
+          const uint32_t e = __ldg(p.exp + lo);
+          if (COUNT) c.bytes += 4;
+          hit = e == 0 || e > p.now;
+        } else {
+          hit = true;
+        }
+      }
+    }
+  }
+  if (hit) npush = 0;
+  sb += nprobe;
+  // ---- edge classes that may push a range (userset subjects, arrows): warp-collective
+  const int maxsteps = __reduce_max_sync(kFull, npush);
   for (int i = 0; i < maxsteps; ++i) {
     bool want = false, l2_want = false;
     uint32_t l2_lo = 0, l2_hi = 0, l2_k = 0;
     uint4 item = make_uint4(0, 0, 0, 0);
-    if (i < nsteps && !hit) {
+    if (i < npush && !hit) {
       const DStep st = pr.steps()[sb + i];
       const bool expiry = (st.flags & CF_EXPIRY) != 0;
-      const bool subject_fits = srel == kNone && stype == st.stype;
-      if (st.kind == ST_DIRECT && subject_fits && inverted && (st.flags & CF_INVERT)) {
-        // direction-optimised probe: is obj among the subject's memberships of this class? Most probes miss: a
-        // 32-bit presence word over (class, object) of the check's set (built at admission) rejects them
-        // without walking the set (the walk was 15 % of cfg4's instructions, profiles/r2d).
-        const uint32_t present = c.rset[(kRsetCap + 5) * 32 + (jslot & 31)];
-        if (!ZG_PRESENCE || ((present >> rset_bit(st.tinv, obj)) & 1u)) {
-          const uint32_t kb = cst_at(cst, st.tinv), ke = cst_at(cst, st.tinv + 1u);
-          for (uint32_t r = kb; r < ke; ++r)
-            hit = hit || c.rset[r * 32 + (jslot & 31)] == obj;
-        }
-      } else if ((st.kind == ST_PUSH || subject_fits) && obj < st.nres) {
+      if (obj < st.nres) {
         const unsigned long long ridx = st.row_base + static_cast<unsigned long long>(obj) * st.ncls;
         const uint32_t lo = __ldg(p.row_ptr + ridx), hi = __ldg(p.row_ptr + ridx + 1);
         if (COUNT) c.bytes += 8;
         if (hi > lo) {
-          if (st.kind == ST_DIRECT) {
-            hit = probe(p, c, lo, hi, sid, expiry);
-          } else if (st.kind == ST_WILD) {
-            if (expiry) {
-              const uint32_t e = __ldg(p.exp + lo);
-              if (COUNT) c.bytes += 4;
-              hit = e == 0 || e > p.now;
-            } else {
-              hit = true;
-            }
-          } else if ((st.flags & kStepTargetLeaf) && inverted && !expiry && depth + 1 <= ZG_MAX_DEPTH) {
+          if ((st.flags & kStepTargetLeaf) && inverted && !expiry && depth + 1 <= ZG_MAX_DEPTH) {
             // Children of this range can only be answered by "is the child one of the
             // subject's memberships of class tinv": meet in the middle. No membership (or a
             // child class for another subject type): nothing can match.
@@ -763,37 +768,48 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
         if (static_cast<int>(lane) < n) it = c.stack[c.top - 1 - lane];
         const bool dead = (c.found >> (it.z & 31)) & 1u;
         const uint32_t len = (static_cast<int>(lane) < n && !dead) ? it.y - it.x : 0u;
-        uint32_t incl = len;
+        uint32_t total, jb, jmeta, jexcl;
+        if (!__ballot_sync(kFull, len > 1u)) {
+          // Every popped range holds at most one edge (arrows to a single parent, singleton usersets: the common
+          // case on document / folder hierarchies): no prefix scan and no owner search -- lane k takes the k-th
+          // live item, found with one ballot and one find-nth-set.
+          const unsigned ones = __ballot_sync(kFull, len == 1u);
+          total = static_cast<uint32_t>(__popc(ones));
+          c.top -= n;
+          const int j = lane < total ? static_cast<int>(__fns(ones, 0, static_cast<int>(lane) + 1)) : 0;
+          jb = __shfl_sync(kFull, it.x, j & 31);
+          jmeta = __shfl_sync(kFull, it.z, j & 31);
+          jexcl = lane;
+          __syncwarp();
+        } else {
+          uint32_t incl = len;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          uint32_t v = __shfl_up_sync(kFull, incl, d);
-          if (static_cast<int>(lane) >= d) incl += v;
-        }
-        const uint32_t excl = incl - len;
-        const unsigned fullm = __ballot_sync(kFull, static_cast<int>(lane) < n && incl <= 32u);
-        const int nfull = __popc(fullm);  // prefix of fully consumed items
-        uint32_t total = __shfl_sync(kFull, incl, 31);
-        if (total > 32u) total = 32u;
-        __syncwarp();
-        if (static_cast<int>(lane) == nfull && static_cast<int>(lane) < n)  // partially consumed item stays on top
-          c.stack[c.top - 1 - lane].x = it.x + (32u - excl);
-        c.top -= nfull;
-        __syncwarp();
-        // ---- lane k takes edge k: owner item j = #items with incl <= k
-        auto owner = [&](uint32_t u) -> int {
+          for (int d = 1; d < 32; d <<= 1) {
+            uint32_t v = __shfl_up_sync(kFull, incl, d);
+            if (static_cast<int>(lane) >= d) incl += v;
+          }
+          const uint32_t excl = incl - len;
+          const unsigned fullm = __ballot_sync(kFull, static_cast<int>(lane) < n && incl <= 32u);
+          const int nfull = __popc(fullm);  // prefix of fully consumed items
+          total = __shfl_sync(kFull, incl, 31);
+          if (total > 32u) total = 32u;
+          __syncwarp();
+          if (static_cast<int>(lane) == nfull && static_cast<int>(lane) < n)  // partially consumed item stays on top
+            c.stack[c.top - 1 - lane].x = it.x + (32u - excl);
+          c.top -= nfull;
+          __syncwarp();
+          // ---- lane k takes edge k: owner item j = #items with incl <= k
           int j = 0;
 #pragma unroll
           for (int step = 16; step >= 1; step >>= 1) {
             const int probe_lane = j + step - 1;
             const uint32_t v = __shfl_sync(kFull, incl, probe_lane & 31);
-            if (probe_lane < 32 && v <= u) j += step;
+            if (probe_lane < 32 && v <= lane) j += step;
           }
-          return j;
-        };
-        const int j = owner(lane);
-        const uint32_t jb = __shfl_sync(kFull, it.x, j & 31);
-        const uint32_t jmeta = __shfl_sync(kFull, it.z, j & 31);
-        const uint32_t jexcl = __shfl_sync(kFull, excl, j & 31);
+          jb = __shfl_sync(kFull, it.x, j & 31);
+          jmeta = __shfl_sync(kFull, it.z, j & 31);
+          jexcl = __shfl_sync(kFull, excl, j & 31);
+        }
         bool active = lane < total;
         const uint32_t jslot = jmeta & 31u, cdepth = (jmeta >> 5) & 63u, tslot = jmeta >> 16;
         uint32_t child = 0;

@@ -651,6 +651,10 @@ std::vector<uint8_t> Schema::blob(const std::vector<DRel>& rels, const std::vect
       }
     }
     u.step_end = static_cast<uint16_t>(steps.size());
+    // probes (answered by the lane on its own) before the edge classes that push ranges (warp-collective)
+    std::stable_partition(steps.begin() + u.step_begin, steps.end(), [](const DStep& x) { return x.kind != ST_PUSH; });
+    u.push_begin = u.step_begin;
+    while (u.push_begin < u.step_end && steps[u.push_begin].kind != ST_PUSH) ++u.push_begin;
     bool leaf = u.step_end > u.step_begin;
     for (int i = u.step_begin; i < u.step_end; ++i)
       leaf = leaf && steps[i].kind == ST_DIRECT && (steps[i].flags & CF_INVERT);

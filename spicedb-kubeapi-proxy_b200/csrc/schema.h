@@ -52,8 +52,8 @@ struct DUnit {   // pure-union program evaluated at one object
   uint16_t op_begin, op_end;    // into ops[]
   uint16_t mem_begin, mem_end;  // into members[]: slots inlined into this unit
   uint16_t flags;               // UnitFlags
-  uint16_t step_begin, step_end;  // into steps[]: the unit flattened for this snapshot
-  uint16_t pad;
+  uint16_t step_begin, step_end;  // into steps[]: the unit flattened for this snapshot, probes first:
+  uint16_t push_begin;            // [step_begin, push_begin) DIRECT / WILD (lane-local), [push_begin, step_end) PUSH
 };
 // One edge class a unit touches, with everything the visit needs in one 24-byte record.
 // Built at publish: classes that are empty in the snapshot produce no step at all.

@@ -137,6 +137,14 @@ static inline T __ldg(const T* p) { return *p; }
 template <class T>
 static inline T __ldcg(const T* p) { return *p; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+// position of the n-th (1-based) set bit of mask at or above `base`; 0xFFFFFFFF if there is none (offset > 0 only)
+static inline unsigned __fns(unsigned mask, unsigned base, int offset) {
+  for (unsigned b = base; b < 32; ++b)
+    if ((mask >> b) & 1u)
+      if (--offset == 0) return b;
+  return 0xFFFFFFFFu;
+}
 static inline int __ffs(unsigned v) { return __builtin_ffs(static_cast<int>(v)); }
 static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
