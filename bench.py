@@ -65,6 +65,8 @@ def parse_args():
     ap.add_argument("--configs", default="cfg2,cfg4",
                     help="other BASELINE configurations reported as sub-results under `configs` ('' = none)")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the object-hash sharded cfg4 leg")
+    ap.add_argument("--sharded-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--sharded-timeout", type=float, default=300.0, help="hard limit of the sharded leg, seconds")
     ap.add_argument("--sustain-s", type=float, default=2.5,
                     help="length of the back-to-back 'sustained' leg of the primary workload (0 = skip)")
     return ap.parse_args()
@@ -485,6 +487,51 @@ def measure_sharded(args, rank, local_rank, world, dist):
     return out
 
 
+def run_sharded_leg(args, rank, world, dist):
+    """The sharded leg runs in CHILD processes (one per rank, their own process group on another port) under a hard
+    timeout: a failure or a hang in the multi-level exchange must never cost the replica numbers of this line."""
+    import torch
+
+    torch.cuda.empty_cache()
+    out_path = os.path.join(tempfile.gettempdir(), f"zgpu_sharded_{os.environ.get('MASTER_PORT', '0')}.json")
+    if rank == 0 and os.path.exists(out_path):
+        os.remove(out_path)
+    dist.barrier()
+    env = dict(os.environ)
+    env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + 17)
+    env["ZGPU_SHARDED_OUT"] = out_path
+    cmd = [sys.executable, os.path.abspath(__file__), "--sharded-child", "--gpus", str(world), "--steps", str(args.steps),
+           "--warmup", str(args.warmup)]
+    err = None
+    try:
+        r = subprocess.run(cmd, env=env, timeout=args.sharded_timeout, capture_output=True, text=True)
+        if r.returncode != 0:
+            err = f"child rc={r.returncode}: {r.stderr[-300:]}"
+    except subprocess.TimeoutExpired:
+        err = f"child timed out after {args.sharded_timeout} s"
+    dist.barrier()
+    if rank != 0:
+        return None
+    if os.path.exists(out_path):
+        with open(out_path) as f:
+            return json.load(f)
+    return {"error": err or "no result"}
+
+
+def sharded_child(args):
+    import torch
+    import torch.distributed as dist
+
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    r = measure_sharded(args, rank, local_rank, world, dist)
+    if rank == 0 and r is not None:
+        with open(os.environ["ZGPU_SHARDED_OUT"], "w") as f:
+            json.dump(r, f)
+    dist.destroy_process_group()
+
+
 def main():
     # stdout must carry exactly ONE JSON line, but libraries print there too (NCCL's version banner
     # under torchrun): point fd 1 at stderr for the whole run and emit the line on the saved fd
@@ -496,6 +543,9 @@ def main():
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
         cpu_reference_arm(args, rank, world)
+        return
+    if args.sharded_child:
+        sharded_child(args)
         return
 
     import torch
@@ -528,10 +578,7 @@ def main():
     # sub-queries are routed device to device (dist.DeviceShardedChecker: NCCL all-to-all of device buffers per
     # level). A second field of the line, never the headline; a failure is reported, not fatal.
     if world > 1 and args.scale == 1.0 and not args.no_sharded:
-        try:
-            r = measure_sharded(args, rank, local_rank, world, dist)
-        except Exception as ex:  # noqa: BLE001
-            r = {"error": repr(ex)[:400]} if rank == 0 else None
+        r = run_sharded_leg(args, rank, world, dist)
         if r is not None:
             extra["cfg4_sharded"] = r
 

@@ -48,7 +48,11 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 #define ZG_RSET_CAP 16
 #endif
 #ifndef ZG_PRESENCE
-#define ZG_PRESENCE 1  // presence word in front of the per-check set walk of a direct inverted probe
+#define ZG_PRESENCE 0  // presence word in front of the per-check set walk of a direct inverted probe (measured: -2 .. -3 %,
+                       // profiles/r2f: the walk is short and the extra shared-memory word costs more than it saves)
+#endif
+#ifndef ZG_POP_FAST
+#define ZG_POP_FAST 1  // pop: when every popped range holds <= 1 edge, skip the prefix scan / owner search
 #endif
 #ifndef ZG_L2_MODE
 #define ZG_L2_MODE 2  // two-level meet: 2 = warp-cooperative (default), 1 = per-lane Bloom word + 128-bit streaming
@@ -58,8 +62,8 @@ constexpr int kMinBlocks = ZG_MIN_BLOCKS;  // resident CTAs per SM the register 
 constexpr int kStackCap = ZG_STACK_CAP;    // range items per warp in shared memory
 constexpr int kRsetCap = ZG_RSET_CAP;      // reverse-row entries kept per check (subject's direct memberships), <= 31
 constexpr int kStateWords = 6;             // per-lane query state parked in shared memory between leaf passes
-constexpr int kFCap = 64;                  // children of a range staged in shared memory by the two-level meet
-constexpr size_t kWarpSmem = kStackCap * sizeof(uint4) + ((kRsetCap + kStateWords) * 32 + kFCap) * sizeof(uint32_t);
+constexpr int kFCap = 64;                  // children of a range the two-level meet hashes into shared memory (table: 2x)
+constexpr size_t kWarpSmem = kStackCap * sizeof(uint4) + ((kRsetCap + kStateWords) * 32 + 2 * kFCap) * sizeof(uint32_t);
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint16_t kJobDepthMask = 0x00FF;  // zg_check.flags of a raised sub-query: hop depth
 
@@ -318,15 +322,24 @@ static_assert(kRsetCap <= 31, "class boundaries are 5-bit fields");
 // lanes working on it. The per-lane form of this (every lane walking its own check's rows) ran with 9 of 32 lanes
 // active on average (profiles/r2d): row counts and early exits differ per check. Here the range's children F
 // (<= kFCap, ascending) go to shared memory with one coalesced load, every membership row gets a fixed group of lanes
-// (neighbouring lanes read neighbouring words of the row), and each lane binary-searches its element in F with a
-// warp-uniform trip count. Returns (warp-uniform) whether some element of some row is a child of the range.
+// (neighbouring lanes read neighbouring words of the row), and each lane looks its element up in F's hash table. Returns (warp-uniform) whether some element of some row is a child of the range.
 template <bool COUNT>
 __device__ __forceinline__ bool coop_l2(const KParams& p, WarpCtx<COUNT>& c, uint32_t lo, uint32_t hi, uint32_t kb, uint32_t ke,
                                         uint32_t jslot, const DCls& cl) {
-  uint32_t* const fs = c.rset + (kRsetCap + kStateWords) * 32;
+  uint32_t* const tab = c.rset + (kRsetCap + kStateWords) * 32;
   const uint32_t nf = hi - lo, ng = ke - kb;  // nf <= kFCap (64), 1 <= ng <= kRsetCap (16)
-  if (c.lane < nf) fs[c.lane] = __ldg(p.col + lo + c.lane);
-  if (c.lane + 32 < nf) fs[c.lane + 32] = __ldg(p.col + lo + c.lane + 32);
+  // F goes into a small open-addressing table (load <= 1/2): a lookup is one or two shared-memory words instead of
+  // the five dependent steps of a binary search (which was half of cfg3's instructions, profiles/r2f)
+  const uint32_t lg = nf > 8 ? 33u - static_cast<uint32_t>(__clz(nf - 1)) : 4u;  // table of 2^lg >= 2 nf slots, >= 16
+  const uint32_t tmask = (1u << lg) - 1u, hshift = 32u - lg;
+  constexpr uint32_t kEmpty = 0xFFFFFFFFu;  // never an object id (ZG_NO_OBJECT)
+  for (uint32_t i = c.lane; i <= tmask; i += 32) tab[i] = kEmpty;
+  __syncwarp();
+  for (uint32_t i = c.lane; i < nf; i += 32) {
+    const uint32_t f = __ldg(p.col + lo + i);
+    uint32_t slot = (f * 0x9E3779B1u) >> hshift;
+    while (atomicCAS(tab + slot, kEmpty, f) != kEmpty) slot = (slot + 1u) & tmask;
+  }
   // W lanes per membership row (32 / next power of two of ng): lane = row * W + k walks elements k, k + W, ... of
   // its row. No prefix sums, no owner search: the lanes of a row read the same two offsets (one broadcast load).
   const uint32_t sh = ng <= 2 ? 4u : (ng <= 4 ? 3u : (ng <= 8 ? 2u : 1u));  // log2(W)
@@ -343,15 +356,18 @@ __device__ __forceinline__ bool coop_l2(const KParams& p, WarpCtx<COUNT>& c, uin
   }
   if (COUNT && c.lane == 0) c.bytes += 4ull * nf;
   __syncwarp();
-  const uint32_t span = nf > 1 ? 1u << (32 - __clz(nf - 1)) : 1u;  // smallest power of two >= nf
   while (__any_sync(kFull, x < h)) {
     bool found = false;
     if (x < h) {
       const uint32_t t = __ldg(p.rcol + x);
-      uint32_t pos = 0;  // lower bound of t in fs[0, nf): warp-uniform trip count
-      for (uint32_t s = span; s >= 1; s >>= 1)
-        if (pos + s <= nf && fs[pos + s - 1] < t) pos += s;
-      found = pos < nf && fs[pos] == t;
+      uint32_t slot = (t * 0x9E3779B1u) >> hshift;
+      for (uint32_t v = tab[slot]; v != kEmpty; v = tab[slot]) {
+        if (v == t) {
+          found = true;
+          break;
+        }
+        slot = (slot + 1u) & tmask;
+      }
       x += w;
     }
     if (__any_sync(kFull, found)) return true;
@@ -769,7 +785,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) check_kernel(const KPara
         const bool dead = (c.found >> (it.z & 31)) & 1u;
         const uint32_t len = (static_cast<int>(lane) < n && !dead) ? it.y - it.x : 0u;
         uint32_t total, jb, jmeta, jexcl;
-        if (!__ballot_sync(kFull, len > 1u)) {
+        if (ZG_POP_FAST && !__ballot_sync(kFull, len > 1u)) {
           // Every popped range holds at most one edge (arrows to a single parent, singleton usersets: the common
           // case on document / folder hierarchies): no prefix scan and no owner search -- lane k takes the k-th
           // live item, found with one ballot and one find-nth-set.

@@ -200,6 +200,10 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
   return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST);
 }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicCAS(unsigned* p, unsigned expected, unsigned desired) {
+  __atomic_compare_exchange_n(p, &expected, desired, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+  return expected;
+}
 static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicOr(unsigned long long* p, unsigned long long v) {
   return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST);
