@@ -52,7 +52,10 @@ constexpr int kThreads = kWarpsPerBlock * 32;
                        // profiles/r2f: the walk is short and the extra shared-memory word costs more than it saves)
 #endif
 #ifndef ZG_POP_FAST
-#define ZG_POP_FAST 1  // pop: when every popped range holds <= 1 edge, skip the prefix scan / owner search
+#define ZG_POP_FAST 0  // pop: when every popped range holds <= 1 edge, skip the prefix scan / owner search (measured: no gain, r2g)
+#endif
+#ifndef ZG_L2_MATCH
+#define ZG_L2_MATCH 1  // cooperative two-level meet: ranges of <= 16 children are matched with match.any instead of searched
 #endif
 #ifndef ZG_L2_MODE
 #define ZG_L2_MODE 2  // two-level meet: 2 = warp-cooperative (default), 1 = per-lane Bloom word + 128-bit streaming
@@ -62,8 +65,8 @@ constexpr int kMinBlocks = ZG_MIN_BLOCKS;  // resident CTAs per SM the register 
 constexpr int kStackCap = ZG_STACK_CAP;    // range items per warp in shared memory
 constexpr int kRsetCap = ZG_RSET_CAP;      // reverse-row entries kept per check (subject's direct memberships), <= 31
 constexpr int kStateWords = 6;             // per-lane query state parked in shared memory between leaf passes
-constexpr int kFCap = 64;                  // children of a range the two-level meet hashes into shared memory (table: 2x)
-constexpr size_t kWarpSmem = kStackCap * sizeof(uint4) + ((kRsetCap + kStateWords) * 32 + 2 * kFCap) * sizeof(uint32_t);
+constexpr int kFCap = 64;                  // children of a range staged in shared memory by the two-level meet
+constexpr size_t kWarpSmem = kStackCap * sizeof(uint4) + ((kRsetCap + kStateWords) * 32 + kFCap) * sizeof(uint32_t);
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint16_t kJobDepthMask = 0x00FF;  // zg_check.flags of a raised sub-query: hop depth
 
@@ -322,52 +325,82 @@ static_assert(kRsetCap <= 31, "class boundaries are 5-bit fields");
 // lanes working on it. The per-lane form of this (every lane walking its own check's rows) ran with 9 of 32 lanes
 // active on average (profiles/r2d): row counts and early exits differ per check. Here the range's children F
 // (<= kFCap, ascending) go to shared memory with one coalesced load, every membership row gets a fixed group of lanes
-// (neighbouring lanes read neighbouring words of the row), and each lane looks its element up in F's hash table. Returns (warp-uniform) whether some element of some row is a child of the range.
+// (neighbouring lanes read neighbouring words of the row), and each lane binary-searches its element in F with a
+// warp-uniform trip count. Returns (warp-uniform) whether some element of some row is a child of the range.
+// Deliberately NOT inlined: inlined, its registers take part in the allocation of the whole traversal loop and cost
+// schemas that never use it 10 % (cfg4: 1 115 -> 944 Mchecks/s, profiles/r2e-r2g); a hash table of the range instead
+// of the binary search was slower still (864 vs 1 094 on cfg3, r2g).
+// (all arguments by value: a reference to the warp context would force it into local memory)
 template <bool COUNT>
-__device__ __forceinline__ bool coop_l2(const KParams& p, WarpCtx<COUNT>& c, uint32_t lo, uint32_t hi, uint32_t kb, uint32_t ke,
-                                        uint32_t jslot, const DCls& cl) {
-  uint32_t* const tab = c.rset + (kRsetCap + kStateWords) * 32;
+__device__ __noinline__ bool coop_l2(const uint32_t* __restrict__ col, const uint32_t* __restrict__ rrow_ptr,
+                                     const uint32_t* __restrict__ rcol, uint32_t* rset, uint32_t lane, uint32_t lo, uint32_t hi,
+                                     uint32_t kb, uint32_t ke, uint32_t jslot, unsigned long long rrow_base, uint32_t rstride,
+                                     uint32_t nsubj, unsigned long long* bytes) {
+  uint32_t* const fs = rset + (kRsetCap + kStateWords) * 32;
   const uint32_t nf = hi - lo, ng = ke - kb;  // nf <= kFCap (64), 1 <= ng <= kRsetCap (16)
-  // F goes into a small open-addressing table (load <= 1/2): a lookup is one or two shared-memory words instead of
-  // the five dependent steps of a binary search (which was half of cfg3's instructions, profiles/r2f)
-  const uint32_t lg = nf > 8 ? 33u - static_cast<uint32_t>(__clz(nf - 1)) : 4u;  // table of 2^lg >= 2 nf slots, >= 16
-  const uint32_t tmask = (1u << lg) - 1u, hshift = 32u - lg;
-  constexpr uint32_t kEmpty = 0xFFFFFFFFu;  // never an object id (ZG_NO_OBJECT)
-  for (uint32_t i = c.lane; i <= tmask; i += 32) tab[i] = kEmpty;
-  __syncwarp();
-  for (uint32_t i = c.lane; i < nf; i += 32) {
-    const uint32_t f = __ldg(p.col + lo + i);
-    uint32_t slot = (f * 0x9E3779B1u) >> hshift;
-    while (atomicCAS(tab + slot, kEmpty, f) != kEmpty) slot = (slot + 1u) & tmask;
+#if ZG_L2_MATCH
+  if (nf <= 16u) {
+    // Short range (the common case): its children sit in lanes 0-15, sixteen row elements at a time in lanes 16-31,
+    // and ONE match.any tells every element lane whether an F lane holds the same value: no search at all.
+    // Unused lanes hold values no object id can take (ids stay below 0xFFFFFFF0), all different.
+    const uint32_t pad = 0xFFFFFFE0u + lane;
+    const uint32_t fval = lane < nf ? __ldg(col + lo + lane) : pad;
+    const uint32_t el = lane - 16u;  // element lane index (lanes 16-31)
+    const uint32_t sh = ng <= 1 ? 4u : (ng <= 2 ? 3u : (ng <= 4 ? 2u : (ng <= 8 ? 1u : 0u)));  // log2(lanes per row)
+    const uint32_t w = 1u << sh, row = el >> sh, k = el & (w - 1u);
+    uint32_t x = 0, h = 0;
+    if (lane >= 16u && row < ng) {
+      const uint32_t g = rset[(kb + row) * 32 + jslot];
+      if (g < nsubj) {
+        const unsigned long long ri = rrow_base + static_cast<unsigned long long>(g) * rstride;
+        x = __ldg(rrow_ptr + ri) + k;
+        h = __ldg(rrow_ptr + ri + 1);
+        if (COUNT && k == 0) *bytes += 8ull + 4ull * (h - (x - k));
+      }
+    }
+    if (COUNT && lane == 0) *bytes += 4ull * nf;
+    while (__any_sync(kFull, x < h)) {
+      uint32_t v = fval;
+      if (lane >= 16u) {
+        v = pad;
+        if (x < h) {
+          v = __ldg(rcol + x);
+          x += w;
+        }
+      }
+      const unsigned same = __match_any_sync(kFull, v);
+      if (__any_sync(kFull, lane >= 16u && (same & 0xFFFFu))) return true;
+    }
+    return false;
   }
+#endif
+  if (lane < nf) fs[lane] = __ldg(col + lo + lane);
+  if (lane + 32 < nf) fs[lane + 32] = __ldg(col + lo + lane + 32);
   // W lanes per membership row (32 / next power of two of ng): lane = row * W + k walks elements k, k + W, ... of
   // its row. No prefix sums, no owner search: the lanes of a row read the same two offsets (one broadcast load).
   const uint32_t sh = ng <= 2 ? 4u : (ng <= 4 ? 3u : (ng <= 8 ? 2u : 1u));  // log2(W)
-  const uint32_t w = 1u << sh, row = c.lane >> sh, k = c.lane & (w - 1u);
+  const uint32_t w = 1u << sh, row = lane >> sh, k = lane & (w - 1u);
   uint32_t x = 0, h = 0;
   if (row < ng) {
-    const uint32_t g = c.rset[(kb + row) * 32 + jslot];
-    if (g < cl.nsubj) {
-      const unsigned long long ri = cl.rrow_base + static_cast<unsigned long long>(g) * cl.rstride;
-      x = __ldg(p.rrow_ptr + ri) + k;
-      h = __ldg(p.rrow_ptr + ri + 1);
-      if (COUNT && k == 0) c.bytes += 8ull + 4ull * (h - (x - k));
+    const uint32_t g = rset[(kb + row) * 32 + jslot];
+    if (g < nsubj) {
+      const unsigned long long ri = rrow_base + static_cast<unsigned long long>(g) * rstride;
+      x = __ldg(rrow_ptr + ri) + k;
+      h = __ldg(rrow_ptr + ri + 1);
+      if (COUNT && k == 0) *bytes += 8ull + 4ull * (h - (x - k));
     }
   }
-  if (COUNT && c.lane == 0) c.bytes += 4ull * nf;
+  if (COUNT && lane == 0) *bytes += 4ull * nf;
   __syncwarp();
+  const uint32_t span = nf > 1 ? 1u << (32 - __clz(nf - 1)) : 1u;  // smallest power of two >= nf
   while (__any_sync(kFull, x < h)) {
     bool found = false;
     if (x < h) {
-      const uint32_t t = __ldg(p.rcol + x);
-      uint32_t slot = (t * 0x9E3779B1u) >> hshift;
-      for (uint32_t v = tab[slot]; v != kEmpty; v = tab[slot]) {
-        if (v == t) {
-          found = true;
-          break;
-        }
-        slot = (slot + 1u) & tmask;
-      }
+      const uint32_t t = __ldg(rcol + x);
+      uint32_t pos = 0;  // lower bound of t in fs[0, nf): warp-uniform trip count
+      for (uint32_t s = span; s >= 1; s >>= 1)
+        if (pos + s <= nf && fs[pos + s - 1] < t) pos += s;
+      found = pos < nf && fs[pos] == t;
       x += w;
     }
     if (__any_sync(kFull, found)) return true;
@@ -551,7 +584,11 @@ __device__ __forceinline__ void visit(const KParams& p, const Prog& pr, WarpCtx<
         const uint32_t rlo = __shfl_sync(kFull, l2_lo, r), rhi = __shfl_sync(kFull, l2_hi, r), rk = __shfl_sync(kFull, l2_k, r);
         const uint32_t rj = __shfl_sync(kFull, jslot, r) & 31u;
         if ((c.found >> rj) & 1u) continue;  // another node of the same check already answered it
-        const bool h = coop_l2(p, c, rlo, rhi, rk & 0xFFu, (rk >> 8) & 0xFFu, rj, pr.cls()[rk >> 16]);
+        const DCls rcl = pr.cls()[rk >> 16];
+        unsigned long long cb = 0;
+        const bool h = coop_l2<COUNT>(p.col, p.rrow_ptr, p.rcol, c.rset, c.lane, rlo, rhi, rk & 0xFFu, (rk >> 8) & 0xFFu, rj,
+                                      rcl.rrow_base, rcl.rstride, rcl.nsubj, &cb);
+        if (COUNT) c.bytes += cb;
         if (h) c.found |= 1u << rj;
         __syncwarp();
       }

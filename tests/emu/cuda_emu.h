@@ -180,6 +180,13 @@ static inline unsigned __ballot_sync(unsigned, bool pred) {
   zg_emu::done();
   return m;
 }
+static inline unsigned __match_any_sync(unsigned, unsigned v) {
+  zg_emu::publish(v);
+  unsigned m = 0;
+  for (unsigned i = 0; i < 32; ++i) m |= (zg_emu::read_lane<unsigned>(i) == v ? 1u : 0u) << i;
+  zg_emu::done();
+  return m;
+}
 static inline bool __any_sync(unsigned mask, bool pred) { return __ballot_sync(mask, pred) != 0; }
 static inline int __reduce_max_sync(unsigned, int v) {
   zg_emu::publish(v);
