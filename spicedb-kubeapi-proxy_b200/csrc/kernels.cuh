@@ -55,7 +55,8 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 #define ZG_POP_FAST 0  // pop: when every popped range holds <= 1 edge, skip the prefix scan / owner search (measured: no gain, r2g)
 #endif
 #ifndef ZG_L2_MATCH
-#define ZG_L2_MATCH 1  // cooperative two-level meet: ranges of <= 16 children are matched with match.any instead of searched
+#define ZG_L2_MATCH 0  // cooperative two-level meet: match.any instead of a search for ranges of <= 16 children.
+                       // Measured 2x SLOWER (cfg3: 532 vs ~1 090 Mchecks/s, profiles/r2h): MATCH.ANY is a slow path on sm_100a
 #endif
 #ifndef ZG_L2_MODE
 #define ZG_L2_MODE 2  // two-level meet: 2 = warp-cooperative (default), 1 = per-lane Bloom word + 128-bit streaming
