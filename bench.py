@@ -419,7 +419,12 @@ def measure_sharded(args, rank, local_rank, world, dist):
     from spicedb_kubeapi_proxy_b200 import dist as zdist
     from spicedb_kubeapi_proxy_b200 import workloads
 
+    def note(msg):
+        print(f"[sharded rank {rank} +{time.perf_counter() - t_start:.1f}s] {msg}", file=sys.stderr, flush=True)
+
+    t_start = time.perf_counter()
     w = workloads.by_name("cfg4", args.scale)
+    note("workload generated")
     eng = zgpu.Engine(w.schema, device=local_rank, shard_rank=rank, shard_count=world, subquery_capacity=1 << 24)
     w.load_into(eng)  # keeps only the relationships this rank owns
     eng.publish()
@@ -438,7 +443,9 @@ def measure_sharded(args, rank, local_rank, world, dist):
             outs.append(ck.check_bulk(d_items[b * 16:e * 16], e - b))
         return torch.cat(outs)
 
+    note(f"shard published: {eng.stats()['tuples']} relationships")
     ans = one_step()  # warm-up
+    note(f"first step done: levels {ck.stats['levels']}, sub-queries sent {ck.stats['subqueries_sent']}")
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -449,6 +456,7 @@ def measure_sharded(args, rank, local_rank, world, dist):
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
+    note(f"{steps} steps in {dt:.2f} s")
     mism = None
     gathered = [torch.empty(zdist.shard_bounds(items.size, r, world)[1] - zdist.shard_bounds(items.size, r, world)[0],
                             dtype=torch.uint8, device="cuda") for r in range(world)]
@@ -499,16 +507,23 @@ def run_sharded_leg(args, rank, world, dist):
     dist.barrier()
     env = dict(os.environ)
     env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + 17)
+    # under torchrun the workers use the AGENT's store; the children form their own group: rank 0's child hosts it
+    env["TORCHELASTIC_USE_AGENT_STORE"] = "False"
     env["ZGPU_SHARDED_OUT"] = out_path
+    log_dir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(log_dir, exist_ok=True)
     cmd = [sys.executable, os.path.abspath(__file__), "--sharded-child", "--gpus", str(world), "--steps", str(args.steps),
            "--warmup", str(args.warmup)]
     err = None
+    log_path = os.path.join(log_dir, f"sharded_child_rank{rank}.log")
     try:
-        r = subprocess.run(cmd, env=env, timeout=args.sharded_timeout, capture_output=True, text=True)
+        with open(log_path, "w") as lf:
+            r = subprocess.run(cmd, env=env, timeout=args.sharded_timeout, stdout=lf, stderr=subprocess.STDOUT)
         if r.returncode != 0:
-            err = f"child rc={r.returncode}: {r.stderr[-300:]}"
+            with open(log_path) as lf:
+                err = f"child rc={r.returncode}: {lf.read()[-300:]}"
     except subprocess.TimeoutExpired:
-        err = f"child timed out after {args.sharded_timeout} s"
+        err = f"child timed out after {args.sharded_timeout} s (see {log_path})"
     dist.barrier()
     if rank != 0:
         return None
