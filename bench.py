@@ -433,7 +433,7 @@ def measure_sharded(args, rank, local_rank, world, dist):
     mine = np.ascontiguousarray(items[lo:hi])
     d_items = torch.from_numpy(mine.view(np.uint8).copy()).cuda()
     ck = zdist.DeviceShardedChecker(eng, zdist.TorchDeviceTransport())
-    chunk = 1 << 16  # checks per rank per round: bounds the sub-queries a pass may raise
+    chunk = 1 << 18  # checks per rank per round: bounds the sub-queries a pass may raise (~20 per check, buffer 16 M)
     steps = max(2, min(args.steps, 5))
 
     def one_step():

@@ -5,7 +5,7 @@ tag=${1:-ci}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_smi.txt 2>&1
 timeout 600 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.txt 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/${tag}_smoke.txt
-( timeout 2400 python -m pytest tests -m gpu -q --timeout=900 -p no:cacheprovider 2>&1 | tail -150 ) > gpurun_out/${tag}_pytest.txt
+( ZGPU_FULLSIZE_SCALE=${ZGPU_FULLSIZE_SCALE:-0.25} timeout 2400 python -m pytest tests -m gpu -q --timeout=900 -p no:cacheprovider --durations=12 2>&1 | tail -150 ) > gpurun_out/${tag}_pytest.txt
 tail -15 gpurun_out/${tag}_pytest.txt
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 echo "bench rc=$?"; tail -3 gpurun_out/${tag}_bench.err; cut -c1-3000 gpurun_out/${tag}_bench.json

@@ -4,7 +4,10 @@ sub-query buffer overflow answered in halves, the path memo. Checker = the CPU o
 against SpiceDB for these operators), on >= 50 000 sampled checks of the very batch bench.py times,
 spanning both `view` and `restricted_view`.
 
-ZGPU_FULLSIZE_SCALE shrinks the store for quick local runs (default 1.0)."""
+ZGPU_FULLSIZE_SCALE picks the store size: 1.0 = the full 95 M relationships (what scripts/gpu_ci.sh runs: the oracle's
+index build alone is 30 s per store then, 12 minutes for this file); the default 0.25 (24 M relationships, a 0.5 GB
+store: still four times the L2) keeps the -m gpu suite within a few minutes. bench.py compares the whole 1 M-check batch
+of cfg4 at scale 1.0 with the oracle on every run."""
 import os
 
 import numpy as np
@@ -12,7 +15,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-SCALE = float(os.environ.get("ZGPU_FULLSIZE_SCALE", "1.0"))
+SCALE = float(os.environ.get("ZGPU_FULLSIZE_SCALE", "0.25"))
 SAMPLE = 60_000
 
 
@@ -150,8 +153,9 @@ def test_thousand_update_write_on_the_large_store_is_a_merge(zg, big):
     rec = {"store_tuples": int(st["tuples"]), "updates_per_write": 1000, "wall_ms": times,
            "device_ms_last": st["last_publish_ms"], "full_rebuild_device_ms": t_full}
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/write_merge_fullsize.json", "w") as f:
+    with open(f"gpurun_out/write_merge_scale{SCALE}.json", "w") as f:
         json.dump(rec, f)
+    rec["scale"] = SCALE
     assert min(times) < 50.0, rec  # target: < 5 ms; the bound leaves room for a noisy box
     # parity after the writes: the oracle replays them (one re-index), probes = touched documents x their checks
     o = Oracle(w.schema)
