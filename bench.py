@@ -206,7 +206,10 @@ def cpu_reference_arm(args, rank, world):
         "config": workload_config(w, args, 1),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
                          "note": "C oracle restating SpiceDB v1.47.1 check semantics; the reference's own engine is an "
-                                 "un-vendored Go module and no Go toolchain exists on this box"},
+                                 "un-vendored Go module and no Go toolchain exists on this box",
+                         "algorithm": "forward recursive evaluation, no caching (pkg/spicedb/spicedb.go:44-46): ~42 KB of "
+                                      "index reads per cfg3 check; the GPU arm is direction-optimised (< 1 KB per check), "
+                                      "so most of the ratio between the arms is algorithmic, not hardware"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
