@@ -3,7 +3,10 @@ concurrent clients each hand one List body to zg_list_postfilter -- scan, resolv
 splice -- against a store whose objects carry real "namespace/name" ids. Reports filtered lists/s and body MB/s,
 and checks a few outputs against the Python mirror of pkg/authz/postfilter.go.
 
-    python scripts/list_replay.py [--pods 200000] [--items 10000] [--clients 32] [--rounds 4] [--dry-run]
+    python scripts/list_replay.py [--pods 200000] [--items 10000] [--clients 32] [--rounds 4] [--devices 1] [--dry-run]
+
+The clients are native threads (tests/cabi/loadgen.c): Python threads would measure the GIL. --devices N: ONE engine
+handle owning N GPUs.
 
 --dry-run builds the store and the bodies and runs the host-only stages (scan, resolve), no GPU call.
 """
@@ -40,11 +43,12 @@ ap.add_argument("--groups", type=int, default=200)
 ap.add_argument("--items", type=int, default=10000)
 ap.add_argument("--clients", type=int, default=32)
 ap.add_argument("--rounds", type=int, default=4)
+ap.add_argument("--devices", type=int, default=1)
 ap.add_argument("--dry-run", action="store_true")
 a = ap.parse_args()
 rng = np.random.default_rng(7)
 
-e = zgpu.Engine(SCHEMA, host_only=a.dry_run)
+e = zgpu.Engine(SCHEMA, host_only=a.dry_run, n_devices=1 if a.dry_run else a.devices)
 t0 = time.perf_counter()
 pod_names = [f"ns-{i % a.namespaces}/pod-{i}" for i in range(a.pods)]
 pod_id = np.array([e.intern("pod", n) for n in pod_names], dtype=np.uint32)
@@ -112,52 +116,58 @@ for i in range(min(3, a.clients)):
 kept = len(json.loads(got)["items"] or [])
 res["kept_of_last_checked_list"] = kept
 
-errors, out_bytes = [], [0] * a.clients
+# ---- native client threads
+import ctypes as C  # noqa: E402
+import subprocess  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "spicedb-kubeapi-proxy_b200")
+lg_so = os.path.join(ROOT, "tests", "cabi", "libloadgen.so")
+subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-std=c11", "-D_GNU_SOURCE", "-I", os.path.join(ROOT, "include"),
+                os.path.join(ROOT, "tests", "cabi", "loadgen.c"), "-o", lg_so, "-L", PKG, "-lzgpu", "-Wl,-rpath," + PKG,
+                "-lpthread"], check=True)
+LG = C.CDLL(lg_so)
 
 
-def run_phase(fn):
-    barrier = threading.Barrier(a.clients + 1)
+class ListClient(C.Structure):
+    _fields_ = [("e", C.c_void_p), ("body", C.c_char_p), ("body_len", C.c_uint64), ("tpl", _lib._ListTemplate),
+                ("out", C.c_void_p), ("out_cap", C.c_uint64), ("out_len", C.c_uint64), ("rounds", C.c_int), ("rc", C.c_int)]
 
-    def body(i):
-        barrier.wait()
-        try:
-            fn(i)
-        except Exception as ex:  # noqa: BLE001
-            errors.append((i, repr(ex)))
 
-    th = [threading.Thread(target=body, args=(i,)) for i in range(a.clients)]
-    [t.start() for t in th]
+LG.loadgen_run_lists.restype = C.c_double
+LG.loadgen_run_lists.argtypes = [C.POINTER(ListClient), C.c_int, C.c_int]
+out_cap = max(len(b) for b in bodies) + 8
+outs = np.empty((a.clients, out_cap), dtype=np.uint8)
+
+
+def run_phase(mode, rounds):
+    cl = (ListClient * a.clients)()
+    for i in range(a.clients):
+        b = bodies[i % n_bodies]
+        cl[i].e, cl[i].body, cl[i].body_len, cl[i].tpl = e._h, b, len(b), tpls[i]
+        cl[i].out, cl[i].out_cap, cl[i].rounds = outs[i].ctypes.data, out_cap, rounds
     s0 = e.stats()
-    barrier.wait()
-    t0 = time.perf_counter()
-    [t.join() for t in th]
-    return time.perf_counter() - t0, s0, e.stats()
+    dt = LG.loadgen_run_lists(cl, a.clients, mode)
+    bad = [(i, c.rc) for i, c in enumerate(cl) if c.rc]
+    assert dt > 0 and not bad, bad[:5]
+    return dt, s0, e.stats(), [int(c.out_len) for c in cl]
 
 
-def lists(i):
-    for _ in range(a.rounds):
-        out_bytes[i] = len(e.list_postfilter(bodies[i % n_bodies], [tpls[i]]))
-
-
-run_phase(lists)  # warm-up
-dt, s0, s1 = run_phase(lists)
+run_phase(0, 1)  # warm-up
+dt, s0, s1, lens = run_phase(0, a.rounds)
+for i in range(min(3, a.clients)):  # the concurrent answers are the single-caller answers
+    assert outs[i, :lens[i]].tobytes() == e.list_postfilter(bodies[i % n_bodies], [tpls[i]]), f"client {i}: concurrent output differs"
 n_lists = a.clients * a.rounds
-res.update({"filtered_lists_per_s": round(n_lists / dt, 1), "body_MB_per_s": round(n_lists * len(bodies[0]) / 1e6 / dt, 1),
+res.update({"clients_are": "native threads (tests/cabi/loadgen.c)", "devices": int(s1["devices"]),
+            "filtered_lists_per_s": round(n_lists / dt, 1), "body_MB_per_s": round(n_lists * len(bodies[0]) / 1e6 / dt, 1),
             "checks_per_s": round(n_lists * a.items / dt), "launches": int(s1["launches"] - s0["launches"]),
-            "coalesced_requests": int(s1["coalesced_requests"] - s0["coalesced_requests"]), "errors": errors[:3]})
+            "coalesced_requests": int(s1["coalesced_requests"] - s0["coalesced_requests"])})
 # the pre-filter shape: LookupResources + scan + keep + splice per list (pkg/authz/lookups.go:65)
 for i in range(min(2, a.clients)):
     r = pf.run_lookup_resources(client, ("pod", "$", "view", "user", users[i], ""), pf.RequestInfo())
     assert e.list_prefilter(bodies[i % n_bodies], tpls[i]) == pf.filter_list(bodies[i % n_bodies], r), f"client {i}: prefilter differs"
-
-
-def prelists(i):
-    for _ in range(a.rounds):
-        out_bytes[i] = len(e.list_prefilter(bodies[i % n_bodies], tpls[i]))
-
-
-run_phase(prelists)
-dt, s0, s1 = run_phase(prelists)
+run_phase(1, 1)
+dt, s0, s1, lens = run_phase(1, a.rounds)
 res.update({"prefiltered_lists_per_s": round(n_lists / dt, 1), "prefilter_launches": int(s1["launches"] - s0["launches"]),
-            "errors": errors[:3]})
+            "prefilter_lookup_batches": int(s1["lookup_batches"] - s0["lookup_batches"])})
 print(json.dumps(res))

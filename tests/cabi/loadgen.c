@@ -71,3 +71,50 @@ double loadgen_run(lg_client *clients, int n, int mode) {
   free(th);
   return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ---- filtered kube lists: every client hands one List body to zg_list_postfilter (mode 0: scan, resolve, ONE bulk
+ * check, splice; pkg/authz/postfilter.go:17-178) or zg_list_prefilter (mode 1: LookupResources + scan + keep + splice;
+ * pkg/authz/lookups.go:44-132). Bodies may be shared between clients (they are read-only); outputs are per client. */
+typedef struct {
+  zg_engine *e;
+  const char *body;
+  uint64_t body_len;
+  zg_list_template tpl;
+  char *out;
+  uint64_t out_cap;
+  uint64_t out_len; /* out: bytes of the last filtered body */
+  int rounds;
+  int rc;
+} lg_list_client;
+
+static void *list_client_main(void *p) {
+  lg_list_client *c = (lg_list_client *)p;
+  pthread_barrier_wait(&g_start);
+  for (int r = 0; r < c->rounds; ++r) {
+    size_t n = 0;
+    int rc = g_mode == 0 ? zg_list_postfilter(c->e, c->body, c->body_len, &c->tpl, 1, c->out, c->out_cap, &n)
+                         : zg_list_prefilter(c->e, c->body, c->body_len, ZG_LIST_ITEMS, &c->tpl, c->out, c->out_cap, &n);
+    if (rc && !c->rc) c->rc = rc;
+    c->out_len = n;
+  }
+  return NULL;
+}
+
+double loadgen_run_lists(lg_list_client *clients, int n, int mode) {
+  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n);
+  pthread_attr_t attr;
+  pthread_attr_init(&attr);
+  pthread_attr_setstacksize(&attr, 1024 * 1024);
+  g_mode = mode;
+  pthread_barrier_init(&g_start, NULL, (unsigned)n + 1);
+  for (int i = 0; i < n; ++i)
+    if (pthread_create(&th[i], &attr, list_client_main, &clients[i])) return -1.0;
+  struct timespec t0, t1;
+  pthread_barrier_wait(&g_start);
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int i = 0; i < n; ++i) pthread_join(th[i], NULL);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  pthread_barrier_destroy(&g_start);
+  free(th);
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
