@@ -124,8 +124,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "spicedb-kubeapi-proxy_b200")
 lg_so = os.path.join(ROOT, "tests", "cabi", "libloadgen.so")
 subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-std=c11", "-D_GNU_SOURCE", "-I", os.path.join(ROOT, "include"),
-                os.path.join(ROOT, "tests", "cabi", "loadgen.c"), "-o", lg_so, "-L", PKG, "-lzgpu", "-Wl,-rpath," + PKG,
-                "-lpthread"], check=True)
+                os.path.join(ROOT, "tests", "cabi", "loadgen.c"), "-o", lg_so,
+                # the library this process already loaded (ZGPU_LIB selects a tuning variant)
+                os.environ.get("ZGPU_LIB") or os.path.join(PKG, "libzgpu.so"), "-Wl,-rpath," + PKG, "-lpthread"], check=True)
 LG = C.CDLL(lg_so)
 
 

@@ -37,11 +37,12 @@ struct BatchReq {
   uint8_t* out;
   int rc = ZG_OK;
   std::string err;
-  bool done = false;
+  bool done = false, lead = false;
+  std::condition_variable cv;  // every waiter sleeps on its own: a finished group wakes exactly its members and
+                               // ONE next leader, not every queued caller (1 000 of them under BASELINE config 5)
 };
 struct Batcher {
   std::mutex m;
-  std::condition_variable cv;
   std::vector<BatchReq*> queue;
   bool leader_active = false;
   static constexpr uint64_t kMaxItemsPerLaunch = 1ull << 24;
@@ -138,11 +139,11 @@ struct zg_engine {
     bool self_member = false;
     int rc = ZG_OK;
     std::string err;
-    bool done = false;
+    bool done = false, lead = false;
+    std::condition_variable cv;
   };
   struct LookupBatcher {
     std::mutex m;
-    std::condition_variable cv;
     std::vector<LookupJob*> queue;
     bool leader_active = false;
   } lookups;
@@ -828,13 +829,10 @@ extern "C" int zg_check_bulk(zg_engine* e, const zg_check* items, uint64_t n, ui
   BatchReq me{items, n, out};
   std::unique_lock<std::mutex> lk(b.m);
   b.queue.push_back(&me);
-  while (!me.done) {
-    if (b.leader_active) {
-      b.cv.wait(lk);
-      continue;
-    }
-    // become the leader: take as many queued requests as fit one launch (mine included,
-    // it is somewhere in the queue), answer them, then hand leadership back
+  if (b.leader_active) me.cv.wait(lk, [&] { return me.done || me.lead; });
+  if (!me.done) {
+    // leader (nobody was leading, or the previous leader handed over to the head of the queue -- me): take as many
+    // queued requests as fit one launch, mine first, answer them, wake their callers, hand leadership on
     b.leader_active = true;
     std::vector<BatchReq*> group;
     uint64_t total = 0;
@@ -847,9 +845,16 @@ extern "C" int zg_check_bulk(zg_engine* e, const zg_check* items, uint64_t n, ui
     lk.unlock();
     run_group(e, group);
     lk.lock();
-    for (BatchReq* r : group) r->done = true;
-    b.leader_active = false;
-    b.cv.notify_all();
+    for (BatchReq* r : group) {
+      r->done = true;
+      if (r != &me) r->cv.notify_one();
+    }
+    if (!b.queue.empty()) {
+      b.queue.front()->lead = true;
+      b.queue.front()->cv.notify_one();
+    } else {
+      b.leader_active = false;
+    }
   }
   lk.unlock();
   return me.rc ? fail(me.rc, me.err) : ZG_OK;
@@ -1436,11 +1441,8 @@ static int lookup_queued(zg_engine* e, uint16_t res_type, uint16_t perm, uint16_
   auto& b = e->lookups;
   std::unique_lock<std::mutex> lk(b.m);
   b.queue.push_back(&me);
-  while (!me.done) {
-    if (b.leader_active) {
-      b.cv.wait(lk);
-      continue;
-    }
+  if (b.leader_active) me.cv.wait(lk, [&] { return me.done || me.lead; });
+  if (!me.done) {  // leader: see zg_check_bulk
     b.leader_active = true;
     std::vector<zg_engine::LookupJob*> group;
     const size_t take = std::min<size_t>(b.queue.size(), kMaxLookupGroup);
@@ -1449,9 +1451,16 @@ static int lookup_queued(zg_engine* e, uint16_t res_type, uint16_t perm, uint16_
     lk.unlock();
     run_lookup_group(e, group);
     lk.lock();
-    for (auto* j : group) j->done = true;
-    b.leader_active = false;
-    b.cv.notify_all();
+    for (auto* j : group) {
+      j->done = true;
+      if (j != &me) j->cv.notify_one();
+    }
+    if (!b.queue.empty()) {
+      b.queue.front()->lead = true;
+      b.queue.front()->cv.notify_one();
+    } else {
+      b.leader_active = false;
+    }
   }
   lk.unlock();
   if (me.rc) return fail(me.rc, me.err);

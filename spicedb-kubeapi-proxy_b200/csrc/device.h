@@ -160,6 +160,8 @@ class Device {
   size_t pin_ready_cap_ = 0;
   static constexpr uint64_t kStreamChunkItems = 1ull << 17;  // 2 MB of items per chunk
   static constexpr uint64_t kStreamMinItems = 1ull << 18;    // smaller calls: one plain copy
+  static constexpr uint64_t kParallelGatherItems = 1ull << 20;  // coalesced groups from here on are gathered by helpers
+  static constexpr unsigned kGatherThreads = 8;
   void* pin_in_ = nullptr;
   void* pin_out_ = nullptr;
   size_t pin_in_cap_ = 0, pin_out_cap_ = 0;

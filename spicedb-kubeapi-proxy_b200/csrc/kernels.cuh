@@ -58,6 +58,13 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 #define ZG_L2_MATCH 0  // cooperative two-level meet: match.any instead of a search for ranges of <= 16 children.
                        // Measured 2x SLOWER (cfg3: 532 vs ~1 090 Mchecks/s, profiles/r2h): MATCH.ANY is a slow path on sm_100a
 #endif
+#ifndef ZG_L2_FILTER
+#define ZG_L2_FILTER 0  // cooperative two-level meet: a 2 048-bit blocked Bloom filter of the range's children in shared memory
+                        // in front of the binary search (the search then runs only for lanes the filter lets through)
+#endif
+#ifndef ZG_L2_SPLIT
+#define ZG_L2_SPLIT 0  // cooperative two-level meet: 32 / ng lanes per membership row (any ng) instead of a power of two
+#endif
 #ifndef ZG_L2_MODE
 #define ZG_L2_MODE 2  // two-level meet: 2 = warp-cooperative (default), 1 = per-lane Bloom word + 128-bit streaming
                       // (measured slower: 919 vs 1 023 Mchecks/s on cfg3), 0 = per-lane sorted-segment intersection
@@ -67,7 +74,8 @@ constexpr int kStackCap = ZG_STACK_CAP;    // range items per warp in shared mem
 constexpr int kRsetCap = ZG_RSET_CAP;      // reverse-row entries kept per check (subject's direct memberships), <= 31
 constexpr int kStateWords = 6;             // per-lane query state parked in shared memory between leaf passes
 constexpr int kFCap = 64;                  // children of a range staged in shared memory by the two-level meet
-constexpr size_t kWarpSmem = kStackCap * sizeof(uint4) + ((kRsetCap + kStateWords) * 32 + kFCap) * sizeof(uint32_t);
+constexpr int kFBloom = ZG_L2_FILTER ? 64 : 0;  // words of the filter over those children
+constexpr size_t kWarpSmem = kStackCap * sizeof(uint4) + ((kRsetCap + kStateWords) * 32 + kFCap + kFBloom) * sizeof(uint32_t);
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint16_t kJobDepthMask = 0x00FF;  // zg_check.flags of a raised sub-query: hop depth
 
@@ -375,12 +383,43 @@ __device__ __noinline__ bool coop_l2(const uint32_t* __restrict__ col, const uin
     return false;
   }
 #endif
+#if ZG_L2_FILTER
+  // filter word = top 6 bits of the hash, two bits inside it from the next 2 x 5 bits
+  uint32_t* const fb = fs + kFCap;
+  fb[lane] = 0;
+  fb[lane + 32] = 0;
+  __syncwarp();
+  if (lane < nf) {
+    const uint32_t v = __ldg(col + lo + lane), hv = v * 0x9E3779B1u;
+    fs[lane] = v;
+    atomicOr(&fb[hv >> 26], (1u << ((hv >> 21) & 31u)) | (1u << ((hv >> 16) & 31u)));
+  }
+  if (lane + 32 < nf) {
+    const uint32_t v = __ldg(col + lo + lane + 32), hv = v * 0x9E3779B1u;
+    fs[lane + 32] = v;
+    atomicOr(&fb[hv >> 26], (1u << ((hv >> 21) & 31u)) | (1u << ((hv >> 16) & 31u)));
+  }
+#else
   if (lane < nf) fs[lane] = __ldg(col + lo + lane);
   if (lane + 32 < nf) fs[lane + 32] = __ldg(col + lo + lane + 32);
-  // W lanes per membership row (32 / next power of two of ng): lane = row * W + k walks elements k, k + W, ... of
-  // its row. No prefix sums, no owner search: the lanes of a row read the same two offsets (one broadcast load).
-  const uint32_t sh = ng <= 2 ? 4u : (ng <= 4 ? 3u : (ng <= 8 ? 2u : 1u));  // log2(W)
+#endif
+  // W lanes per membership row: lane = row * W + k walks elements k, k + W, ... of its row. No prefix sums, no owner
+  // search: the lanes of a row read the same two offsets (one broadcast load).
+#if ZG_L2_SPLIT
+  uint32_t w, magic;  // W = 32 / ng; row = lane / W as (lane * ceil(256 / W)) >> 8, exact for lane < 32
+  if (ng <= 2) { w = 16; magic = 16; }
+  else if (ng == 3) { w = 10; magic = 26; }
+  else if (ng == 4) { w = 8; magic = 32; }
+  else if (ng == 5) { w = 6; magic = 43; }
+  else if (ng == 6) { w = 5; magic = 52; }
+  else if (ng <= 8) { w = 4; magic = 64; }
+  else if (ng <= 10) { w = 3; magic = 86; }
+  else { w = 2; magic = 128; }
+  const uint32_t row = (lane * magic) >> 8, k = lane - row * w;
+#else
+  const uint32_t sh = ng <= 2 ? 4u : (ng <= 4 ? 3u : (ng <= 8 ? 2u : 1u));  // log2(W): 32 / next power of two of ng
   const uint32_t w = 1u << sh, row = lane >> sh, k = lane & (w - 1u);
+#endif
   uint32_t x = 0, h = 0;
   if (row < ng) {
     const uint32_t g = rset[(kb + row) * 32 + jslot];
@@ -396,6 +435,22 @@ __device__ __noinline__ bool coop_l2(const uint32_t* __restrict__ col, const uin
   const uint32_t span = nf > 1 ? 1u << (32 - __clz(nf - 1)) : 1u;  // smallest power of two >= nf
   while (__any_sync(kFull, x < h)) {
     bool found = false;
+#if ZG_L2_FILTER
+    uint32_t t = 0;
+    if (x < h) {
+      t = __ldg(rcol + x);
+      const uint32_t ht = t * 0x9E3779B1u, m = (1u << ((ht >> 21) & 31u)) | (1u << ((ht >> 16) & 31u));
+      found = (fb[ht >> 26] & m) == m;  // "maybe": verified below
+      x += w;
+    }
+    if (__any_sync(kFull, found)) {
+      uint32_t pos = 0;  // lower bound of t in fs[0, nf): warp-uniform trip count
+      for (uint32_t s = span; s >= 1; s >>= 1)
+        if (pos + s <= nf && fs[pos + s - 1] < t) pos += s;
+      found = found && pos < nf && fs[pos] == t;
+      if (__any_sync(kFull, found)) return true;
+    }
+#else
     if (x < h) {
       const uint32_t t = __ldg(rcol + x);
       uint32_t pos = 0;  // lower bound of t in fs[0, nf): warp-uniform trip count
@@ -405,6 +460,7 @@ __device__ __noinline__ bool coop_l2(const uint32_t* __restrict__ col, const uin
       x += w;
     }
     if (__any_sync(kFull, found)) return true;
+#endif
   }
   return false;
 }

@@ -32,11 +32,12 @@ def default_opts(**kw):
 
 
 def build() -> str:
-    so = os.path.join(_HERE, "libzgemu.so")
+    extra = os.environ.get("ZGPU_EMU_CFLAGS", "").split()  # tuning macros of kernels.cuh (-DZG_L2_FILTER=1 ...)
+    so = os.path.join(_HERE, "libzgemu" + ("_" + "".join(c if c.isalnum() else "_" for c in "".join(extra)) if extra else "") + ".so")
     srcs = [os.path.join(_HERE, f) for f in ("emu_main.cc", "cuda_emu.h")] + \
            [os.path.join(_CSRC, f) for f in ("kernels.cuh", "delta.cuh", "schema.cc", "schema.h", "store.cc", "store.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I", _HERE,
+        subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-pthread", *extra, "-I", _HERE,
                         os.path.join(_HERE, "emu_main.cc"), os.path.join(_CSRC, "schema.cc"), os.path.join(_CSRC, "store.cc"),
                         "-o", so], check=True)
     return so
