@@ -57,7 +57,7 @@ for wl in table:
                f"under ncu; {inst / 1048576:.0f} warp-instructions per check (batch 1 048 576).")
 
 # hottest source lines (needs the cubin of the same build for the line table)
-so = os.path.join(ROOT, "spicedb-kubeapi-proxy_b200", "libzgpu.so")
+so = os.environ.get("ZG_PROF_LIB") or os.path.join(ROOT, "spicedb-kubeapi-proxy_b200", "libzgpu.so")  # the build that was profiled
 tmp = f"/tmp/zg_prof_{tag}"
 os.makedirs(tmp, exist_ok=True)
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
@@ -74,7 +74,7 @@ for l in sec.split("\n"):
     if mm:
         off2line[int(mm.group(1), 16)] = line
         ops[mm.group(2).split(".")[0]] += 1
-src = open(os.path.join(ROOT, "spicedb-kubeapi-proxy_b200", "csrc", "kernels.cuh")).read().split("\n")
+src = open(os.environ.get("ZG_PROF_SRC") or os.path.join(ROOT, "spicedb-kubeapi-proxy_b200", "csrc", "kernels.cuh")).read().split("\n")
 for wl in table:
     rep = os.path.join(ROOT, "gpurun_out", f"{tag}_prof_{wl}.ncu-rep")
     rows = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--csv"]))))[1:]

@@ -756,9 +756,8 @@ static int publish_if_needed(zg_engine* e) {
   return ZG_OK;
 }
 
-// Runs one group of queued requests under the engine lock.
+// Runs one group of queued requests; the caller holds the device lock.
 static void run_group(zg_engine* e, std::vector<BatchReq*>& group) {
-  std::lock_guard<std::mutex> g(e->mu);
   int rc = ZG_OK;
   std::string err;
   if (e->dev.shard_count > 1) {
@@ -835,15 +834,22 @@ extern "C" int zg_check_bulk(zg_engine* e, const zg_check* items, uint64_t n, ui
     // queued requests as fit one launch, mine first, answer them, wake their callers, hand leadership on
     b.leader_active = true;
     std::vector<BatchReq*> group;
-    uint64_t total = 0;
-    size_t take = 0;
-    while (take < b.queue.size() && (group.empty() || total + b.queue[take]->n <= Batcher::kMaxItemsPerLaunch)) {
-      total += b.queue[take]->n;
-      group.push_back(b.queue[take++]);
-    }
-    b.queue.erase(b.queue.begin(), b.queue.begin() + static_cast<long>(take));
     lk.unlock();
-    run_group(e, group);
+    {
+      // the device first, the group second: whatever queued while this leader waited for the GPU (behind a batch of
+      // lookups, a publish, the previous group's tail) rides along
+      std::lock_guard<std::mutex> dev_lock(e->mu);
+      lk.lock();
+      uint64_t total = 0;
+      size_t take = 0;
+      while (take < b.queue.size() && (group.empty() || total + b.queue[take]->n <= Batcher::kMaxItemsPerLaunch)) {
+        total += b.queue[take]->n;
+        group.push_back(b.queue[take++]);
+      }
+      b.queue.erase(b.queue.begin(), b.queue.begin() + static_cast<long>(take));
+      lk.unlock();
+      run_group(e, group);
+    }
     lk.lock();
     for (BatchReq* r : group) {
       r->done = true;
@@ -1282,8 +1288,7 @@ extern "C" int zg_list_postfilter(zg_engine* e, const char* body, size_t len, co
 
 // Answers a group of queued lookups under the engine lock: cache hits first, the rest in one batched launch
 // sequence, then the self-membership of userset subjects (Check is the arbiter of LookupResources).
-static void run_lookup_group(zg_engine* e, std::vector<zg_engine::LookupJob*>& group) {
-  std::lock_guard<std::mutex> g(e->mu);
+static void run_lookup_group(zg_engine* e, std::vector<zg_engine::LookupJob*>& group) {  // device lock held
   auto fail_all = [&](int rc, const std::string& msg) {
     for (auto* j : group) {
       j->rc = rc;
@@ -1445,11 +1450,16 @@ static int lookup_queued(zg_engine* e, uint16_t res_type, uint16_t perm, uint16_
   if (!me.done) {  // leader: see zg_check_bulk
     b.leader_active = true;
     std::vector<zg_engine::LookupJob*> group;
-    const size_t take = std::min<size_t>(b.queue.size(), kMaxLookupGroup);
-    group.assign(b.queue.begin(), b.queue.begin() + static_cast<long>(take));
-    b.queue.erase(b.queue.begin(), b.queue.begin() + static_cast<long>(take));
     lk.unlock();
-    run_lookup_group(e, group);
+    {
+      std::lock_guard<std::mutex> dev_lock(e->mu);  // the device first, the group second (as for checks)
+      lk.lock();
+      const size_t take = std::min<size_t>(b.queue.size(), kMaxLookupGroup);
+      group.assign(b.queue.begin(), b.queue.begin() + static_cast<long>(take));
+      b.queue.erase(b.queue.begin(), b.queue.begin() + static_cast<long>(take));
+      lk.unlock();
+      run_lookup_group(e, group);
+    }
     lk.lock();
     for (auto* j : group) {
       j->done = true;

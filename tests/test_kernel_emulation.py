@@ -122,6 +122,36 @@ definition doc {
         _compare_strings(emu, schema, rels, checks, now=now, expires=expires)
 
 
+def test_two_level_meet_over_every_range_size_and_membership_count_under_the_emulator(emu):
+    """The cooperative two-level meet stages <= 64 children of a range (plus their filter) in shared memory and gives
+    every membership row 32 / ng lanes: ranges of 1 .. 70 children (beyond 64: the walk takes over), subjects with
+    1 .. 17 memberships (beyond 16: the per-check set overflows into forward probes), hits on the first / last child,
+    near misses (ids that differ in one bit from a child: filter false positives must die in the search)."""
+    schema = """definition user {}
+definition group { relation member: user }
+definition team { relation member: group#member }
+definition namespace { relation viewer: team#member  permission view = viewer }"""
+    rng = np.random.default_rng(11)
+    rels, checks = [], []
+    n_teams = 400
+    for g in range(300):  # every group sits in 1 .. 12 teams
+        for t in rng.choice(n_teams, 1 + g % 12, replace=False):
+            rels.append(f"team:t{t}#member@group:g{g}#member")
+    sizes = [1, 2, 3, 15, 16, 17, 31, 32, 33, 63, 64, 65, 70]
+    for i, nf in enumerate(sizes):
+        for t in rng.choice(n_teams, nf, replace=False):
+            rels.append(f"namespace:n{i}#viewer@team:t{t}#member")
+    for u in range(1, 18):  # user u<k> is a member of k groups
+        for g in rng.choice(300, u, replace=False):
+            rels.append(f"group:g{g}#member@user:u{u}")
+    for i in range(len(sizes)):
+        for u in range(1, 18):
+            checks.append(f"namespace:n{i}#view@user:u{u}")
+    e, o = _compare_strings(emu, schema, rels, checks)
+    got = e.check_bulk(e.items_from_strings(checks, split_rel))
+    assert 0.1 < (got == 2).mean() < 0.9  # both answers occur
+
+
 @pytest.mark.parametrize("wl,scale,n", [("cfg2", 0.01, 2000), ("cfg3", 0.003, 3000), ("cfg4", 0.001, 3000)])
 def test_baseline_workloads_scaled_under_the_emulator(emu, wl, scale, n):
     """The BASELINE shapes (scaled): cfg3 resolves every namespace -> team -> group range by the two-level meet in the

@@ -150,3 +150,39 @@ def test_lookup_resources_agrees_with_check_for_userset_subjects():
         got = sorted(r.resource_object_id for r in cl.LookupResources(C.LookupResourcesRequest(
             rt, perm, C.SubjectReference(C.ObjectReference(st, sid), srel))))
         assert got == want, f"{rt}#{perm}@{st}:{sid}#{srel}: {got} != {want}"
+
+
+def test_two_level_meet_over_every_range_size_and_membership_count():
+    """Same sweep as the emulator test of the same name (tests/test_kernel_emulation.py), on the real kernel: ranges of
+    1 .. 70 children against subjects with 1 .. 17 memberships, answers against the oracle."""
+    import zgpu
+    from oracle.pyoracle import Oracle
+
+    schema = """definition user {}
+definition group { relation member: user }
+definition team { relation member: group#member }
+definition namespace { relation viewer: team#member  permission view = viewer }"""
+    rng = np.random.default_rng(11)
+    rels, checks = [], []
+    n_teams = 400
+    for g in range(300):
+        for t in rng.choice(n_teams, 1 + g % 12, replace=False):
+            rels.append(f"team:t{t}#member@group:g{g}#member")
+    sizes = [1, 2, 3, 15, 16, 17, 31, 32, 33, 63, 64, 65, 70]
+    for i, nf in enumerate(sizes):
+        for t in rng.choice(n_teams, nf, replace=False):
+            rels.append(f"namespace:n{i}#viewer@team:t{t}#member")
+    for u in range(1, 18):
+        for g in rng.choice(300, u, replace=False):
+            rels.append(f"group:g{g}#member@user:u{u}")
+    for i in range(len(sizes)):
+        for u in range(1, 18):
+            checks.append(f"namespace:n{i}#view@user:u{u}")
+    c = zgpu.client.PermissionsClient(schema, rels)
+    o = Oracle(schema)
+    for r in rels:
+        o.touch(r)
+    got = c.engine.check_bulk_str(checks)
+    want = np.array([o.check_rel(q) for q in checks], dtype=np.uint8)
+    assert np.array_equal(got, want), [checks[i] for i in np.flatnonzero(got != want)[:5]]
+    assert 0.1 < (got == 2).mean() < 0.9
