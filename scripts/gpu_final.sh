@@ -19,8 +19,15 @@ for wl in cfg3 cfg4; do
     python bench.py --workload $wl --configs '' --steps 2 --warmup 3 --no-cpu-baseline --sustain-s 0 > /dev/null 2> gpurun_out/${tag}_ncu_full_${wl}.err
 done
 timeout 600 python scripts/write_bench.py --writes 6 > gpurun_out/${tag}_write_bench.json 2> gpurun_out/${tag}_write_bench.err; cut -c1-400 gpurun_out/${tag}_write_bench.json
-K="golden or fixed_schemas or depth_cap or expiration or incremental_publish_equals or known_divergence or device_resident_sharded_store_depth"
+K="two_level_meet or golden or fixed_schemas or depth_cap or expiration or incremental_publish_equals or known_divergence or device_resident_sharded_store_depth"
 ( timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_zz_gpu_new_paths.py -q -x -p no:cacheprovider -k "$K" 2>&1 | tail -25 ) > gpurun_out/${tag}_compute_sanitizer_memcheck.log
 tail -4 gpurun_out/${tag}_compute_sanitizer_memcheck.log
-( timeout 600 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -q -x -p no:cacheprovider -k "fixed_schemas or baseline_configs_scaled or depth_cap" 2>&1 | tail -25 ) > gpurun_out/${tag}_compute_sanitizer_racecheck.log
+( timeout 600 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_zz_gpu_new_paths.py -q -x -p no:cacheprovider -k "two_level_meet or fixed_schemas or baseline_configs_scaled or depth_cap" 2>&1 | tail -25 ) > gpurun_out/${tag}_compute_sanitizer_racecheck.log
 tail -4 gpurun_out/${tag}_compute_sanitizer_racecheck.log
+# config 5 at the C ABI on this one GPU (the 8-GPU run is scripts/gpu_multi2.sh) and filtered kube lists on real bodies
+for sc in 0.1 1.0; do
+  timeout 600 python scripts/cfg5_replay.py --scale $sc --devices 1 --rounds 4 > gpurun_out/${tag}_cfg5_1gpu_s$sc.json 2> gpurun_out/${tag}_cfg5_1gpu_s$sc.err
+  echo "cfg5 $sc rc=$?"; python -c "
+import json; b=json.load(open('gpurun_out/${tag}_cfg5_1gpu_s$sc.json')); print('CFG5 $sc lists/s', round(b['postfilter']['filtered_lists_per_s']), 'lookups/s', round(b['prefilter']['lookups_per_s']), 'mixed', round(b['mixed']['filtered_lists_per_s']))"
+done
+timeout 600 python scripts/list_replay.py --clients 256 --rounds 2 > gpurun_out/${tag}_list_replay.json 2> gpurun_out/${tag}_list_replay.err; echo "list_replay rc=$?"; cut -c1-500 gpurun_out/${tag}_list_replay.json

@@ -263,7 +263,10 @@ std::string gpu_build_snapshot(const Store& store, const Schema& sc, HostSnapsho
   }
   const size_t nu = n_unique ? n_unique : 1;
   // + 64: the check kernel streams rows with aligned 128-bit loads, which may read (and ignore) up to 12 bytes past a row
-  if (!s->col.ensure(nu * 4 + 64) || !s->rcol.ensure(nu * 4 + 64) || (with_exp && !s->exp.ensure(nu * 4 + 64)) ||
+  // edge arrays of a large store get the growth headroom of the incremental publish from the start (see below)
+  const size_t edge_bytes = static_cast<size_t>(nu) * 4 + 64,
+               edge_cap = nu >= (1u << 20) ? edge_bytes + edge_bytes / 32 + (4u << 20) : edge_bytes;
+  if (!s->col.ensure(edge_cap) || !s->rcol.ensure(edge_cap) || (with_exp && !s->exp.ensure(edge_cap)) ||
       !d_rkey[0].ensure(nu * 8) || !d_rkey[1].ensure(nu * 8) || !d_rres[0].ensure(nu * 4) || !d_rres[1].ensure(nu * 4))
     return "out of device memory (edge arrays)";
   if (n) {
@@ -303,6 +306,16 @@ std::string gpu_build_snapshot(const Store& store, const Schema& sc, HostSnapsho
   s->type_ncls = lay->type_ncls;
   s->n_objects = lay->n_objects;
   s->delta_ok = true;
+  if (nu >= (1u << 20)) {
+    // The alternates of the incremental publish (merge_direction), with its headroom, come with the snapshot: the first
+    // write after a bulk load must not pay for three store-sized allocations (8 .. 560 ms, profiles/r2l_write_bench.json).
+    // Best effort: a failure here is met again, and reported, by the write that needs them.
+    const size_t need = static_cast<size_t>(nu) * 4 + 64, roomy = need + need / 32 + (4u << 20);
+    s->col_alt.ensure(roomy);
+    s->rcol_alt.ensure(roomy);
+    if (with_exp) s->exp_alt.ensure(roomy);
+    cudaGetLastError();
+  }
   {
     std::string rerr = gpu_resource_lists(s, st);
     if (!rerr.empty()) return rerr;
@@ -361,7 +374,10 @@ std::string merge_direction(const HostDelta& h, bool with_exp, DevBuf& row_ptr, 
   if (keys) delta_locate_kernel<<<static_cast<unsigned>((keys + blk - 1) / blk), blk, 0, st>>>(row_ptr.as<uint32_t>(),
                                                                                              edges.as<uint32_t>(), d, d_bad);
   if (ni || nd) {
-    if (!edges_alt.ensure(std::max<uint64_t>(n_new, 1) * 4 + 64) || (with_exp && !exp_alt.ensure(std::max<uint64_t>(n_new, 1) * 4 + 64)))
+    // headroom when the alternate has to grow (3 % + 4 MB): without it every write that adds edges re-allocates a
+    // store-sized buffer, and a cudaMalloc / cudaFree of 400 MB costs 100 ms on some boxes (profiles/r2k_write_bench.json)
+    const size_t need = std::max<uint64_t>(n_new, 1) * 4 + 64, roomy = need + need / 32 + (4u << 20);
+    if (!edges_alt.ensure(edges_alt.cap < need ? roomy : need) || (with_exp && !exp_alt.ensure(exp_alt.cap < need ? roomy : need)))
       return "out of device memory (edge arrays)";
     if (n_old)
       delta_merge_kernel<<<static_cast<unsigned>((n_old + kMergeTile - 1) / kMergeTile), 256, 0, st>>>(

@@ -178,7 +178,11 @@ definition namespace { relation viewer: team#member  permission view = viewer }"
     for i in range(len(sizes)):
         for u in range(1, 18):
             checks.append(f"namespace:n{i}#view@user:u{u}")
-    c = zgpu.client.PermissionsClient(schema, rels)
+    C = zgpu.client
+    c = C.PermissionsClient(schema)
+    for i in range(0, len(rels), 1000):  # a write carries at most 1 000 updates (pkg/spicedb/spicedb.go:34)
+        c.WriteRelationships(C.WriteRelationshipsRequest(
+            [C.RelationshipUpdate(C.OPERATION_TOUCH, C.Relationship.parse(r)) for r in rels[i:i + 1000]]))
     o = Oracle(schema)
     for r in rels:
         o.touch(r)
