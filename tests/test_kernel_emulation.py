@@ -152,6 +152,23 @@ definition namespace { relation viewer: team#member  permission view = viewer }"
     assert 0.1 < (got == 2).mean() < 0.9  # both answers occur
 
 
+def test_two_level_meet_filter_false_positives_die_in_the_search_under_the_emulator(emu):
+    """Ids that collide in the filter of the range's children (tests/l2_cases.py): the subject reaches a team that the
+    filter cannot tell from a child of the range; only the search behind the filter may answer."""
+    import l2_cases as L
+
+    e = emu.EmuEngine(L.L2_SCHEMA)
+    e.write_rels(L.padding_rels(), split_rel)
+    rels, cases = L.collision_cases(lambda name: e._id("team", name, False))
+    e.write_rels(rels, split_rel)
+    e.publish()
+    got = e.check_bulk(e.items_from_strings([q for q, _ in cases], split_rel))
+    assert [int(x) for x in got] == [w for _, w in cases]
+    e2 = emu.EmuEngine(L.L2_SCHEMA)  # forward-only probes agree
+    e2.write_rels(L.padding_rels() + rels, split_rel), e2.publish()
+    assert np.array_equal(e2.check_bulk(e2.items_from_strings([q for q, _ in cases], split_rel), emu.default_opts(invert=0)), got)
+
+
 @pytest.mark.parametrize("wl,scale,n", [("cfg2", 0.01, 2000), ("cfg3", 0.003, 3000), ("cfg4", 0.001, 3000)])
 def test_baseline_workloads_scaled_under_the_emulator(emu, wl, scale, n):
     """The BASELINE shapes (scaled): cfg3 resolves every namespace -> team -> group range by the two-level meet in the

@@ -190,3 +190,24 @@ definition namespace { relation viewer: team#member  permission view = viewer }"
     want = np.array([o.check_rel(q) for q in checks], dtype=np.uint8)
     assert np.array_equal(got, want), [checks[i] for i in np.flatnonzero(got != want)[:5]]
     assert 0.1 < (got == 2).mean() < 0.9
+
+
+def test_two_level_meet_filter_false_positives_die_in_the_search():
+    """Ids that collide in the filter over a range's children (tests/l2_cases.py): the filter lets the subject's team
+    through, the search behind it must say no. Same cases as under the emulator."""
+    import l2_cases as L
+    import zgpu
+
+    C = zgpu.client
+    c = C.PermissionsClient(L.L2_SCHEMA)
+
+    def write(rels):
+        for i in range(0, len(rels), 1000):
+            c.WriteRelationships(C.WriteRelationshipsRequest(
+                [C.RelationshipUpdate(C.OPERATION_TOUCH, C.Relationship.parse(r)) for r in rels[i:i + 1000]]))
+
+    write(L.padding_rels())
+    rels, cases = L.collision_cases(lambda name: int(c.engine.find("team", name)))
+    write(rels)
+    got = c.engine.check_bulk_str([q for q, _ in cases])
+    assert [int(x) for x in got] == [w for _, w in cases]
