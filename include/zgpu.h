@@ -326,9 +326,17 @@ typedef struct zg_list_item {
 #define ZG_ITEM_IS_OBJECT 1u    /* the item is a JSON object (others are never checked)  */
 #define ZG_ITEM_HAS_METADATA 2u /* ... with an object-valued "metadata"                  */
 #define ZG_ITEM_HAS_OBJECT 4u   /* table rows: the row has an "object" key (any value)   */
+#define ZG_ITEM_RAW_NAMES 8u    /* name / namespace ranges are plain bytes (protobuf), not escaped JSON */
 #define ZG_LIST_ITEMS 0u        /* scan "items"; metadata at item level                  */
 #define ZG_LIST_TABLE_ROWS 1u   /* scan "rows"; metadata under rows[i].object (metav1.Table,
                                    pkg/authz/responsefilterer.go:349-374)                */
+#define ZG_LIST_PROTOBUF 2u     /* a protobuf-encoded <Kind>List (Content-Type application/vnd.kubernetes.protobuf,
+                                   pkg/authz/responsefilterer.go:256-266,:301-313): magic "k8s\0", runtime.Unknown,
+                                   raw = { ListMeta metadata = 1; repeated <Kind> items = 2 }. Items: begin/end =
+                                   the whole `items` entry (tag, length, message), names = plain bytes;
+                                   *items_begin = offset of raw's length varint, *items_end = end of raw. Only
+                                   the pre-filter has a protobuf path in the reference (the post-filter
+                                   json.Unmarshals the body, postfilter.go:19). */
 #define ZG_LIST_EMPTY_AS_NULL 1u /* zg_list_filter flag: nothing kept -> null, not []    */
 /* Scans a kube List (or Table) body. Returns the number of elements of the top-level "items" ("rows") array
  * (0 if there is no such array: the reference then passes the body through), ZG_EINVAL on
@@ -337,7 +345,8 @@ typedef struct zg_list_item {
 int64_t zg_list_scan(const char *body, size_t len, uint32_t mode, zg_list_item *out, uint64_t cap,
                      uint64_t *items_begin, uint64_t *items_end);
 /* Writes the body with only the items whose keep[i] != 0; every other byte is preserved.
- * With nothing kept the array becomes `[]` (the pre-filter's filterList / filterTable,
+ * A protobuf body (recognised by its magic) loses the dropped `items` entries and gets the length of `raw` rewritten;
+ * pass the items_begin / items_end its scan returned. With nothing kept the JSON array becomes `[]` (the pre-filter's filterList / filterTable,
  * responsefilterer.go:356,377) or, with ZG_LIST_EMPTY_AS_NULL, `null` (the post-filter's re-marshal of
  * a nil slice, postfilter.go:138). Returns 0, or ZG_E2BIG with *out_len = bytes required. */
 int zg_list_filter(const char *body, size_t len, const zg_list_item *items, uint64_t n,

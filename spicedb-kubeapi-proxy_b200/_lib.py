@@ -84,8 +84,8 @@ class _ListItem(C.Structure):
 
 LIST_ITEM_DTYPE = np.dtype([("begin", "<u8"), ("end", "<u8"), ("name_off", "<u8"), ("ns_off", "<u8"),
                             ("name_len", "<u4"), ("ns_len", "<u4"), ("flags", "<u4"), ("reserved", "<u4")])
-ITEM_IS_OBJECT, ITEM_HAS_METADATA, ITEM_HAS_OBJECT = 1, 2, 4
-LIST_ITEMS, LIST_TABLE_ROWS = 0, 1
+ITEM_IS_OBJECT, ITEM_HAS_METADATA, ITEM_HAS_OBJECT, ITEM_RAW_NAMES = 1, 2, 4, 8
+LIST_ITEMS, LIST_TABLE_ROWS, LIST_PROTOBUF = 0, 1, 2
 LIST_EMPTY_AS_NULL = 1
 
 
@@ -237,7 +237,9 @@ def split_rel(rel: str):
 
 def list_scan(body: bytes, mode: int = LIST_ITEMS):
     """zg_list_scan: (items structured array, items_begin, items_end), or None when the body has no
-    top-level "items" ("rows" with LIST_TABLE_ROWS) array. Raises ZgpuError(-1) on malformed JSON."""
+    top-level "items" ("rows" with LIST_TABLE_ROWS) array. LIST_PROTOBUF: a protobuf-encoded <Kind>List
+    (items = whole `items` entries, items_begin = offset of raw's length, items_end = end of raw).
+    Raises ZgpuError(-1) on a malformed body."""
     L = lib()
     ib, ie = C.c_uint64(0), C.c_uint64(0)
     cap = len(body) // 128 + 16  # an item is rarely shorter; untouched pages of the buffer cost nothing

@@ -1202,7 +1202,10 @@ extern "C" int zg_list_resolve(zg_engine* e, const char* body, size_t len, const
       return fail(ZG_EINVAL, "item range outside the body");
     name.clear();
     ns.clear();
-    if (it.flags & ZG_ITEM_HAS_METADATA) {
+    if ((it.flags & ZG_ITEM_HAS_METADATA) && (it.flags & ZG_ITEM_RAW_NAMES)) {
+      name.assign(body + it.name_off, it.name_len);
+      ns.assign(body + it.ns_off, it.ns_len);
+    } else if (it.flags & ZG_ITEM_HAS_METADATA) {
       json_unescape_append(body + it.name_off, it.name_len, &name);
       json_unescape_append(body + it.ns_off, it.ns_len, &ns);
     }
@@ -1563,7 +1566,7 @@ extern "C" int zg_list_keep_allowed(zg_engine* e, const char* body, size_t len, 
                                     uint64_t n_allowed, const char* self_name, uint8_t* keep) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if (!res_type || ((!body || !items || !keep) && n) || (!allowed && n_allowed)) return fail(ZG_EINVAL, "NULL argument");
-  if (mode > ZG_LIST_TABLE_ROWS) return fail(ZG_EINVAL, "unknown mode");
+  if (mode > ZG_LIST_PROTOBUF) return fail(ZG_EINVAL, "unknown mode");
   LOCK_NAMES_SHARED(e);
   const int rt = e->schema.type_id(res_type);
   if (rt < 0) return fail(ZG_EINVAL, std::string("object definition `") + res_type + "` not found");
@@ -1584,7 +1587,10 @@ extern "C" int zg_list_keep_allowed(zg_engine* e, const char* body, size_t len, 
       return fail(ZG_EINVAL, "item range outside the body");
     name.clear();
     ns.clear();
-    if (it.flags & ZG_ITEM_HAS_METADATA) {
+    if ((it.flags & ZG_ITEM_HAS_METADATA) && (it.flags & ZG_ITEM_RAW_NAMES)) {
+      name.assign(body + it.name_off, it.name_len);  // protobuf strings: plain bytes
+      ns.assign(body + it.ns_off, it.ns_len);
+    } else if (it.flags & ZG_ITEM_HAS_METADATA) {
       json_unescape_append(body + it.name_off, it.name_len, &name);
       json_unescape_append(body + it.ns_off, it.ns_len, &ns);
     }
@@ -1605,7 +1611,7 @@ extern "C" int zg_list_prefilter(zg_engine* e, const char* body, size_t len, uin
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if (!body || !out_len || !tpl) return fail(ZG_EINVAL, "NULL argument");
   if (!tpl->res_type || !tpl->permission || !tpl->subj_type || !tpl->subj_id) return fail(ZG_EINVAL, "NULL template field");
-  if (mode > ZG_LIST_TABLE_ROWS) return fail(ZG_EINVAL, "unknown mode");
+  if (mode > ZG_LIST_PROTOBUF) return fail(ZG_EINVAL, "unknown mode");
   // 1. the allowed ids (one LookupResources on the GPU; concurrent list requests share launches)
   std::vector<uint32_t> ids;
   std::string self;

@@ -330,9 +330,200 @@ bool scan_item(Cur& c, zg_list_item* it, uint32_t mode) {
 
 }  // namespace
 
+
+// ---- protobuf-encoded lists (application/vnd.kubernetes.protobuf) --------------------------------
+// The reference decodes a list response with the serializer the Content-Type names
+// (pkg/authz/responsefilterer.go:256-266, :301-313); for built-in types kube clients ask for protobuf. Wire format
+// (k8s.io/apimachinery v0.34.1, pinned in the reference's go.mod; not vendored there, restated from the published
+// .proto files: pkg/runtime/generated.proto, pkg/apis/meta/v1/generated.proto, pkg/runtime/serializer/protobuf):
+//   body   = 'k' '8' 's' 0x00  Unknown
+//   Unknown  { TypeMeta typeMeta = 1; bytes raw = 2; string contentEncoding = 3; string contentType = 4; }
+//   raw      = <Kind>List { ListMeta metadata = 1; repeated <Kind> items = 2; }
+//   <Kind>   { ObjectMeta metadata = 1; ... }      ObjectMeta { string name = 1; ... string namespace = 3; ... }
+// The filter drops `items` entries and rewrites ONE length (that of `raw`); every other byte is preserved.
+namespace {
+
+struct Pb {
+  const uint8_t* s;
+  size_t n, i;
+};
+inline bool pb_varint(Pb& c, uint64_t* v) {
+  uint64_t r = 0;
+  for (int shift = 0; shift < 64; shift += 7) {
+    if (c.i >= c.n) return false;
+    const uint8_t b = c.s[c.i++];
+    r |= static_cast<uint64_t>(b & 0x7F) << shift;
+    if (!(b & 0x80)) {
+      *v = r;
+      return true;
+    }
+  }
+  return false;  // more than 10 bytes
+}
+// One field: *num / *wt, and for length-delimited fields the payload range [*b, *e). Skips the value.
+inline bool pb_field(Pb& c, uint32_t* num, uint32_t* wt, size_t* b, size_t* e, size_t* len_at = nullptr) {
+  uint64_t tag, v;
+  if (!pb_varint(c, &tag) || (tag >> 3) == 0 || (tag >> 3) > 0x1FFFFFFFull) return false;
+  *num = static_cast<uint32_t>(tag >> 3);
+  *wt = static_cast<uint32_t>(tag & 7);
+  *b = *e = c.i;
+  if (len_at) *len_at = c.i;
+  switch (*wt) {
+    case 0: return pb_varint(c, &v);
+    case 1:
+      if (c.n - c.i < 8) return false;
+      c.i += 8;
+      return true;
+    case 2:
+      if (!pb_varint(c, &v) || v > c.n - c.i) return false;
+      *b = c.i;
+      *e = c.i + static_cast<size_t>(v);
+      c.i = *e;
+      return true;
+    case 5:
+      if (c.n - c.i < 4) return false;
+      c.i += 4;
+      return true;
+    default: return false;  // groups: never emitted by kube's generated marshallers
+  }
+}
+inline size_t pb_varint_len(uint64_t v) {
+  size_t n = 1;
+  while (v >= 0x80) {
+    v >>= 7;
+    ++n;
+  }
+  return n;
+}
+inline size_t pb_put_varint(char* out, uint64_t v) {
+  size_t n = 0;
+  while (v >= 0x80) {
+    out[n++] = static_cast<char>((v & 0x7F) | 0x80);
+    v >>= 7;
+  }
+  out[n++] = static_cast<char>(v);
+  return n;
+}
+constexpr char kPbMagic[4] = {'k', '8', 's', 0};
+
+// Locates `raw` inside the envelope: *len_pos = offset of its length varint, [*rb, *re) its payload.
+// found = false when the Unknown has no raw field (an empty object).
+bool pb_envelope(const char* body, size_t len, size_t* len_pos, size_t* rb, size_t* re, bool* found) {
+  *found = false;
+  if (len < 4 || std::memcmp(body, kPbMagic, 4) != 0) return false;
+  Pb c{reinterpret_cast<const uint8_t*>(body), len, 4};
+  while (c.i < c.n) {
+    uint32_t num, wt;
+    size_t b, e, at;
+    if (!pb_field(c, &num, &wt, &b, &e, &at)) return false;
+    if (num == 2) {
+      if (wt != 2) return false;
+      // proto3 / gogo semantics for a repeated scalar-bytes field seen twice: last wins. Kube emits it once;
+      // a second one would make "the raw the reference filters" ambiguous for a splice: refuse (fail closed).
+      if (*found) return false;
+      *found = true;
+      *rb = b;
+      *re = e;
+      *len_pos = at;
+    }
+  }
+  return true;
+}
+
+int64_t pb_scan(const char* body, size_t len, zg_list_item* out, uint64_t cap, uint64_t* items_begin, uint64_t* items_end) {
+  size_t len_pos = 0, rb = 0, re = 0;
+  bool found = false;
+  if (!pb_envelope(body, len, &len_pos, &rb, &re, &found)) return ZG_EINVAL;
+  if (items_begin) *items_begin = found ? len_pos : 0;
+  if (items_end) *items_end = found ? re : 0;
+  if (!found) return 0;
+  Pb c{reinterpret_cast<const uint8_t*>(body), re, rb};
+  int64_t n = 0;
+  while (c.i < c.n) {
+    const size_t at = c.i;
+    uint32_t num, wt;
+    size_t b, e;
+    if (!pb_field(c, &num, &wt, &b, &e)) return ZG_EINVAL;
+    if (num != 2) continue;  // ListMeta (1) and anything newer: kept as they are
+    if (wt != 2) return ZG_EINVAL;
+    zg_list_item it{};
+    it.begin = at;  // the whole entry: tag, length, message
+    it.end = e;
+    it.flags = ZG_ITEM_IS_OBJECT | ZG_ITEM_RAW_NAMES;
+    // the item message: its ObjectMeta is field 1 (last one wins, as a decoder would merge ... kube emits one)
+    Pb m{c.s, e, b};
+    while (m.i < m.n) {
+      uint32_t fn, fw;
+      size_t fb, fe;
+      if (!pb_field(m, &fn, &fw, &fb, &fe)) return ZG_EINVAL;
+      if (fn != 1) continue;
+      if (fw != 2) return ZG_EINVAL;
+      it.flags |= ZG_ITEM_HAS_METADATA;
+      Pb o{c.s, fe, fb};
+      while (o.i < o.n) {
+        uint32_t on, ow;
+        size_t ob, oe;
+        if (!pb_field(o, &on, &ow, &ob, &oe)) return ZG_EINVAL;
+        if (on != 1 && on != 3) continue;
+        if (ow != 2 || oe - ob > 0xFFFFFFFFull) return ZG_EINVAL;
+        if (on == 1) {
+          it.name_off = ob;
+          it.name_len = static_cast<uint32_t>(oe - ob);
+        } else {
+          it.ns_off = ob;
+          it.ns_len = static_cast<uint32_t>(oe - ob);
+        }
+      }
+    }
+    if (static_cast<uint64_t>(n) < cap && out) out[n] = it;
+    ++n;
+  }
+  if (out && static_cast<uint64_t>(n) > cap) return ZG_E2BIG;
+  return n;
+}
+
+int pb_filter(const char* body, size_t len, const zg_list_item* items, uint64_t n, const uint8_t* keep, uint64_t len_pos,
+              uint64_t raw_end, char* out, size_t cap, size_t* out_len) {
+  if (len_pos < 5 || len_pos >= raw_end || raw_end > len) return ZG_EINVAL;
+  Pb c{reinterpret_cast<const uint8_t*>(body), static_cast<size_t>(raw_end), static_cast<size_t>(len_pos)};
+  uint64_t raw_len;
+  if (!pb_varint(c, &raw_len) || raw_len != raw_end - c.i) return ZG_EINVAL;
+  const size_t rb = c.i;
+  uint64_t dropped = 0, prev_end = rb;
+  for (uint64_t i = 0; i < n; ++i) {  // entries in body order, inside raw, not overlapping
+    if (items[i].begin < prev_end || items[i].begin > items[i].end || items[i].end > raw_end) return ZG_EINVAL;
+    prev_end = items[i].end;
+    if (!keep[i]) dropped += items[i].end - items[i].begin;
+  }
+  const uint64_t new_raw = raw_len - dropped;
+  const size_t need = len_pos + pb_varint_len(new_raw) + static_cast<size_t>(new_raw) + (len - raw_end);
+  *out_len = need;
+  if (need > cap || !out) return ZG_E2BIG;
+  size_t w = 0;
+  std::memcpy(out, body, len_pos);
+  w = len_pos;
+  w += pb_put_varint(out + w, new_raw);
+  size_t from = rb;
+  for (uint64_t i = 0; i < n; ++i)
+    if (!keep[i]) {
+      std::memcpy(out + w, body + from, items[i].begin - from);
+      w += items[i].begin - from;
+      from = items[i].end;
+    }
+  std::memcpy(out + w, body + from, raw_end - from);
+  w += raw_end - from;
+  std::memcpy(out + w, body + raw_end, len - raw_end);
+  w += len - raw_end;
+  *out_len = w;
+  return ZG_OK;
+}
+
+}  // namespace
+
 extern "C" int64_t zg_list_scan(const char* body, size_t len, uint32_t mode, zg_list_item* out, uint64_t cap,
                                 uint64_t* items_begin, uint64_t* items_end) {
-  if (!body || mode > ZG_LIST_TABLE_ROWS) return ZG_EINVAL;
+  if (!body || mode > ZG_LIST_PROTOBUF) return ZG_EINVAL;
+  if (mode == ZG_LIST_PROTOBUF) return pb_scan(body, len, out, cap, items_begin, items_end);
   const char* const array_key = mode == ZG_LIST_ITEMS ? "items" : "rows";
   Cur c{body, len, 0, true};
   ws(c);
@@ -392,6 +583,8 @@ extern "C" int zg_list_filter(const char* body, size_t len, const zg_list_item* 
                               size_t* out_len) {
   if (!body || (!items && n) || (!keep && n) || !out_len) return ZG_EINVAL;
   if (items_begin > items_end || items_end > len) return ZG_EINVAL;
+  if (len >= 4 && std::memcmp(body, kPbMagic, 4) == 0)  // a protobuf body (no JSON document starts with 'k')
+    return pb_filter(body, len, items, n, keep, items_begin, items_end, out, cap, out_len);
   size_t need = items_begin + (len - items_end);
   uint64_t kept = 0;
   for (uint64_t i = 0; i < n; ++i)

@@ -224,13 +224,25 @@ def _filter_by_result(body: bytes, result: PrefilterResult, mode: int, what: str
         if mode == _lib.LIST_TABLE_ROWS and not flags & _lib.ITEM_HAS_OBJECT:
             # an empty RawExtension does not decode (responsefilterer.go:361-365)
             raise ValueError("error decoding partial object metadata from table row")
-        keep[i] = result.IsAllowed(_text(body, int(it["ns_off"]), int(it["ns_len"])),
-                                   _text(body, int(it["name_off"]), int(it["name_len"])))
+        if flags & _lib.ITEM_RAW_NAMES:  # protobuf strings: plain UTF-8, nothing to unescape
+            ns = body[int(it["ns_off"]):int(it["ns_off"]) + int(it["ns_len"])].decode("utf-8", "replace")
+            name = body[int(it["name_off"]):int(it["name_off"]) + int(it["name_len"])].decode("utf-8", "replace")
+        else:
+            ns = _text(body, int(it["ns_off"]), int(it["ns_len"]))
+            name = _text(body, int(it["name_off"]), int(it["name_len"]))
+        keep[i] = result.IsAllowed(ns, name)
     return _lib.list_filter(body, items, keep, ib, ie)
 
 
-def filter_list(body: bytes, result: PrefilterResult) -> bytes:
-    """responsefilterer.go:376-400: keep the items whose (namespace, name) is allowed; [] when none."""
+PROTOBUF_MEDIA_TYPE = "application/vnd.kubernetes.protobuf"
+
+
+def filter_list(body: bytes, result: PrefilterResult, content_type: str = "application/json") -> bytes:
+    """responsefilterer.go:376-400: keep the items whose (namespace, name) is allowed; [] when none. The body is
+    decoded with the serializer its Content-Type names (responsefilterer.go:241-266): JSON, or kube's protobuf
+    envelope for built-in types -- there the dropped `items` entries disappear and every other byte stays."""
+    if content_type.split(";")[0].strip() == PROTOBUF_MEDIA_TYPE:
+        return _filter_by_result(body, result, _lib.LIST_PROTOBUF, "list")
     return _filter_by_result(body, result, _lib.LIST_ITEMS, "list")
 
 

@@ -95,6 +95,96 @@ int main(int argc, char** argv) {
     }
     std::free(body);
   }
-  std::printf("ok iterations=%ld accepted=%ld filtered=%ld\n", iters, accepted, filtered);
+  // ---- protobuf-encoded lists (mode ZG_LIST_PROTOBUF): byte-level mutations of small valid envelopes
+  auto put_varint = [](std::string& o, uint64_t v) {
+    while (v >= 0x80) {
+      o.push_back(static_cast<char>((v & 0x7F) | 0x80));
+      v >>= 7;
+    }
+    o.push_back(static_cast<char>(v));
+  };
+  auto field = [&](std::string& o, uint32_t num, const std::string& payload) {
+    put_varint(o, (static_cast<uint64_t>(num) << 3) | 2);
+    put_varint(o, payload.size());
+    o += payload;
+  };
+  long pb_accepted = 0, pb_filtered = 0;
+  for (long it = 0; it < iters / 2; ++it) {
+    std::string raw, lm;
+    field(lm, 2, "12345");  // ListMeta.resourceVersion
+    field(raw, 1, lm);
+    const int ni = static_cast<int>(rnd() % 5);
+    for (int i = 0; i < ni; ++i) {
+      std::string om, item;
+      if (rnd() % 8) field(om, 1, std::string(1 + rnd() % 140, static_cast<char>('a' + i)));
+      if (rnd() % 3) field(om, 3, "ns-" + std::to_string(rnd() % 3));
+      field(om, 5, "uid");
+      if (rnd() % 8) field(item, 1, om);
+      field(item, 2, std::string(rnd() % 200, 's'));
+      if (rnd() % 4 == 0) {  // a varint and a fixed64 field the scanner must skip
+        put_varint(item, (7u << 3) | 0);
+        put_varint(item, rnd());
+        put_varint(item, (9u << 3) | 1);
+        item += std::string(8, '\x01');
+      }
+      field(raw, 2, item);
+    }
+    std::string s("k8s\0", 4), tm;
+    field(tm, 1, "v1");
+    field(tm, 2, "PodList");
+    field(s, 1, tm);
+    field(s, 2, raw);
+    field(s, 3, "");
+    field(s, 4, "");
+    const int muts = static_cast<int>(rnd() % 3);
+    for (int m = 0; m < muts && !s.empty(); ++m) {
+      const size_t p = rnd() % s.size();
+      switch (rnd() % 5) {
+        case 0: s[p] = static_cast<char>(rnd()); break;
+        case 1: s.erase(p, 1 + rnd() % 3); break;
+        case 2: s.insert(p, 1, static_cast<char>(rnd())); break;
+        case 3: s.resize(p); break;
+        default: s[p] = static_cast<char>(s[p] ^ (1 << (rnd() % 8))); break;
+      }
+    }
+    char* body = static_cast<char*>(std::malloc(s.size() ? s.size() : 1));
+    std::memcpy(body, s.data(), s.size());
+    uint64_t ib = 0, ie = 0;
+    const int64_t n = zg_list_scan(body, s.size(), ZG_LIST_PROTOBUF, items.data(), items.size(), &ib, &ie);
+    if (n < 0) {
+      if (n != ZG_EINVAL && n != ZG_E2BIG) return std::printf("pb: unexpected code %lld\n", static_cast<long long>(n)), 1;
+      std::free(body);
+      continue;
+    }
+    ++pb_accepted;
+    if (ib > ie || ie > s.size()) return std::printf("pb: raw range out of bounds\n"), 1;
+    if (n > 0) {
+      uint64_t prev = ib;
+      int64_t kept = 0;
+      for (int64_t i = 0; i < n; ++i) {
+        const zg_list_item& x = items[static_cast<size_t>(i)];
+        if (x.begin < prev || x.end < x.begin || x.end > ie) return std::printf("pb: item range out of order\n"), 1;
+        if (x.name_len && (x.name_off < x.begin || x.name_off + x.name_len > x.end)) return std::printf("pb: name range\n"), 1;
+        if (x.ns_len && (x.ns_off < x.begin || x.ns_off + x.ns_len > x.end)) return std::printf("pb: ns range\n"), 1;
+        prev = x.end;
+        kept += (keep[static_cast<size_t>(i)] = rnd() & 1);
+      }
+      size_t need = 0;
+      if (zg_list_filter(body, s.size(), items.data(), static_cast<uint64_t>(n), keep.data(), ib, ie, 0, nullptr, 0, &need) != ZG_E2BIG)
+        return std::printf("pb: size query did not return E2BIG\n"), 1;
+      char* o = static_cast<char*>(std::malloc(need ? need : 1));
+      size_t wrote = 0;
+      if (zg_list_filter(body, s.size(), items.data(), static_cast<uint64_t>(n), keep.data(), ib, ie, 0, o, need, &wrote) != ZG_OK || wrote != need)
+        return std::printf("pb: filter wrote %zu, announced %zu\n", wrote, need), 1;
+      uint64_t ib2, ie2;
+      const int64_t n2 = zg_list_scan(o, wrote, ZG_LIST_PROTOBUF, nullptr, 0, &ib2, &ie2);
+      if (n2 != kept) return std::printf("pb: rescan found %lld items, kept %lld\n", static_cast<long long>(n2), static_cast<long long>(kept)), 1;
+      std::free(o);
+      ++pb_filtered;
+    }
+    std::free(body);
+  }
+  std::printf("ok iterations=%ld accepted=%ld filtered=%ld pb_accepted=%ld pb_filtered=%ld\n", iters, accepted, filtered, pb_accepted,
+              pb_filtered);
   return 0;
 }

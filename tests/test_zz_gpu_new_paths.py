@@ -211,3 +211,27 @@ def test_two_level_meet_filter_false_positives_die_in_the_search():
     write(rels)
     got = c.engine.check_bulk_str([q for q, _ in cases])
     assert [int(x) for x in got] == [w for _, w in cases]
+
+
+def test_prefilter_of_a_protobuf_encoded_list():
+    """zg_list_prefilter with ZG_LIST_PROTOBUF: LookupResources on the GPU, then the items of a protobuf-encoded PodList
+    (what kube clients receive for built-in types) whose namespace/name it returned are kept, byte for byte
+    (pkg/authz/responsefilterer.go:241-313,:376-400). Encoder / decoder: tests/test_listfilter_protobuf.py."""
+    import test_listfilter_protobuf as P
+    import zgpu
+    from spicedb_kubeapi_proxy_b200 import _lib
+
+    schema = """definition user {}
+definition namespace { relation viewer: user  permission view = viewer }
+definition pod { relation namespace: namespace  relation viewer: user  permission view = viewer + namespace->view }"""
+    c = zgpu.client.PermissionsClient(schema, ["namespace:n1#viewer@user:alice", "pod:n1/a#namespace@namespace:n1",
+                                               "pod:n1/b#namespace@namespace:n1", "pod:n2/c#namespace@namespace:n2",
+                                               "pod:n2/d#viewer@user:alice", "pod:n2/e#viewer@user:bob"])
+    pods = [P.pod("a", "n1"), P.pod("b", "n1"), P.pod("c", "n2"), P.pod("d", "n2"), P.pod("e", "n2"), P.pod("ghost", "n1")]
+    body = P.pod_list(pods)
+    tpl = c.engine.list_template("pod", "view", "user", "alice")
+    out = c.engine.list_prefilter(body, tpl, _lib.LIST_PROTOBUF)
+    assert P.decode_items(out) == [("n1", "a"), ("n1", "b"), ("n2", "d")]
+    assert out == P.pod_list([pods[0], pods[1], pods[3]])
+    nobody = c.engine.list_template("pod", "view", "user", "nobody")
+    assert P.decode_items(c.engine.list_prefilter(body, nobody, _lib.LIST_PROTOBUF)) == []
