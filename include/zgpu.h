@@ -337,6 +337,9 @@ typedef struct zg_list_item {
                                    *items_begin = offset of raw's length varint, *items_end = end of raw. Only
                                    the pre-filter has a protobuf path in the reference (the post-filter
                                    json.Unmarshals the body, postfilter.go:19). */
+#define ZG_LIST_PROTOBUF_OBJECT 3u /* zg_list_scan only: ONE protobuf-encoded object (a get: responsefilterer.go:320-341,
+                                     filterObject :403-415): a single item = the raw payload, with its names; the
+                                     caller passes the body through or answers "unauthorized" */
 #define ZG_LIST_EMPTY_AS_NULL 1u /* zg_list_filter flag: nothing kept -> null, not []    */
 /* Scans a kube List (or Table) body. Returns the number of elements of the top-level "items" ("rows") array
  * (0 if there is no such array: the reference then passes the body through), ZG_EINVAL on

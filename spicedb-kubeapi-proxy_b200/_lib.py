@@ -85,7 +85,7 @@ class _ListItem(C.Structure):
 LIST_ITEM_DTYPE = np.dtype([("begin", "<u8"), ("end", "<u8"), ("name_off", "<u8"), ("ns_off", "<u8"),
                             ("name_len", "<u4"), ("ns_len", "<u4"), ("flags", "<u4"), ("reserved", "<u4")])
 ITEM_IS_OBJECT, ITEM_HAS_METADATA, ITEM_HAS_OBJECT, ITEM_RAW_NAMES = 1, 2, 4, 8
-LIST_ITEMS, LIST_TABLE_ROWS, LIST_PROTOBUF = 0, 1, 2
+LIST_ITEMS, LIST_TABLE_ROWS, LIST_PROTOBUF, LIST_PROTOBUF_OBJECT = 0, 1, 2, 3
 LIST_EMPTY_AS_NULL = 1
 
 

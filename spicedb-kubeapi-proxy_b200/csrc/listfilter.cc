@@ -430,6 +430,57 @@ bool pb_envelope(const char* body, size_t len, size_t* len_pos, size_t* rb, size
   return true;
 }
 
+// One object message [b, e): its ObjectMeta is field 1 (the last one wins; kube emits one), name = 1, namespace = 3.
+bool pb_object_names(const uint8_t* s, size_t b, size_t e, zg_list_item* it) {
+  it->flags = ZG_ITEM_IS_OBJECT | ZG_ITEM_RAW_NAMES;
+  Pb m{s, e, b};
+  while (m.i < m.n) {
+    uint32_t fn, fw;
+    size_t fb, fe;
+    if (!pb_field(m, &fn, &fw, &fb, &fe)) return false;
+    if (fn != 1) continue;
+    if (fw != 2) return false;
+    it->flags |= ZG_ITEM_HAS_METADATA;
+    it->name_off = it->ns_off = 0;
+    it->name_len = it->ns_len = 0;
+    Pb o{s, fe, fb};
+    while (o.i < o.n) {
+      uint32_t on, ow;
+      size_t ob, oe;
+      if (!pb_field(o, &on, &ow, &ob, &oe)) return false;
+      if (on != 1 && on != 3) continue;
+      if (ow != 2 || oe - ob > 0xFFFFFFFFull) return false;
+      if (on == 1) {
+        it->name_off = ob;
+        it->name_len = static_cast<uint32_t>(oe - ob);
+      } else {
+        it->ns_off = ob;
+        it->ns_len = static_cast<uint32_t>(oe - ob);
+      }
+    }
+  }
+  return true;
+}
+
+// A single protobuf-encoded object (the `default:` branch of the reference's filter, responsefilterer.go:320-341):
+// one item = the raw payload itself.
+int64_t pb_scan_object(const char* body, size_t len, zg_list_item* out, uint64_t cap, uint64_t* items_begin,
+                       uint64_t* items_end) {
+  size_t len_pos = 0, rb = 0, re = 0;
+  bool found = false;
+  if (!pb_envelope(body, len, &len_pos, &rb, &re, &found)) return ZG_EINVAL;
+  if (items_begin) *items_begin = found ? len_pos : 0;
+  if (items_end) *items_end = found ? re : 0;
+  if (!found) return 0;
+  zg_list_item it{};
+  it.begin = rb;
+  it.end = re;
+  if (!pb_object_names(reinterpret_cast<const uint8_t*>(body), rb, re, &it)) return ZG_EINVAL;
+  if (out && cap < 1) return ZG_E2BIG;
+  if (out) out[0] = it;
+  return 1;
+}
+
 int64_t pb_scan(const char* body, size_t len, zg_list_item* out, uint64_t cap, uint64_t* items_begin, uint64_t* items_end) {
   size_t len_pos = 0, rb = 0, re = 0;
   bool found = false;
@@ -449,32 +500,7 @@ int64_t pb_scan(const char* body, size_t len, zg_list_item* out, uint64_t cap, u
     zg_list_item it{};
     it.begin = at;  // the whole entry: tag, length, message
     it.end = e;
-    it.flags = ZG_ITEM_IS_OBJECT | ZG_ITEM_RAW_NAMES;
-    // the item message: its ObjectMeta is field 1 (last one wins, as a decoder would merge ... kube emits one)
-    Pb m{c.s, e, b};
-    while (m.i < m.n) {
-      uint32_t fn, fw;
-      size_t fb, fe;
-      if (!pb_field(m, &fn, &fw, &fb, &fe)) return ZG_EINVAL;
-      if (fn != 1) continue;
-      if (fw != 2) return ZG_EINVAL;
-      it.flags |= ZG_ITEM_HAS_METADATA;
-      Pb o{c.s, fe, fb};
-      while (o.i < o.n) {
-        uint32_t on, ow;
-        size_t ob, oe;
-        if (!pb_field(o, &on, &ow, &ob, &oe)) return ZG_EINVAL;
-        if (on != 1 && on != 3) continue;
-        if (ow != 2 || oe - ob > 0xFFFFFFFFull) return ZG_EINVAL;
-        if (on == 1) {
-          it.name_off = ob;
-          it.name_len = static_cast<uint32_t>(oe - ob);
-        } else {
-          it.ns_off = ob;
-          it.ns_len = static_cast<uint32_t>(oe - ob);
-        }
-      }
-    }
+    if (!pb_object_names(c.s, b, e, &it)) return ZG_EINVAL;
     if (static_cast<uint64_t>(n) < cap && out) out[n] = it;
     ++n;
   }
@@ -522,8 +548,9 @@ int pb_filter(const char* body, size_t len, const zg_list_item* items, uint64_t 
 
 extern "C" int64_t zg_list_scan(const char* body, size_t len, uint32_t mode, zg_list_item* out, uint64_t cap,
                                 uint64_t* items_begin, uint64_t* items_end) {
-  if (!body || mode > ZG_LIST_PROTOBUF) return ZG_EINVAL;
+  if (!body || mode > ZG_LIST_PROTOBUF_OBJECT) return ZG_EINVAL;
   if (mode == ZG_LIST_PROTOBUF) return pb_scan(body, len, out, cap, items_begin, items_end);
+  if (mode == ZG_LIST_PROTOBUF_OBJECT) return pb_scan_object(body, len, out, cap, items_begin, items_end);
   const char* const array_key = mode == ZG_LIST_ITEMS ? "items" : "rows";
   Cur c{body, len, 0, true};
   ws(c);

@@ -251,8 +251,21 @@ def filter_table(body: bytes, result: PrefilterResult) -> bytes:
     return _filter_by_result(body, result, _lib.LIST_TABLE_ROWS, "table")
 
 
-def filter_object(body: bytes, result: PrefilterResult) -> bytes:
-    """responsefilterer.go:403-415: a single object passes unchanged or the request is unauthorized."""
+def filter_object(body: bytes, result: PrefilterResult, content_type: str = "application/json") -> bytes:
+    """responsefilterer.go:320-341, :403-415: a single object passes unchanged or the request is unauthorized."""
+    if content_type.split(";")[0].strip() == PROTOBUF_MEDIA_TYPE:
+        try:
+            scanned = _lib.list_scan(body, _lib.LIST_PROTOBUF_OBJECT)
+        except _lib.ZgpuError:
+            raise ValueError("failed to decode response body") from None
+        ns = name = ""
+        if scanned:  # an envelope without raw decodes to an empty object: no name, never allowed by name
+            it = scanned[0][0]
+            ns = body[int(it["ns_off"]):int(it["ns_off"]) + int(it["ns_len"])].decode("utf-8", "replace")
+            name = body[int(it["name_off"]):int(it["name_off"]) + int(it["name_len"])].decode("utf-8", "replace")
+        if not result.IsAllowed(ns, name):
+            raise Unauthorized("unauthorized")
+        return body
     wrapped = b'{"items":[' + body + b']}'  # reuse the item scanner for the one object
     try:
         scanned = _lib.list_scan(wrapped)

@@ -150,6 +150,14 @@ int main(int argc, char** argv) {
     char* body = static_cast<char*>(std::malloc(s.size() ? s.size() : 1));
     std::memcpy(body, s.data(), s.size());
     uint64_t ib = 0, ie = 0;
+    {  // the single-object view of the same bytes: one item, inside raw
+      zg_list_item one;
+      const int64_t n1 = zg_list_scan(body, s.size(), ZG_LIST_PROTOBUF_OBJECT, &one, 1, &ib, &ie);
+      if (n1 > 1 || (n1 < 0 && n1 != ZG_EINVAL)) return std::printf("pb object: code %lld\n", static_cast<long long>(n1)), 1;
+      if (n1 == 1 && (one.begin > one.end || one.end > ie || ie > s.size() ||
+                      (one.name_len && (one.name_off < one.begin || one.name_off + one.name_len > one.end))))
+        return std::printf("pb object: ranges\n"), 1;
+    }
     const int64_t n = zg_list_scan(body, s.size(), ZG_LIST_PROTOBUF, items.data(), items.size(), &ib, &ie);
     if (n < 0) {
       if (n != ZG_EINVAL && n != ZG_E2BIG) return std::printf("pb: unexpected code %lld\n", static_cast<long long>(n)), 1;

@@ -221,3 +221,25 @@ def test_random_lists_round_trip():
         keep = [rng.random() < 0.6 for _ in range(n)]
         out = _lib.list_filter(body, items, np.array(keep, dtype=np.uint8), ib, ie)
         assert out == pod_list([p for p, k in zip(pods, keep) if k], body.endswith(ld(4, b"")))
+
+
+def pod_object(p):
+    return MAGIC + ld(1, ld(1, b"v1") + ld(2, b"Pod")) + ld(2, p) + ld(3, b"") + ld(4, b"")
+
+
+def test_single_protobuf_object_passes_or_is_unauthorized():
+    """The `default:` branch (a get) on a protobuf body: responsefilterer.go:320-341, filterObject :403-415."""
+    body = pod_object(pod("a", "n1"))
+    r = _lib.list_scan(body, _lib.LIST_PROTOBUF_OBJECT)
+    items, ib, ie = r
+    assert len(items) == 1 and names_of(body, items) == [("n1", "a")]
+    assert body[int(items[0]["begin"]):int(items[0]["end"])] == pod("a", "n1")
+    ct = "application/vnd.kubernetes.protobuf"
+    assert pf.filter_object(body, pf.PrefilterResult(allowed_results={("n1", "a")}), ct) == body
+    with pytest.raises(pf.Unauthorized):
+        pf.filter_object(body, pf.PrefilterResult(allowed_results={("n2", "a")}), ct)
+    with pytest.raises(pf.Unauthorized):
+        pf.filter_object(pod_object(pod(meta=False)), pf.PrefilterResult(allowed_results={("n1", "a")}), ct)
+    assert pf.filter_object(pod_object(pod("node-1")), pf.PrefilterResult(allowed_results={("", "node-1")}), ct)
+    with pytest.raises(ValueError):
+        pf.filter_object(body[:-9], pf.PrefilterResult(all_allowed=True), ct)
