@@ -336,8 +336,8 @@ static_assert(kRsetCap <= 31, "class boundaries are 5-bit fields");
 // lanes working on it. The per-lane form of this (every lane walking its own check's rows) ran with 9 of 32 lanes
 // active on average (profiles/r2d): row counts and early exits differ per check. Here the range's children F
 // (<= kFCap, ascending) go to shared memory with one coalesced load, every membership row gets a fixed group of lanes
-// (neighbouring lanes read neighbouring words of the row), and each lane binary-searches its element in F with a
-// warp-uniform trip count. Returns (warp-uniform) whether some element of some row is a child of the range.
+// (neighbouring lanes read neighbouring words of the row), and each lane tests its element against a Bloom filter of F;
+// F itself is binary-searched (warp-uniform trip count) only for what the filter lets through. Returns (warp-uniform) whether some element of some row is a child of the range.
 // Deliberately NOT inlined: inlined, its registers take part in the allocation of the whole traversal loop and cost
 // schemas that never use it 10 % (cfg4: 1 115 -> 944 Mchecks/s, profiles/r2e-r2g); a hash table of the range instead
 // of the binary search was slower still (864 vs 1 094 on cfg3, r2g).
