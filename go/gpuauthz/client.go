@@ -464,5 +464,43 @@ func (c *Client) FilterListResponse(body []byte, tpls []ListTemplate) ([]byte, e
 	return out[:outLen], nil
 }
 
+// PrefilterListResponse replaces runLookupResources + filterList / filterTable (pkg/authz/lookups.go:44-132,
+// pkg/authz/responsefilterer.go:349-400) for rules whose pre-filter is the usual "namespace/name" split: one
+// LookupResources on the GPU (concurrent list requests share launches), one scan of the body, one splice.
+// contentType is the response's Content-Type header: kube clients get protobuf for built-in types and the reference
+// decodes with the serializer it names (responsefilterer.go:241-266); asTable = the request's Accept carried
+// "as=Table" (always JSON, responsefilterer.go:344-346).
+func (c *Client) PrefilterListResponse(body []byte, contentType string, asTable bool, t ListTemplate) ([]byte, error) {
+	if len(body) == 0 {
+		return nil, fmt.Errorf("failed to decode response body: empty body")
+	}
+	mode := C.uint32_t(C.ZG_LIST_ITEMS)
+	switch {
+	case asTable:
+		mode = C.ZG_LIST_TABLE_ROWS
+	case strings.HasPrefix(strings.TrimSpace(contentType), "application/vnd.kubernetes.protobuf"):
+		mode = C.ZG_LIST_PROTOBUF
+	}
+	var cs cstrs
+	defer cs.free()
+	ct := C.zg_list_template{
+		res_type: cs.add(t.ResourceType), permission: cs.add(t.Permission),
+		subj_type: cs.add(t.SubjectType), subj_id: cs.add(t.SubjectID), subj_rel: cs.add(t.SubjectRelation),
+		req_name: cs.add(t.RequestName), req_namespace: cs.add(t.RequestNamespace),
+	}
+	out := make([]byte, len(body)+8)
+	var outLen C.size_t
+	if c.broken.Load() {
+		return nil, errBroken
+	}
+	if err := call(func() C.int {
+		return C.zg_list_prefilter(c.engine, (*C.char)(unsafe.Pointer(&body[0])), C.size_t(len(body)), mode, &ct,
+			(*C.char)(unsafe.Pointer(&out[0])), C.size_t(len(out)), &outLen)
+	}); err != nil {
+		return nil, fmt.Errorf("failed to filter response: %w", err)
+	}
+	return out[:outLen], nil
+}
+
 var _ v1.PermissionsServiceClient = (*Client)(nil)
 var _ = fmt.Sprintf
