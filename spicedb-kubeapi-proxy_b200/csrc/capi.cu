@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <condition_variable>
 #include <cctype>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
@@ -25,6 +26,30 @@
 
 using namespace zg;
 
+// The device lock is FIFO. std::mutex makes no fairness promise, and glibc's lets a thread that unlocks and locks again
+// at once overtake every sleeper: a caller issuing writes back to back (each publishes under this lock) starved the
+// leaders of the check and lookup queues for seconds in tests/cabi/batcher_stress.c. Few threads ever wait here (one
+// leader per queue, writers, direct callers), so one shared condition variable is enough.
+class FairMutex {
+  std::mutex m_;
+  std::condition_variable cv_;
+  uint64_t next_ = 0, serving_ = 0;
+
+ public:
+  void lock() {
+    std::unique_lock<std::mutex> lk(m_);
+    const uint64_t ticket = next_++;
+    cv_.wait(lk, [&] { return serving_ == ticket; });
+  }
+  void unlock() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      ++serving_;
+    }
+    cv_.notify_all();
+  }
+};
+
 // Coalescing batcher ("group commit") for zg_check_bulk. The proxy calls the boundary
 // from one goroutine per rule check (pkg/authz/check.go:77-93) and per list request
 // (pkg/authz/postfilter.go:127-134): many concurrent, mostly small calls. The first
@@ -45,6 +70,7 @@ struct Batcher {
   std::mutex m;
   std::vector<BatchReq*> queue;
   bool leader_active = false;
+  uint64_t groups = 0, waited = 0, handed_over = 0;  // protocol counters (ZGPU_BATCHER_STATS=1 prints them at destroy)
   static constexpr uint64_t kMaxItemsPerLaunch = 1ull << 24;
 };
 
@@ -108,7 +134,7 @@ struct zg_engine {
   //   names  the schema and the store (interning tables, relationship set): shared by everything that resolves
   //          or renders names, exclusive for writers. Never held across GPU work except by a publish, so that
   //          callers can resolve their strings and QUEUE behind a running group instead of waiting for it.
-  std::mutex mu;
+  FairMutex mu;  // the device lock: one launch sequence or publish at a time
   mutable std::shared_mutex names;
   std::vector<std::unique_ptr<Replica>> replicas;  // devices 1 .. n-1 (device 0 is `dev`)
   Batcher batcher;
@@ -186,7 +212,7 @@ static void on_all_devices(zg_engine* e, const std::function<void(Device&, size_
   for (auto& r : e->replicas) r->worker.wait();
 }
 
-#define LOCK_DEVICE(e) std::lock_guard<std::mutex> g((e)->mu)
+#define LOCK_DEVICE(e) std::lock_guard<FairMutex> g((e)->mu)
 #define LOCK_NAMES_SHARED(e) std::shared_lock<std::shared_mutex> ng((e)->names)
 #define LOCK_NAMES_UNIQUE(e) std::unique_lock<std::shared_mutex> ng((e)->names)
 
@@ -273,7 +299,13 @@ extern "C" int zg_engine_create(const zg_config* cfg, zg_engine** out) {
   *out = e;
   return ZG_OK;
 }
-extern "C" void zg_engine_destroy(zg_engine* e) { delete e; }
+extern "C" void zg_engine_destroy(zg_engine* e) {
+  if (e && std::getenv("ZGPU_BATCHER_STATS"))
+    std::fprintf(stderr, "zgpu batcher: %llu groups, %llu callers waited, %llu hand-overs\n",
+                 static_cast<unsigned long long>(e->batcher.groups), static_cast<unsigned long long>(e->batcher.waited),
+                 static_cast<unsigned long long>(e->batcher.handed_over));
+  delete e;
+}
 
 extern "C" int zg_load_schema(zg_engine* e, const char* dsl, size_t len) {
   if (!e || !dsl) return fail(ZG_EINVAL, "NULL argument");
@@ -828,7 +860,10 @@ extern "C" int zg_check_bulk(zg_engine* e, const zg_check* items, uint64_t n, ui
   BatchReq me{items, n, out};
   std::unique_lock<std::mutex> lk(b.m);
   b.queue.push_back(&me);
-  if (b.leader_active) me.cv.wait(lk, [&] { return me.done || me.lead; });
+  if (b.leader_active) {
+    ++b.waited;
+    me.cv.wait(lk, [&] { return me.done || me.lead; });
+  }
   if (!me.done) {
     // leader (nobody was leading, or the previous leader handed over to the head of the queue -- me): take as many
     // queued requests as fit one launch, mine first, answer them, wake their callers, hand leadership on
@@ -838,7 +873,7 @@ extern "C" int zg_check_bulk(zg_engine* e, const zg_check* items, uint64_t n, ui
     {
       // the device first, the group second: whatever queued while this leader waited for the GPU (behind a batch of
       // lookups, a publish, the previous group's tail) rides along
-      std::lock_guard<std::mutex> dev_lock(e->mu);
+      std::lock_guard<FairMutex> dev_lock(e->mu);
       lk.lock();
       uint64_t total = 0;
       size_t take = 0;
@@ -851,11 +886,13 @@ extern "C" int zg_check_bulk(zg_engine* e, const zg_check* items, uint64_t n, ui
       run_group(e, group);
     }
     lk.lock();
+    ++b.groups;
     for (BatchReq* r : group) {
       r->done = true;
       if (r != &me) r->cv.notify_one();
     }
     if (!b.queue.empty()) {
+      ++b.handed_over;
       b.queue.front()->lead = true;
       b.queue.front()->cv.notify_one();
     } else {
@@ -869,7 +906,7 @@ extern "C" int zg_check_bulk(zg_engine* e, const zg_check* items, uint64_t n, ui
 extern "C" int zg_check_bulk_device(zg_engine* e, const zg_check* d_items, uint64_t n, uint8_t* d_out, void* stream) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if ((!d_items || !d_out) && n) return fail(ZG_EINVAL, "NULL argument");
-  std::lock_guard<std::mutex> g(e->mu);
+  std::lock_guard<FairMutex> g(e->mu);
   if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
   if (e->dev.shard_count > 1) return fail(ZG_EINVAL, kShardedMsg);
   e->dev.now = now_of(e);
@@ -881,7 +918,7 @@ extern "C" int zg_check_bulk_device(zg_engine* e, const zg_check* d_items, uint6
 extern "C" int zg_count_alg_bytes(zg_engine* e, const zg_check* items, uint64_t n, uint64_t* bytes) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if (!items || !bytes) return fail(ZG_EINVAL, "NULL argument");
-  std::lock_guard<std::mutex> g(e->mu);
+  std::lock_guard<FairMutex> g(e->mu);
   if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
   e->dev.now = now_of(e);
   std::string err;
@@ -1455,7 +1492,7 @@ static int lookup_queued(zg_engine* e, uint16_t res_type, uint16_t perm, uint16_
     std::vector<zg_engine::LookupJob*> group;
     lk.unlock();
     {
-      std::lock_guard<std::mutex> dev_lock(e->mu);  // the device first, the group second (as for checks)
+      std::lock_guard<FairMutex> dev_lock(e->mu);  // the device first, the group second (as for checks)
       lk.lock();
       const size_t take = std::min<size_t>(b.queue.size(), kMaxLookupGroup);
       group.assign(b.queue.begin(), b.queue.begin() + static_cast<long>(take));
@@ -1669,7 +1706,7 @@ extern "C" int zg_list_prefilter(zg_engine* e, const char* body, size_t len, uin
 
 extern "C" int zg_stats_get(zg_engine* e, zg_stats* out) {
   if (!e || !out) return fail(ZG_EINVAL, "NULL argument");
-  std::lock_guard<std::mutex> g(e->mu);
+  std::lock_guard<FairMutex> g(e->mu);
   if (!e->host_only) e->dev.finish_timing();
   std::memset(out, 0, sizeof *out);
   out->checks = e->dev.checks;
@@ -1711,7 +1748,7 @@ extern "C" int zg_stats_get(zg_engine* e, zg_stats* out) {
 extern "C" int zg_shard_pass(zg_engine* e, const zg_check* queries, uint64_t n, int level, uint64_t* n_sub) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if ((!queries && n) || !n_sub || level < 0 || level > ZG_MAX_DEPTH + 2) return fail(ZG_EINVAL, "bad argument");
-  std::lock_guard<std::mutex> g(e->mu);
+  std::lock_guard<FairMutex> g(e->mu);
   if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
   if (!e->dev.snap) return fail(ZG_ENOSNAPSHOT, "no snapshot published (call zg_publish)");
   e->dev.now = now_of(e);
@@ -1722,7 +1759,7 @@ extern "C" int zg_shard_pass(zg_engine* e, const zg_check* queries, uint64_t n, 
 extern "C" int zg_shard_subqueries(zg_engine* e, int level, zg_check* out, uint64_t n) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if ((!out && n) || level < 0) return fail(ZG_EINVAL, "bad argument");
-  std::lock_guard<std::mutex> g(e->mu);
+  std::lock_guard<FairMutex> g(e->mu);
   if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
   std::string err;
   int rc = e->dev.shard_subqueries(level, out, n, &err);
@@ -1731,7 +1768,7 @@ extern "C" int zg_shard_subqueries(zg_engine* e, int level, zg_check* out, uint6
 extern "C" int zg_shard_fold(zg_engine* e, int level, const uint8_t* child_vals, uint64_t n_sub, uint8_t* out) {
   NEED_SCHEMA(e, ZG_ENOSCHEMA);
   if ((!child_vals && n_sub) || level < 0) return fail(ZG_EINVAL, "bad argument");
-  std::lock_guard<std::mutex> g(e->mu);
+  std::lock_guard<FairMutex> g(e->mu);
   if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");
   std::string err;
   int rc = e->dev.shard_fold(level, child_vals, n_sub, out, &err);
@@ -1741,7 +1778,7 @@ extern "C" int zg_shard_fold(zg_engine* e, int level, const uint8_t* child_vals,
 // ---- sharded store, device-resident protocol (no host staging between passes) ----
 #define SHARD_PROLOGUE()                                                                                              \
   NEED_SCHEMA(e, ZG_ENOSCHEMA);                                                                                       \
-  std::lock_guard<std::mutex> g(e->mu);                                                                               \
+  std::lock_guard<FairMutex> g(e->mu);                                                                               \
   if (e->host_only) return fail(ZG_ECUDA, "host-only engine: no CUDA device, and libzgpu has no CPU fallback");      \
   if (!e->dev.snap) return fail(ZG_ENOSNAPSHOT, "no snapshot published (call zg_publish)");
 
